@@ -1,0 +1,120 @@
+/*
+ * vnpcc.h -- C ABI of libvnpcc.so: the B200 (sm_100a) kernels behind the Vector-Neuron point-cloud-completion hot
+ * path.  Plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host; `stream`
+ * is a cudaStream_t passed as void*.  Every function only enqueues work (no synchronisation) and returns 0 on
+ * success, a cudaError_t value if a launch failed, or one of the VNPCC_ERR_* codes below.  Callers must raise on a
+ * non-zero return (the reference prints and ignores errors: extensions/chamfer_distance/chamfer3D.cu:145-151).
+ *
+ * Row layout ("channels-last", the physical layout the reference's nn.Linear calls produce): a logical
+ * VN tensor [B, C, 3, N] is a row-major matrix X[R, C], R = 3*B*N, row r = (b*N + n)*3 + v, leading dimension `ld`
+ * (floats).  "P" below is the number of 3-vectors per channel (P = R / 3).
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *   vnpcc_chamfer_forward / _backward   extensions/chamfer_distance/chamfer_cuda.cpp:17-27 (pybind `forward` /
+ *                                       `backward`), kernels chamfer3D.cu:12-134 and :155-174
+ *   vnpcc_cd_l1_* / vnpcc_cd_l2_*       metrics/loss.py:20-43, metrics/metric.py:12-23 (sqrt / mean tails)
+ *   vnpcc_gemm_*                        nn.Linear(bias=False) inside VNLinear & friends: models/vn_layers.py:21,38,65,69,162,194
+ *   vnpcc_vn_norm_stats / bn_finalize / vn_bn_leaky_*   VNBatchNorm models/vn_layers.py:116-127 + the leaky projection
+ *                                       models/vn_layers.py:39-42,70-73 (forward) and their autograd
+ *   vnpcc_vn_maxpool_*                  VNMaxPool models/vn_layers.py:158-167
+ *   vnpcc_rows_*                        cat/expand of a broadcast global feature models/pcn.py:172,383-385 (folded into a
+ *                                       per-sample bias), VNLinear(256,1) + residual models/pcn.py:345,387
+ */
+#ifndef VNPCC_H_
+#define VNPCC_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNPCC_OK 0
+#define VNPCC_ERR_WORKSPACE 10001
+#define VNPCC_ERR_BAD_ARG 10002
+#define VNPCC_ERR_UNSUPPORTED 10003
+#define VNPCC_ERR_DRIVER 10004
+
+#define VNPCC_ABI_VERSION 1
+int vnpcc_abi_version(void);
+/* number of kernel launches enqueued by this library in this process (bench.py's gpu_launches) */
+unsigned long long vnpcc_launch_count(void);
+
+/* ---------------------------------------------------------------- Chamfer ---------------------------------------- */
+size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M);
+/* xyz1 [B,N,3], xyz2 [B,M,3] contiguous fp32 -> dist1 [B,N], dist2 [B,M] (squared), idx1 [B,N], idx2 [B,M] int32.
+ * Bit-identical to the reference kernel for finite inputs; lowest index wins exact ties.  N==0 or M==0: outputs untouched. */
+int vnpcc_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1, float* dist2,
+                          int* idx1, int* idx2, void* workspace, size_t workspace_bytes, void* stream);
+/* gradxyz1 [B,N,3] / gradxyz2 [B,M,3] are fully overwritten (no pre-zeroing); either may be NULL. */
+int vnpcc_chamfer_backward(const float* xyz1, const float* xyz2, int B, int N, int M, const float* graddist1,
+                           const float* graddist2, const int* idx1, const int* idx2, float* gradxyz1, float* gradxyz2,
+                           void* stream);
+void vnpcc_chamfer_set_packed_math(int on);
+/* reductions of the CD entry points.  mode 0: cd_loss_L1 (mean sqrt, /2)  1: cd_loss_L2 (mean)  2: l1_cd  3: l2_cd
+ * (per-sample means summed over the batch).  out: 1 float, written (not accumulated).  scratch: 2 doubles. */
+int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M, int mode, double* scratch, float* out,
+                    void* stream);
+/* gradient of the CD entry point w.r.t. dist1/dist2 for upstream scalar *gout (device) : writes graddist1/2. */
+int vnpcc_cd_reduce_bwd(const float* dist1, const float* dist2, int B, int N, int M, int mode, const float* gout,
+                        float* graddist1, float* graddist2, void* stream);
+
+/* ---------------------------------------------------------------- GEMMs ------------------------------------------ */
+/* Y[r,o] (+)= sum_k X[r,k] * Wop[o,k] (+ bias[(r / rows_per_sample)*3 + r%3, o]);  trans_w: 0 -> W [Cout,K], 1 -> W [K,Cout] */
+int vnpcc_gemm_rows_fp32(const float* X, long long ldx, const float* W, long long ldw, int trans_w, float* Y,
+                         long long ldy, long long R, int K, int Cout, const float* bias, long long ldbias,
+                         long long rows_per_sample, int accumulate, void* stream);
+/* G[o,k] (+)= sum_r dY[r,o] * X[r,k] */
+int vnpcc_gemm_wgrad_fp32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg,
+                          long long R, int Cout, int K, int accumulate, void* stream);
+int vnpcc_transpose(const float* in, long long ldi, float* out, long long ldo, int rows, int cols, void* stream);
+
+/* tensor-core (tcgen05 / TMEM / TMA) versions, TF32 operands, fp32 accumulation.  Same contracts as the _fp32 ones;
+ * return VNPCC_ERR_UNSUPPORTED for shapes/alignments they do not take (callers then use the _fp32 entry points). */
+int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy,
+                         long long R, int K, int Cout, const float* bias, long long ldbias, long long rows_per_sample,
+                         void* stream);
+int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg,
+                          long long R, int Cout, int K, float* workspace, size_t workspace_bytes, void* stream);
+size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long R, int Cout, int K);
+
+/* ---------------------------------------------------------------- VN elementwise / reductions ------------------- */
+int vnpcc_vn_norm_stats(const float* p, long long ldp, long long P, int C, double* sums, void* stream);
+int vnpcc_bn_finalize(const double* sums, double count, int C, int training, float* running_mean, float* running_var,
+                      float momentum, float bn_eps, float* stat, void* stream);
+int vnpcc_vn_bn_leaky_fwd(const float* p, long long ldp, const float* d, long long ldd, float* out, long long ldo,
+                          long long P, int C, const float* stat, const float* gamma, const float* beta, float ns,
+                          void* stream);
+int vnpcc_vn_bn_leaky_bwd1(const float* g, long long ldg, const float* p, long long ldp, const float* d, long long ldd,
+                           float* gp, long long ldgp, float* gd, long long ldgd, long long P, int C, const float* stat,
+                           const float* gamma, const float* beta, float ns, double* sums, void* stream);
+int vnpcc_vn_bn_bwd2(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat,
+                     const float* gamma, const float* beta, const double* sums, double count, int training,
+                     float* gweight, float* gbias, void* stream);
+/* VNMaxPool over groups of N consecutive points: ws = B*C u64, idx int64 [B,C] */
+int vnpcc_vn_maxpool_argmax(const float* x, long long ldx, const float* d, long long ldd, int B, int N, int C,
+                            unsigned long long* ws, long long* idx, void* stream);
+int vnpcc_vn_maxpool_gather(const float* x, long long ldx, const long long* idx, int B, int N, int C, float* out,
+                            long long ldo, void* stream);
+int vnpcc_vn_maxpool_scatter_add(const float* g, long long ldg, const long long* idx, int B, int N, int C, float* gx,
+                                 long long ldgx, void* stream);
+int vnpcc_rows_add_sample_bias(float* y, long long ldy, const float* bias, long long ldb, int B, int N, int C,
+                               void* stream);
+int vnpcc_rows_sample_sum(const float* g, long long ldg, int B, int N, int C, float* out, long long ldo, void* stream);
+int vnpcc_rows_dot(const float* x, long long ldx, const float* w, long long R, int C, const float* res, float* y,
+                   void* stream);
+int vnpcc_rows_dot_bwd(const float* gy, const float* x, long long ldx, const float* w, long long R, int C, float* gx,
+                       long long ldgx, float* gw, void* stream);
+
+/* ---------------------------------------------------------------- optimiser / misc ------------------------------ */
+/* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
+int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* FP32-pipe peak micro-benchmark used for the Chamfer roofline (mode 0: FFMA, 1: FFMA2, 2: Chamfer mix) */
+int vnpcc_measure_fp32_peak(int mode, int iters, float* scratch_dev, float* ms_out_host, double* lane_ops_out_host,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNPCC_H_ */

@@ -1,0 +1,266 @@
+"""tests/golden/make_golden.py -- generates the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference; it does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference modules through the stub shim of SURVEY.md Appendix F (pointnet2_ops / knn_cuda / timm are
+import-time-only dependencies of the reference package; they are never executed on this path), runs the reference's
+own classes on CPU with seeded inputs, and stores inputs, parameters, outputs and autograd gradients as .npz files
+next to this script.  Nothing from the reference is copied: only its numerical outputs are stored.
+
+Fixtures:
+  chamfer_unit.npz      the reference's only test (ChamferDistancePytorch/unit_test.py:14-35): rand(4,100,3) vs
+                        rand(4,200,3) through chamfer_python.distChamfer (the reference's CPU-capable Chamfer),
+                        plus a ragged/edge set and autograd gradients of sum(dist1)+sum(dist2) and of CD-L1.
+  vn_layers.npz         every class of models/vn_layers.py on small seeded inputs: forward, backward, BN buffers.
+  pcn_b6.npz            same as pcn_small at B=6, N=128, GT 1024 (better-conditioned BatchNorm statistics).
+  pcn_small.npz         VN_PointNet + VN_FoldingNet (models/pcn.py) at B=2, N=256 under torch.manual_seed(0):
+                        inputs, rotation, VNMaxPool selections, coarse / fine, CD-L1 losses, gradient digests,
+                        and a digest of the seeded state_dict (so the weights can be regenerated, not shipped).
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+
+def install_shim():
+    sys.path.insert(0, REF)
+    pn = types.ModuleType("pointnet2_ops")
+    pu = types.ModuleType("pointnet2_ops.pointnet2_utils")
+    pn.pointnet2_utils = pu
+    sys.modules.update({"pointnet2_ops": pn, "pointnet2_ops.pointnet2_utils": pu})
+    kc = types.ModuleType("knn_cuda")
+    kc.KNN = type("KNN", (), {"__init__": lambda self, k, transpose_mode=False: None})
+    sys.modules["knn_cuda"] = kc
+    tl = types.ModuleType("timm.models.layers")
+    tl.DropPath = torch.nn.Identity
+    tl.trunc_normal_ = torch.nn.init.trunc_normal_
+    sys.modules.update({"timm": types.ModuleType("timm"), "timm.models": types.ModuleType("timm.models"),
+                        "timm.models.layers": tl})
+    if not hasattr(importlib, "find_loader"):
+        importlib.find_loader = lambda name: importlib.util.find_spec(name)
+    sys.path.insert(0, os.path.join(REF, "extensions/ChamferDistancePytorch"))
+
+
+def npy(t):
+    return t.detach().cpu().numpy().copy()
+
+
+class Rot:
+    """pytorch3d.transforms.Rotate stand-in: row-vector convention, transform_points(p) = p @ R."""
+
+    def __init__(self, R):
+        self.R = R
+
+    def transform_points(self, p):
+        return torch.matmul(p, self.R)
+
+
+def ref_cd_l1(distChamfer, a, b):
+    # metrics/loss.py:28-31 restated on top of the reference's CPU Chamfer
+    d1, d2, _, _ = distChamfer(a, b)
+    return (torch.mean(torch.sqrt(d1)) + torch.mean(torch.sqrt(d2))) / 2.0
+
+
+def gen_chamfer(out):
+    import chamfer_python
+    g = torch.Generator().manual_seed(1234)
+    cases = {"unit": (4, 100, 200), "ragged": (3, 37, 531), "tiny": (2, 1, 5), "one2one": (1, 7, 1), "big": (2, 1500, 1100)}
+    for name, (B, N, M) in cases.items():
+        p1 = torch.rand(B, N, 3, generator=g)
+        p2 = torch.rand(B, M, 3, generator=g)
+        a = p1.clone().requires_grad_(True)
+        b = p2.clone().requires_grad_(True)
+        d1, d2, i1, i2 = chamfer_python.distChamfer(a, b)
+        w1 = torch.rand(B, N, generator=g)
+        w2 = torch.rand(B, M, generator=g)
+        ((d1 * w1).sum() + (d2 * w2).sum()).backward()
+        out[f"ch_{name}_p1"], out[f"ch_{name}_p2"] = npy(p1), npy(p2)
+        out[f"ch_{name}_d1"], out[f"ch_{name}_d2"] = npy(d1), npy(d2)
+        out[f"ch_{name}_i1"], out[f"ch_{name}_i2"] = npy(i1), npy(i2)
+        out[f"ch_{name}_w1"], out[f"ch_{name}_w2"] = npy(w1), npy(w2)
+        out[f"ch_{name}_g1"], out[f"ch_{name}_g2"] = npy(a.grad), npy(b.grad)
+        a2 = p1.clone().requires_grad_(True)
+        b2 = p2.clone().requires_grad_(True)
+        l = ref_cd_l1(chamfer_python.distChamfer, a2, b2)
+        l.backward()
+        out[f"ch_{name}_l1"] = npy(l)
+        out[f"ch_{name}_l1_g1"], out[f"ch_{name}_l1_g2"] = npy(a2.grad), npy(b2.grad)
+        d1, d2, _, _ = chamfer_python.distChamfer(p1, p2)
+        out[f"ch_{name}_l2"] = npy(torch.mean(d1) + torch.mean(d2))                       # metrics/loss.py:42-43
+        out[f"ch_{name}_l2cd"] = npy(torch.sum(d1.mean(1) + d2.mean(1)))                  # metrics/metric.py:12-16
+        out[f"ch_{name}_l1cd"] = npy(torch.sum(torch.sqrt(d1).mean(1) + torch.sqrt(d2).mean(1)) / 2)  # :19-23
+
+
+def _sd(mod, out, key):
+    for k, v in mod.state_dict().items():
+        out[f"{key}.sd.{k}"] = npy(v)
+
+
+def gen_layers(out):
+    import models.vn_layers as V
+    g = torch.Generator().manual_seed(4321)
+
+    def rnd(*s):
+        return torch.randn(*s, generator=g)
+
+    def run(key, mod, x, train=True, tuple_out=False):
+        mod.train(train)
+        _sd(mod, out, key + ".pre")
+        xi = x.clone().requires_grad_(True)
+        y = mod(xi)
+        ys = y if tuple_out else (y,)
+        gys = [rnd(*t.shape) for t in ys]
+        sum((t * gy).sum() for t, gy in zip(ys, gys)).backward()
+        out[key + ".x"] = npy(x)
+        for i, (t, gy) in enumerate(zip(ys, gys)):
+            out[f"{key}.y{i}"] = npy(t)
+            out[f"{key}.gy{i}"] = npy(gy)
+        out[key + ".gx"] = npy(xi.grad)
+        for n_, p in mod.named_parameters():
+            out[f"{key}.grad.{n_}"] = npy(p.grad) if p.grad is not None else np.zeros(0, np.float32)
+        _sd(mod, out, key + ".post")
+        mod.zero_grad()
+
+    B, N = 3, 40
+    torch.manual_seed(7)
+    run("VNLinear", V.VNLinear(12, 20), rnd(B, 12, 3, N))
+    run("VNLinear_dim3", V.VNLinear(12, 20), rnd(B, 12, 3))
+    run("VNLeakyReLU", V.VNLeakyReLU(16), rnd(B, 16, 3, N))
+    run("VNLeakyReLU_shared", V.VNLeakyReLU(16, share_nonlinearity=True), rnd(B, 16, 3, N))
+    run("VNLeakyReLU_ns", V.VNLeakyReLU(16, negative_slope=0.0), rnd(B, 16, 3, N))
+    m = V.VNLinearLeakyReLU(12, 24, dim=4)
+    with torch.no_grad():
+        m.batchnorm.bn.weight.copy_(rnd(24))
+        m.batchnorm.bn.bias.copy_(rnd(24) * 0.3)
+    run("VNLinearLeakyReLU", m, rnd(B, 12, 3, N))
+    run("VNLinearLeakyReLU_eval", m, rnd(B, 12, 3, N), train=False)
+    run("VNLinearLeakyReLU_k1", V.VNLinearLeakyReLU(1, 16, dim=4), rnd(B, 1, 3, N))
+    run("VNLinearLeakyReLU_dim5", V.VNLinearLeakyReLU(6, 10), rnd(2, 6, 3, 9, 5))
+    run("VNLinearLeakyReLU_shared", V.VNLinearLeakyReLU(12, 24, dim=4, share_nonlinearity=True), rnd(B, 12, 3, N))
+    run("VNLinearAndLeakyReLU_none", V.VNLinearAndLeakyReLU(12, 24, dim=4, use_batchnorm="none"), rnd(B, 12, 3, 1))
+    run("VNLinearAndLeakyReLU_norm", V.VNLinearAndLeakyReLU(12, 24, dim=4), rnd(B, 12, 3, N))
+    m = V.VNBatchNorm(16, dim=4)
+    with torch.no_grad():
+        m.bn.weight.copy_(rnd(16))
+        m.bn.bias.copy_(rnd(16) * 0.3)
+    run("VNBatchNorm", m, rnd(B, 16, 3, N))
+    run("VNBatchNorm_eval", m, rnd(B, 16, 3, N), train=False)
+    run("VNBatchNorm_dim3", V.VNBatchNorm(16, dim=3), rnd(5, 16, 3))
+    mp = V.VNMaxPool(16)
+    x = rnd(B, 16, 3, N)
+    run("VNMaxPool", mp, x)
+    with torch.no_grad():
+        d = mp.map_to_dir(x.transpose(1, -1)).transpose(1, -1)
+        out["VNMaxPool.idx"] = npy((x * d).sum(2, keepdims=True).max(dim=-1)[1])
+    run("VNStdFeature", V.VNStdFeature(16, dim=4), rnd(B, 16, 3, N), tuple_out=True)
+    # B=2 here: the reference calls torch.cross without dim (vn_layers.py:208), which picks the FIRST size-3 axis --
+    # the batch axis when B==3.  The intended (and for B!=3 actual) axis is 1.
+    run("VNStdFeature_frame", V.VNStdFeature(16, dim=4, normalize_frame=True), rnd(2, 16, 3, N), tuple_out=True)
+    out["mean_pool.x"] = npy(x)
+    out["mean_pool.y"] = npy(V.mean_pool(x))
+
+
+def digest(t):
+    a = npy(t).astype(np.float64).ravel()
+    return np.array([a.sum(), np.abs(a).sum(), (a * a).sum(), a[:: max(1, a.size // 97)][:64].sum()], np.float64)
+
+
+def gen_pcn(out, B=2, n_partial=256, n_gt=2048, seed=99):
+    import chamfer_python
+    import models.pcn as P
+    from vn_pointcloudcompletion_b200.synthetic import make_batch
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cpu", enc_pretrained="none")
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # models/pcn.py:362 hard-codes .cuda()
+    try:
+        torch.manual_seed(0)
+        enc = P.VN_PointNet(cfg)
+        dec = P.VN_FoldingNet(cfg)
+    finally:
+        torch.Tensor.cuda = _cuda
+    enc.train()
+    dec.train()
+    p, c, R = make_batch(B, n_partial=n_partial, n_gt=n_gt, seed=seed)
+    p_t, c_t, R_t = torch.from_numpy(p), torch.from_numpy(c), torch.from_numpy(R)
+    sel = {}
+
+    def hook(name):
+        def f(mod, inp, outp):
+            x = inp[0]
+            with torch.no_grad():
+                d = mod.map_to_dir(x.transpose(1, -1)).transpose(1, -1)
+                dot = (x * d).sum(2, keepdims=True)
+                sel[name] = dot.max(dim=-1)[1]
+                top2 = dot.squeeze(2).topk(2, dim=-1)[0]
+                sel[name + "_gap"] = (top2[..., 0] - top2[..., 1]) / top2[..., 0].abs().clamp_min(1e-30)
+        return f
+
+    enc.maxpool1.register_forward_hook(hook("idx1"))
+    enc.maxpool2.register_forward_hook(hook("idx2"))
+    for k, v in list(enc.state_dict().items()):
+        out["sd_digest.encoder." + k] = digest(v.float())
+    for k, v in list(dec.state_dict().items()):
+        out["sd_digest.decoder." + k] = digest(v.float())
+    coarse, fg = enc(p_t)
+    fine = dec(coarse, fg, Rot(R_t))
+    l1 = ref_cd_l1(chamfer_python.distChamfer, coarse, c_t)
+    l2 = ref_cd_l1(chamfer_python.distChamfer, fine, c_t)
+    (l1 + l2).backward()
+    out["p"], out["c"], out["R"] = p, c, R
+    out["idx1"], out["idx2"] = npy(sel["idx1"]), npy(sel["idx2"])
+    out["gap1"], out["gap2"] = npy(sel["idx1_gap"]), npy(sel["idx2_gap"])
+    out["coarse"], out["fg"], out["fine"] = npy(coarse), npy(fg), npy(fine)
+    out["loss1"], out["loss2"] = npy(l1), npy(l2)
+    for pref, mod in (("encoder.", enc), ("decoder.", dec)):
+        for n_, prm in mod.named_parameters():
+            if prm.grad is None:
+                out["grad_none." + pref + n_] = np.zeros(0, np.float32)
+            elif prm.numel() <= 4096:
+                out["grad." + pref + n_] = npy(prm.grad)
+            else:
+                out["grad_digest." + pref + n_] = digest(prm.grad)
+                out["grad_head." + pref + n_] = npy(prm.grad).ravel()[:256].copy()
+        for n_, buf in mod.named_buffers():
+            out["buf_post." + pref + n_] = npy(buf)
+    # eval-mode forward on the post-step buffers (no parameter update happened)
+    enc.eval()
+    dec.eval()
+    with torch.no_grad():
+        coarse_e, fg_e = enc(p_t)
+        fine_e = dec(coarse_e, fg_e, Rot(R_t))
+    out["eval_idx1"], out["eval_idx2"] = npy(sel["idx1"]), npy(sel["idx2"])
+    out["eval_coarse"], out["eval_fine"] = npy(coarse_e), npy(fine_e)
+
+
+def main():
+    install_shim()
+    torch.set_num_threads(os.cpu_count())
+    # pcn_b6: same network at B=6 -- with more samples per batch the decoder's BatchNorm-on-norms is far better
+    # conditioned than at B=2 (see DESIGN.md "conditioning"), so values can be compared at the north-star 1e-4.
+    only = set(sys.argv[1:])
+    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn),
+                     ("pcn_b6", lambda o: gen_pcn(o, B=6, n_partial=128, n_gt=1024, seed=17))):
+        if only and name not in only:
+            continue
+        out = {}
+        fn(out)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

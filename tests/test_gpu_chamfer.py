@@ -1,0 +1,135 @@
+"""GPU parity of the Chamfer path (through the C-ABI) against the CPU oracle and the golden fixtures generated from
+the reference (tests/golden/make_golden.py).  Indices: bit-exact.  Distances: bit-exact vs the oracle (same fp32
+arithmetic as the reference kernel), reference tolerance vs the float64 distChamfer goldens."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CH_CASES = ["unit", "ragged", "tiny", "one2one", "big"]
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("case", CH_CASES)
+@pytest.mark.parametrize("packed", [1, 0])
+def test_forward_backward_vs_golden_and_oracle(golden, case, packed):
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import _lib
+    from oracle import vn_oracle as O
+    _lib.load().vnpcc_chamfer_set_packed_math(packed)
+    g = golden("chamfer_unit")
+    p1, p2 = g[f"ch_{case}_p1"], g[f"ch_{case}_p2"]
+    a = _dev(p1).requires_grad_(True)
+    b = _dev(p2).requires_grad_(True)
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(a, b)
+    # the reference's own acceptance test (ChamferDistancePytorch/unit_test.py:23-33)
+    e = np.mean((d1.detach().cpu().numpy() - g[f"ch_{case}_d1"]) ** 2) + np.mean((d2.detach().cpu().numpy() - g[f"ch_{case}_d2"]) ** 2)
+    assert e < 1e-8
+    assert np.array_equal(i1.cpu().numpy(), g[f"ch_{case}_i1"]) and np.array_equal(i2.cpu().numpy(), g[f"ch_{case}_i2"])
+    # bit-exact vs the oracle (the reference kernel's arithmetic)
+    od1, od2, oi1, oi2 = O.chamfer_forward(p1, p2)
+    assert np.array_equal(d1.detach().cpu().numpy(), od1) and np.array_equal(d2.detach().cpu().numpy(), od2)
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    w1, w2 = _dev(g[f"ch_{case}_w1"]), _dev(g[f"ch_{case}_w2"])
+    ((d1 * w1).sum() + (d2 * w2).sum()).backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g[f"ch_{case}_g1"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), g[f"ch_{case}_g2"], rtol=1e-4, atol=1e-6)
+    _lib.load().vnpcc_chamfer_set_packed_math(1)
+
+
+@pytest.mark.parametrize("case", CH_CASES)
+def test_cd_entry_points(golden, case):
+    import vn_pointcloudcompletion_b200 as V
+    g = golden("chamfer_unit")
+    a = _dev(g[f"ch_{case}_p1"]).requires_grad_(True)
+    b = _dev(g[f"ch_{case}_p2"]).requires_grad_(True)
+    l = V.cd_loss_L1(a, b)
+    np.testing.assert_allclose(l.item(), g[f"ch_{case}_l1"], rtol=1e-5)
+    l.backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g[f"ch_{case}_l1_g1"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), g[f"ch_{case}_l1_g2"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(V.cd_loss_L2(a, b).item(), g[f"ch_{case}_l2"], rtol=1e-5)
+    np.testing.assert_allclose(V.l2_cd(a, b).item(), g[f"ch_{case}_l2cd"], rtol=1e-5)
+    np.testing.assert_allclose(V.l1_cd(a, b).item(), g[f"ch_{case}_l1cd"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 1024, 16384), (1, 4099, 2050), (3, 513, 511), (2, 16384, 1024), (1, 5, 70000)])
+def test_vs_oracle_seeded(B, N, M):
+    """seeded clouds at sizes the oracle finishes in seconds, incl. the training shape (coarse 1024 vs gt 16384),
+    split candidate ranges and ragged tiles"""
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import vn_oracle as O
+    rng = np.random.RandomState(B * 1000 + N + M)
+    p1 = rng.uniform(-0.5, 0.5, (B, N, 3)).astype(np.float32)
+    p2 = rng.uniform(-0.5, 0.5, (B, M, 3)).astype(np.float32)
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(_dev(p1), _dev(p2))
+    od1, od2, oi1, oi2 = O.chamfer_forward(p1, p2)
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    gd1 = rng.uniform(0.1, 1, (B, N)).astype(np.float32)
+    gd2 = rng.uniform(0.1, 1, (B, M)).astype(np.float32)
+    og1, og2 = O.chamfer_backward(p1, p2, gd1, gd2, oi1, oi2)
+    a = _dev(p1).requires_grad_(True)
+    b = _dev(p2).requires_grad_(True)
+    r = V.chamfer_3DFunction.apply(a, b)
+    ((r[0] * _dev(gd1)).sum() + (r[1] * _dev(gd2)).sum()).backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), og1, rtol=1e-4, atol=1e-5)   # scatter order differs (atomics)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), og2, rtol=1e-4, atol=1e-5)
+
+
+def test_ties_and_duplicates():
+    """all candidates equidistant across several tiles/chunks/splits: the lowest index must win (chamfer3D.cu:36,126)"""
+    import vn_pointcloudcompletion_b200 as V
+    p1 = np.zeros((1, 3, 3), np.float32)
+    p2 = np.tile(np.array([[1, 0, 0]], np.float32), (1, 9000, 1))
+    p2[0, 7000] = [0.5, 0, 0]
+    p2[0, 8100] = [0.5, 0, 0]
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(_dev(p1), _dev(p2))
+    assert (i1.cpu().numpy() == 7000).all() and np.allclose(d1.cpu().numpy(), 0.25)
+    assert (i2.cpu().numpy() == 0).all()
+    # exact duplicates of the query -> distance 0, first duplicate wins
+    q = np.random.RandomState(0).rand(1, 300, 3).astype(np.float32)
+    c = np.concatenate([q, q], axis=1)
+    d1, _, i1, _ = V.chamfer_3DFunction.apply(_dev(q), _dev(c))
+    assert (d1.cpu().numpy() == 0).all() and np.array_equal(i1.cpu().numpy()[0], np.arange(300))
+
+
+def test_empty_clouds_leave_zero_outputs():
+    import vn_pointcloudcompletion_b200 as V
+    a = torch.rand(2, 5, 3, device="cuda")
+    b = torch.zeros(2, 0, 3, device="cuda")
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(a, b)
+    assert d1.shape == (2, 5) and d2.shape == (2, 0) and (d1 == 0).all() and (i1 == 0).all()
+
+
+def test_full_size_properties():
+    """BASELINE sizes (B=32, 16384 x 16384): size-independent properties instead of the O(N*M) oracle --
+    symmetry under swapping the clouds, self-distance zero with identity indices, d(idx) consistency, idempotence."""
+    import vn_pointcloudcompletion_b200 as V
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.rand(32, 16384, 3, device="cuda", generator=g) - 0.5
+    b = torch.rand(32, 16384, 3, device="cuda", generator=g) - 0.5
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(a, b)
+    e1, e2, j1, j2 = V.chamfer_3DFunction.apply(b, a)
+    assert torch.equal(d1, e2) and torch.equal(d2, e1) and torch.equal(i1, j2) and torch.equal(i2, j1)
+    # recompute the distance at the reported index with the reference arithmetic: fma(dz,dz,fma(dx,dx,dy*dy))
+    nb = torch.gather(b, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))
+    df = (nb.double() - a.double())
+    dd = (nb - a)
+    approx = (df * df).sum(-1)
+    assert torch.allclose(d1.double(), approx, rtol=1e-5, atol=1e-12)
+    assert (dd.abs().max() < 0.2)
+    # no candidate in a random subset beats the reported minimum
+    sub = b[:, ::97]
+    dsub = ((a[:, :512, None, :] - sub[:, None, :, :]) ** 2).sum(-1).min(-1)[0]
+    assert (d1[:, :512] <= dsub * (1 + 1e-5) + 1e-12).all()
+    s1, s2, k1, k2 = V.chamfer_3DFunction.apply(a, a)
+    assert (s1 == 0).all() and (s2 == 0).all()
+    ar = torch.arange(16384, device="cuda", dtype=torch.int32).expand(32, -1)
+    assert torch.equal(k1, ar) and torch.equal(k2, ar)
+    d1b, d2b, i1b, i2b = V.chamfer_3DFunction.apply(a, b)
+    assert torch.equal(d1, d1b) and torch.equal(i1, i1b)

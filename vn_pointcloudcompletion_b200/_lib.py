@@ -1,0 +1,94 @@
+"""ctypes binding of libvnpcc.so (include/vnpcc.h).  There is NO fallback: if the library is missing or a call
+returns non-zero, an exception is raised (the reference ignores its kernels' error returns,
+extensions/chamfer_distance/chamfer_distance.py:52,68)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libvnpcc.so")
+
+_p, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/vnpcc.h declares (tests check this)
+SIGNATURES = {
+    "vnpcc_abi_version": (_i, []),
+    "vnpcc_launch_count": (C.c_ulonglong, []),
+    "vnpcc_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vnpcc_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "vnpcc_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "vnpcc_chamfer_set_packed_math": (None, [_i]),
+    "vnpcc_cd_reduce": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "vnpcc_cd_reduce_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vnpcc_gemm_rows_fp32": (_i, [_p, _ll, _p, _ll, _i, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _i, _p]),
+    "vnpcc_gemm_wgrad_fp32": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
+    "vnpcc_transpose": (_i, [_p, _ll, _p, _ll, _i, _i, _p]),
+    "vnpcc_gemm_rows_tf32": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _p]),
+    "vnpcc_gemm_wgrad_tf32": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p, _sz, _p]),
+    "vnpcc_gemm_wgrad_tf32_workspace_bytes": (_sz, [_ll, _i, _i]),
+    "vnpcc_vn_norm_stats": (_i, [_p, _ll, _ll, _i, _p, _p]),
+    "vnpcc_bn_finalize": (_i, [_p, _d, _i, _i, _p, _p, _f, _f, _p, _p]),
+    "vnpcc_vn_bn_leaky_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p]),
+    "vnpcc_vn_bn_leaky_bwd1": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p, _p]),
+    "vnpcc_vn_bn_bwd2": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _d, _i, _p, _p, _p]),
+    "vnpcc_vn_maxpool_argmax": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _p, _p, _p]),
+    "vnpcc_vn_maxpool_gather": (_i, [_p, _ll, _p, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_vn_maxpool_scatter_add": (_i, [_p, _ll, _p, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_rows_add_sample_bias": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _p]),
+    "vnpcc_rows_sample_sum": (_i, [_p, _ll, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_rows_dot": (_i, [_p, _ll, _p, _ll, _i, _p, _p, _p]),
+    "vnpcc_rows_dot_bwd": (_i, [_p, _p, _ll, _p, _ll, _i, _p, _ll, _p, _p]),
+    "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class VnpccError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libvnpcc.so and bind every symbol; raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VnpccError(f"{LIB_PATH} is missing: build it with `python -m vn_pointcloudcompletion_b200.build` "
+                         "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """call an int-returning entry point and raise on a non-zero return"""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise VnpccError(f"{name} failed with code {rc}")
+    return rc
+
+
+def raw(name, *args):
+    return getattr(load(), name)(*args)
+
+
+def launch_count():
+    return int(load().vnpcc_launch_count())

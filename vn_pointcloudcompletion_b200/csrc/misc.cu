@@ -1,0 +1,149 @@
+// misc.cu -- ABI bookkeeping, the CD entry-point reductions (metrics/loss.py:20-43, metrics/metric.py:12-23) and
+// the fused Adam update (train.py:70 torch.optim.Adam(lr, betas=(0.9, 0.999)) semantics) for sm_100a.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "vnpcc_internal.h"
+
+namespace vnpcc {
+
+unsigned long long& launch_counter() {
+    static unsigned long long n = 0;
+    return n;
+}
+
+// ---- CD reductions ------------------------------------------------------------------------------------------
+// All four entry points are  sum_b [ w1 * sum_j f(dist1[b,j]) + w2 * sum_k f(dist2[b,k]) ]  with f = sqrt or id:
+//   cd_loss_L1: f=sqrt, w1 = 1/(2 B N), w2 = 1/(2 B M)      cd_loss_L2: f=id, w1 = 1/(B N), w2 = 1/(B M)
+//   l1_cd     : f=sqrt, w1 = 1/(2 N),   w2 = 1/(2 M)        l2_cd     : f=id, w1 = 1/N,     w2 = 1/M
+template <bool SQRT>
+__global__ void __launch_bounds__(256) cd_sum_kernel(const float* __restrict__ d1, long long n1, const float* __restrict__ d2,
+                                                      long long n2, double* __restrict__ sums) {
+    double s1 = 0.0, s2 = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) {
+        const float v = __ldg(d1 + i);
+        s1 += (double)(SQRT ? sqrtf(v) : v);
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const float v = __ldg(d2 + i);
+        s2 += (double)(SQRT ? sqrtf(v) : v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    __shared__ double sh[2][8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh[0][w] = s1;
+        sh[1][w] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            s1 += sh[0][k];
+            s2 += sh[1][k];
+        }
+        atomicAdd(sums, s1);
+        atomicAdd(sums + 1, s2);
+    }
+}
+
+__global__ void cd_finish_kernel(const double* __restrict__ sums, double w1, double w2, float* __restrict__ out) {
+    // the reference rounds each mean to fp32 before combining them (torch.mean returns fp32)
+    const float a = (float)(sums[0] * w1), b = (float)(sums[1] * w2);
+    out[0] = a + b;
+}
+
+template <bool SQRT>
+__global__ void __launch_bounds__(256) cd_bwd_kernel(const float* __restrict__ d, long long n, float w,
+                                                      const float* __restrict__ gout, float* __restrict__ gd) {
+    const float g = __ldg(gout) * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        gd[i] = SQRT ? g * (0.5f / sqrtf(__ldg(d + i))) : g;   // d == 0 -> inf, exactly like autograd through torch.sqrt
+}
+
+static void cd_weights(int B, int N, int M, int mode, double* w1, double* w2) {
+    switch (mode) {
+        case 0: *w1 = 0.5 / ((double)B * N); *w2 = 0.5 / ((double)B * M); break;
+        case 1: *w1 = 1.0 / ((double)B * N); *w2 = 1.0 / ((double)B * M); break;
+        case 2: *w1 = 0.5 / (double)N; *w2 = 0.5 / (double)M; break;
+        default: *w1 = 1.0 / (double)N; *w2 = 1.0 / (double)M; break;
+    }
+}
+
+// ---- Adam ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2_sqrt, float gscale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+}  // namespace vnpcc
+
+using namespace vnpcc;
+
+extern "C" {
+
+int vnpcc_abi_version(void) { return 1; }
+unsigned long long vnpcc_launch_count(void) { return launch_counter(); }
+
+int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M, int mode, double* scratch, float* out,
+                    void* stream) {
+    if (mode < 0 || mode > 3 || B <= 0 || N <= 0 || M <= 0) return VNPCC_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st);
+    const long long n1 = (long long)B * N, n2 = (long long)B * M;
+    const int grid = grid_for((size_t)(n1 > n2 ? n1 : n2), 256, 2);
+    if (mode == 0 || mode == 2) count_launch(), cd_sum_kernel<true><<<grid, 256, 0, st>>>(dist1, n1, dist2, n2, scratch);
+    else count_launch(), cd_sum_kernel<false><<<grid, 256, 0, st>>>(dist1, n1, dist2, n2, scratch);
+    double w1, w2;
+    cd_weights(B, N, M, mode, &w1, &w2);
+    count_launch(), cd_finish_kernel<<<1, 1, 0, st>>>(scratch, w1, w2, out);
+    return last_error();
+}
+
+int vnpcc_cd_reduce_bwd(const float* dist1, const float* dist2, int B, int N, int M, int mode, const float* gout,
+                        float* graddist1, float* graddist2, void* stream) {
+    if (mode < 0 || mode > 3 || B <= 0 || N <= 0 || M <= 0) return VNPCC_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    double w1, w2;
+    cd_weights(B, N, M, mode, &w1, &w2);
+    const long long n1 = (long long)B * N, n2 = (long long)B * M;
+    const bool sq = (mode == 0 || mode == 2);
+    if (graddist1) {
+        if (sq) count_launch(), cd_bwd_kernel<true><<<grid_for((size_t)n1, 256, 4), 256, 0, st>>>(dist1, n1, (float)w1, gout, graddist1);
+        else count_launch(), cd_bwd_kernel<false><<<grid_for((size_t)n1, 256, 4), 256, 0, st>>>(dist1, n1, (float)w1, gout, graddist1);
+    }
+    if (graddist2) {
+        if (sq) count_launch(), cd_bwd_kernel<true><<<grid_for((size_t)n2, 256, 4), 256, 0, st>>>(dist2, n2, (float)w2, gout, graddist2);
+        else count_launch(), cd_bwd_kernel<false><<<grid_for((size_t)n2, 256, 4), 256, 0, st>>>(dist2, n2, (float)w2, gout, graddist2);
+    }
+    return last_error();
+}
+
+int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    if (step < 1) return VNPCC_ERR_BAD_ARG;
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    count_launch(), adam_kernel<<<grid_for((size_t)n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                             weight_decay, bc1, bc2_sqrt, grad_scale);
+    return last_error();
+}
+
+}  // extern "C"

@@ -1,0 +1,626 @@
+// vn_kernels.cu -- HBM-bound Vector-Neuron kernels for sm_100a (norm statistics, BatchNorm-on-norms + leaky
+// projection forward/backward, arg-max pooling, per-sample bias / reductions, the C->1 VNLinear).
+//
+// Physical layout ("channels-last", the same one the reference's nn.Linear calls physically produce):
+// a logical VN tensor [B, C, 3, N] is stored as a row-major matrix X[R, C] with R = 3*B*N rows, row index
+// r = (b*N + n)*3 + v, channel contiguous, leading dimension `ld` floats (so halves of a stacked [R, 2C] buffer
+// can be addressed in place).  A warp reads 32 (or 128 with float4) consecutive channels of one row: every access
+// is a full 128-byte line.  The three components of one vector sit in three consecutive rows.
+//
+// Reference semantics restated (file:line under /root/reference):
+//   VNBatchNorm        models/vn_layers.py:116-127   norm = ||x|| + 1e-6 ; x / norm * BN(norm)
+//   leaky projection   models/vn_layers.py:39-42, 70-73   (mask = dot >= 0, eps on ||d||^2)
+//   VNMaxPool          models/vn_layers.py:162-166   argmax_n <x,d>, first maximum wins
+// Backward formulas: SURVEY.md Appendix C (derived from the forward definitions, the reference uses autograd).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "vnpcc_internal.h"
+
+namespace vnpcc {
+
+constexpr float VN_EPS = 1e-6f;      // models/vn_layers.py:10
+typedef unsigned long long u64;
+
+struct V3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ float dot3(const V3& a, const V3& b) {
+    // (a*b).sum(2): three rounded products summed left to right (no contraction)
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ V3 ld3(const float* __restrict__ p, size_t ld) {
+    V3 r;
+    r.x = __ldg(p);
+    r.y = __ldg(p + ld);
+    r.z = __ldg(p + 2 * ld);
+    return r;
+}
+__device__ __forceinline__ void st3(float* __restrict__ p, size_t ld, const V3& v) {
+    p[0] = v.x;
+    p[ld] = v.y;
+    p[2 * ld] = v.z;
+}
+
+// BatchNorm-on-norm for one vector: returns the scale nb/n and the pieces the backward needs
+struct BNPiece {
+    float r, n, nhat, nb;
+};
+__device__ __forceinline__ BNPiece bn_piece(const V3& p, float mean, float invstd, float gamma, float beta) {
+    BNPiece o;
+    o.r = sqrtf(dot3(p, p));
+    o.n = o.r + VN_EPS;
+    o.nhat = (o.n - mean) * invstd;
+    o.nb = o.nhat * gamma + beta;
+    return o;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 1. per-channel statistics of the vector norms:  sums[c] += sum n ; sums[C+c] += sum n^2   (double)
+//    block = (32 channel lanes) x (8 point lanes); grid.x tiles channels by 32, grid.y strides over points.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vn_norm_stats_kernel(const float* __restrict__ p, size_t ld, long long P, int C,
+                                                             double* __restrict__ sums) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        long long pt = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+        const long long stride = (long long)gridDim.y * blockDim.y;
+        // accumulate n and n*n in double: var = E[n^2] - mean^2 cancels catastrophically in fp32 when the norms of a
+        // channel barely vary (decoder final_conv[0]: the per-sample global feature dominates every point's norm)
+#pragma unroll 4
+        for (; pt < P; pt += stride) {
+            V3 v = ld3(p + (size_t)pt * 3 * ld + c, ld);
+            const double n = (double)(sqrtf(dot3(v, v)) + VN_EPS);
+            s1 += n;
+            s2 = fma(n, n, s2);
+        }
+    }
+    __shared__ double sh1[8][33], sh2[8][33];
+    sh1[threadIdx.y][threadIdx.x] = s1;
+    sh2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) {
+            s1 += sh1[k][threadIdx.x];
+            s2 += sh2[k][threadIdx.x];
+        }
+        atomicAdd(sums + c, s1);
+        atomicAdd(sums + C + c, s2);
+    }
+}
+
+// finalize: stat[c] = mean, stat[C+c] = 1/sqrt(var+eps).  training: batch stats (+ running update, unbiased var);
+// eval: running stats.  One thread per channel.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, int training,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float bn_eps, float* __restrict__ stat) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (training) {
+        const double mean = sums[c] / count;
+        double var = sums[C + c] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[c] = (float)mean;
+        stat[C + c] = (float)(1.0 / sqrt(var + (double)bn_eps));
+        if (running_mean) {
+            const double unb = count > 1.0 ? var * (count / (count - 1.0)) : var;
+            running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+        }
+    } else {
+        stat[c] = running_mean[c];
+        stat[C + c] = (float)(1.0 / sqrt((double)running_var[c] + (double)bn_eps));
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 2. forward apply:  out = leaky( BN(p), d )     (BN optional: stat == NULL ; leaky optional: d == NULL)
+//    one thread per (point, channel); consecutive threads -> consecutive channels.
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 leaky_fwd(const V3& p, const V3& d, float ns) {
+    // op-by-op rounding of the eager expression  ns*p + (1-ns)*(mask*p + (1-mask)*(p - (dot/(dsq+EPS))*d))
+    const float dot = dot3(p, d);
+    const float k = 1.f - ns;
+    V3 in = p;
+    if (!(dot >= 0.f)) {
+        const float a = dot / __fadd_rn(dot3(d, d), VN_EPS);
+        in.x = __fsub_rn(p.x, __fmul_rn(a, d.x));
+        in.y = __fsub_rn(p.y, __fmul_rn(a, d.y));
+        in.z = __fsub_rn(p.z, __fmul_rn(a, d.z));
+    }
+    V3 o;
+    o.x = __fadd_rn(__fmul_rn(ns, p.x), __fmul_rn(k, in.x));
+    o.y = __fadd_rn(__fmul_rn(ns, p.y), __fmul_rn(k, in.y));
+    o.z = __fadd_rn(__fmul_rn(ns, p.z), __fmul_rn(k, in.z));
+    return o;
+}
+
+__global__ void __launch_bounds__(256) vn_bn_leaky_fwd_kernel(const float* __restrict__ p, size_t ldp,
+                                                               const float* __restrict__ d, size_t ldd,
+                                                               float* __restrict__ out, size_t ldo, long long P, int C,
+                                                               const float* __restrict__ stat,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float ns) {
+    const long long total = P * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long pt = t / C;
+        const int c = (int)(t - pt * C);
+        V3 v = ld3(p + (size_t)pt * 3 * ldp + c, ldp);
+        if (stat) {
+            BNPiece b = bn_piece(v, __ldg(stat + c), __ldg(stat + C + c), __ldg(gamma + c), __ldg(beta + c));
+            v.x = v.x / b.n * b.nb;    // x / norm * norm_bn  (vn_layers.py:125)
+            v.y = v.y / b.n * b.nb;
+            v.z = v.z / b.n * b.nb;
+        }
+        if (d) {
+            V3 dv = ld3(d + (size_t)pt * 3 * ldd + c, ldd);
+            v = leaky_fwd(v, dv, ns);
+        }
+        st3(out + (size_t)pt * 3 * ldo + c, ldo, v);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 3. backward pass 1: from g = dL/dout recompute BN(p), back through the leaky projection ->
+//      gp <- dL/d(BN(p))   (grad w.r.t. the post-BN vector; pass 2 turns it into dL/dp)
+//      gd <- dL/dd
+//    and, when BN is on, accumulate S1 = sum d_nb and S2 = sum d_nb*nhat per channel (d_nb = <gp,p>/n).
+//    Same 32x8 thread shape as the stats kernel so the per-channel sums stay in registers.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vn_bn_leaky_bwd1_kernel(const float* __restrict__ g, size_t ldg,
+                                                                const float* __restrict__ p, size_t ldp,
+                                                                const float* __restrict__ d, size_t ldd,
+                                                                float* __restrict__ gp, size_t ldgp,
+                                                                float* __restrict__ gd, size_t ldgd, long long P, int C,
+                                                                const float* __restrict__ stat,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float ns,
+                                                                double* __restrict__ sums) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        float mean = 0.f, invstd = 0.f, ga = 0.f, be = 0.f;
+        if (stat) {
+            mean = __ldg(stat + c);
+            invstd = __ldg(stat + C + c);
+            ga = __ldg(gamma + c);
+            be = __ldg(beta + c);
+        }
+        const float k = 1.f - ns;
+        long long pt = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+        const long long stride = (long long)gridDim.y * blockDim.y;
+        {
+            for (; pt < P; pt += stride) {
+                const V3 pr = ld3(p + (size_t)pt * 3 * ldp + c, ldp);
+                const V3 gv = ld3(g + (size_t)pt * 3 * ldg + c, ldg);
+                V3 pb = pr;
+                BNPiece b;
+                if (stat) {
+                    b = bn_piece(pr, mean, invstd, ga, be);
+                    pb.x = pr.x / b.n * b.nb;
+                    pb.y = pr.y / b.n * b.nb;
+                    pb.z = pr.z / b.n * b.nb;
+                }
+                V3 gpb = gv;
+                if (d) {
+                    const V3 dv = ld3(d + (size_t)pt * 3 * ldd + c, ldd);
+                    const float s = dot3(pb, dv);
+                    V3 gdv = {0.f, 0.f, 0.f};
+                    if (s < 0.f) {
+                        const float q = dot3(dv, dv) + VN_EPS;
+                        const float a = s / q;
+                        const float gdq = dot3(gv, dv) / q;
+                        gpb.x = gv.x - k * gdq * dv.x;
+                        gpb.y = gv.y - k * gdq * dv.y;
+                        gpb.z = gv.z - k * gdq * dv.z;
+                        gdv.x = -k * (a * gv.x + gdq * pb.x - 2.f * a * gdq * dv.x);
+                        gdv.y = -k * (a * gv.y + gdq * pb.y - 2.f * a * gdq * dv.y);
+                        gdv.z = -k * (a * gv.z + gdq * pb.z - 2.f * a * gdq * dv.z);
+                    }
+                    st3(gd + (size_t)pt * 3 * ldgd + c, ldgd, gdv);
+                }
+                st3(gp + (size_t)pt * 3 * ldgp + c, ldgp, gpb);
+                if (stat) {
+                    const float dnb = dot3(gpb, pr) / b.n;
+                    s1 += (double)dnb;
+                    s2 = fma((double)dnb, (double)b.nhat, s2);
+                }
+            }
+        }
+    }
+    if (sums) {
+        __shared__ double sh1[8][33], sh2[8][33];
+        sh1[threadIdx.y][threadIdx.x] = s1;
+        sh2[threadIdx.y][threadIdx.x] = s2;
+        __syncthreads();
+        if (threadIdx.y == 0 && c < C) {
+            for (int kk = 1; kk < 8; ++kk) {
+                s1 += sh1[kk][threadIdx.x];
+                s2 += sh2[kk][threadIdx.x];
+            }
+            atomicAdd(sums + c, s1);
+            atomicAdd(sums + C + c, s2);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 4. backward pass 2 (BatchNorm-on-norm backward, in place on gp):  gp <- dL/dp
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vn_bn_bwd2_kernel(float* __restrict__ gp, size_t ldgp,
+                                                          const float* __restrict__ p, size_t ldp, long long P, int C,
+                                                          const float* __restrict__ stat,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const double* __restrict__ sums, double count, int training) {
+    const long long total = P * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long pt = t / C;
+        const int c = (int)(t - pt * C);
+        const V3 pr = ld3(p + (size_t)pt * 3 * ldp + c, ldp);
+        float* gptr = gp + (size_t)pt * 3 * ldgp + c;
+        V3 gv;
+        gv.x = gptr[0];
+        gv.y = gptr[ldgp];
+        gv.z = gptr[2 * ldgp];
+        const float ga = __ldg(gamma + c), invstd = __ldg(stat + C + c);
+        const BNPiece b = bn_piece(pr, __ldg(stat + c), invstd, ga, __ldg(beta + c));
+        const float gx = dot3(gv, pr);
+        const float dnb = gx / b.n;
+        float dn = ga * dnb;
+        if (training) {
+            const float m1 = (float)(sums[c] / count) * ga;
+            const float m2 = (float)(sums[C + c] / count) * ga;
+            dn = dn - m1 - b.nhat * m2;
+        }
+        dn = dn * invstd - gx * b.nb / (b.n * b.n);
+        const float sc = b.nb / b.n;
+        const float ur = b.r > 0.f ? dn / b.r : 0.f;
+        V3 o;
+        o.x = gv.x * sc + ur * pr.x;
+        o.y = gv.y * sc + ur * pr.y;
+        o.z = gv.z * sc + ur * pr.z;
+        st3(gptr, ldgp, o);
+    }
+}
+
+__global__ void double_to_float_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 5. VNMaxPool.  score(b,c,n) = <x,d> ; winner = max score, lowest n on ties (torch.max picks the first maximum).
+//    Partial winners are merged with a 64-bit atomicMax on (orderable score bits << 32 | ~n).
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned orderable(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) vn_maxpool_argmax_kernel(const float* __restrict__ x, size_t ldx,
+                                                                 const float* __restrict__ d, size_t ldd, int B, int N,
+                                                                 int C, int n_chunk, u64* __restrict__ best) {
+    // grid: x -> channel tiles of 32, y -> (sample, chunk of points); block (32, 8)
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int chunks_per_b = (N + n_chunk - 1) / n_chunk;
+    const int b = blockIdx.y / chunks_per_b;
+    const int ck = blockIdx.y - b * chunks_per_b;
+    const int n0 = ck * n_chunk, n1 = min(N, n0 + n_chunk);
+    u64 mine = 0ull;
+    if (c < C) {
+        for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+            const size_t row = ((size_t)b * N + n) * 3;
+            const V3 xv = ld3(x + row * ldx + c, ldx);
+            const V3 dv = ld3(d + row * ldd + c, ldd);
+            const float s = dot3(xv, dv);
+            const u64 key = ((u64)orderable(s) << 32) | (u64)(0xffffffffu - (unsigned)n);
+            mine = key > mine ? key : mine;
+        }
+    }
+    __shared__ u64 sh[8][33];
+    sh[threadIdx.y][threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) mine = sh[k][threadIdx.x] > mine ? sh[k][threadIdx.x] : mine;
+        atomicMax(best + (size_t)b * C + c, mine);
+    }
+}
+
+__global__ void vn_maxpool_decode_kernel(const u64* __restrict__ best, long long total, long long* __restrict__ idx) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) idx[t] = (long long)(0xffffffffu - (unsigned)(best[t] & 0xffffffffu));
+}
+
+// out[(b,v), c] = x[(b, idx[b,c], v), c]
+__global__ void vn_maxpool_gather_kernel(const float* __restrict__ x, size_t ldx, const long long* __restrict__ idx,
+                                         int B, int N, int C, float* __restrict__ out, size_t ldo) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * C) return;
+    const int b = (int)(t / C), c = (int)(t - (long long)b * C);
+    const long long n = idx[t];
+    const V3 v = ld3(x + (((size_t)b * N + n) * 3) * ldx + c, ldx);
+    st3(out + ((size_t)b * 3) * ldo + c, ldo, v);
+}
+
+// gx[(b, idx[b,c], v), c] += g[(b,v), c]     (one owner per element: plain read-modify-write)
+__global__ void vn_maxpool_scatter_kernel(const float* __restrict__ g, size_t ldg, const long long* __restrict__ idx,
+                                          int B, int N, int C, float* __restrict__ gx, size_t ldgx) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * C) return;
+    const int b = (int)(t / C), c = (int)(t - (long long)b * C);
+    const long long n = idx[t];
+    float* dst = gx + (((size_t)b * N + n) * 3) * ldgx + c;
+    const float* src = g + ((size_t)b * 3) * ldg + c;
+    dst[0] += src[0];
+    dst[ldgx] += src[ldg];
+    dst[2 * ldgx] += src[2 * ldg];
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 6. per-sample bias (broadcast channels folded out of a GEMM) and its adjoint
+//    y[(b,n,v), c] += bias[(b,v), c]            ;   out[(b,v), c] = sum_n g[(b,n,v), c]
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rows_add_sample_bias_kernel(float* __restrict__ y, size_t ldy,
+                                                                    const float* __restrict__ bias, size_t ldb, int B,
+                                                                    int N, int C) {
+    const long long total = (long long)B * N * 3 * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / C;
+        const int c = (int)(t - row * C);
+        const int v = (int)(row % 3);
+        const int b = (int)(row / (3LL * N));
+        y[(size_t)row * ldy + c] += __ldg(bias + ((size_t)b * 3 + v) * ldb + c);
+    }
+}
+
+__global__ void __launch_bounds__(256) rows_sample_sum_kernel(const float* __restrict__ g, size_t ldg, int B, int N,
+                                                               int C, int n_chunk, float* __restrict__ out, size_t ldo) {
+    // grid: x -> channel tiles of 32, y -> (sample, chunk); block (32, 8); out must be zeroed
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int chunks_per_b = (N + n_chunk - 1) / n_chunk;
+    const int b = blockIdx.y / chunks_per_b;
+    const int ck = blockIdx.y - b * chunks_per_b;
+    const int n0 = ck * n_chunk, n1 = min(N, n0 + n_chunk);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (c < C) {
+        for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+            const V3 v = ld3(g + (((size_t)b * N + n) * 3) * ldg + c, ldg);
+            sx += v.x;
+            sy += v.y;
+            sz += v.z;
+        }
+    }
+    __shared__ float sh[3][8][33];
+    sh[0][threadIdx.y][threadIdx.x] = sx;
+    sh[1][threadIdx.y][threadIdx.x] = sy;
+    sh[2][threadIdx.y][threadIdx.x] = sz;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) {
+            sx += sh[0][k][threadIdx.x];
+            sy += sh[1][k][threadIdx.x];
+            sz += sh[2][k][threadIdx.x];
+        }
+        float* o = out + ((size_t)b * 3) * ldo + c;
+        atomicAdd(o, sx);
+        atomicAdd(o + ldo, sy);
+        atomicAdd(o + 2 * ldo, sz);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 7. VNLinear(C -> 1): y[r] = sum_c x[r,c] w[c] (+ res[r]) ; one warp per row.
+//    backward: gx[r,c] = gy[r] w[c] ; gw[c] = sum_r gy[r] x[r,c]
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rows_dot_kernel(const float* __restrict__ x, size_t ldx,
+                                                        const float* __restrict__ w, long long R, int C,
+                                                        const float* __restrict__ res, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < R; r += nwarps) {
+        const float* xr = x + (size_t)r * ldx;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(xr + c), __ldg(w + c), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[r] = res ? acc + __ldg(res + r) : acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) rows_outer_kernel(const float* __restrict__ gy, const float* __restrict__ w,
+                                                          long long R, int C, float* __restrict__ gx, size_t ldgx) {
+    const long long total = R * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / C;
+        const int c = (int)(t - r * C);
+        gx[(size_t)r * ldgx + c] = __ldg(gy + r) * __ldg(w + c);
+    }
+}
+
+__global__ void __launch_bounds__(256) rows_wsum_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                         size_t ldx, long long R, int C, float* __restrict__ gw) {
+    // block (32, 8): channel tile x row lanes; gw must be zeroed
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (c < C) {
+        for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.y * blockDim.y)
+            acc = fmaf(__ldg(gy + r), __ldg(x + (size_t)r * ldx + c), acc);
+    }
+    __shared__ float sh[8][33];
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) acc += sh[k][threadIdx.x];
+        atomicAdd(gw + c, acc);
+    }
+}
+
+}  // namespace vnpcc
+
+using namespace vnpcc;
+
+extern "C" {
+
+// sums: 2*C doubles, zeroed here.
+int vnpcc_vn_norm_stats(const float* p, long long ldp, long long P, int C, double* sums, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (P > 0 && C > 0) {
+        dim3 block(32, 8);
+        const int gx = (C + 31) / 32;
+        long long gy = (P + 8 * 16 - 1) / (8 * 16);
+        const long long cap = ((long long)sm_count() * 16 + gx - 1) / gx;
+        if (gy > cap) gy = cap;
+        if (gy < 1) gy = 1;
+        count_launch(), vn_norm_stats_kernel<<<dim3(gx, (unsigned)gy), block, 0, st>>>(p, (size_t)ldp, P, C, sums);
+    }
+    return last_error();
+}
+
+int vnpcc_bn_finalize(const double* sums, double count, int C, int training, float* running_mean, float* running_var,
+                      float momentum, float bn_eps, float* stat, void* stream) {
+    if (C <= 0) return 0;
+    count_launch(), bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, C, training, running_mean,
+                                                                        running_var, momentum, bn_eps, stat);
+    return last_error();
+}
+
+int vnpcc_vn_bn_leaky_fwd(const float* p, long long ldp, const float* d, long long ldd, float* out, long long ldo,
+                          long long P, int C, const float* stat, const float* gamma, const float* beta, float ns,
+                          void* stream) {
+    if (P <= 0 || C <= 0) return 0;
+    count_launch(), vn_bn_leaky_fwd_kernel<<<grid_for((size_t)P * C, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma, beta, ns);
+    return last_error();
+}
+
+// sums (2*C doubles) is zeroed here when stat != NULL; pass NULL sums/stat for "no BatchNorm".
+int vnpcc_vn_bn_leaky_bwd1(const float* g, long long ldg, const float* p, long long ldp, const float* d, long long ldd,
+                           float* gp, long long ldgp, float* gd, long long ldgd, long long P, int C, const float* stat,
+                           const float* gamma, const float* beta, float ns, double* sums, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stat && !sums) return VNPCC_ERR_BAD_ARG;
+    if (stat) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (P > 0 && C > 0) {
+        dim3 block(32, 8);
+        const int gx = (C + 31) / 32;
+        long long gy = (P + 8 * 16 - 1) / (8 * 16);
+        const long long cap = ((long long)sm_count() * 16 + gx - 1) / gx;
+        if (gy > cap) gy = cap;
+        if (gy < 1) gy = 1;
+        count_launch(), vn_bn_leaky_bwd1_kernel<<<dim3(gx, (unsigned)gy), block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp,
+                                                                        (size_t)ldgp, gd, (size_t)ldgd, P, C, stat, gamma,
+                                                                        beta, ns, stat ? sums : nullptr);
+    }
+    return last_error();
+}
+
+// dgamma = S2, dbeta = S1 are written to gweight / gbias (fp32) when non-NULL.
+int vnpcc_vn_bn_bwd2(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat,
+                     const float* gamma, const float* beta, const double* sums, double count, int training,
+                     float* gweight, float* gbias, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 0) return 0;
+    if (P > 0)
+        count_launch(), vn_bn_bwd2_kernel<<<grid_for((size_t)P * C, 256, 16), 256, 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma,
+                                                                          beta, sums, count, training);
+    if (gbias) count_launch(), double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gbias, C);
+    if (gweight) count_launch(), double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums + C, gweight, C);
+    return last_error();
+}
+
+// ws: B*C u64.  idx (int64 [B,C]) receives the selections.
+int vnpcc_vn_maxpool_argmax(const float* x, long long ldx, const float* d, long long ldd, int B, int N, int C,
+                            unsigned long long* ws, long long* idx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || C <= 0 || N <= 0) return 0;
+    cudaMemsetAsync(ws, 0, sizeof(u64) * (size_t)B * C, st);
+    const int gx = (C + 31) / 32;
+    // enough (sample, chunk) blocks to fill the machine; chunks of >= 64 points
+    int chunks = (int)(((long long)sm_count() * 8 + (long long)gx * B - 1) / ((long long)gx * B));
+    if (chunks < 1) chunks = 1;
+    int n_chunk = (N + chunks - 1) / chunks;
+    if (n_chunk < 64) n_chunk = 64;
+    chunks = (N + n_chunk - 1) / n_chunk;
+    count_launch(), vn_maxpool_argmax_kernel<<<dim3(gx, (unsigned)(B * chunks)), dim3(32, 8), 0, st>>>(x, (size_t)ldx, d, (size_t)ldd, B, N, C,
+                                                                                     n_chunk, ws);
+    const long long total = (long long)B * C;
+    count_launch(), vn_maxpool_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, total, idx);
+    return last_error();
+}
+
+int vnpcc_vn_maxpool_gather(const float* x, long long ldx, const long long* idx, int B, int N, int C, float* out,
+                            long long ldo, void* stream) {
+    const long long total = (long long)B * C;
+    if (total <= 0) return 0;
+    count_launch(), vn_maxpool_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)ldx, idx, B, N, C,
+                                                                                              out, (size_t)ldo);
+    return last_error();
+}
+
+int vnpcc_vn_maxpool_scatter_add(const float* g, long long ldg, const long long* idx, int B, int N, int C, float* gx,
+                                 long long ldgx, void* stream) {
+    const long long total = (long long)B * C;
+    if (total <= 0) return 0;
+    count_launch(), vn_maxpool_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, (size_t)ldg, idx, B, N, C,
+                                                                                               gx, (size_t)ldgx);
+    return last_error();
+}
+
+int vnpcc_rows_add_sample_bias(float* y, long long ldy, const float* bias, long long ldb, int B, int N, int C,
+                               void* stream) {
+    const size_t total = (size_t)B * N * 3 * C;
+    if (total == 0) return 0;
+    count_launch(), rows_add_sample_bias_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(y, (size_t)ldy, bias, (size_t)ldb,
+                                                                                          B, N, C);
+    return last_error();
+}
+
+// out [B*3, C] (ld ldo) is zeroed here.
+int vnpcc_rows_sample_sum(const float* g, long long ldg, int B, int N, int C, float* out, long long ldo, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || C <= 0) return 0;
+    cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)C * sizeof(float), (size_t)B * 3, st);
+    if (N <= 0) return last_error();
+    const int gx = (C + 31) / 32;
+    int chunks = (int)(((long long)sm_count() * 8 + (long long)gx * B - 1) / ((long long)gx * B));
+    if (chunks < 1) chunks = 1;
+    int n_chunk = (N + chunks - 1) / chunks;
+    if (n_chunk < 64) n_chunk = 64;
+    chunks = (N + n_chunk - 1) / n_chunk;
+    count_launch(), rows_sample_sum_kernel<<<dim3(gx, (unsigned)(B * chunks)), dim3(32, 8), 0, st>>>(g, (size_t)ldg, B, N, C, n_chunk, out,
+                                                                                   (size_t)ldo);
+    return last_error();
+}
+
+int vnpcc_rows_dot(const float* x, long long ldx, const float* w, long long R, int C, const float* res, float* y,
+                   void* stream) {
+    if (R <= 0) return 0;
+    count_launch(), rows_dot_kernel<<<grid_for((size_t)R * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, (size_t)ldx, w, R, C, res, y);
+    return last_error();
+}
+
+// gx[r,c] = gy[r]*w[c]  and  gw[c] = sum_r gy[r]*x[r,c]  (gw zeroed here; either output may be NULL)
+int vnpcc_rows_dot_bwd(const float* gy, const float* x, long long ldx, const float* w, long long R, int C, float* gx,
+                       long long ldgx, float* gw, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gw) cudaMemsetAsync(gw, 0, sizeof(float) * C, st);
+    if (R <= 0 || C <= 0) return last_error();
+    if (gx) count_launch(), rows_outer_kernel<<<grid_for((size_t)R * C, 256, 16), 256, 0, st>>>(gy, w, R, C, gx, (size_t)ldgx);
+    if (gw) {
+        const int gxx = (C + 31) / 32;
+        long long gy_ = (R + 8 * 64 - 1) / (8 * 64);
+        const long long cap = ((long long)sm_count() * 8 + gxx - 1) / gxx;
+        if (gy_ > cap) gy_ = cap;
+        if (gy_ < 1) gy_ = 1;
+        count_launch(), rows_wsum_kernel<<<dim3(gxx, (unsigned)gy_), dim3(32, 8), 0, st>>>(gy, x, (size_t)ldx, R, C, gw);
+    }
+    return last_error();
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+"""Host-side operators over the channels-last ROW layout, each a torch.autograd.Function whose forward and backward
+enqueue kernels of libvnpcc.so on the current CUDA stream (include/vnpcc.h).  PyTorch is used for device memory,
+streams and autograd bookkeeping only; no arithmetic of the hot path runs in ATen, and there is no CPU fallback.
+
+Row layout: a logical VN tensor [B, C, 3, *spatial] is a matrix [R, C] with R = B*prod(spatial)*3 rows, row
+r = (point)*3 + v, channels contiguous (the physical layout the reference's nn.Linear calls produce).
+
+Reference semantics (paths under /root/reference):
+  linear_rows            nn.Linear(bias=False) of VNLinear & friends   models/vn_layers.py:21,38,65,69,162,194
+  bn_leaky               VNBatchNorm + leaky projection                models/vn_layers.py:116-127, 39-42, 70-73
+  maxpool_rows           VNMaxPool                                     models/vn_layers.py:158-167
+  rows_dot               VNLinear(C, 1) (+ residual)                   models/pcn.py:345,387
+  chamfer_3DFunction     extensions/chamfer_distance/chamfer_distance.py:29-71
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+EPS = 1e-6  # models/vn_layers.py:10
+
+_GEMM_MODE = "fp32"      # "fp32": SIMT fp32-exact ; "tf32": tcgen05 tensor cores (TF32 operands, fp32 accumulate)
+
+
+def set_gemm_mode(mode):
+    """'fp32' (parity mode, exact fp32 FMAs) or 'tf32' (tcgen05 tensor cores; SURVEY 8d tolerance applies)."""
+    global _GEMM_MODE
+    if mode not in ("fp32", "tf32"):
+        raise ValueError(mode)
+    _GEMM_MODE = mode
+
+
+def get_gemm_mode():
+    return _GEMM_MODE
+
+
+def _check(t, name="tensor"):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.VnpccError(f"{name} must be a CUDA tensor: the B200 kernels have no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+
+
+def _rows2d(t, name="rows"):
+    """accept a 2-D tensor whose last stride is 1 (row stride = leading dimension); make it so otherwise"""
+    _check(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [rows, channels]")
+    if t.stride(1) != 1 and t.shape[1] != 1:
+        t = t.contiguous()
+    if t.shape[1] == 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# raw launch helpers (no autograd)
+# ---------------------------------------------------------------------------------------------------------------
+def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accumulate=False):
+    """y[r,o] = sum_k x[r,k] * (w[o,k] | w[k,o] if trans_w) (+ bias[(r // rows_per_sample)*3 + r%3, o])"""
+    R, K = x.shape
+    Cout = w.shape[1] if trans_w else w.shape[0]
+    assert (w.shape[0] if trans_w else w.shape[1]) == K, (x.shape, w.shape, trans_w)
+    if out is None:
+        out = torch.empty((R, Cout), device=x.device, dtype=torch.float32)
+    if R == 0 or Cout == 0:
+        return out
+    if _GEMM_MODE == "tf32" and not accumulate:
+        wt = w
+        if trans_w:   # the tensor-core kernel wants K-contiguous weights; weights are small, transpose them
+            wt = torch.empty((Cout, K), device=w.device, dtype=torch.float32)
+            call("vnpcc_transpose", ptr(w), _ld(w), ptr(wt), K, K, Cout, stream())
+        rc = _lib.raw("vnpcc_gemm_rows_tf32", ptr(x), _ld(x), ptr(wt), _ld(wt), ptr(out), _ld(out), R, K, Cout, ptr(bias),
+                      _ld(bias) if bias is not None else 0, rows_per_sample, stream())
+        if rc == 0:
+            return out
+        if rc != 10003:   # VNPCC_ERR_UNSUPPORTED -> shape not taken by the tensor-core kernel
+            raise _lib.VnpccError(f"vnpcc_gemm_rows_tf32 failed with code {rc}")
+    call("vnpcc_gemm_rows_fp32", ptr(x), _ld(x), ptr(w), _ld(w), 1 if trans_w else 0, ptr(out), _ld(out), R, K, Cout,
+         ptr(bias), _ld(bias) if bias is not None else 0, rows_per_sample, 1 if accumulate else 0, stream())
+    return out
+
+
+_WS = {}
+
+
+def _workspace(nbytes, device, key="ws"):
+    k = (key, device)
+    buf = _WS.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _WS[k] = buf
+    return buf
+
+
+def gemm_wgrad(dy, x, out=None, accumulate=False):
+    """g[o,k] (+)= sum_r dy[r,o] * x[r,k]"""
+    R, Cout = dy.shape
+    K = x.shape[1]
+    if out is None:
+        out = torch.empty((Cout, K), device=x.device, dtype=torch.float32)
+        accumulate = False
+    if _GEMM_MODE == "tf32" and not accumulate and R > 0:
+        nb = _lib.raw("vnpcc_gemm_wgrad_tf32_workspace_bytes", R, Cout, K)
+        ws = _workspace(nb, x.device, "wgrad")
+        rc = _lib.raw("vnpcc_gemm_wgrad_tf32", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(out), _ld(out), R, Cout, K, ptr(ws),
+                      ws.numel(), stream())
+        if rc == 0:
+            return out
+        if rc != 10003:
+            raise _lib.VnpccError(f"vnpcc_gemm_wgrad_tf32 failed with code {rc}")
+    call("vnpcc_gemm_wgrad_fp32", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(out), _ld(out), R, Cout, K, 1 if accumulate else 0,
+         stream())
+    return out
+
+
+def rows_sample_sum(g, B, N):
+    """out[(b,v), c] = sum_n g[(b,n,v), c]"""
+    C = g.shape[1]
+    out = torch.empty((B * 3, C), device=g.device, dtype=torch.float32)
+    call("vnpcc_rows_sample_sum", ptr(g), _ld(g), B, N, C, ptr(out), C, stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VNLinear on rows
+# ---------------------------------------------------------------------------------------------------------------
+class _LinearRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, rows_per_sample):
+        x = _rows2d(x, "x")
+        _check(w, "weight")
+        if w.stride(1) != 1:
+            w = w.contiguous()
+        if bias is not None:
+            bias = _rows2d(bias, "bias")
+        y = gemm_rows(x, w, False, bias, rows_per_sample)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        ctx.rps = rows_per_sample
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _rows2d(gy, "grad")
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_rows(gy, w, True)
+        if ctx.needs_input_grad[1]:
+            gw = gemm_wgrad(gy, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            R = gy.shape[0]
+            B = R // ctx.rps
+            gb = rows_sample_sum(gy, B, ctx.rps // 3)
+        return gx, gw, gb, None
+
+
+def linear_rows(x, w, bias=None, rows_per_sample=0):
+    """x [R,K], w [Cout,K] -> [R,Cout]; optional per-sample bias rows [B*3, Cout] (row (b,v)) added to every point of
+    sample b (the broadcast half of torch.cat([global.expand(N), local]) folded out of the GEMM, models/pcn.py:172,385)"""
+    return _LinearRows.apply(x, w, bias, rows_per_sample)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VNBatchNorm (+ leaky projection) on rows
+# ---------------------------------------------------------------------------------------------------------------
+def _bn_prepare(p, C, bn, training, count):
+    """returns stat [2C] (mean | invstd) and updates the running buffers in training mode"""
+    dev = p.device
+    stat = torch.empty(2 * C, device=dev, dtype=torch.float32)
+    sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+    use_batch = training or bn.running_mean is None
+    if use_batch:
+        call("vnpcc_vn_norm_stats", ptr(p), _ld(p), count, C, ptr(sums), stream())
+    momentum = bn.momentum
+    upd = training and bn.track_running_stats and bn.running_mean is not None
+    if upd:
+        bn.num_batches_tracked += 1
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    call("vnpcc_bn_finalize", ptr(sums), float(count), C, 1 if use_batch else 0,
+         ptr(bn.running_mean) if (upd or not use_batch) else None, ptr(bn.running_var) if (upd or not use_batch) else None,
+         float(momentum if momentum is not None else 0.0), float(bn.eps), ptr(stat), stream())
+    return stat, use_batch
+
+
+class _BNLeaky(torch.autograd.Function):
+    """out = leaky(BN(p), d).  `pd` is either the stacked [R, 2C] buffer (p | d) or p alone with d passed separately
+    (d may be None: BatchNorm only; stat may be None: leaky only)."""
+
+    @staticmethod
+    def forward(ctx, p, d, gamma, beta, stat, use_batch, ns, stacked):
+        p = _rows2d(p, "p")
+        if stacked:
+            C = p.shape[1] // 2
+            pv, dv = p[:, :C], p[:, C:]
+        else:
+            C = p.shape[1]
+            pv, dv = p, (_rows2d(d, "d") if d is not None else None)
+        R = p.shape[0]
+        P = R // 3
+        out = torch.empty((R, C), device=p.device, dtype=torch.float32)
+        if R > 0:
+            call("vnpcc_vn_bn_leaky_fwd", ptr(pv), _ld(p), ptr(dv), _ld(dv) if dv is not None else 0, ptr(out), C, P, C,
+                 ptr(stat), ptr(gamma), ptr(beta), float(ns), stream())
+        ctx.save_for_backward(p, d if not stacked else None, gamma, beta, stat)
+        ctx.cfg = (C, P, float(ns), bool(stacked), bool(use_batch))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, d, gamma, beta, stat = ctx.saved_tensors
+        C, P, ns, stacked, use_batch = ctx.cfg
+        g = _rows2d(g, "grad")
+        R = p.shape[0]
+        dev = p.device
+        if stacked:
+            pv, dv = p[:, :C], p[:, C:]
+            gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
+            gp, gd = gpd[:, :C], gpd[:, C:]
+            ldg_ = 2 * C
+        else:
+            pv, dv = p, d
+            gp = torch.empty((R, C), device=dev, dtype=torch.float32)
+            gd = torch.empty((R, C), device=dev, dtype=torch.float32) if d is not None else None
+            ldg_ = C
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64) if stat is not None else None
+        ggamma = gbeta = None
+        if R > 0:
+            call("vnpcc_vn_bn_leaky_bwd1", ptr(g), _ld(g), ptr(pv), _ld(p), ptr(dv), _ld(dv) if dv is not None else 0, ptr(gp),
+                 ldg_, ptr(gd), ldg_ if gd is not None else 0, P, C, ptr(stat), ptr(gamma), ptr(beta), ns, ptr(sums), stream())
+            if stat is not None:
+                ggamma = torch.empty(C, device=dev, dtype=torch.float32)
+                gbeta = torch.empty(C, device=dev, dtype=torch.float32)
+                call("vnpcc_vn_bn_bwd2", ptr(gp), ldg_, ptr(pv), _ld(p), P, C, ptr(stat), ptr(gamma), ptr(beta), ptr(sums),
+                     float(P), 1 if use_batch else 0, ptr(ggamma), ptr(gbeta), stream())
+        if stacked:
+            return gpd, None, ggamma, gbeta, None, None, None, None
+        return gp, gd, ggamma, gbeta, None, None, None, None
+
+
+def bn_leaky(p, d, bn, training, ns, stacked=False):
+    """p (and d) rows; bn: an nn.BatchNorm1d/2d module or None; returns leaky(BN(p), d) rows [R, C]"""
+    p = _rows2d(p, "p")
+    C = p.shape[1] // 2 if stacked else p.shape[1]
+    stat, use_batch, gamma, beta = None, False, None, None
+    if bn is not None:
+        stat, use_batch = _bn_prepare(p[:, :C] if stacked else p, C, bn, training, p.shape[0] // 3)
+        gamma = bn.weight if bn.weight is not None else torch.ones(C, device=p.device)
+        beta = bn.bias if bn.bias is not None else torch.zeros(C, device=p.device)
+    return _BNLeaky.apply(p, d, gamma, beta, stat, use_batch, ns, stacked)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VNMaxPool on rows: groups of N consecutive points
+# ---------------------------------------------------------------------------------------------------------------
+def maxpool_select(x, d, G, N):
+    """idx [G, C] int64 = argmax_n <x, d> within each group of N consecutive points (first maximum wins)"""
+    C = x.shape[1]
+    ws = torch.empty(G * C, device=x.device, dtype=torch.int64)
+    idx = torch.empty((G, C), device=x.device, dtype=torch.int64)
+    call("vnpcc_vn_maxpool_argmax", ptr(x), _ld(x), ptr(d), _ld(d), G, N, C, ptr(ws), ptr(idx), stream())
+    return idx
+
+
+class _MaxPoolGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, G, N):
+        x = _rows2d(x, "x")
+        C = x.shape[1]
+        out = torch.empty((G * 3, C), device=x.device, dtype=torch.float32)
+        call("vnpcc_vn_maxpool_gather", ptr(x), _ld(x), ptr(idx), G, N, C, ptr(out), C, stream())
+        ctx.save_for_backward(idx)
+        ctx.cfg = (G, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        G, N, C = ctx.cfg
+        g = _rows2d(g, "grad")
+        gx = torch.zeros((G * N * 3, C), device=g.device, dtype=torch.float32)
+        call("vnpcc_vn_maxpool_scatter_add", ptr(g), _ld(g), ptr(idx), G, N, C, ptr(gx), C, stream())
+        return gx, None, None, None
+
+
+def maxpool_rows(x, d, G, N, forced_idx=None):
+    """x, d rows [G*N*3, C] -> (pooled rows [G*3, C], idx [G, C]).  d carries no gradient (argmax), SURVEY B.3."""
+    x = _rows2d(x, "x")
+    with torch.no_grad():
+        idx = maxpool_select(x, _rows2d(d.detach(), "d"), G, N) if forced_idx is None else forced_idx.reshape(G, -1).contiguous()
+    return _MaxPoolGather.apply(x, idx, G, N), idx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VNLinear(C -> 1) (+ residual)
+# ---------------------------------------------------------------------------------------------------------------
+class _RowsDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, res):
+        x = _rows2d(x, "x")
+        R, C = x.shape
+        w = w.reshape(-1).contiguous()
+        y = torch.empty(R, device=x.device, dtype=torch.float32)
+        if res is not None:
+            res = res.reshape(-1).contiguous()
+        call("vnpcc_rows_dot", ptr(x), _ld(x), ptr(w), R, C, ptr(res), ptr(y), stream())
+        ctx.save_for_backward(x, w)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        R, C = x.shape
+        gx = torch.empty((R, C), device=x.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        gw = torch.empty(C, device=x.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        call("vnpcc_rows_dot_bwd", ptr(gy), ptr(x), _ld(x), ptr(w), R, C, ptr(gx), C, ptr(gw), stream())
+        return gx, (gw.view(1, C) if gw is not None else None), (gy if ctx.has_res else None)
+
+
+def rows_dot(x, w, res=None):
+    """y[r] = sum_c x[r,c] w[0,c] (+ res[r]);  w is the [1, C] weight of VNLinear(C, 1)"""
+    return _RowsDot.apply(x, w, res)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Chamfer
+# ---------------------------------------------------------------------------------------------------------------
+class chamfer_3DFunction(torch.autograd.Function):
+    """Same contract as the reference's chamfer_3DFunction (extensions/chamfer_distance/chamfer_distance.py:29-71):
+    forward(xyz1 [B,N,3], xyz2 [B,M,3]) -> (dist1 [B,N], dist2 [B,M], idx1, idx2 int32), squared distances."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        _check(xyz1, "xyz1")
+        _check(xyz2, "xyz2")
+        if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[2] != 3 or xyz2.shape[2] != 3 or xyz1.shape[0] != xyz2.shape[0]:
+            raise ValueError(f"expected [B,N,3] and [B,M,3], got {tuple(xyz1.shape)} and {tuple(xyz2.shape)}")
+        xyz1 = xyz1.contiguous()
+        xyz2 = xyz2.contiguous()
+        B, N, _ = xyz1.shape
+        M = xyz2.shape[1]
+        dev = xyz1.device
+        # zero-initialised like the reference (outputs stay 0 when the other cloud is empty)
+        dist1 = torch.zeros((B, N), device=dev, dtype=torch.float32)
+        dist2 = torch.zeros((B, M), device=dev, dtype=torch.float32)
+        idx1 = torch.zeros((B, N), device=dev, dtype=torch.int32)
+        idx2 = torch.zeros((B, M), device=dev, dtype=torch.int32)
+        if B > 0 and N > 0 and M > 0:
+            nb = _lib.raw("vnpcc_chamfer_workspace_bytes", B, N, M)
+            ws = _workspace(nb, dev, "chamfer")
+            with torch.cuda.device(dev):
+                call("vnpcc_chamfer_forward", ptr(xyz1), ptr(xyz2), B, N, M, ptr(dist1), ptr(dist2), ptr(idx1), ptr(idx2),
+                     ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, gradidx1=None, gradidx2=None):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        B, N, _ = xyz1.shape
+        M = xyz2.shape[1]
+        dev = xyz1.device
+        graddist1 = graddist1.contiguous()
+        graddist2 = graddist2.contiguous()
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g1 = torch.empty_like(xyz1) if need1 else None
+        g2 = torch.empty_like(xyz2) if need2 else None
+        if B > 0 and (need1 or need2):
+            with torch.cuda.device(dev):
+                call("vnpcc_chamfer_backward", ptr(xyz1), ptr(xyz2), B, N, M, ptr(graddist1), ptr(graddist2), ptr(idx1),
+                     ptr(idx2), ptr(g1), ptr(g2), stream())
+        return g1, g2
+
+
+class _CDReduce(torch.autograd.Function):
+    """the sqrt/mean tails of cd_loss_L1/L2, l1_cd/l2_cd fused into one reduction (+ its backward)"""
+
+    @staticmethod
+    def forward(ctx, dist1, dist2, mode):
+        dist1 = dist1.contiguous()
+        dist2 = dist2.contiguous()
+        B, N = dist1.shape
+        M = dist2.shape[1]
+        out = torch.empty(1, device=dist1.device, dtype=torch.float32)
+        scratch = torch.empty(2, device=dist1.device, dtype=torch.float64)
+        call("vnpcc_cd_reduce", ptr(dist1), ptr(dist2), B, N, M, mode, ptr(scratch), ptr(out), stream())
+        ctx.save_for_backward(dist1, dist2)
+        ctx.mode = mode
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        dist1, dist2 = ctx.saved_tensors
+        B, N = dist1.shape
+        M = dist2.shape[1]
+        gout = gout.reshape(1).contiguous().float()
+        g1 = torch.empty_like(dist1)
+        g2 = torch.empty_like(dist2)
+        call("vnpcc_cd_reduce_bwd", ptr(dist1), ptr(dist2), B, N, M, ctx.mode, ptr(gout), ptr(g1), ptr(g2), stream())
+        return g1, g2, None
+
+
+def cd_reduce(dist1, dist2, mode):
+    return _CDReduce.apply(dist1, dist2, mode)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused Adam over flat buffers
+# ---------------------------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    call("vnpcc_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), int(step), float(grad_scale), stream())

@@ -1,0 +1,117 @@
+"""Drop-in VN_PointNet encoder and VN_FoldingNet decoder (reference: models/pcn.py:110-184 and :319-389): same
+constructor signature, sub-module names and state_dict keys, same inputs/outputs, executed on the row layout by the
+sm_100a kernels.
+
+B200-first restructuring (results equal to the reference's up to fp32 rounding):
+  * torch.cat([global.expand(-1,-1,-1,N), local], 1) -> VNLinearLeakyReLU (pcn.py:172-173 and :383-387) never
+    materialises the concatenation ([B,2050,3,16384] = 12.9 GB at B=32).  The weight columns that multiply the
+    broadcast global feature are applied once per sample ([B*3, C] rows) and enter the per-point GEMM as a
+    per-sample bias; only the local channels (512 of 1024 in the encoder, 2 of 2050 in the decoder) form the GEMM K.
+  * VNMaxPool's index grids (CPU arange/meshgrid + H2D, vn_layers.py:165) are replaced by an in-kernel arg-max.
+  * activations stay channels-last rows between layers; `coarse` and `fine` come out contiguous [B, n, 3] directly.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .vn_layers import VNLinear, VNLinearAndLeakyReLU, VNLinearLeakyReLU, VNMaxPool
+
+
+class VN_PointNet(nn.Module):
+    """models/pcn.py:110-184"""
+
+    def __init__(self, config, num_dense=16384, latent_dim=1024):
+        super().__init__()
+        self.num_dense = num_dense
+        self.latent_dim = latent_dim
+        if config.num_coarse == 448:
+            self.num_coarse = config.num_coarse // 2
+        else:
+            self.num_coarse = config.num_coarse
+        self.first_conv = nn.Sequential(VNLinearLeakyReLU(1, 128, dim=4), VNLinear(128, 512))
+        self.maxpool1 = VNMaxPool(512)
+        self.second_conv = nn.Sequential(VNLinearLeakyReLU(1024, 1024, dim=4), VNLinear(1024, self.latent_dim * 2))
+        self.maxpool2 = VNMaxPool(self.latent_dim * 2)
+        self.mlp = nn.Sequential(
+            VNLinearAndLeakyReLU(self.latent_dim * 2, 1024 * 2, dim=4, use_batchnorm='none'),
+            VNLinearAndLeakyReLU(1024 * 2, 1024, dim=4, use_batchnorm='none'),
+            VNLinear(1024, self.num_coarse))
+
+    def forward(self, xyz):
+        B, N, _ = xyz.shape
+        if self.num_coarse == 224:
+            raise NotImplementedError("the 448-coarse variant needs pointnet2 furthest-point sampling (out of scope, SURVEY 8f)")
+        # xyz.transpose(2,1).unsqueeze(1) is logical [B,1,3,N]; its rows (b,n,v) x 1 channel are xyz itself
+        x0 = xyz.contiguous().view(B * N * 3, 1)
+        f0 = self.first_conv[0].forward_rows(x0)                                          # [R,128]
+        f1 = ops.linear_rows(f0, self.first_conv[1].map_to_feat.weight)                  # [R,512]
+        g1 = self.maxpool1.forward_rows(f1, B, N)                                         # [B*3,512]
+        Cg = g1.shape[1]
+        l0 = self.second_conv[0]
+        wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [2048,1024]
+        bias = ops.linear_rows(g1, wcat[:, :Cg])                                          # [B*3,2048]
+        pd = ops.linear_rows(f1, wcat[:, Cg:], bias, 3 * N)                               # [R,2048]
+        f2 = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)   # [R,1024]
+        f3 = ops.linear_rows(f2, self.second_conv[1].map_to_feat.weight)                 # [R,2048]
+        fg = self.maxpool2.forward_rows(f3, B, N)                                         # [B*3,2048]
+        m = self.mlp[0].forward_rows(fg)
+        m = self.mlp[1].forward_rows(m)
+        m = ops.linear_rows(m, self.mlp[2].map_to_feat.weight)                            # [B*3,num_coarse] rows (b,v)
+        # reference: mlp(...)[B,nc,3,1].reshape(-1,nc,3)
+        coarse = m.view(B, 3, self.num_coarse).transpose(1, 2).contiguous()
+        feature_global = fg.view(B, 3, -1).transpose(1, 2).unsqueeze(-1)                   # logical [B,2048,3,1]
+        return coarse, feature_global
+
+
+class VN_FoldingNet(nn.Module):
+    """models/pcn.py:319-389"""
+
+    def __init__(self, config, grid_size=4):
+        super().__init__()
+        self.grid_size = grid_size
+        self.latent_dim = config.latent_dim
+        self.num_dense = 16384
+        if config.num_coarse == 448:
+            self.num_coarse = config.num_coarse // 2
+            self.num_dense = 14336
+            self.grid_size = 8
+        else:
+            self.num_coarse = config.num_coarse
+            self.num_dense = 16384
+            self.grid_size = 4
+        self.final_conv = nn.Sequential(VNLinearLeakyReLU(self.latent_dim + 1 + 1, 256, dim=4),
+                                        VNLinearLeakyReLU(256, 256, dim=4), VNLinear(256, 1))
+        gs = self.grid_size
+        a = torch.linspace(-0.05, 0.05, steps=gs, dtype=torch.float).view(1, gs).expand(gs, gs).reshape(1, -1)
+        b = torch.linspace(-0.05, 0.05, steps=gs, dtype=torch.float).view(gs, 1).expand(gs, gs).reshape(1, -1)
+        c = torch.zeros_like(a, dtype=torch.float)
+        # a plain attribute (not a buffer) like the reference (pcn.py:362), so state_dict keys match; follows the module's device lazily
+        self.folding_seed = torch.cat([a, b, c], dim=0).reshape(1, 1, 3, -1)
+
+    def forward(self, coarse, feature_global, rot=None):
+        dev = coarse.device
+        if self.folding_seed.device != dev:
+            self.folding_seed = self.folding_seed.to(dev)
+        B = coarse.shape[0]
+        S = self.grid_size ** 2
+        nc = self.num_coarse
+        nd = nc * S
+        seed_pts = self.folding_seed.squeeze(1).transpose(1, 2)                            # [1,S,3]
+        if rot is not None:
+            seed_pts = rot.transform_points(seed_pts)                                      # [B,S,3]   pcn.py:369-370
+        seed_pts = seed_pts.expand(B, S, 3)
+        # local channels of the concatenation (pcn.py:375-385): [seed, point_feat] per dense point, rows (b, n, v)
+        local = torch.stack([seed_pts[:, None, :, :].expand(B, nc, S, 3), coarse[:, :, None, :].expand(B, nc, S, 3)], dim=-1)
+        local = local.reshape(B * nd * 3, 2)
+        fg_rows = feature_global.squeeze(-1).transpose(1, 2).reshape(B * 3, -1)            # [B*3,Cg] rows (b,v)
+        Cg = fg_rows.shape[1]
+        l0, l1, l2 = self.final_conv[0], self.final_conv[1], self.final_conv[2]
+        wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [512, Cg+2]
+        bias = ops.linear_rows(fg_rows, wcat[:, :Cg])                                      # [B*3,512]
+        pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                            # [R,512]
+        h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
+        h = l1.forward_rows(h)
+        fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                         # final VNLinear(256,1) + point_feat
+        return fine.view(B, nd, 3)
