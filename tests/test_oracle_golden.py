@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import vn_oracle as O
+from conftest import assert_grad_close
 
 CH_CASES = ["unit", "ragged", "tiny", "one2one", "big"]
 
@@ -197,11 +198,9 @@ def test_pcn_oracle_vs_reference_golden(golden, fixture, ftol):
     np.testing.assert_allclose(l2, g["loss2"], rtol=1e-4)
     for k in g.files:
         if k.startswith("grad."):
-            ref = g[k]
-            np.testing.assert_allclose(G[k[5:]], ref, rtol=2e-3, atol=2e-4 * (np.abs(ref).max() + 1e-12), err_msg=k)
+            assert_grad_close(G[k[5:]], g[k], k)
         elif k.startswith("grad_head."):
-            ref = g[k]
-            np.testing.assert_allclose(G[k[10:]].ravel()[:256], ref, rtol=5e-3, atol=5e-4 * (np.abs(ref).max() + 1e-12), err_msg=k)
+            assert_grad_close(G[k[10:]].ravel()[:256], g[k], k)
         elif k.startswith("grad_none."):
             assert k[10:] not in G
         elif k.startswith("buf_post.") and not k.endswith("num_batches_tracked"):
