@@ -36,6 +36,31 @@ def get_gemm_mode():
     return _GEMM_MODE
 
 
+# optional kernel-class timer (bench.py): an object with .start(cls, work) -> token and .stop(token); CUDA events on
+# the launching stream, so it adds no synchronisation
+_TIMER = None
+
+
+def set_timer(timer):
+    global _TIMER
+    _TIMER = timer
+
+
+class _Timed:
+    __slots__ = ("tok",)
+
+    def __init__(self, cls, work):
+        self.tok = _TIMER.start(cls, work) if _TIMER is not None else None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        if self.tok is not None:
+            _TIMER.stop(self.tok)
+        return False
+
+
 def _check(t, name="tensor"):
     if t is None:
         return
@@ -73,6 +98,11 @@ def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accum
         out = torch.empty((R, Cout), device=x.device, dtype=torch.float32)
     if R == 0 or Cout == 0:
         return out
+    with _Timed("gemm", 2.0 * R * K * Cout):
+        return _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout)
+
+
+def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout):
     if _GEMM_MODE == "tf32" and not accumulate:
         wt = w
         if trans_w:   # the tensor-core kernel wants K-contiguous weights; weights are small, transpose them
@@ -108,6 +138,11 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
     if out is None:
         out = torch.empty((Cout, K), device=x.device, dtype=torch.float32)
         accumulate = False
+    with _Timed("gemm", 2.0 * R * K * Cout):
+        return _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K)
+
+
+def _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K):
     if _GEMM_MODE == "tf32" and not accumulate and R > 0:
         nb = _lib.raw("vnpcc_gemm_wgrad_tf32_workspace_bytes", R, Cout, K)
         ws = _workspace(nb, x.device, "wgrad")
@@ -360,7 +395,7 @@ class chamfer_3DFunction(torch.autograd.Function):
         if B > 0 and N > 0 and M > 0:
             nb = _lib.raw("vnpcc_chamfer_workspace_bytes", B, N, M)
             ws = _workspace(nb, dev, "chamfer")
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), _Timed("chamfer_fwd", 2.0 * B * N * M):
                 call("vnpcc_chamfer_forward", ptr(xyz1), ptr(xyz2), B, N, M, ptr(dist1), ptr(dist2), ptr(idx1), ptr(idx2),
                      ptr(ws), ws.numel(), stream())
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
