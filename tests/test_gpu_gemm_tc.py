@@ -1,0 +1,120 @@
+"""GPU tests of the tcgen05/TMEM/TMA GEMMs (TF32 operands, fp32 accumulate) through the C-ABI.
+With operands pre-truncated to TF32 (10-bit mantissa) every product is exact, so the kernel must match float64 to
+fp32-accumulation accuracy -- this pins tile addressing, swizzle/descriptor layout and the epilogue mapping.  With raw
+fp32 operands the stated TF32 tolerance applies: |err| <= 2^-9 * sqrt(K) * rms(x) * rms(w) * 4."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _tf32(a):
+    return (a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.fixture()
+def tf32_mode():
+    import vn_pointcloudcompletion_b200 as V
+    V.set_gemm_mode("tf32")
+    yield
+    V.set_gemm_mode("fp32")
+
+
+SHAPES = [(512, 128, 512), (768, 512, 2048), (1000, 96, 200), (96, 2048, 1024), (4096, 256, 256), (300, 1024, 130), (70000, 64, 128)]
+
+
+@pytest.mark.parametrize("R,K,Cout", SHAPES)
+def test_rows_gemm_tf32_exact_on_truncated_operands(tf32_mode, R, K, Cout):
+    from vn_pointcloudcompletion_b200 import _lib, ops
+    rng = np.random.RandomState(R + K + Cout)
+    x = _tf32(rng.standard_normal((R, K)).astype(np.float32))
+    w = _tf32(rng.standard_normal((Cout, K)).astype(np.float32))
+    y = torch.empty((R, Cout), device="cuda")
+    rc = _lib.raw("vnpcc_gemm_rows_tf32", _dev(x).data_ptr(), K, _dev(w).data_ptr(), K, y.data_ptr(), Cout, R, K, Cout, None, 0, 0,
+                  torch.cuda.current_stream().cuda_stream)
+    xd, wd = _dev(x), _dev(w)
+    rc = _lib.raw("vnpcc_gemm_rows_tf32", xd.data_ptr(), K, wd.data_ptr(), K, y.data_ptr(), Cout, R, K, Cout, None, 0, 0,
+                  torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, f"tensor-core kernel refused the shape (rc={rc})"
+    torch.cuda.synchronize()
+    ref = x.astype(np.float64) @ w.astype(np.float64).T
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=1e-4 * np.sqrt(K / 64))
+
+
+def test_rows_gemm_tf32_bias_and_strides(tf32_mode):
+    from vn_pointcloudcompletion_b200 import ops
+    rng = np.random.RandomState(1)
+    B, N, K, Cout = 3, 100, 64, 256
+    R = B * N * 3
+    xfull = _tf32(rng.standard_normal((R, K + 32)).astype(np.float32))
+    wfull = _tf32(rng.standard_normal((Cout, 2 * K)).astype(np.float32))
+    bias = rng.standard_normal((B * 3, Cout)).astype(np.float32)
+    xd, wd = _dev(xfull), _dev(wfull)
+    y = ops.gemm_rows(xd[:, 32:], wd[:, K:], False, _dev(bias), 3 * N).cpu().numpy()     # strided views: ld != K
+    ref = xfull[:, 32:].astype(np.float64) @ wfull[:, K:].astype(np.float64).T
+    ref = ref + np.repeat(bias.reshape(B, 1, 3, Cout), N, axis=1).reshape(R, Cout)
+    np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("R,K,Cout", [(4096, 256, 256), (768, 512, 1024)])
+def test_rows_gemm_tf32_tolerance_on_raw_operands(tf32_mode, R, K, Cout):
+    from vn_pointcloudcompletion_b200 import ops
+    rng = np.random.RandomState(7)
+    x = rng.standard_normal((R, K)).astype(np.float32)
+    w = rng.standard_normal((Cout, K)).astype(np.float32)
+    y = ops.gemm_rows(_dev(x), _dev(w)).cpu().numpy()
+    ref = x.astype(np.float64) @ w.astype(np.float64).T
+    assert np.abs(y - ref).max() <= 2.0 ** -9 * np.sqrt(K) * 4
+    gx = ops.gemm_rows(_dev(ref.astype(np.float32)), _dev(w), True).cpu().numpy()       # dgrad form (weight transposed on the fly)
+    ref2 = ref.astype(np.float32).astype(np.float64) @ w.astype(np.float64)
+    assert np.abs(gx - ref2).max() <= 2.0 ** -9 * np.sqrt(Cout) * np.abs(ref).std() * 4
+
+
+@pytest.mark.parametrize("R,K,Cout", [(4096, 256, 256), (6000, 128, 512), (3000, 1024, 2048), (1536, 96, 160), (100000, 256, 512)])
+def test_wgrad_tf32_exact_on_truncated_operands(tf32_mode, R, K, Cout):
+    from vn_pointcloudcompletion_b200 import _lib
+    rng = np.random.RandomState(R + K)
+    x = _tf32(rng.standard_normal((R, K)).astype(np.float32))
+    gy = _tf32(rng.standard_normal((R, Cout)).astype(np.float32))
+    xd, gd = _dev(x), _dev(gy)
+    g = torch.empty((Cout, K), device="cuda")
+    rc = _lib.raw("vnpcc_gemm_wgrad_tf32", gd.data_ptr(), Cout, xd.data_ptr(), K, g.data_ptr(), K, R, Cout, K, None, 0,
+                  torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, f"tensor-core wgrad refused the shape (rc={rc})"
+    torch.cuda.synchronize()
+    ref = gy.astype(np.float64).T @ x.astype(np.float64)
+    np.testing.assert_allclose(g.cpu().numpy(), ref, rtol=1e-4, atol=2e-4 * np.sqrt(R / 64))
+
+
+def test_pcn_train_step_tf32_close_to_fp32(tf32_mode):
+    """whole train step in TF32 mode vs fp32 mode on the same seeded input with teacher-forced selections: stated
+    tolerance for the tensor-core path = 2e-2 relative on coarse/fine, loss within 1e-2 relative"""
+    from types import SimpleNamespace
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200.synthetic import make_batch
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cuda", enc_pretrained="none")
+    p, c, R = (torch.from_numpy(a).cuda() for a in make_batch(4, 256, 2048, seed=11))
+    outs = {}
+    idx = None
+    for mode in ("fp32", "tf32"):
+        V.set_gemm_mode(mode)
+        torch.manual_seed(0)
+        net = V.PCNNet(cfg).train()
+        if idx is not None:
+            net.encoder.maxpool1.forced_idx, net.encoder.maxpool2.forced_idx = idx
+        coarse, fine = net(p, V.Rotate(R))
+        loss = V.cd_loss_L1(coarse, c) + V.cd_loss_L1(fine, c)
+        loss.backward()
+        if idx is None:
+            idx = (net.encoder.maxpool1.last_idx.clone(), net.encoder.maxpool2.last_idx.clone())
+        outs[mode] = (coarse.detach(), fine.detach(), loss.item(), net.decoder.final_conv[1].map_to_feat.weight.grad.clone())
+    a, b = outs["fp32"], outs["tf32"]
+    assert (a[0] - b[0]).abs().max() <= 2e-2 * a[0].abs().max()
+    assert (a[1] - b[1]).abs().max() <= 2e-2 * a[1].abs().max()
+    assert abs(a[2] - b[2]) <= 1e-2 * abs(a[2])
+    assert (a[3] - b[3]).norm() <= 5e-2 * a[3].norm()

@@ -1,9 +1,530 @@
-// gemm_tcgen05.cu -- placeholder until the tensor-core kernels land (returns UNSUPPORTED so callers take the fp32 path)
+// gemm_tcgen05.cu -- the VNLinear contraction on Blackwell tensor cores (sm_100a): TMA -> shared memory ->
+// tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) -> tcgen05.ld epilogue.  Hand-written PTX, no CUTLASS.
+//
+// Replaces the cuBLAS SGEMM behind nn.Linear(bias=False) in models/vn_layers.py:21,38,65,69,162,194.
+//
+// Orientation ("channels on lanes"): for  Y[r, o] = sum_k X[r, k] W[o, k]  the WEIGHT tile is the MMA A operand
+// (M = 128 output channels = 128 TMEM lanes) and the activation tile is the B operand (N = up to 256 rows r).  Both
+// are K-major in memory (channels-last rows / nn.Linear weight), so both load with plain 2-D TMA boxes of 32 floats
+// (128 bytes, SWIZZLE_128B).  An epilogue thread therefore owns ONE output channel and walks over rows: for every
+// row the 32 lanes of a warp store 32 consecutive channels = one 128-byte line of the channels-last output, the three
+// components of a 3-vector sit in three consecutive TMEM columns of the same thread, and per-channel reductions
+// (BatchNorm-on-norm statistics, arg-max pooling) are thread-local -- the layout the fused VN epilogues need.
+//
+// Pipeline per CTA (persistent over output tiles, m-tiles fastest so concurrently running CTAs share the activation
+// tile through L2):  warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4..7 =
+// epilogue (TMEM lane quadrant = warp % 4).  Shared-memory ring of STAGES x {A 128x32, B BNx32} fp32 tiles with
+// full/empty mbarriers; the 512 TMEM columns hold two BN-column accumulators so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+//
+// The weight-gradient kernel (G[o,k] = sum_r dY[r,o] X[r,k]) uses the same machinery with both operands MN-major
+// (the reduction index r is the slow axis of both row matrices) and the reduction split over CTAs.
+//
+// Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
 #include "vnpcc_internal.h"
-extern "C" {
-int vnpcc_gemm_rows_tf32(const float*, long long, const float*, long long, float*, long long, long long, int, int,
-                         const float*, long long, long long, void*) { return VNPCC_ERR_UNSUPPORTED; }
-int vnpcc_gemm_wgrad_tf32(const float*, long long, const float*, long long, float*, long long, long long, int, int,
-                          float*, size_t, void*) { return VNPCC_ERR_UNSUPPORTED; }
-size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long, int, int) { return 0; }
+
+namespace vnpcc {
+namespace tc {
+
+constexpr int BM = 128;            // output channels per tile (TMEM lanes)
+constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
+constexpr int UMMA_K = 8;          // tf32: 32 bytes of K per instruction
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;   // x (try_wait latency ~0.1-1 us): a protocol error traps within seconds
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();   // protocol error: never hang the device
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t of the warp gets lane (quadrant*32 + t), v[j] = column (col0 + j)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B)
+// layout: 2 = SWIZZLE_128B (16-byte chunks XOR row%8, K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR
+// row%4 -- the only swizzled layout tcgen05 accepts for MN-major 32-bit (tf32) operands)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format TF32=2 [7,10)/[10,13),
+// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct PipeState {
+    int stage = 0;
+    uint32_t phase = 0;
+    template <int STAGES>
+    __device__ __forceinline__ void advance() {
+        if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// rows GEMM:  Y[r, o] = sum_k X[r, k] W[o, k] (+ bias[(r / rps)*3 + r%3, o])
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct RowsSmem {
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ Y,
+                      size_t ldy, long long R, int K, int Cout, const float* __restrict__ bias, size_t ldbias,
+                      long long rows_per_sample, int num_m, long long num_tiles) {
+    using L = RowsSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            PipeState ps;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (int)(tile % num_m) * BM;
+                const long long n0 = (tile / num_m) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+                    uint8_t* sa = smem + ps.stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::A_BYTES;
+                    mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
+                    tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
+                    tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
+                    ps.advance<STAGES>();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+            PipeState ps;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[ps.stage], ps.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ps.stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = make_desc(sa + k * UMMA_K * 4, 16, 1024);
+                        const uint64_t bd = make_desc(sb + k * UMMA_K * 4, 16, 1024);
+                        umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[ps.stage]);     // frees this smem stage once the MMAs above have read it
+                    ps.advance<STAGES>();
+                }
+                umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (int)(tile % num_m) * BM;
+            const long long n0 = (tile / num_m) * BN;
+            const int o = m0 + quad * 32 + lane;
+            const bool o_ok = o < Cout;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= R) break;      // warp-uniform
+                float v[32];
+                tmem_ld32(t_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const long long r = n0 + c0 + j;
+                    if (r < R && o_ok) {
+                        float val = v[j];
+                        if (bias) val += __ldg(bias + (size_t)((r / rows_per_sample) * 3 + (r % 3)) * ldbias + o);
+                        Y[(size_t)r * ldy + o] = val;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient:  G[o, k] += sum_{r in chunk} dY[r, o] X[r, k]      (both operands MN-major, split over r)
+//   A = dY^T : MN-major, 4 slabs of {32 o} x BR rows ; B = X : MN-major, BNW/32 slabs of {32 k} x BR rows
+//   (TMA swizzle mode 128B_ATOM_32B <-> UMMA layout SWIZZLE_128B_BASE32B, the pairing tf32 MN-major requires)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BR = 32;   // reduction rows per stage (4 MMAs of K = 8)
+
+template <int BNW, int STAGES>
+struct WgradSmem {
+    static constexpr int A_BYTES = BM * BR * 4;
+    static constexpr int B_BYTES = BNW * BR * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BNW, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, float* __restrict__ G,
+                       size_t ldg, long long R, int Cout, int K, long long rows_per_split) {
+    using L = WgradSmem<BNW, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;        // output-channel tile
+    const int k0 = blockIdx.y * BNW;       // input-channel tile
+    const long long r_begin = (long long)blockIdx.z * rows_per_split;
+    const long long r_end = (r_begin + rows_per_split < R) ? r_begin + rows_per_split : R;
+    const int num_rb = (int)((r_end - r_begin + BR - 1) / BR);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_dy);
+        tma_prefetch_desc(&map_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tfull_bar[0], 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BNW < 32 ? 32 : BNW);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            PipeState ps;
+            for (int rb = 0; rb < num_rb; ++rb) {
+                mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+                uint8_t* sa = smem + ps.stage * L::STAGE_BYTES;
+                uint8_t* sb = sa + L::A_BYTES;
+                mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
+                const int r0 = (int)(r_begin + (long long)rb * BR);
+                // NOTE: rows past r_end (but < R) inside the last box of a split belong to the next split: they are
+                // excluded by loading them into the box only when r_end is BR-aligned (the host aligns splits to BR);
+                // rows >= R are zero-filled by TMA.
+#pragma unroll
+                for (int s = 0; s < BM / 32; ++s) tma_load_2d(&map_dy, &full_bar[ps.stage], sa + s * (BR * 128), m0 + s * 32, r0);
+#pragma unroll
+                for (int s = 0; s < BNW / 32; ++s) tma_load_2d(&map_x, &full_bar[ps.stage], sb + s * (BR * 128), k0 + s * 32, r0);
+                ps.advance<STAGES>();
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BNW, 1, 1);
+            PipeState ps;
+            for (int rb = 0; rb < num_rb; ++rb) {
+                mbar_wait(&full_bar[ps.stage], ps.phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + ps.stage * L::STAGE_BYTES);
+                const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BR / UMMA_K; ++k) {
+                    // MN-major, SWIZZLE_128B_BASE32B: a slab is BR rows (reduction index) x 128 bytes (32 channels); the
+                    // swizzle atom is 4 rows, so one K=8 instruction spans two atoms: SBO = 512 B between them,
+                    // LBO = BR*128 B between the 32-channel slabs along M / N
+                    const uint64_t ad = make_desc(sa + k * 1024, BR * 128, 512, 1);
+                    const uint64_t bd = make_desc(sb + k * 1024, BR * 128, 512, 1);
+                    umma_tf32(tmem_base, ad, bd, idesc, (rb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[ps.stage]);
+                ps.advance<STAGES>();
+            }
+            umma_commit(&tfull_bar[0]);
+        }
+    } else if (warp >= 4) {
+        const int quad = warp & 3;
+        const int o = m0 + quad * 32 + lane;
+        if (num_rb > 0) {
+            mbar_wait(&tfull_bar[0], 0);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BNW; c0 += 32) {
+                if (k0 + c0 >= K) break;
+                float v[32];
+                tmem_ld32(t_base + c0, v);
+                if (o < Cout) {
+                    float* dst = G + (size_t)o * ldg + k0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (k0 + c0 + j < K) atomicAdd(dst + j, v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, BNW < 32 ? 32 : BNW);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major matrix [rows, cols] with leading dimension ld; box = {box_cols (inner), box_rows}; 128B swizzle
+static bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, int STAGES>
+static int launch_rows(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K,
+                       int Cout, const float* bias, long long ldbias, long long rps, cudaStream_t st) {
+    using L = RowsSmem<BN, STAGES>;
+    CUtensorMap mw, mx;
+    if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
+    if (!make_map(&mx, X, R, K, ldx, BK, BN)) return VNPCC_ERR_DRIVER;
+    static bool attr_done = false;
+    auto kern = gemm_rows_tf32_kernel<BN, STAGES>;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
+        attr_done = true;
+    }
+    const int num_m = (Cout + BM - 1) / BM;
+    const long long num_n = (R + BN - 1) / BN;
+    const long long num_tiles = num_m * num_n;
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    count_launch(), kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(mw, mx, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
+                                                             rps > 0 ? rps : 1, num_m, num_tiles);
+    return last_error();
+}
+
+}  // namespace tc
+}  // namespace vnpcc
+
+using namespace vnpcc;
+
+extern "C" {
+
+int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R,
+                         int K, int Cout, const float* bias, long long ldbias, long long rows_per_sample, void* stream) {
+    if (R <= 0 || Cout <= 0) return 0;
+    // TMA needs 16-byte aligned bases and row pitches; tiny K is better served by the SIMT kernel
+    if (K < 32 || (K & 3) || (ldx & 3) || (ldw & 3) || !tc::aligned16(X) || !tc::aligned16(W) || R >= (1ll << 31))
+        return VNPCC_ERR_UNSUPPORTED;
+    if (Cout < 64 || R < 64) return VNPCC_ERR_UNSUPPORTED;
+    if (bias && rows_per_sample <= 0) return VNPCC_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R <= 128) return tc::launch_rows<128, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
+    return tc::launch_rows<256, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
+}
+
+size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long, int, int) { return 0; }
+
+int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg, long long R,
+                          int Cout, int K, float* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    if (Cout <= 0 || K <= 0) return 0;
+    if ((lddy & 3) || (ldx & 3) || !tc::aligned16(dY) || !tc::aligned16(X) || R >= (1ll << 31) || R < 256 || Cout < 32 || K < 32 ||
+        (Cout & 3) || (K & 3))
+        return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int BNW = 256, STAGES = 4;
+    using L = tc::WgradSmem<BNW, STAGES>;
+    CUtensorMap mdy, mx;
+    // boxes of {32 channels (inner, 128 bytes), BR rows}
+    if (!tc::make_map(&mdy, dY, R, Cout, lddy, 32, tc::BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
+    if (!tc::make_map(&mx, X, R, K, ldx, 32, tc::BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
+    auto kern = tc::gemm_wgrad_tf32_kernel<BNW, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
+        attr_done = true;
+    }
+    const int gm = (Cout + tc::BM - 1) / tc::BM, gn = (K + BNW - 1) / BNW;
+    long long splits = ((long long)sm_count() * 2 + (long long)gm * gn - 1) / ((long long)gm * gn);
+    const long long max_splits = (R + 1023) / 1024;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long rows_per_split = ((R + splits - 1) / splits + tc::BR - 1) / tc::BR * tc::BR;
+    splits = (R + rows_per_split - 1) / rows_per_split;
+    // G is accumulated with atomics: clear it first (rows of K floats with pitch ldg)
+    cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)Cout, st);
+    count_launch(), kern<<<dim3(gm, gn, (unsigned)splits), tc::NUM_THREADS, L::TOTAL, st>>>(mdy, mx, G, (size_t)ldg, R, Cout, K,
+                                                                                          rows_per_split);
+    return last_error();
+}
+
+}  // extern "C"
