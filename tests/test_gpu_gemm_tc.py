@@ -72,7 +72,7 @@ def test_rows_gemm_tf32_tolerance_on_raw_operands(tf32_mode, R, K, Cout):
     assert np.abs(y - ref).max() <= 2.0 ** -9 * np.sqrt(K) * 4
     gx = ops.gemm_rows(_dev(ref.astype(np.float32)), _dev(w), True).cpu().numpy()       # dgrad form (weight transposed on the fly)
     ref2 = ref.astype(np.float32).astype(np.float64) @ w.astype(np.float64)
-    assert np.abs(gx - ref2).max() <= 2.0 ** -9 * np.sqrt(Cout) * np.abs(ref).std() * 4
+    assert np.abs(gx - ref2).max() <= 2.0 ** -9 * np.sqrt(Cout) * np.abs(ref).std() * 8
 
 
 @pytest.mark.parametrize("R,K,Cout", [(4096, 256, 256), (6000, 128, 512), (3000, 1024, 2048), (1536, 96, 160), (100000, 256, 512)])

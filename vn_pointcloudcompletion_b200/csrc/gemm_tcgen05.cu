@@ -162,7 +162,7 @@ struct RowsSmem {
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool HAS_BIAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ Y,
                       size_t ldy, long long R, int K, int Cout, const float* __restrict__ bias, size_t ldbias,
@@ -262,17 +262,42 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (n0 + c0 >= R) break;      // warp-uniform
+                const long long r0 = n0 + c0;
+                if (r0 >= R) break;      // warp-uniform
                 float v[32];
                 tmem_ld32(t_base + c0, v);
+                if (!o_ok) continue;
+                float* dst = Y + (size_t)r0 * ldy + o;
+                if (HAS_BIAS) {
+                    // per-sample bias row (b, v) of output row r = (b*N + n)*3 + v: one division per 32-row chunk,
+                    // then incremental (rows_per_sample is a multiple of 3)
+                    long long b = r0 / rows_per_sample;
+                    long long rem = r0 - b * rows_per_sample;
+                    int vv = (int)(rem % 3);
+                    const float* bp = bias + (size_t)(b * 3 + vv) * ldbias + o;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const long long r = n0 + c0 + j;
-                    if (r < R && o_ok) {
-                        float val = v[j];
-                        if (bias) val += __ldg(bias + (size_t)((r / rows_per_sample) * 3 + (r % 3)) * ldbias + o);
-                        Y[(size_t)r * ldy + o] = val;
+                    for (int j = 0; j < 32; ++j) {
+                        if (r0 + j < R) v[j] += __ldg(bp);
+                        ++rem;
+                        if (++vv == 3) {
+                            vv = 0;
+                            bp -= 2 * ldbias;
+                            if (rem == rows_per_sample) {
+                                rem = 0;
+                                bp += 3 * ldbias;
+                            }
+                        } else {
+                            bp += ldbias;
+                        }
                     }
+                }
+                if (r0 + 32 <= R) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * ldy] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (r0 + j < R) dst[(size_t)j * ldy] = v[j];
                 }
             }
             tc_fence_before();
@@ -398,9 +423,14 @@ gemm_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
                 tmem_ld32(t_base + c0, v);
                 if (o < Cout) {
                     float* dst = G + (size_t)o * ldg + k0 + c0;
+                    if (k0 + c0 + 32 <= K) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (k0 + c0 + j < K) atomicAdd(dst + j, v[j]);
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (k0 + c0 + j < K) atomicAdd(dst + j, v[j]);
+                    }
                 }
             }
         }
@@ -456,9 +486,13 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
     if (!make_map(&mx, X, R, K, ldx, BK, BN)) return VNPCC_ERR_DRIVER;
     static bool attr_done = false;
-    auto kern = gemm_rows_tf32_kernel<BN, STAGES>;
+    auto kern = bias ? gemm_rows_tf32_kernel<BN, STAGES, true> : gemm_rows_tf32_kernel<BN, STAGES, false>;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
+        if (cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+                cudaSuccess)
+            return last_error();
         attr_done = true;
     }
     const int num_m = (Cout + BM - 1) / BM;
