@@ -106,6 +106,18 @@ int vnpcc_rows_dot(const float* x, long long ldx, const float* w, long long R, i
 int vnpcc_rows_dot_bwd(const float* gy, const float* x, long long ldx, const float* w, long long R, int C, float* gx,
                        long long ldgx, float* gw, void* stream);
 
+/* backward of VNLinear -> VNMaxPool without the dense gradient (gx zeroed + scattered, gW gathered; either may be NULL) */
+int vnpcc_pool_linear_bwd(const float* g, long long ldg, const long long* idx, const float* x, long long ldx, const float* W,
+                          long long ldw, int B, int N, int C, int K, float* gx, long long ldgx, float* gW, long long ldgw,
+                          void* stream);
+/* small-K VNLinear (1 <= K <= 4 input channels): HBM-bound streaming kernels (first_conv[0], the local channels of final_conv[0]) */
+int vnpcc_smallk_fwd(const float* x, long long ldx, const float* W, long long ldw, const float* bias, long long ldbias,
+                     long long rows_per_sample, float* y, long long ldy, long long R, int K, int Cout, void* stream);
+int vnpcc_smallk_dgrad(const float* gy, long long ldgy, const float* W, long long ldw, float* gx, long long ldgx, long long R,
+                       int K, int Cout, void* stream);
+int vnpcc_smallk_wgrad(const float* gy, long long ldgy, const float* x, long long ldx, int B, int N, int K, int Cout, float* gW,
+                       long long ldgw, float* gbias, long long ldgb, void* stream);
+
 /* ---------------------------------------------------------------- optimiser / misc ------------------------------ */
 /* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
 int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -41,6 +41,10 @@ SIGNATURES = {
     "vnpcc_rows_sample_sum": (_i, [_p, _ll, _i, _i, _i, _p, _ll, _p]),
     "vnpcc_rows_dot": (_i, [_p, _ll, _p, _ll, _i, _p, _p, _p]),
     "vnpcc_rows_dot_bwd": (_i, [_p, _p, _ll, _p, _ll, _i, _p, _ll, _p, _p]),
+    "vnpcc_pool_linear_bwd": (_i, [_p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _ll, _p, _ll, _p]),
+    "vnpcc_smallk_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _p]),
+    "vnpcc_smallk_dgrad": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p]),
+    "vnpcc_smallk_wgrad": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _ll, _p, _ll, _p]),
     "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
 }

@@ -460,6 +460,186 @@ __global__ void __launch_bounds__(256) rows_wsum_kernel(const float* __restrict_
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------
+// 8. small-K VNLinear (K <= 4 input channels: first_conv[0] has K=1, the decoder's final_conv[0] has K=2 local
+//    channels after the broadcast global feature is folded into the per-sample bias).  These are HBM-bound
+//    streaming kernels, not GEMMs: the weight fits in registers.
+//      fwd  : y[r, o] = bias[(b,v), o] + sum_k x[r, k] W[o, k]
+//      dgrad: gx[r, k] = sum_o gy[r, o] W[o, k]
+//      wgrad: gW[o, k] = sum_r gy[r, o] x[r, k]   and (optionally)  gbias[(b,v), o] = sum_n gy[(b,n,v), o]
+// -------------------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) smallk_fwd_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ W,
+                                                          size_t ldw, const float* __restrict__ bias, size_t ldb,
+                                                          long long rps, float* __restrict__ y, size_t ldy, long long R,
+                                                          int Cout) {
+    // block (64, 4): x -> channel quads (grid-stride over quads), y -> rows
+    const int nq = Cout >> 2;
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
+        float xv[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) xv[k] = __ldg(x + (size_t)r * ldx + k);
+        const float* brow = nullptr;
+        if (bias) brow = bias + (size_t)((r / rps) * 3 + (r % 3)) * ldb;
+        float* yr = y + (size_t)r * ldy;
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            float4 acc = brow ? __ldg(reinterpret_cast<const float4*>(brow) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                acc.x = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 0) * ldw + k), acc.x);
+                acc.y = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 1) * ldw + k), acc.y);
+                acc.z = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 2) * ldw + k), acc.z);
+                acc.w = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 3) * ldw + k), acc.w);
+            }
+            reinterpret_cast<float4*>(yr)[q] = acc;
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) smallk_dgrad_kernel(const float* __restrict__ gy, size_t ldgy, const float* __restrict__ W,
+                                                            size_t ldw, float* __restrict__ gx, size_t ldgx, long long R,
+                                                            int Cout) {
+    // one warp per row
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nq = Cout >> 2;
+    for (long long r = warp; r < R; r += nwarps) {
+        const float4* g4 = reinterpret_cast<const float4*>(gy + (size_t)r * ldgy);
+        float acc[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[k] = 0.f;
+        for (int q = lane; q < nq; q += 32) {
+            const float4 g = __ldg(g4 + q);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                acc[k] = fmaf(g.x, __ldg(W + (size_t)(4 * q + 0) * ldw + k), acc[k]);
+                acc[k] = fmaf(g.y, __ldg(W + (size_t)(4 * q + 1) * ldw + k), acc[k]);
+                acc[k] = fmaf(g.z, __ldg(W + (size_t)(4 * q + 2) * ldw + k), acc[k]);
+                acc[k] = fmaf(g.w, __ldg(W + (size_t)(4 * q + 3) * ldw + k), acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            if (lane == 0) gx[(size_t)r * ldgx + k] = acc[k];
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) smallk_wgrad_kernel(const float* __restrict__ gy, size_t ldgy, const float* __restrict__ x,
+                                                            size_t ldx, int B, int N, int Cout, int n_chunk,
+                                                            float* __restrict__ gW, size_t ldgw, float* __restrict__ gbias,
+                                                            size_t ldgb) {
+    // grid: x -> channel tiles of 32, y -> (sample, chunk of points); block (32, 8); gW / gbias zeroed by the launcher
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int chunks_per_b = (N + n_chunk - 1) / n_chunk;
+    const int b = blockIdx.y / chunks_per_b;
+    const int ck = blockIdx.y - b * chunks_per_b;
+    const int n0 = ck * n_chunk, n1 = min(N, n0 + n_chunk);
+    float sb[3] = {0.f, 0.f, 0.f};
+    float sw[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) sw[k] = 0.f;
+    if (c < Cout) {
+        for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+            const size_t row = ((size_t)b * N + n) * 3;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const float g = __ldg(gy + (row + v) * ldgy + c);
+                sb[v] += g;
+#pragma unroll
+                for (int k = 0; k < KS; ++k) sw[k] = fmaf(g, __ldg(x + (row + v) * ldx + k), sw[k]);
+            }
+        }
+    }
+    __shared__ float sh[3 + KS][8][33];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) sh[v][threadIdx.y][threadIdx.x] = sb[v];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) sh[3 + k][threadIdx.y][threadIdx.x] = sw[k];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < Cout) {
+        for (int i = 1; i < 8; ++i) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) sb[v] += sh[v][i][threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) sw[k] += sh[3 + k][i][threadIdx.x];
+        }
+        if (gbias) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) atomicAdd(gbias + ((size_t)b * 3 + v) * ldgb + c, sb[v]);
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) atomicAdd(gW + (size_t)c * ldgw + k, sw[k]);
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------------------------
+// 9. backward of  VNLinear -> VNMaxPool  (f = x W^T, out[b,c,:] = f[b,c,:,idx[b,c]]) without the dense [R, C] gradient:
+//    only one point per (sample, channel) receives a gradient, so
+//      gx[(b, idx[b,c], v), k] += g[(b,v), c] * W[c, k]                       (scatter, vector red.add)
+//      gW[c, k]                 = sum_{b,v} g[(b,v), c] * x[(b, idx[b,c], v), k]   (gather, no atomics)
+//    replaces a C x K x R dgrad GEMM and a C x K x R wgrad GEMM (825 GFLOP each for second_conv[1] at B=32).
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_linear_bwd_x_kernel(const float* __restrict__ g, size_t ldg,
+                                                                 const long long* __restrict__ idx,
+                                                                 const float* __restrict__ W, size_t ldw, int B, int N,
+                                                                 int C, int K, float* __restrict__ gx, size_t ldgx) {
+    // grid (C / CPB, B); block 256 threads = K/4 float4 lanes (grid-stride over k quads)
+    const int b = blockIdx.y;
+    const int kq = K >> 2;
+    constexpr int CPB = 8;
+    const int c0 = blockIdx.x * CPB;
+    for (int ci = 0; ci < CPB; ++ci) {
+        const int c = c0 + ci;
+        if (c >= C) break;
+        const long long n = idx[(size_t)b * C + c];
+        const float g0 = __ldg(g + ((size_t)b * 3 + 0) * ldg + c);
+        const float g1 = __ldg(g + ((size_t)b * 3 + 1) * ldg + c);
+        const float g2 = __ldg(g + ((size_t)b * 3 + 2) * ldg + c);
+        float* row = gx + (((size_t)b * N + n) * 3) * ldgx;
+        const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)c * ldw);
+        for (int q = threadIdx.x; q < kq; q += blockDim.x) {
+            const float4 w = __ldg(w4 + q);
+            atomicAdd(reinterpret_cast<float4*>(row) + q, make_float4(g0 * w.x, g0 * w.y, g0 * w.z, g0 * w.w));
+            atomicAdd(reinterpret_cast<float4*>(row + ldgx) + q, make_float4(g1 * w.x, g1 * w.y, g1 * w.z, g1 * w.w));
+            atomicAdd(reinterpret_cast<float4*>(row + 2 * ldgx) + q, make_float4(g2 * w.x, g2 * w.y, g2 * w.z, g2 * w.w));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pool_linear_bwd_w_kernel(const float* __restrict__ g, size_t ldg,
+                                                                 const long long* __restrict__ idx,
+                                                                 const float* __restrict__ x, size_t ldx, int B, int N,
+                                                                 int C, int K, float* __restrict__ gW, size_t ldgw) {
+    // one block per output channel c; threads over k quads; loop over the B*3 gathered rows
+    const int c = blockIdx.x;
+    const int kq = K >> 2;
+    for (int q = threadIdx.x; q < kq; q += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < B; ++b) {
+            const long long n = idx[(size_t)b * C + c];
+            const float* row = x + (((size_t)b * N + n) * 3) * ldx;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const float gv = __ldg(g + ((size_t)b * 3 + v) * ldg + c);
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(row + v * ldx) + q);
+                acc.x = fmaf(gv, xv.x, acc.x);
+                acc.y = fmaf(gv, xv.y, acc.y);
+                acc.z = fmaf(gv, xv.z, acc.z);
+                acc.w = fmaf(gv, xv.w, acc.w);
+            }
+        }
+        reinterpret_cast<float4*>(gW + (size_t)c * ldgw)[q] = acc;
+    }
+}
+
 }  // namespace vnpcc
 
 using namespace vnpcc;
@@ -620,6 +800,84 @@ int vnpcc_rows_dot_bwd(const float* gy, const float* x, long long ldx, const flo
         if (gy_ < 1) gy_ = 1;
         count_launch(), rows_wsum_kernel<<<dim3(gxx, (unsigned)gy_), dim3(32, 8), 0, st>>>(gy, x, (size_t)ldx, R, C, gw);
     }
+    return last_error();
+}
+
+// ---- small-K VNLinear (1 <= K <= 4); Cout % 4 == 0 and 16-byte aligned y/gy/bias rows required ----
+#define VNPCC_KS_DISPATCH(KS, CALL) \
+    switch (KS) {                   \
+        case 1: { constexpr int K_ = 1; CALL; } break; \
+        case 2: { constexpr int K_ = 2; CALL; } break; \
+        case 3: { constexpr int K_ = 3; CALL; } break; \
+        default: { constexpr int K_ = 4; CALL; } break; \
+    }
+
+static bool smallk_ok(int K, int Cout, const void* a, long long lda, const void* b, long long ldb_) {
+    return K >= 1 && K <= 4 && Cout >= 4 && (Cout & 3) == 0 && (lda & 3) == 0 && ((uintptr_t)a & 15) == 0 &&
+           (b == nullptr || ((ldb_ & 3) == 0 && ((uintptr_t)b & 15) == 0));
+}
+
+int vnpcc_smallk_fwd(const float* x, long long ldx, const float* W, long long ldw, const float* bias, long long ldbias,
+                     long long rows_per_sample, float* y, long long ldy, long long R, int K, int Cout, void* stream) {
+    if (R <= 0) return 0;
+    if (!smallk_ok(K, Cout, y, ldy, bias, ldbias)) return VNPCC_ERR_UNSUPPORTED;
+    if (bias && rows_per_sample <= 0) return VNPCC_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long g = (R + 3) / 4;
+    const long long cap = (long long)sm_count() * 8;
+    if (g > cap) g = cap;
+    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_fwd_kernel<K_><<<(unsigned)g, dim3(64, 4), 0, st>>>(
+                             x, (size_t)ldx, W, (size_t)ldw, bias, (size_t)ldbias, rows_per_sample > 0 ? rows_per_sample : 1, y,
+                             (size_t)ldy, R, Cout)));
+    return last_error();
+}
+
+int vnpcc_smallk_dgrad(const float* gy, long long ldgy, const float* W, long long ldw, float* gx, long long ldgx, long long R,
+                       int K, int Cout, void* stream) {
+    if (R <= 0) return 0;
+    if (!smallk_ok(K, Cout, gy, ldgy, nullptr, 0)) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for((size_t)R * 32, 256, 8);
+    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_dgrad_kernel<K_><<<grid, 256, 0, st>>>(gy, (size_t)ldgy, W, (size_t)ldw, gx, (size_t)ldgx, R, Cout)));
+    return last_error();
+}
+
+// gW [Cout, K] (pitch ldgw) and, when gbias != NULL, gbias [B*3, Cout] are zeroed here and then accumulated.
+// rows are grouped as B samples x N points x 3 (pass B = 1, N = R/3 when there is no bias).
+int vnpcc_smallk_wgrad(const float* gy, long long ldgy, const float* x, long long ldx, int B, int N, int K, int Cout, float* gW,
+                       long long ldgw, float* gbias, long long ldgb, void* stream) {
+    if (K < 1 || K > 4 || Cout <= 0) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemset2DAsync(gW, (size_t)ldgw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)Cout, st);
+    if (gbias) cudaMemset2DAsync(gbias, (size_t)ldgb * sizeof(float), 0, (size_t)Cout * sizeof(float), (size_t)B * 3, st);
+    if (B <= 0 || N <= 0) return last_error();
+    const int gx = (Cout + 31) / 32;
+    int chunks = (int)(((long long)sm_count() * 8 + (long long)gx * B - 1) / ((long long)gx * B));
+    if (chunks < 1) chunks = 1;
+    int n_chunk = (N + chunks - 1) / chunks;
+    if (n_chunk < 64) n_chunk = 64;
+    chunks = (N + n_chunk - 1) / n_chunk;
+    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_wgrad_kernel<K_><<<dim3(gx, (unsigned)(B * chunks)), dim3(32, 8), 0, st>>>(
+                             gy, (size_t)ldgy, x, (size_t)ldx, B, N, Cout, n_chunk, gW, (size_t)ldgw, gbias, (size_t)ldgb)));
+    return last_error();
+}
+
+// backward of VNLinear -> VNMaxPool (see section 9).  g [B*3, C] rows (b,v); idx [B, C] int64; x [R, K]; W [C, K].
+// gx [R, K] is zeroed here and then scattered into (pass NULL to skip); gW [C, K] is overwritten (pass NULL to skip).
+int vnpcc_pool_linear_bwd(const float* g, long long ldg, const long long* idx, const float* x, long long ldx, const float* W,
+                          long long ldw, int B, int N, int C, int K, float* gx, long long ldgx, float* gW, long long ldgw,
+                          void* stream) {
+    if (B <= 0 || C <= 0 || K <= 0) return 0;
+    if ((K & 3) || (ldx & 3) || (ldw & 3) || (ldgx & 3) || (ldgw & 3) || ((uintptr_t)x & 15) || ((uintptr_t)W & 15) ||
+        ((uintptr_t)gx & 15) || ((uintptr_t)gW & 15))
+        return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gx) {
+        cudaMemset2DAsync(gx, (size_t)ldgx * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)B * N * 3, st);
+        count_launch(), pool_linear_bwd_x_kernel<<<dim3((C + 7) / 8, B), 256, 0, st>>>(g, (size_t)ldg, idx, W, (size_t)ldw, B, N, C, K, gx,
+                                                                                 (size_t)ldgx);
+    }
+    if (gW) count_launch(), pool_linear_bwd_w_kernel<<<C, 256, 0, st>>>(g, (size_t)ldg, idx, x, (size_t)ldx, B, N, C, K, gW, (size_t)ldgw);
     return last_error();
 }
 

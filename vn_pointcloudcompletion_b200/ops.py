@@ -103,6 +103,20 @@ def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accum
 
 
 def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout):
+    # <= 4 input (or, for the dgrad form, output) channels: HBM-bound streaming kernels, exact fp32 in both modes
+    if not accumulate and not trans_w and K <= 4:
+        rc = _lib.raw("vnpcc_smallk_fwd", ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0,
+                      rows_per_sample, ptr(out), _ld(out), R, K, Cout, stream())
+        if rc == 0:
+            return out
+        if rc != 10003:
+            raise _lib.VnpccError(f"vnpcc_smallk_fwd failed with code {rc}")
+    if not accumulate and trans_w and Cout <= 4 and bias is None:
+        rc = _lib.raw("vnpcc_smallk_dgrad", ptr(x), _ld(x), ptr(w), _ld(w), ptr(out), _ld(out), R, Cout, K, stream())
+        if rc == 0:
+            return out
+        if rc != 10003:
+            raise _lib.VnpccError(f"vnpcc_smallk_dgrad failed with code {rc}")
     if _GEMM_MODE == "tf32" and not accumulate:
         wt = w
         if trans_w:   # the tensor-core kernel wants K-contiguous weights; weights are small, transpose them
@@ -142,7 +156,20 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
         return _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K)
 
 
+def smallk_wgrad(dy, x, B, N, want_bias):
+    """K <= 4: gW [Cout, K] and (optionally) the per-sample bias gradient [B*3, Cout] in ONE pass over dy"""
+    R, Cout = dy.shape
+    K = x.shape[1]
+    gw = torch.empty((Cout, K), device=x.device, dtype=torch.float32)
+    gb = torch.empty((B * 3, Cout), device=x.device, dtype=torch.float32) if want_bias else None
+    call("vnpcc_smallk_wgrad", ptr(dy), _ld(dy), ptr(x), _ld(x), B, N, K, Cout, ptr(gw), K, ptr(gb), Cout, stream())
+    return gw, gb
+
+
 def _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K):
+    if not accumulate and K <= 4 and R % 3 == 0 and out.stride(0) == K:
+        call("vnpcc_smallk_wgrad", ptr(dy), _ld(dy), ptr(x), _ld(x), 1, R // 3, K, Cout, ptr(out), K, None, 0, stream())
+        return out
     if _GEMM_MODE == "tf32" and not accumulate and R > 0:
         nb = _lib.raw("vnpcc_gemm_wgrad_tf32_workspace_bytes", R, Cout, K)
         ws = _workspace(nb, x.device, "wgrad")
@@ -190,6 +217,10 @@ class _LinearRows(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = gemm_rows(gy, w, True)
+        if ctx.has_bias and x.shape[1] <= 4 and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            R = gy.shape[0]
+            gw, gb = smallk_wgrad(gy, x, R // ctx.rps, ctx.rps // 3, True)
+            return gx, gw, gb, None
         if ctx.needs_input_grad[1]:
             gw = gemm_wgrad(gy, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -334,6 +365,53 @@ def maxpool_rows(x, d, G, N, forced_idx=None):
     with torch.no_grad():
         idx = maxpool_select(x, _rows2d(d.detach(), "d"), G, N) if forced_idx is None else forced_idx.reshape(G, -1).contiguous()
     return _MaxPoolGather.apply(x, idx, G, N), idx
+
+
+class _LinearMaxPool(torch.autograd.Function):
+    """out = VNMaxPool(VNLinear(x)) with the pooled layer's [R, C] activation kept only transiently and NO dense
+    gradient: the backward scatters / gathers the one selected point per (sample, channel)."""
+
+    @staticmethod
+    def forward(ctx, x, w, wdir, G, N, forced_idx):
+        x = _rows2d(x, "x")
+        if w.stride(1) != 1:
+            w = w.contiguous()
+        f = gemm_rows(x, w)
+        if forced_idx is None:
+            if _GEMM_MODE == "tf32":
+                # d = Wdir (W x) = (Wdir W) x : contract over K (the layer's input width) instead of C >= K
+                wc = gemm_rows(wdir, w, True)
+                d = gemm_rows(x, wc)
+            else:
+                d = gemm_rows(f, wdir)       # reference order of operations (parity mode)
+            idx = maxpool_select(f, d, G, N)
+            del d
+        else:
+            idx = forced_idx.reshape(G, -1).contiguous()
+        C = f.shape[1]
+        out = torch.empty((G * 3, C), device=x.device, dtype=torch.float32)
+        call("vnpcc_vn_maxpool_gather", ptr(f), _ld(f), ptr(idx), G, N, C, ptr(out), C, stream())
+        ctx.save_for_backward(x, w, idx)
+        ctx.cfg = (G, N)
+        ctx.mark_non_differentiable(idx)
+        return out, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        x, w, idx = ctx.saved_tensors
+        G, N = ctx.cfg
+        g = _rows2d(g, "grad")
+        C, K = w.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty((C, K), device=x.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        call("vnpcc_pool_linear_bwd", ptr(g), _ld(g), ptr(idx), ptr(x), _ld(x), ptr(w), _ld(w), G, N, C, K, ptr(gx),
+             _ld(gx) if gx is not None else 0, ptr(gw), K, stream())
+        return gx, gw, None, None, None, None
+
+
+def linear_maxpool_rows(x, w, wdir, G, N, forced_idx=None):
+    """VNLinear(K -> C) followed by VNMaxPool(C) over groups of N points: (pooled rows [G*3, C], idx [G, C])"""
+    return _LinearMaxPool.apply(x, w, wdir.detach(), G, N, forced_idx)
 
 
 # ---------------------------------------------------------------------------------------------------------------

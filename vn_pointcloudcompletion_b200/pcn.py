@@ -54,8 +54,10 @@ class VN_PointNet(nn.Module):
         bias = ops.linear_rows(g1, wcat[:, :Cg])                                          # [B*3,2048]
         pd = ops.linear_rows(f1, wcat[:, Cg:], bias, 3 * N)                               # [R,2048]
         f2 = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)   # [R,1024]
-        f3 = ops.linear_rows(f2, self.second_conv[1].map_to_feat.weight)                 # [R,2048]
-        fg = self.maxpool2.forward_rows(f3, B, N)                                         # [B*3,2048]
+        # second_conv[1] feeds only maxpool2: fused, its [R,2048] output is transient and its backward is sparse
+        fg, idx2 = ops.linear_maxpool_rows(f2, self.second_conv[1].map_to_feat.weight, self.maxpool2.map_to_dir.weight, B, N,
+                                           self.maxpool2.forced_idx)                       # [B*3,2048]
+        self.maxpool2.last_idx = idx2
         m = self.mlp[0].forward_rows(fg)
         m = self.mlp[1].forward_rows(m)
         m = ops.linear_rows(m, self.mlp[2].map_to_feat.weight)                            # [B*3,num_coarse] rows (b,v)
