@@ -470,57 +470,92 @@ __global__ void __launch_bounds__(256) rows_wsum_kernel(const float* __restrict_
 //      wgrad: gW[o, k] = sum_r gy[r, o] x[r, k]   and (optionally)  gbias[(b,v), o] = sum_n gy[(b,n,v), o]
 // -------------------------------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(256) smallk_fwd_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ W,
-                                                          size_t ldw, const float* __restrict__ bias, size_t ldb,
-                                                          long long rps, float* __restrict__ y, size_t ldy, long long R,
-                                                          int Cout) {
-    // block (64, 4): x -> channel quads (grid-stride over quads), y -> rows
-    const int nq = Cout >> 2;
-    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
-        float xv[KS];
+__global__ void __launch_bounds__(128) smallk_fwd_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ W,
+                                                          size_t ldw, const float* __restrict__ bias, size_t ldb, long long n_per_sample,
+                                                          float* __restrict__ y, size_t ldy, long long P, int Cout,
+                                                          long long pts_per_block) {
+    // thread owns one channel quad (weights in registers) and streams over a contiguous chunk of points (3 rows each);
+    // the per-sample bias rows are reloaded only when the sample changes
+    const int q = blockIdx.y * 128 + threadIdx.x;
+    if (4 * q >= Cout) return;
+    float w[4][KS];
 #pragma unroll
-        for (int k = 0; k < KS; ++k) xv[k] = __ldg(x + (size_t)r * ldx + k);
-        const float* brow = nullptr;
-        if (bias) brow = bias + (size_t)((r / rps) * 3 + (r % 3)) * ldb;
-        float* yr = y + (size_t)r * ldy;
-        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-            float4 acc = brow ? __ldg(reinterpret_cast<const float4*>(brow) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) w[j][k] = __ldg(W + (size_t)(4 * q + j) * ldw + k);
+    const long long p0 = (long long)blockIdx.x * pts_per_block;
+    const long long p1 = (p0 + pts_per_block < P) ? p0 + pts_per_block : P;
+    long long b = bias ? p0 / n_per_sample : 0;
+    long long nrem = bias ? p0 - b * n_per_sample : 0;
+    float4 bz[3];
+    bz[0] = bz[1] = bz[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool reload = bias != nullptr;
+#pragma unroll 2
+    for (long long pt = p0; pt < p1; ++pt) {
+        if (reload) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) bz[v] = __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb) + q);
+            reload = false;
+        }
+        const size_t row = (size_t)pt * 3;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            float4 acc = bz[v];
 #pragma unroll
             for (int k = 0; k < KS; ++k) {
-                acc.x = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 0) * ldw + k), acc.x);
-                acc.y = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 1) * ldw + k), acc.y);
-                acc.z = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 2) * ldw + k), acc.z);
-                acc.w = fmaf(xv[k], __ldg(W + (size_t)(4 * q + 3) * ldw + k), acc.w);
+                const float xv = __ldg(x + (row + v) * ldx + k);
+                acc.x = fmaf(xv, w[0][k], acc.x);
+                acc.y = fmaf(xv, w[1][k], acc.y);
+                acc.z = fmaf(xv, w[2][k], acc.z);
+                acc.w = fmaf(xv, w[3][k], acc.w);
             }
-            reinterpret_cast<float4*>(yr)[q] = acc;
+            reinterpret_cast<float4*>(y + (row + v) * ldy)[q] = acc;
+        }
+        if (bias && ++nrem == n_per_sample) {
+            nrem = 0;
+            ++b;
+            reload = true;
         }
     }
 }
 
-template <int KS>
+template <int KS, int NQL>
 __global__ void __launch_bounds__(256) smallk_dgrad_kernel(const float* __restrict__ gy, size_t ldgy, const float* __restrict__ W,
                                                             size_t ldw, float* __restrict__ gx, size_t ldgx, long long R,
                                                             int Cout) {
-    // one warp per row
+    // one warp per row; lane owns channel quads lane + 32*i (weights in registers)
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int nq = Cout >> 2;
+    float w[NQL][4][KS];
+#pragma unroll
+    for (int i = 0; i < NQL; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const int q = lane + 32 * i;
+                w[i][j][k] = q < nq ? __ldg(W + (size_t)(4 * q + j) * ldw + k) : 0.f;
+            }
+#pragma unroll 2
     for (long long r = warp; r < R; r += nwarps) {
         const float4* g4 = reinterpret_cast<const float4*>(gy + (size_t)r * ldgy);
+        float4 g[NQL];
+#pragma unroll
+        for (int i = 0; i < NQL; ++i) g[i] = (lane + 32 * i < nq) ? __ldg(g4 + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
         float acc[KS];
 #pragma unroll
         for (int k = 0; k < KS; ++k) acc[k] = 0.f;
-        for (int q = lane; q < nq; q += 32) {
-            const float4 g = __ldg(g4 + q);
+#pragma unroll
+        for (int i = 0; i < NQL; ++i)
 #pragma unroll
             for (int k = 0; k < KS; ++k) {
-                acc[k] = fmaf(g.x, __ldg(W + (size_t)(4 * q + 0) * ldw + k), acc[k]);
-                acc[k] = fmaf(g.y, __ldg(W + (size_t)(4 * q + 1) * ldw + k), acc[k]);
-                acc[k] = fmaf(g.z, __ldg(W + (size_t)(4 * q + 2) * ldw + k), acc[k]);
-                acc[k] = fmaf(g.w, __ldg(W + (size_t)(4 * q + 3) * ldw + k), acc[k]);
+                acc[k] = fmaf(g[i].x, w[i][0][k], acc[k]);
+                acc[k] = fmaf(g[i].y, w[i][1][k], acc[k]);
+                acc[k] = fmaf(g[i].z, w[i][2][k], acc[k]);
+                acc[k] = fmaf(g[i].w, w[i][3][k], acc[k]);
             }
-        }
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
 #pragma unroll
@@ -535,50 +570,72 @@ __global__ void __launch_bounds__(256) smallk_wgrad_kernel(const float* __restri
                                                             size_t ldx, int B, int N, int Cout, int n_chunk,
                                                             float* __restrict__ gW, size_t ldgw, float* __restrict__ gbias,
                                                             size_t ldgb) {
-    // grid: x -> channel tiles of 32, y -> (sample, chunk of points); block (32, 8); gW / gbias zeroed by the launcher
-    const int c = blockIdx.x * 32 + threadIdx.x;
+    // grid: x -> tiles of 32 channel quads, y -> (sample, chunk of points); block (32, 8); gW / gbias zeroed by the launcher
+    const int q = blockIdx.x * 32 + threadIdx.x;
+    const bool active = 4 * q < Cout;
     const int chunks_per_b = (N + n_chunk - 1) / n_chunk;
     const int b = blockIdx.y / chunks_per_b;
     const int ck = blockIdx.y - b * chunks_per_b;
     const int n0 = ck * n_chunk, n1 = min(N, n0 + n_chunk);
-    float sb[3] = {0.f, 0.f, 0.f};
-    float sw[KS];
+    float sb[3][4], sw[KS][4];
 #pragma unroll
-    for (int k = 0; k < KS; ++k) sw[k] = 0.f;
-    if (c < Cout) {
-        for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) sb[v][l] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) sw[k][l] = 0.f;
+    if (active) {
+#pragma unroll 2
+        for (int n = n0 + threadIdx.y; n < n1; n += 8) {
             const size_t row = ((size_t)b * N + n) * 3;
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
-                const float g = __ldg(gy + (row + v) * ldgy + c);
-                sb[v] += g;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gy + (row + v) * ldgy) + q);
+                sb[v][0] += g.x;
+                sb[v][1] += g.y;
+                sb[v][2] += g.z;
+                sb[v][3] += g.w;
 #pragma unroll
-                for (int k = 0; k < KS; ++k) sw[k] = fmaf(g, __ldg(x + (row + v) * ldx + k), sw[k]);
+                for (int k = 0; k < KS; ++k) {
+                    const float xv = __ldg(x + (row + v) * ldx + k);
+                    sw[k][0] = fmaf(g.x, xv, sw[k][0]);
+                    sw[k][1] = fmaf(g.y, xv, sw[k][1]);
+                    sw[k][2] = fmaf(g.z, xv, sw[k][2]);
+                    sw[k][3] = fmaf(g.w, xv, sw[k][3]);
+                }
             }
         }
     }
-    __shared__ float sh[3 + KS][8][33];
+    __shared__ float sh[3 + KS][8][32][4];
 #pragma unroll
-    for (int v = 0; v < 3; ++v) sh[v][threadIdx.y][threadIdx.x] = sb[v];
+    for (int l = 0; l < 4; ++l) {
 #pragma unroll
-    for (int k = 0; k < KS; ++k) sh[3 + k][threadIdx.y][threadIdx.x] = sw[k];
+        for (int v = 0; v < 3; ++v) sh[v][threadIdx.y][threadIdx.x][l] = sb[v][l];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) sh[3 + k][threadIdx.y][threadIdx.x][l] = sw[k][l];
+    }
     __syncthreads();
-    if (threadIdx.y == 0 && c < Cout) {
-        for (int i = 1; i < 8; ++i) {
+    if (threadIdx.y == 0 && active) {
 #pragma unroll
-            for (int v = 0; v < 3; ++v) sb[v] += sh[v][i][threadIdx.x];
+        for (int l = 0; l < 4; ++l) {
+            const int c = 4 * q + l;
 #pragma unroll
-            for (int k = 0; k < KS; ++k) sw[k] += sh[3 + k][i][threadIdx.x];
+            for (int v = 0; v < 3; ++v) {
+                float a = 0.f;
+                for (int i = 0; i < 8; ++i) a += sh[v][i][threadIdx.x][l];
+                if (gbias) atomicAdd(gbias + ((size_t)b * 3 + v) * ldgb + c, a);
+            }
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                float a = 0.f;
+                for (int i = 0; i < 8; ++i) a += sh[3 + k][i][threadIdx.x][l];
+                atomicAdd(gW + (size_t)c * ldgw + k, a);
+            }
         }
-        if (gbias) {
-#pragma unroll
-            for (int v = 0; v < 3; ++v) atomicAdd(gbias + ((size_t)b * 3 + v) * ldgb + c, sb[v]);
-        }
-#pragma unroll
-        for (int k = 0; k < KS; ++k) atomicAdd(gW + (size_t)c * ldgw + k, sw[k]);
     }
 }
-
 
 // -------------------------------------------------------------------------------------------------------------
 // 9. backward of  VNLinear -> VNMaxPool  (f = x W^T, out[b,c,:] = f[b,c,:,idx[b,c]]) without the dense [R, C] gradient:
@@ -650,6 +707,7 @@ extern "C" {
 int vnpcc_vn_norm_stats(const float* p, long long ldp, long long P, int C, double* sums, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (P > 0 && C > 0 && try_norm_stats_v4(p, ldp, P, C, sums, st)) return last_error();
     if (P > 0 && C > 0) {
         dim3 block(32, 8);
         const int gx = (C + 31) / 32;
@@ -674,6 +732,7 @@ int vnpcc_vn_bn_leaky_fwd(const float* p, long long ldp, const float* d, long lo
                           long long P, int C, const float* stat, const float* gamma, const float* beta, float ns,
                           void* stream) {
     if (P <= 0 || C <= 0) return 0;
+    if (try_bn_leaky_fwd_v4(p, ldp, d, ldd, out, ldo, P, C, stat, gamma, beta, ns, (cudaStream_t)stream)) return last_error();
     count_launch(), vn_bn_leaky_fwd_kernel<<<grid_for((size_t)P * C, 256, 16), 256, 0, (cudaStream_t)stream>>>(
         p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma, beta, ns);
     return last_error();
@@ -686,6 +745,9 @@ int vnpcc_vn_bn_leaky_bwd1(const float* g, long long ldg, const float* p, long l
     cudaStream_t st = (cudaStream_t)stream;
     if (stat && !sums) return VNPCC_ERR_BAD_ARG;
     if (stat) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (P > 0 && C > 0 && try_bn_leaky_bwd1_v4(g, ldg, p, ldp, d, ldd, gp, ldgp, gd, ldgd, P, C, stat, gamma, beta, ns,
+                                               stat ? sums : nullptr, st))
+        return last_error();
     if (P > 0 && C > 0) {
         dim3 block(32, 8);
         const int gx = (C + 31) / 32;
@@ -706,7 +768,8 @@ int vnpcc_vn_bn_bwd2(float* gp, long long ldgp, const float* p, long long ldp, l
                      float* gweight, float* gbias, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (C <= 0) return 0;
-    if (P > 0)
+    if (P > 0 && try_bn_bwd2_v4(gp, ldgp, p, ldp, P, C, stat, gamma, beta, sums, count, training, st)) {
+    } else if (P > 0)
         count_launch(), vn_bn_bwd2_kernel<<<grid_for((size_t)P * C, 256, 16), 256, 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma,
                                                                           beta, sums, count, training);
     if (gbias) count_launch(), double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gbias, C);
@@ -820,25 +883,35 @@ static bool smallk_ok(int K, int Cout, const void* a, long long lda, const void*
 int vnpcc_smallk_fwd(const float* x, long long ldx, const float* W, long long ldw, const float* bias, long long ldbias,
                      long long rows_per_sample, float* y, long long ldy, long long R, int K, int Cout, void* stream) {
     if (R <= 0) return 0;
-    if (!smallk_ok(K, Cout, y, ldy, bias, ldbias)) return VNPCC_ERR_UNSUPPORTED;
-    if (bias && rows_per_sample <= 0) return VNPCC_ERR_BAD_ARG;
+    if (!smallk_ok(K, Cout, y, ldy, bias, ldbias) || (R % 3) != 0) return VNPCC_ERR_UNSUPPORTED;
+    if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    long long g = (R + 3) / 4;
-    const long long cap = (long long)sm_count() * 8;
-    if (g > cap) g = cap;
-    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_fwd_kernel<K_><<<(unsigned)g, dim3(64, 4), 0, st>>>(
-                             x, (size_t)ldx, W, (size_t)ldw, bias, (size_t)ldbias, rows_per_sample > 0 ? rows_per_sample : 1, y,
-                             (size_t)ldy, R, Cout)));
+    const long long P = R / 3;
+    const int gy = (Cout / 4 + 127) / 128;
+    long long blocks = ((long long)sm_count() * 16 + gy - 1) / gy;
+    long long ppb = (P + blocks - 1) / blocks;
+    if (ppb < 16) ppb = 16;
+    blocks = (P + ppb - 1) / ppb;
+    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_fwd_kernel<K_><<<dim3((unsigned)blocks, gy), 128, 0, st>>>(
+                             x, (size_t)ldx, W, (size_t)ldw, bias, (size_t)ldbias, bias ? rows_per_sample / 3 : 1, y, (size_t)ldy, P, Cout,
+                             ppb)));
     return last_error();
 }
 
 int vnpcc_smallk_dgrad(const float* gy, long long ldgy, const float* W, long long ldw, float* gx, long long ldgx, long long R,
                        int K, int Cout, void* stream) {
     if (R <= 0) return 0;
-    if (!smallk_ok(K, Cout, gy, ldgy, nullptr, 0)) return VNPCC_ERR_UNSUPPORTED;
+    if (!smallk_ok(K, Cout, gy, ldgy, nullptr, 0) || Cout > 1024) return VNPCC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for((size_t)R * 32, 256, 8);
-    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_dgrad_kernel<K_><<<grid, 256, 0, st>>>(gy, (size_t)ldgy, W, (size_t)ldw, gx, (size_t)ldgx, R, Cout)));
+    const int nql = (Cout / 4 + 31) / 32;
+#define VNPCC_DG(NQL_) \
+    VNPCC_KS_DISPATCH(K, (count_launch(), smallk_dgrad_kernel<K_, NQL_><<<grid, 256, 0, st>>>(gy, (size_t)ldgy, W, (size_t)ldw, gx, (size_t)ldgx, R, Cout)))
+    if (nql <= 1) { VNPCC_DG(1); }
+    else if (nql <= 2) { VNPCC_DG(2); }
+    else if (nql <= 4) { VNPCC_DG(4); }
+    else { VNPCC_DG(8); }
+#undef VNPCC_DG
     return last_error();
 }
 
@@ -847,11 +920,12 @@ int vnpcc_smallk_dgrad(const float* gy, long long ldgy, const float* W, long lon
 int vnpcc_smallk_wgrad(const float* gy, long long ldgy, const float* x, long long ldx, int B, int N, int K, int Cout, float* gW,
                        long long ldgw, float* gbias, long long ldgb, void* stream) {
     if (K < 1 || K > 4 || Cout <= 0) return VNPCC_ERR_UNSUPPORTED;
+    if (!smallk_ok(K, Cout, gy, ldgy, nullptr, 0)) return VNPCC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemset2DAsync(gW, (size_t)ldgw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)Cout, st);
     if (gbias) cudaMemset2DAsync(gbias, (size_t)ldgb * sizeof(float), 0, (size_t)Cout * sizeof(float), (size_t)B * 3, st);
     if (B <= 0 || N <= 0) return last_error();
-    const int gx = (Cout + 31) / 32;
+    const int gx = (Cout / 4 + 31) / 32;
     int chunks = (int)(((long long)sm_count() * 8 + (long long)gx * B - 1) / ((long long)gx * B));
     if (chunks < 1) chunks = 1;
     int n_chunk = (N + chunks - 1) / chunks;

@@ -1,0 +1,315 @@
+// vn_stream.cu -- 128-bit vectorised versions of the HBM-bound Vector-Neuron row kernels (norm statistics, BatchNorm
+// + leaky projection forward / backward).  Same arithmetic as the scalar kernels in vn_kernels.cu (which remain the
+// path for channel counts / pitches that are not multiples of 4); each thread owns FOUR consecutive channels, so a warp
+// reads 512 contiguous bytes per row, per-channel parameters live in registers, and up to nine 16-byte loads are in
+// flight per thread per point.
+//
+// Reference semantics: VNBatchNorm models/vn_layers.py:116-127, leaky projection :39-42/:70-73; backward formulas
+// SURVEY.md Appendix C.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "vnpcc_internal.h"
+
+namespace vnpcc {
+
+constexpr float VS_EPS = 1e-6f;
+
+struct V4x3 {
+    float v[3][4];   // [component][channel lane]
+};
+
+__device__ __forceinline__ V4x3 ld43(const float* __restrict__ base, size_t ld) {
+    V4x3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + c * ld));
+        r.v[c][0] = t.x;
+        r.v[c][1] = t.y;
+        r.v[c][2] = t.z;
+        r.v[c][3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ V4x3 ld43_rw(const float* base, size_t ld) {
+    V4x3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(base + c * ld);
+        r.v[c][0] = t.x;
+        r.v[c][1] = t.y;
+        r.v[c][2] = t.z;
+        r.v[c][3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void st43(float* __restrict__ base, size_t ld, const V4x3& r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(base + c * ld) = make_float4(r.v[c][0], r.v[c][1], r.v[c][2], r.v[c][3]);
+}
+// (a*b).sum over the 3 components: three rounded products summed left to right, no contraction
+__device__ __forceinline__ float dot3l(const V4x3& a, const V4x3& b, int l) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.v[0][l], b.v[0][l]), __fmul_rn(a.v[1][l], b.v[1][l])), __fmul_rn(a.v[2][l], b.v[2][l]));
+}
+
+struct ChanParams {
+    float mean[4], invstd[4], gamma[4], beta[4];
+};
+__device__ __forceinline__ ChanParams load_params(const float* stat, const float* gamma, const float* beta, int C, int c0) {
+    ChanParams p;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        p.mean[l] = stat ? __ldg(stat + c0 + l) : 0.f;
+        p.invstd[l] = stat ? __ldg(stat + C + c0 + l) : 0.f;
+        p.gamma[l] = stat ? __ldg(gamma + c0 + l) : 0.f;
+        p.beta[l] = stat ? __ldg(beta + c0 + l) : 0.f;
+    }
+    return p;
+}
+
+// block (32, 8): lane -> channel quad, y -> point lane; grid.x tiles quads by 32, grid.y strides over points
+#define VS_BLOCK_REDUCE2(S1, S2, sums, C, c0)                                   \
+    {                                                                           \
+        __shared__ double sh[2][8][32][4];                                      \
+        _Pragma("unroll") for (int l = 0; l < 4; ++l) {                         \
+            sh[0][threadIdx.y][threadIdx.x][l] = S1[l];                         \
+            sh[1][threadIdx.y][threadIdx.x][l] = S2[l];                         \
+        }                                                                       \
+        __syncthreads();                                                        \
+        if (threadIdx.y == 0 && active) {                                       \
+            _Pragma("unroll") for (int l = 0; l < 4; ++l) {                     \
+                double a = 0.0, b = 0.0;                                        \
+                for (int k = 0; k < 8; ++k) {                                   \
+                    a += sh[0][k][threadIdx.x][l];                              \
+                    b += sh[1][k][threadIdx.x][l];                              \
+                }                                                               \
+                atomicAdd(sums + c0 + l, a);                                    \
+                atomicAdd(sums + C + c0 + l, b);                                \
+            }                                                                   \
+        }                                                                       \
+    }
+
+__global__ void __launch_bounds__(256) norm_stats_v4_kernel(const float* __restrict__ p, size_t ld, long long P, int C,
+                                                             double* __restrict__ sums) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const bool active = c0 < C;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (active) {
+        const long long stride = (long long)gridDim.y * 8;
+#pragma unroll 2
+        for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+            const V4x3 v = ld43(p + (size_t)pt * 3 * ld + c0, ld);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const double n = (double)(sqrtf(dot3l(v, v, l)) + VS_EPS);
+                s1[l] += n;
+                s2[l] = fma(n, n, s2[l]);
+            }
+        }
+    }
+    VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)
+}
+
+__device__ __forceinline__ void bn_apply_lane(V4x3& v, int l, const ChanParams& cp, float& n_out, float& nhat_out, float& nb_out) {
+    const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v.v[0][l], v.v[0][l]), __fmul_rn(v.v[1][l], v.v[1][l])),
+                                    __fmul_rn(v.v[2][l], v.v[2][l])));
+    const float n = r + VS_EPS;
+    const float nhat = (n - cp.mean[l]) * cp.invstd[l];
+    const float nb = nhat * cp.gamma[l] + cp.beta[l];
+    v.v[0][l] = v.v[0][l] / n * nb;
+    v.v[1][l] = v.v[1][l] / n * nb;
+    v.v[2][l] = v.v[2][l] / n * nb;
+    n_out = n;
+    nhat_out = nhat;
+    nb_out = nb;
+}
+
+template <bool HAS_BN, bool HAS_D>
+__global__ void __launch_bounds__(256) bn_leaky_fwd_v4_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
+                                                               size_t ldd, float* __restrict__ out, size_t ldo, long long P, int C,
+                                                               const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float ns) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (c0 >= C) return;
+    const ChanParams cp = load_params(HAS_BN ? stat : nullptr, gamma, beta, C, c0);
+    const float k = 1.f - ns;
+    const long long stride = (long long)gridDim.y * 8;
+#pragma unroll 2
+    for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+        V4x3 v = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
+        V4x3 dv;
+        if (HAS_D) dv = ld43(d + (size_t)pt * 3 * ldd + c0, ldd);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (HAS_BN) {
+                float n, nhat, nb;
+                bn_apply_lane(v, l, cp, n, nhat, nb);
+            }
+            if (HAS_D) {
+                // op-by-op rounding of  ns*p + (1-ns)*(mask*p + (1-mask)*(p - (dot/(dsq+EPS))*d))
+                const float dot = dot3l(v, dv, l);
+                float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
+                if (!(dot >= 0.f)) {
+                    const float a = dot / __fadd_rn(dot3l(dv, dv, l), VS_EPS);
+                    in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
+                    in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
+                    in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
+                }
+                v.v[0][l] = __fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k, in0));
+                v.v[1][l] = __fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k, in1));
+                v.v[2][l] = __fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k, in2));
+            }
+        }
+        st43(out + (size_t)pt * 3 * ldo + c0, ldo, v);
+    }
+}
+
+template <bool HAS_BN, bool HAS_D>
+__global__ void __launch_bounds__(256) bn_leaky_bwd1_v4_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ p,
+                                                                size_t ldp, const float* __restrict__ d, size_t ldd,
+                                                                float* __restrict__ gp, size_t ldgp, float* __restrict__ gd,
+                                                                size_t ldgd, long long P, int C, const float* __restrict__ stat,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float ns, double* __restrict__ sums) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const bool active = c0 < C;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (active) {
+        const ChanParams cp = load_params(HAS_BN ? stat : nullptr, gamma, beta, C, c0);
+        const float k = 1.f - ns;
+        const long long stride = (long long)gridDim.y * 8;
+        for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+            const V4x3 pr = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
+            const V4x3 gv = ld43(g + (size_t)pt * 3 * ldg + c0, ldg);
+            V4x3 dv;
+            if (HAS_D) dv = ld43(d + (size_t)pt * 3 * ldd + c0, ldd);
+            V4x3 pb = pr, gpb = gv, gdv;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                float n = 1.f, nhat = 0.f, nb = 0.f;
+                if (HAS_BN) bn_apply_lane(pb, l, cp, n, nhat, nb);
+                if (HAS_D) {
+                    const float s = dot3l(pb, dv, l);
+                    gdv.v[0][l] = gdv.v[1][l] = gdv.v[2][l] = 0.f;
+                    if (s < 0.f) {
+                        const float q = dot3l(dv, dv, l) + VS_EPS;
+                        const float a = s / q;
+                        const float gdq = dot3l(gv, dv, l) / q;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            gpb.v[c][l] = gv.v[c][l] - k * gdq * dv.v[c][l];
+                            gdv.v[c][l] = -k * (a * gv.v[c][l] + gdq * pb.v[c][l] - 2.f * a * gdq * dv.v[c][l]);
+                        }
+                    }
+                }
+                if (HAS_BN) {
+                    const float dnb = dot3l(gpb, pr, l) / n;
+                    s1[l] += (double)dnb;
+                    s2[l] = fma((double)dnb, (double)nhat, s2[l]);
+                }
+            }
+            st43(gp + (size_t)pt * 3 * ldgp + c0, ldgp, gpb);
+            if (HAS_D) st43(gd + (size_t)pt * 3 * ldgd + c0, ldgd, gdv);
+        }
+    }
+    if (HAS_BN) VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)
+}
+
+__global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp, size_t ldgp, const float* __restrict__ p, size_t ldp,
+                                                          long long P, int C, const float* __restrict__ stat,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const double* __restrict__ sums, double count, int training) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (c0 >= C) return;
+    const ChanParams cp = load_params(stat, gamma, beta, C, c0);
+    float m1[4], m2[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        m1[l] = training ? (float)(sums[c0 + l] / count) * cp.gamma[l] : 0.f;
+        m2[l] = training ? (float)(sums[C + c0 + l] / count) * cp.gamma[l] : 0.f;
+    }
+    const long long stride = (long long)gridDim.y * 8;
+#pragma unroll 2
+    for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+        const V4x3 pr = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
+        float* gptr = gp + (size_t)pt * 3 * ldgp + c0;
+        V4x3 gv = ld43_rw(gptr, ldgp);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const float r = sqrtf(dot3l(pr, pr, l));
+            const float n = r + VS_EPS;
+            const float nhat = (n - cp.mean[l]) * cp.invstd[l];
+            const float nb = nhat * cp.gamma[l] + cp.beta[l];
+            const float gx = dot3l(gv, pr, l);
+            const float dnb = gx / n;
+            float dn = cp.gamma[l] * dnb;
+            if (training) dn = dn - m1[l] - nhat * m2[l];
+            dn = dn * cp.invstd[l] - gx * nb / (n * n);
+            const float sc = nb / n;
+            const float ur = r > 0.f ? dn / r : 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gv.v[c][l] = gv.v[c][l] * sc + ur * pr.v[c][l];
+        }
+        st43(gptr, ldgp, gv);
+    }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool ok4(const void* p, long long ld) { return p == nullptr || (al16(p) && (ld & 3) == 0); }
+
+static dim3 stream_grid(long long P, int C) {
+    const int gx = (C / 4 + 31) / 32;
+    long long gy = (P + 7) / 8;
+    const long long cap = ((long long)sm_count() * 8 + gx - 1) / gx;   // ~8 CTAs of 256 threads per SM in total
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    return dim3((unsigned)gx, (unsigned)gy);
+}
+
+bool try_norm_stats_v4(const float* p, long long ldp, long long P, int C, double* sums, cudaStream_t st) {
+    if ((C & 3) || !ok4(p, ldp)) return false;
+    count_launch(), norm_stats_v4_kernel<<<stream_grid(P, C), dim3(32, 8), 0, st>>>(p, (size_t)ldp, P, C, sums);
+    return true;
+}
+
+bool try_bn_leaky_fwd_v4(const float* p, long long ldp, const float* d, long long ldd, float* out, long long ldo, long long P, int C,
+                         const float* stat, const float* gamma, const float* beta, float ns, cudaStream_t st) {
+    if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(out, ldo)) return false;
+    const dim3 grid = stream_grid(P, C), block(32, 8);
+#define VS_FWD(BN_, D_)                                                                                                          \
+    count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, \
+                                                                             gamma, beta, ns)
+    if (stat && d) VS_FWD(true, true);
+    else if (stat) VS_FWD(true, false);
+    else if (d) VS_FWD(false, true);
+    else VS_FWD(false, false);
+#undef VS_FWD
+    return true;
+}
+
+bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long long ldp, const float* d, long long ldd, float* gp,
+                          long long ldgp, float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma,
+                          const float* beta, float ns, double* sums, cudaStream_t st) {
+    if ((C & 3) || !ok4(g, ldg) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(gp, ldgp) || !ok4(gd, ldgd)) return false;
+    const dim3 grid = stream_grid(P, C), block(32, 8);
+#define VS_BWD(BN_, D_)                                                                                                            \
+    count_launch(), bn_leaky_bwd1_v4_kernel<BN_, D_><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, \
+                                                                              gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums)
+    if (stat && d) VS_BWD(true, true);
+    else if (stat) VS_BWD(true, false);
+    else if (d) VS_BWD(false, true);
+    else VS_BWD(false, false);
+#undef VS_BWD
+    return true;
+}
+
+bool try_bn_bwd2_v4(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
+                    const float* beta, const double* sums, double count, int training, cudaStream_t st) {
+    if ((C & 3) || !ok4(gp, ldgp) || !ok4(p, ldp)) return false;
+    count_launch(), bn_bwd2_v4_kernel<<<stream_grid(P, C), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
+                                                                             sums, count, training);
+    return true;
+}
+
+}  // namespace vnpcc

@@ -44,4 +44,14 @@ inline int grid_for(size_t total, int block, int per_sm) {
     return (int)g;
 }
 
+// vectorised (4 channels / thread) streaming kernels, vn_stream.cu: return false when the shape / alignment does not allow them
+bool try_norm_stats_v4(const float* p, long long ldp, long long P, int C, double* sums, cudaStream_t st);
+bool try_bn_leaky_fwd_v4(const float* p, long long ldp, const float* d, long long ldd, float* out, long long ldo, long long P, int C,
+                         const float* stat, const float* gamma, const float* beta, float ns, cudaStream_t st);
+bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long long ldp, const float* d, long long ldd, float* gp,
+                          long long ldgp, float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma,
+                          const float* beta, float ns, double* sums, cudaStream_t st);
+bool try_bn_bwd2_v4(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
+                    const float* beta, const double* sums, double count, int training, cudaStream_t st);
+
 }  // namespace vnpcc

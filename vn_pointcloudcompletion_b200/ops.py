@@ -168,8 +168,11 @@ def smallk_wgrad(dy, x, B, N, want_bias):
 
 def _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K):
     if not accumulate and K <= 4 and R % 3 == 0 and out.stride(0) == K:
-        call("vnpcc_smallk_wgrad", ptr(dy), _ld(dy), ptr(x), _ld(x), 1, R // 3, K, Cout, ptr(out), K, None, 0, stream())
-        return out
+        rc = _lib.raw("vnpcc_smallk_wgrad", ptr(dy), _ld(dy), ptr(x), _ld(x), 1, R // 3, K, Cout, ptr(out), K, None, 0, stream())
+        if rc == 0:
+            return out
+        if rc != 10003:
+            raise _lib.VnpccError(f"vnpcc_smallk_wgrad failed with code {rc}")
     if _GEMM_MODE == "tf32" and not accumulate and R > 0:
         nb = _lib.raw("vnpcc_gemm_wgrad_tf32_workspace_bytes", R, Cout, K)
         ws = _workspace(nb, x.device, "wgrad")
@@ -217,7 +220,8 @@ class _LinearRows(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = gemm_rows(gy, w, True)
-        if ctx.has_bias and x.shape[1] <= 4 and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+        if (ctx.has_bias and x.shape[1] <= 4 and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
+                and gy.shape[1] % 4 == 0 and _ld(gy) % 4 == 0):
             R = gy.shape[0]
             gw, gb = smallk_wgrad(gy, x, R // ctx.rps, ctx.rps // 3, True)
             return gx, gw, gb, None
