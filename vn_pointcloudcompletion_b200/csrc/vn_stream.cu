@@ -166,12 +166,13 @@ __global__ void __launch_bounds__(256) bn_leaky_fwd_v4_kernel(const float* __res
 }
 
 template <bool HAS_BN, bool HAS_D>
-__global__ void __launch_bounds__(256) bn_leaky_bwd1_v4_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ p,
-                                                                size_t ldp, const float* __restrict__ d, size_t ldd,
-                                                                float* __restrict__ gp, size_t ldgp, float* __restrict__ gd,
-                                                                size_t ldgd, long long P, int C, const float* __restrict__ stat,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                float ns, double* __restrict__ sums) {
+__global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ p,
+                                                                   size_t ldp, const float* __restrict__ d, size_t ldd,
+                                                                   float* __restrict__ gp, size_t ldgp, float* __restrict__ gd,
+                                                                   size_t ldgd, long long P, int C, const float* __restrict__ stat,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float ns, double* __restrict__ sums) {
+    // register diet (two CTAs per SM): the post-BN vector is kept as pr * sc, and gp / gd overwrite g / d in place
     const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const bool active = c0 < C;
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
@@ -181,36 +182,46 @@ __global__ void __launch_bounds__(256) bn_leaky_bwd1_v4_kernel(const float* __re
         const long long stride = (long long)gridDim.y * 8;
         for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
             const V4x3 pr = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
-            const V4x3 gv = ld43(g + (size_t)pt * 3 * ldg + c0, ldg);
+            V4x3 gv = ld43(g + (size_t)pt * 3 * ldg + c0, ldg);
             V4x3 dv;
             if (HAS_D) dv = ld43(d + (size_t)pt * 3 * ldd + c0, ldd);
-            V4x3 pb = pr, gpb = gv, gdv;
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
-                float n = 1.f, nhat = 0.f, nb = 0.f;
-                if (HAS_BN) bn_apply_lane(pb, l, cp, n, nhat, nb);
+                float n = 1.f, nhat = 0.f;
+                float pb0 = pr.v[0][l], pb1 = pr.v[1][l], pb2 = pr.v[2][l];      // BN(p), same op order as the forward
+                if (HAS_BN) {
+                    n = sqrtf(dot3l(pr, pr, l)) + VS_EPS;
+                    nhat = (n - cp.mean[l]) * cp.invstd[l];
+                    const float nb = nhat * cp.gamma[l] + cp.beta[l];
+                    pb0 = pb0 / n * nb;
+                    pb1 = pb1 / n * nb;
+                    pb2 = pb2 / n * nb;
+                }
                 if (HAS_D) {
-                    const float s = dot3l(pb, dv, l);
-                    gdv.v[0][l] = gdv.v[1][l] = gdv.v[2][l] = 0.f;
+                    const float s = __fadd_rn(__fadd_rn(__fmul_rn(pb0, dv.v[0][l]), __fmul_rn(pb1, dv.v[1][l])), __fmul_rn(pb2, dv.v[2][l]));
                     if (s < 0.f) {
                         const float q = dot3l(dv, dv, l) + VS_EPS;
                         const float a = s / q;
                         const float gdq = dot3l(gv, dv, l) / q;
+                        const float pbv[3] = {pb0, pb1, pb2};
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            gpb.v[c][l] = gv.v[c][l] - k * gdq * dv.v[c][l];
-                            gdv.v[c][l] = -k * (a * gv.v[c][l] + gdq * pb.v[c][l] - 2.f * a * gdq * dv.v[c][l]);
+                            const float gval = gv.v[c][l], dval = dv.v[c][l];
+                            gv.v[c][l] = gval - k * gdq * dval;                                        // dL/d BN(p)
+                            dv.v[c][l] = -k * (a * gval + gdq * pbv[c] - 2.f * a * gdq * dval);        // dL/d d
                         }
+                    } else {
+                        dv.v[0][l] = dv.v[1][l] = dv.v[2][l] = 0.f;
                     }
                 }
                 if (HAS_BN) {
-                    const float dnb = dot3l(gpb, pr, l) / n;
+                    const float dnb = dot3l(gv, pr, l) / n;
                     s1[l] += (double)dnb;
                     s2[l] = fma((double)dnb, (double)nhat, s2[l]);
                 }
             }
-            st43(gp + (size_t)pt * 3 * ldgp + c0, ldgp, gpb);
-            if (HAS_D) st43(gd + (size_t)pt * 3 * ldgd + c0, ldgd, gdv);
+            st43(gp + (size_t)pt * 3 * ldgp + c0, ldgp, gv);
+            if (HAS_D) st43(gd + (size_t)pt * 3 * ldgd + c0, ldgd, dv);
         }
     }
     if (HAS_BN) VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)

@@ -17,6 +17,20 @@ from .loss import cd_loss_L1
 from .model import Rotate
 
 
+def exchange_gradients(flat_grad, world_size, process_group=None):
+    """the ONE exchange step of the data-parallel path: sum the flat gradient buffer over ranks (NCCL over NVLink on
+    the GPUs; any backend works -- the CPU tests run it over gloo).  Returns the scale (1/world) the optimiser applies,
+    so that the mean is never materialised in a separate pass."""
+    if world_size > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=process_group)
+    return 1.0 / world_size
+
+
+def rank_seed(base_seed, rank, step=0):
+    """per-rank, per-step data seed: ranks draw disjoint synthetic shards (bench.py)"""
+    return base_seed + rank + 1000 * step
+
+
 class FlatAdam:
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.params = [p for p in params if p.requires_grad]
@@ -73,7 +87,6 @@ class DataParallelTrainer:
         if dense is not None:
             loss = loss + cd_loss_L1(dense, c)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-        self.opt.step(grad_scale=1.0 / self.world)
+        scale = exchange_gradients(self.opt.flat_g, self.world, self.pg)
+        self.opt.step(grad_scale=scale)
         return loss.detach()
