@@ -106,6 +106,14 @@ int vnpcc_rows_dot(const float* x, long long ldx, const float* w, long long R, i
 int vnpcc_rows_dot_bwd(const float* gy, const float* x, long long ldx, const float* w, long long R, int C, float* gx,
                        long long ldgx, float* gw, void* stream);
 
+/* fused tail VNLinearLeakyReLU -> VNLinear(C,1) (+ residual), models/pcn.py:340-345,387: no [R,C] activation / gradient in HBM */
+int vnpcc_bn_leaky_dot_fwd(const float* p, long long ldp, const float* d, long long ldd, long long P, int C, const float* stat,
+                           const float* gamma, const float* beta, float ns, const float* w2, const float* res, float* y,
+                           void* stream);
+int vnpcc_bn_leaky_dot_bwd1(const float* gy, const float* p, long long ldp, const float* d, long long ldd, float* gp, long long ldgp,
+                            float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
+                            float ns, double* sums, const float* w2, double* gw2, void* stream);
+int vnpcc_double_to_float(const double* in, float* out, int n, void* stream);
 /* backward of VNLinear -> VNMaxPool without the dense gradient (gx zeroed + scattered, gW gathered; either may be NULL) */
 int vnpcc_pool_linear_bwd(const float* g, long long ldg, const long long* idx, const float* x, long long ldx, const float* W,
                           long long ldw, int B, int N, int C, int K, float* gx, long long ldgx, float* gW, long long ldgw,

@@ -955,4 +955,37 @@ int vnpcc_pool_linear_bwd(const float* g, long long ldg, const long long* idx, c
     return last_error();
 }
 
+// Fused tail  VNLinearLeakyReLU -> VNLinear(C,1) (+ residual)  (models/pcn.py:340-345,387): the [R,C] activation of the
+// last VNLinearLeakyReLU and its gradient are never written.  Returns VNPCC_ERR_UNSUPPORTED for shapes it does not take.
+//   fwd : y[r] = sum_c leaky(BN(p), d)[r,c] * w2[c] (+ res[r])
+//   bwd1: like vnpcc_vn_bn_leaky_bwd1 with g[r,c] = gy[r]*w2[c]; additionally gw2 (C doubles, zeroed here) accumulates
+//         sum_r gy[r]*out[r,c].  Follow with vnpcc_vn_bn_bwd2 as usual.
+int vnpcc_bn_leaky_dot_fwd(const float* p, long long ldp, const float* d, long long ldd, long long P, int C, const float* stat,
+                           const float* gamma, const float* beta, float ns, const float* w2, const float* res, float* y,
+                           void* stream) {
+    if (P <= 0 || C <= 0) return 0;
+    if (!try_bn_leaky_dot_fwd_v4(p, ldp, d, ldd, P, C, stat, gamma, beta, ns, w2, res, y, (cudaStream_t)stream))
+        return VNPCC_ERR_UNSUPPORTED;
+    return last_error();
+}
+
+int vnpcc_bn_leaky_dot_bwd1(const float* gy, const float* p, long long ldp, const float* d, long long ldd, float* gp, long long ldgp,
+                            float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
+                            float ns, double* sums, const float* w2, double* gw2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stat && !sums) return VNPCC_ERR_BAD_ARG;
+    if (stat) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    cudaMemsetAsync(gw2, 0, sizeof(double) * C, st);
+    if (P <= 0 || C <= 0) return last_error();
+    if (!try_bn_leaky_dot_bwd1_v4(gy, p, ldp, d, ldd, gp, ldgp, gd, ldgd, P, C, stat, gamma, beta, ns, stat ? sums : nullptr, w2, gw2, st))
+        return VNPCC_ERR_UNSUPPORTED;
+    return last_error();
+}
+
+int vnpcc_double_to_float(const double* in, float* out, int n, void* stream) {
+    if (n <= 0) return 0;
+    count_launch(), double_to_float_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, out, n);
+    return last_error();
+}
+
 }  // extern "C"

@@ -165,24 +165,45 @@ __global__ void __launch_bounds__(256) bn_leaky_fwd_v4_kernel(const float* __res
     }
 }
 
-template <bool HAS_BN, bool HAS_D>
+// TAIL: the consumer of this layer is VNLinear(C,1) (+ residual): its gradient is rank one, g[r,c] = gy[r]*w2[c], so it is
+// formed on the fly (g = gy, ldg unused) and the weight gradient gw2[c] = sum_r gy[r]*out[r,c] is accumulated from the
+// recomputed layer output -- the [R,C] activation and its gradient never exist in HBM.
+template <bool HAS_BN, bool HAS_D, bool TAIL>
 __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ p,
                                                                    size_t ldp, const float* __restrict__ d, size_t ldd,
                                                                    float* __restrict__ gp, size_t ldgp, float* __restrict__ gd,
                                                                    size_t ldgd, long long P, int C, const float* __restrict__ stat,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   float ns, double* __restrict__ sums) {
+                                                                   float ns, double* __restrict__ sums,
+                                                                   const float* __restrict__ w2, double* __restrict__ gw2) {
     // register diet (two CTAs per SM): the post-BN vector is kept as pr * sc, and gp / gd overwrite g / d in place
     const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const bool active = c0 < C;
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float s3[4] = {0.f, 0.f, 0.f, 0.f};
     if (active) {
         const ChanParams cp = load_params(HAS_BN ? stat : nullptr, gamma, beta, C, c0);
         const float k = 1.f - ns;
+        float w2l[4] = {0.f, 0.f, 0.f, 0.f};
+        if (TAIL) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) w2l[l] = __ldg(w2 + c0 + l);
+        }
         const long long stride = (long long)gridDim.y * 8;
         for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
             const V4x3 pr = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
-            V4x3 gv = ld43(g + (size_t)pt * 3 * ldg + c0, ldg);
+            V4x3 gv;
+            float gy3[3] = {0.f, 0.f, 0.f};
+            if (TAIL) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    gy3[c] = __ldg(g + (size_t)pt * 3 + c);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) gv.v[c][l] = gy3[c] * w2l[l];
+                }
+            } else {
+                gv = ld43(g + (size_t)pt * 3 * ldg + c0, ldg);
+            }
             V4x3 dv;
             if (HAS_D) dv = ld43(d + (size_t)pt * 3 * ldd + c0, ldd);
 #pragma unroll
@@ -199,6 +220,14 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
                 }
                 if (HAS_D) {
                     const float s = __fadd_rn(__fadd_rn(__fmul_rn(pb0, dv.v[0][l]), __fmul_rn(pb1, dv.v[1][l])), __fmul_rn(pb2, dv.v[2][l]));
+                    if (TAIL) {
+                        // recomputed layer output (same expression as the forward) for the tail weight gradient
+                        const float af = (s < 0.f) ? s / __fadd_rn(dot3l(dv, dv, l), VS_EPS) : 0.f;
+                        const float o0 = __fadd_rn(__fmul_rn(ns, pb0), __fmul_rn(k, __fsub_rn(pb0, __fmul_rn(af, dv.v[0][l]))));
+                        const float o1 = __fadd_rn(__fmul_rn(ns, pb1), __fmul_rn(k, __fsub_rn(pb1, __fmul_rn(af, dv.v[1][l]))));
+                        const float o2 = __fadd_rn(__fmul_rn(ns, pb2), __fmul_rn(k, __fsub_rn(pb2, __fmul_rn(af, dv.v[2][l]))));
+                        s3[l] += gy3[0] * o0 + gy3[1] * o1 + gy3[2] * o2;
+                    }
                     if (s < 0.f) {
                         const float q = dot3l(dv, dv, l) + VS_EPS;
                         const float a = s / q;
@@ -225,6 +254,82 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
         }
     }
     if (HAS_BN) VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)
+    if (TAIL) {
+        __shared__ float sh3[8][32][4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) sh3[threadIdx.y][threadIdx.x][l] = s3[l];
+        __syncthreads();
+        if (threadIdx.y == 0 && active) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                double a = 0.0;
+                for (int i = 0; i < 8; ++i) a += (double)sh3[i][threadIdx.x][l];
+                atomicAdd(gw2 + c0 + l, a);
+            }
+        }
+    }
+}
+
+// fused forward tail: y[r] = sum_c leaky(BN(p), d)[r, c] * w2[c] (+ res[r]); block (C/4, 256/(C/4)): one point per block row
+template <bool HAS_BN>
+__global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
+                                                                   size_t ldd, long long P, int C, const float* __restrict__ stat,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float ns, const float* __restrict__ w2,
+                                                                   const float* __restrict__ res, float* __restrict__ y) {
+    __shared__ float part[8][8][3];     // [block row][warp within row][component]
+    const int c0 = threadIdx.x * 4;
+    const ChanParams cp = load_params(HAS_BN ? stat : nullptr, gamma, beta, C, c0);
+    float w2l[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) w2l[l] = __ldg(w2 + c0 + l);
+    const float k = 1.f - ns;
+    const int wx = threadIdx.x >> 5, nwx = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.y;
+    const long long iters = (P + stride - 1) / stride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long pt = it * stride + (long long)blockIdx.x * blockDim.y + threadIdx.y;
+        float acc[3] = {0.f, 0.f, 0.f};
+        if (pt < P) {
+            V4x3 v = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
+            const V4x3 dv = ld43(d + (size_t)pt * 3 * ldd + c0, ldd);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                if (HAS_BN) {
+                    float n, nhat, nb;
+                    bn_apply_lane(v, l, cp, n, nhat, nb);
+                }
+                const float dot = dot3l(v, dv, l);
+                float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
+                if (!(dot >= 0.f)) {
+                    const float a = dot / __fadd_rn(dot3l(dv, dv, l), VS_EPS);
+                    in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
+                    in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
+                    in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
+                }
+                acc[0] = fmaf(__fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k, in0)), w2l[l], acc[0]);
+                acc[1] = fmaf(__fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k, in1)), w2l[l], acc[1]);
+                acc[2] = fmaf(__fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k, in2)), w2l[l], acc[2]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if (lane == 0) {
+            part[threadIdx.y][wx][0] = acc[0];
+            part[threadIdx.y][wx][1] = acc[1];
+            part[threadIdx.y][wx][2] = acc[2];
+        }
+        __syncthreads();
+        if (threadIdx.x < 3 && pt < P) {
+            float t = 0.f;
+            for (int w = 0; w < nwx; ++w) t += part[threadIdx.y][w][threadIdx.x];
+            const size_t r = (size_t)pt * 3 + threadIdx.x;
+            y[r] = res ? t + __ldg(res + r) : t;
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp, size_t ldgp, const float* __restrict__ p, size_t ldp,
@@ -305,8 +410,9 @@ bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long lo
     if ((C & 3) || !ok4(g, ldg) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(gp, ldgp) || !ok4(gd, ldgd)) return false;
     const dim3 grid = stream_grid(P, C), block(32, 8);
 #define VS_BWD(BN_, D_)                                                                                                            \
-    count_launch(), bn_leaky_bwd1_v4_kernel<BN_, D_><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, \
-                                                                              gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums)
+    count_launch(), bn_leaky_bwd1_v4_kernel<BN_, D_, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp,    \
+                                                                                     (size_t)ldgp, gd, (size_t)ldgd, P, C, stat, gamma, beta, \
+                                                                                     ns, sums, nullptr, nullptr)
     if (stat && d) VS_BWD(true, true);
     else if (stat) VS_BWD(true, false);
     else if (d) VS_BWD(false, true);
@@ -320,6 +426,37 @@ bool try_bn_bwd2_v4(float* gp, long long ldgp, const float* p, long long ldp, lo
     if ((C & 3) || !ok4(gp, ldgp) || !ok4(p, ldp)) return false;
     count_launch(), bn_bwd2_v4_kernel<<<stream_grid(P, C), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
                                                                              sums, count, training);
+    return true;
+}
+
+bool try_bn_leaky_dot_fwd_v4(const float* p, long long ldp, const float* d, long long ldd, long long P, int C, const float* stat,
+                             const float* gamma, const float* beta, float ns, const float* w2, const float* res, float* y,
+                             cudaStream_t st) {
+    if ((C & 127) || C > 1024 || !ok4(p, ldp) || !ok4(d, ldd) || d == nullptr) return false;
+    const int bx = C / 4, by = 256 / bx;
+    long long g = (P + by - 1) / by;
+    const long long cap = (long long)sm_count() * 8;
+    if (g > cap) g = cap;
+    if (stat)
+        count_launch(), bn_leaky_dot_fwd_v4_kernel<true><<<(unsigned)g, dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma,
+                                                                                           beta, ns, w2, res, y);
+    else
+        count_launch(), bn_leaky_dot_fwd_v4_kernel<false><<<(unsigned)g, dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma,
+                                                                                            beta, ns, w2, res, y);
+    return true;
+}
+
+bool try_bn_leaky_dot_bwd1_v4(const float* gy, const float* p, long long ldp, const float* d, long long ldd, float* gp, long long ldgp,
+                              float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
+                              float ns, double* sums, const float* w2, double* gw2, cudaStream_t st) {
+    if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(gp, ldgp) || !ok4(gd, ldgd) || d == nullptr) return false;
+    const dim3 grid = stream_grid(P, C), block(32, 8);
+    if (stat)
+        count_launch(), bn_leaky_bwd1_v4_kernel<true, true, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
+                                                                                      (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
+    else
+        count_launch(), bn_leaky_bwd1_v4_kernel<false, true, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
+                                                                                       gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
     return true;
 }
 

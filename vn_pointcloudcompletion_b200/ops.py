@@ -330,6 +330,65 @@ def bn_leaky(p, d, bn, training, ns, stacked=False):
     return _BNLeaky.apply(p, d, gamma, beta, stat, use_batch, ns, stacked)
 
 
+class _BNLeakyDot(torch.autograd.Function):
+    """y[r] = sum_c leaky(BN(p), d)[r,c] * w2[c] (+ res[r]) on the stacked buffer pd = (p | d): the last
+    VNLinearLeakyReLU of the decoder fused with VNLinear(C,1) and the residual (models/pcn.py:340-345,387)."""
+
+    @staticmethod
+    def forward(ctx, pd, gamma, beta, stat, use_batch, ns, w2, res):
+        pd = _rows2d(pd, "pd")
+        R = pd.shape[0]
+        C = pd.shape[1] // 2
+        P = R // 3
+        w2 = w2.reshape(-1).contiguous()
+        if res is not None:
+            res = res.reshape(-1).contiguous()
+        y = torch.empty(R, device=pd.device, dtype=torch.float32)
+        call("vnpcc_bn_leaky_dot_fwd", ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), float(ns),
+             ptr(w2), ptr(res), ptr(y), stream())
+        ctx.save_for_backward(pd, gamma, beta, stat, w2)
+        ctx.cfg = (C, P, float(ns), bool(use_batch), res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        pd, gamma, beta, stat, w2 = ctx.saved_tensors
+        C, P, ns, use_batch, has_res = ctx.cfg
+        gy = gy.contiguous()
+        R = pd.shape[0]
+        dev = pd.device
+        gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64) if stat is not None else None
+        gw2d = torch.empty(C, device=dev, dtype=torch.float64)
+        call("vnpcc_bn_leaky_dot_bwd1", ptr(gy), ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), ptr(gpd), 2 * C, ptr(gpd[:, C:]), 2 * C, P, C,
+             ptr(stat), ptr(gamma), ptr(beta), ns, ptr(sums), ptr(w2), ptr(gw2d), stream())
+        ggamma = gbeta = None
+        if stat is not None:
+            ggamma = torch.empty(C, device=dev, dtype=torch.float32)
+            gbeta = torch.empty(C, device=dev, dtype=torch.float32)
+            call("vnpcc_vn_bn_bwd2", ptr(gpd), 2 * C, ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ptr(sums), float(P),
+                 1 if use_batch else 0, ptr(ggamma), ptr(gbeta), stream())
+        gw2 = torch.empty(C, device=dev, dtype=torch.float32)
+        call("vnpcc_double_to_float", ptr(gw2d), ptr(gw2), C, stream())
+        return gpd, ggamma, gbeta, None, None, None, gw2.view(1, C), (gy if has_res else None)
+
+
+def bn_leaky_dot_supported(C):
+    return C % 128 == 0 and C <= 1024
+
+
+def bn_leaky_dot(pd, bn, training, ns, w2, res=None):
+    """fused  leaky(BN(p), d) . w2 (+ res)  on the stacked (p | d) rows; w2 is the [1, C] weight of VNLinear(C, 1)"""
+    pd = _rows2d(pd, "pd")
+    C = pd.shape[1] // 2
+    stat, use_batch, gamma, beta = None, False, None, None
+    if bn is not None:
+        stat, use_batch = _bn_prepare(pd[:, :C], C, bn, training, pd.shape[0] // 3)
+        gamma = bn.weight if bn.weight is not None else torch.ones(C, device=pd.device)
+        beta = bn.bias if bn.bias is not None else torch.zeros(C, device=pd.device)
+    return _BNLeakyDot.apply(pd, gamma, beta, stat, use_batch, ns, w2, res)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # VNMaxPool on rows: groups of N consecutive points
 # ---------------------------------------------------------------------------------------------------------------

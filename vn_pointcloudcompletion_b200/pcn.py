@@ -114,6 +114,13 @@ class VN_FoldingNet(nn.Module):
         bias = ops.linear_rows(fg_rows, wcat[:, :Cg])                                      # [B*3,512]
         pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                            # [R,512]
         h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
-        h = l1.forward_rows(h)
-        fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                         # final VNLinear(256,1) + point_feat
+        C1 = l1.map_to_feat.weight.shape[0]
+        if l1.map_to_dir.weight.shape[0] == C1 and ops.bn_leaky_dot_supported(C1):
+            # final_conv[1] (BN + leaky) fused with final_conv[2] = VNLinear(256,1) and the residual: its [R,256] output
+            # and gradient never touch HBM
+            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0))
+            fine = ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, local[:, 1])
+        else:
+            h = l1.forward_rows(h)
+            fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                     # final VNLinear(256,1) + point_feat
         return fine.view(B, nd, 3)
