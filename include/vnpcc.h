@@ -114,6 +114,17 @@ int vnpcc_bn_leaky_dot_bwd1(const float* gy, const float* p, long long ldp, cons
                             float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
                             float ns, double* sums, const float* w2, double* gw2, void* stream);
 int vnpcc_double_to_float(const double* in, float* out, int n, void* stream);
+/* VNLinearLeakyReLU with <= 4 local input channels + per-sample bias, never materialising p / d (decoder final_conv[0]):
+ * x [B*N*3, K], w [2C, K] (feat | dir), bias [B*3, 2C] or NULL.  See csrc/vn_fused.cu. */
+int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ldw, const float* bias, long long ldb, int B, int N,
+                     int K, int C, double* sums, void* stream);
+int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* bias, long long ldb, int B, int N,
+                   int K, int C, const float* stat, const float* gamma, const float* beta, float ns, float* out, long long ldo,
+                   void* stream);
+int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx, const float* w, long long ldw, const float* bias,
+                   long long ldb, int B, int N, int K, int C, const float* stat, const float* gamma, const float* beta, float ns,
+                   int training, double* sums, float* gx, long long ldgx, float* gw, long long ldgw, float* gbias, long long ldgb,
+                   float* ggamma, float* gbeta, void* stream);
 /* backward of VNLinear -> VNMaxPool without the dense gradient (gx zeroed + scattered, gW gathered; either may be NULL) */
 int vnpcc_pool_linear_bwd(const float* g, long long ldg, const long long* idx, const float* x, long long ldx, const float* W,
                           long long ldw, int B, int N, int C, int K, float* gx, long long ldgx, float* gW, long long ldgw,

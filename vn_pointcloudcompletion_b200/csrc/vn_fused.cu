@@ -1,0 +1,463 @@
+// vn_fused.cu -- VNLinearLeakyReLU whose GEMM input has at most four channels plus a per-sample bias, executed WITHOUT
+// materialising the linear outputs p = W_feat x + b_p and d = W_dir x + b_d.
+//
+// This is the decoder's first layer (models/pcn.py:336, :383-387): of its 2050 input channels 2048 are the broadcast
+// global feature (folded into the per-sample bias rows b_p | b_d, see pcn.py in this package) and only {seed,
+// point_feat} vary per point.  p and d are two FMAs per component, so every pass recomputes them from the [R, 2] local
+// rows instead of reading 2 x 1.6 GB from HBM:
+//   stats : per-channel sum ||p||, sum ||p||^2          (no large tensor touched)
+//   fwd   : out = leaky(BN(p), d)                       (writes out only)
+//   bwd A : per-channel S1 = sum d_nb, S2 = sum d_nb nhat   (reads g = dL/dout)
+//   bwd B : reads g again, forms dL/dp, dL/dd in registers and reduces them on the fly into
+//             gW[2C, K], gbias[B*3, 2C] (per-channel reductions) and gx[R, K] (per-row reduction over channels)
+// Reference semantics: VNLinearLeakyReLU models/vn_layers.py:60-74, VNBatchNorm :116-127; backward SURVEY.md App. C.
+//
+// Thread layout: block (C/4, 256/(C/4)); threadIdx.x owns 4 consecutive channels (weights + the sample's bias rows in
+// registers), each block row walks over a chunk of points of ONE sample.  grid = (chunks per sample, B).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "vn_math.cuh"
+#include "vnpcc.h"
+#include "vnpcc_internal.h"
+
+namespace vnpcc {
+
+template <int KS>
+struct FoldCtx {
+    float wf[4][KS], wd[4][KS];   // [lane][k]
+    float bp[3][4], bd[3][4];     // per-sample bias rows [component][lane]
+};
+
+template <int KS>
+__device__ __forceinline__ void fold_load_ctx(FoldCtx<KS>& cx, const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+                                              size_t ldb, int b, int C, int c0) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            cx.wf[l][k] = __ldg(w + (size_t)(c0 + l) * ldw + k);
+            cx.wd[l][k] = __ldg(w + (size_t)(C + c0 + l) * ldw + k);
+        }
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const float4 p4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb + c0)) : make_float4(0, 0, 0, 0);
+        const float4 d4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb + C + c0)) : make_float4(0, 0, 0, 0);
+        cx.bp[v][0] = p4.x; cx.bp[v][1] = p4.y; cx.bp[v][2] = p4.z; cx.bp[v][3] = p4.w;
+        cx.bd[v][0] = d4.x; cx.bd[v][1] = d4.y; cx.bd[v][2] = d4.z; cx.bd[v][3] = d4.w;
+    }
+}
+
+// p (and d) of one point for this thread's 4 channels; xv[v][k] = x[(pt*3+v), k]
+template <int KS, bool WITH_D>
+__device__ __forceinline__ void fold_pd(const FoldCtx<KS>& cx, const float (&xv)[3][KS], V4x3& p, V4x3& d) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            float a = cx.bp[v][l], e = cx.bd[v][l];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                a = fmaf(xv[v][k], cx.wf[l][k], a);
+                if (WITH_D) e = fmaf(xv[v][k], cx.wd[l][k], e);
+            }
+            p.v[v][l] = a;
+            if (WITH_D) d.v[v][l] = e;
+        }
+}
+
+template <int KS>
+__device__ __forceinline__ void fold_load_x(const float* __restrict__ x, size_t ldx, size_t row, float (&xv)[3][KS]) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) xv[v][k] = __ldg(x + (row + v) * ldx + k);
+}
+
+#define FOLD_PROLOGUE                                                        \
+    const int c0 = threadIdx.x * 4;                                          \
+    const int b = blockIdx.y;                                                \
+    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);          \
+    FoldCtx<KS> cx;                                                          \
+    fold_load_ctx<KS>(cx, w, ldw, bias, ldb, b, C, c0);
+
+// per-channel reduction of NRED double values per lane over the block rows, then one atomicAdd per channel
+template <int NRED>
+__device__ __forceinline__ void fold_reduce_channels(double (&acc)[NRED][4], double* __restrict__ out, int C, int c0, double* sh) {
+    // sh: [blockDim.y][blockDim.x][4] doubles, reused NRED times
+    for (int i = 0; i < NRED; ++i) {
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < 4; ++l) sh[((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4 + l] = acc[i][l];
+        __syncthreads();
+        if (threadIdx.y == 0) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                double a = 0.0;
+                for (int y = 0; y < (int)blockDim.y; ++y) a += sh[((size_t)y * blockDim.x + threadIdx.x) * 4 + l];
+                atomicAdd(out + (size_t)i * C + c0 + l, a);
+            }
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
+                                                          const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
+                                                          double* __restrict__ sums) {
+    extern __shared__ double fold_sh[];
+    FOLD_PROLOGUE
+    double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+        float xv[3][KS];
+        fold_load_x<KS>(x, ldx, ((size_t)b * N + n) * 3, xv);
+        V4x3 p, d;
+        fold_pd<KS, false>(cx, xv, p, d);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const double nn = (double)(sqrtf(dot3l(p, p, l)) + VS_EPS);
+            acc[0][l] += nn;
+            acc[1][l] = fma(nn, nn, acc[1][l]);
+        }
+    }
+    fold_reduce_channels<2>(acc, sums, C, c0, fold_sh);
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) fold_fwd_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
+                                                        const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
+                                                        const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float ns, float* __restrict__ out, size_t ldo) {
+    FOLD_PROLOGUE
+    const ChanParams cp = load_params(stat, gamma, beta, C, c0);
+    const float k1 = 1.f - ns;
+#pragma unroll 2
+    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+        const size_t row = ((size_t)b * N + n) * 3;
+        float xv[3][KS];
+        fold_load_x<KS>(x, ldx, row, xv);
+        V4x3 v, dv;
+        fold_pd<KS, true>(cx, xv, v, dv);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (stat) {
+                float nn, nhat, nb;
+                bn_apply_lane(v, l, cp, nn, nhat, nb);
+            }
+            const float dot = dot3l(v, dv, l);
+            float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
+            if (!(dot >= 0.f)) {
+                const float a = dot / __fadd_rn(dot3l(dv, dv, l), VS_EPS);
+                in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
+                in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
+                in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
+            }
+            v.v[0][l] = __fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k1, in0));
+            v.v[1][l] = __fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k1, in1));
+            v.v[2][l] = __fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k1, in2));
+        }
+        st43(out + row * ldo + c0, ldo, v);
+    }
+}
+
+// shared lane math of the two backward passes: given raw p (pr), d (dv) and g (gv, dL/dout) of one lane, turn gv into
+// dL/dBN(p) and dv into dL/dd in place; returns n, nhat, nb of the BatchNorm-on-norm
+__device__ __forceinline__ void fold_lane_bwd(const V4x3& pr, V4x3& dv, V4x3& gv, int l, const ChanParams& cp, bool has_bn, float k1,
+                                              float& n, float& nhat, float& nb) {
+    n = 1.f;
+    nhat = 0.f;
+    nb = 1.f;
+    float pb0 = pr.v[0][l], pb1 = pr.v[1][l], pb2 = pr.v[2][l];
+    if (has_bn) {
+        n = fsqrt_fast(dot3l(pr, pr, l)) + VS_EPS;
+        nhat = (n - cp.mean[l]) * cp.invstd[l];
+        nb = nhat * cp.gamma[l] + cp.beta[l];
+        const float t = nb * frcp(n);
+        pb0 *= t;
+        pb1 *= t;
+        pb2 *= t;
+    }
+    const float s = pb0 * dv.v[0][l] + pb1 * dv.v[1][l] + pb2 * dv.v[2][l];
+    if (s < 0.f) {
+        const float rq = frcp(dot3l(dv, dv, l) + VS_EPS);
+        const float a = s * rq;
+        const float gdq = dot3l(gv, dv, l) * rq;
+        const float pbv[3] = {pb0, pb1, pb2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float gval = gv.v[c][l], dval = dv.v[c][l];
+            gv.v[c][l] = gval - k1 * gdq * dval;
+            dv.v[c][l] = -k1 * (a * gval + gdq * pbv[c] - 2.f * a * gdq * dval);
+        }
+    } else {
+        dv.v[0][l] = dv.v[1][l] = dv.v[2][l] = 0.f;
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+                                                             const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+                                                             size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
+                                                             double* __restrict__ sums) {
+    extern __shared__ double fold_sh[];
+    FOLD_PROLOGUE
+    const ChanParams cp = load_params(stat, gamma, beta, C, c0);
+    const float k1 = 1.f - ns;
+    double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    constexpr int U = 2;     // points in flight per thread: 6 independent 16-byte loads hide the HBM latency at 1 CTA / SM
+    for (int nb0 = n0 + threadIdx.y; nb0 < n1; nb0 += blockDim.y * U) {
+        V4x3 gvu[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = nb0 + u * blockDim.y;
+            if (n < n1) gvu[u] = ld43(g + (((size_t)b * N + n) * 3) * ldg + c0, ldg);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = nb0 + u * blockDim.y;
+            if (n >= n1) break;
+            const size_t row = ((size_t)b * N + n) * 3;
+            float xv[3][KS];
+            fold_load_x<KS>(x, ldx, row, xv);
+            V4x3 pr, dv;
+            fold_pd<KS, true>(cx, xv, pr, dv);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                float nn, nhat, nb;
+                fold_lane_bwd(pr, dv, gvu[u], l, cp, true, k1, nn, nhat, nb);
+                const float dnb = dot3l(gvu[u], pr, l) * frcp(nn);
+                acc[0][l] += (double)dnb;
+                acc[1][l] = fma((double)dnb, (double)nhat, acc[1][l]);
+            }
+        }
+    }
+    fold_reduce_channels<2>(acc, sums, C, c0, fold_sh);
+}
+
+// pass B: gW (2C x KS, fp32 atomics), gbias ([B*3, 2C], fp32 atomics), gx ([R, KS], plain stores)
+template <int KS>
+__global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+                                                             const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+                                                             size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
+                                                             const double* __restrict__ sums, double count, int training,
+                                                             float* __restrict__ gx, size_t ldgx, float* __restrict__ gw, size_t ldgw,
+                                                             float* __restrict__ gbias, size_t ldgb) {
+    extern __shared__ double fold_sh[];
+    float* shf = reinterpret_cast<float*>(fold_sh);
+    FOLD_PROLOGUE
+    const bool has_bn = stat != nullptr;
+    const ChanParams cp = load_params(stat, gamma, beta, C, c0);
+    const float k1 = 1.f - ns;
+    float m1[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
+    if (has_bn && training) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            m1[l] = (float)(sums[c0 + l] / count) * cp.gamma[l];
+            m2[l] = (float)(sums[C + c0 + l] / count) * cp.gamma[l];
+        }
+    }
+    float awf[KS][4], awd[KS][4], abp[3][4], abd[3][4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) awf[k][l] = awd[k][l] = 0.f;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) abp[v][l] = abd[v][l] = 0.f;
+    }
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 2;     // points in flight per thread
+    for (int nb0 = n0 + threadIdx.y; nb0 < n1; nb0 += blockDim.y * U) {
+        V4x3 gvu[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = nb0 + u * blockDim.y;
+            if (n < n1) gvu[u] = ld43(g + (((size_t)b * N + n) * 3) * ldg + c0, ldg);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = nb0 + u * blockDim.y;
+            if (n >= n1) break;          // uniform within a warp (a block row spans whole warps)
+            V4x3& gv = gvu[u];
+            const size_t row = ((size_t)b * N + n) * 3;
+            float xv[3][KS];
+            fold_load_x<KS>(x, ldx, row, xv);
+            V4x3 pr, dv;
+            fold_pd<KS, true>(cx, xv, pr, dv);
+            float gxp[3][KS];
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+#pragma unroll
+                for (int k = 0; k < KS; ++k) gxp[v][k] = 0.f;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                float nn, nhat, nb;
+                fold_lane_bwd(pr, dv, gv, l, cp, has_bn, k1, nn, nhat, nb);
+                if (has_bn) {
+                    // BatchNorm-on-norm backward (vn_bn_bwd2): gv <- dL/dp
+                    const float r = nn - VS_EPS;
+                    const float rn = frcp(nn);
+                    const float gxd = dot3l(gv, pr, l);
+                    const float dnb = gxd * rn;
+                    float dn = cp.gamma[l] * dnb;
+                    if (training) dn = dn - m1[l] - nhat * m2[l];
+                    dn = dn * cp.invstd[l] - gxd * nb * rn * rn;
+                    const float sc = nb * rn;
+                    const float ur = r > 0.f ? dn * frcp(r) : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) gv.v[c][l] = gv.v[c][l] * sc + ur * pr.v[c][l];
+                }
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    const float gpv = gv.v[v][l], gdv = dv.v[v][l];
+                    abp[v][l] += gpv;
+                    abd[v][l] += gdv;
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+                        awf[k][l] = fmaf(gpv, xv[v][k], awf[k][l]);
+                        awd[k][l] = fmaf(gdv, xv[v][k], awd[k][l]);
+                        gxp[v][k] = fmaf(gpv, cx.wf[l][k], fmaf(gdv, cx.wd[l][k], gxp[v][k]));
+                    }
+                }
+            }
+            if (gx) {
+                // per-row reduction over channels: warp shuffle, then one red.add per warp (gx is zeroed by the launcher)
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) gxp[v][k] += __shfl_xor_sync(0xffffffffu, gxp[v][k], o);
+                        if (lane == 0) atomicAdd(gx + (row + v) * ldgx + k, gxp[v][k]);
+                    }
+            }
+        }
+    }
+    // per-channel reductions over the block rows
+    __syncthreads();
+    float* red = shf;   // [blockDim.y][blockDim.x][4]
+    auto reduce_store = [&](float (&a)[4], float* dst, size_t stride_lane) {
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < 4; ++l) red[((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4 + l] = a[l];
+        __syncthreads();
+        if (threadIdx.y == 0) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                float t = 0.f;
+                for (int y = 0; y < (int)blockDim.y; ++y) t += red[((size_t)y * blockDim.x + threadIdx.x) * 4 + l];
+                atomicAdd(dst + (size_t)l * stride_lane, t);
+            }
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        reduce_store(awf[k], gw + (size_t)c0 * ldgw + k, ldgw);
+        reduce_store(awd[k], gw + (size_t)(C + c0) * ldgw + k, ldgw);
+    }
+    if (gbias) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            reduce_store(abp[v], gbias + (size_t)(b * 3 + v) * ldgb + c0, 1);
+            reduce_store(abd[v], gbias + (size_t)(b * 3 + v) * ldgb + C + c0, 1);
+        }
+    }
+}
+
+static bool fold_ok(int KS, int C, const void* bias, long long ldb, const void* big, long long ldbig) {
+    return KS >= 1 && KS <= 4 && (C & 127) == 0 && C <= 1024 && (bias == nullptr || ((ldb & 3) == 0 && ((uintptr_t)bias & 15) == 0)) &&
+           (big == nullptr || ((ldbig & 3) == 0 && ((uintptr_t)big & 15) == 0));
+}
+
+static void fold_geometry(int B, int N, int C, dim3& grid, dim3& block, int& n_chunk, size_t& smem) {
+    const int bx = C / 4, by = 256 / bx;
+    int chunks = (int)(((long long)sm_count() * 4 + B - 1) / B);
+    if (chunks < 1) chunks = 1;
+    n_chunk = (N + chunks - 1) / chunks;
+    if (n_chunk < by * 8) n_chunk = by * 8;
+    chunks = (N + n_chunk - 1) / n_chunk;
+    grid = dim3((unsigned)chunks, (unsigned)B);
+    block = dim3(bx, by);
+    smem = sizeof(double) * 256 * 4;
+}
+
+}  // namespace vnpcc
+
+using namespace vnpcc;
+
+#define FOLD_KS_DISPATCH(KS, CALL)                        \
+    switch (KS) {                                         \
+        case 1: { constexpr int K_ = 1; CALL; } break;    \
+        case 2: { constexpr int K_ = 2; CALL; } break;    \
+        case 3: { constexpr int K_ = 3; CALL; } break;    \
+        default: { constexpr int K_ = 4; CALL; } break;   \
+    }
+
+extern "C" {
+
+// x [B*N*3, K] local rows, w [2C, K] stacked (feat | dir) weights of the local channels, bias [B*3, 2C] per-sample rows
+// (may be NULL).  sums: 2C doubles (zeroed here).
+int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ldw, const float* bias, long long ldb, int B, int N,
+                     int K, int C, double* sums, void* stream) {
+    if (!fold_ok(K, C, bias, ldb, nullptr, 0)) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (B <= 0 || N <= 0) return last_error();
+    dim3 grid, block;
+    int n_chunk;
+    size_t smem;
+    fold_geometry(B, N, C, grid, block, n_chunk, smem);
+    FOLD_KS_DISPATCH(K, (count_launch(), fold_stats_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
+                                                                                       C, n_chunk, sums)));
+    return last_error();
+}
+
+int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* bias, long long ldb, int B, int N,
+                   int K, int C, const float* stat, const float* gamma, const float* beta, float ns, float* out, long long ldo,
+                   void* stream) {
+    if (!fold_ok(K, C, bias, ldb, out, ldo)) return VNPCC_ERR_UNSUPPORTED;
+    if (B <= 0 || N <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid, block;
+    int n_chunk;
+    size_t smem;
+    fold_geometry(B, N, C, grid, block, n_chunk, smem);
+    FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C,
+                                                                                  n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+    return last_error();
+}
+
+// g [R, C] = dL/dout.  Outputs: gx [R, K] (may be NULL), gw [2C, K] and gbias [B*3, 2C] (zeroed here, gbias may be NULL),
+// ggamma / gbeta [C] (written when stat != NULL).  sums: workspace of 2C doubles.
+int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx, const float* w, long long ldw, const float* bias,
+                   long long ldb, int B, int N, int K, int C, const float* stat, const float* gamma, const float* beta, float ns,
+                   int training, double* sums, float* gx, long long ldgx, float* gw, long long ldgw, float* gbias, long long ldgb,
+                   float* ggamma, float* gbeta, void* stream) {
+    if (!fold_ok(K, C, bias, ldb, g, ldg) || (gbias && ((ldgb & 3) || ((uintptr_t)gbias & 15)))) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemset2DAsync(gw, (size_t)ldgw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)2 * C, st);
+    if (gbias) cudaMemset2DAsync(gbias, (size_t)ldgb * sizeof(float), 0, (size_t)2 * C * sizeof(float), (size_t)B * 3, st);
+    if (stat) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (gx) cudaMemset2DAsync(gx, (size_t)ldgx * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)B * N * 3, st);
+    if (B <= 0 || N <= 0) return last_error();
+    dim3 grid, block;
+    int n_chunk;
+    size_t smem;
+    fold_geometry(B, N, C, grid, block, n_chunk, smem);
+    const double count = (double)B * (double)N;
+    if (stat) {
+        FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_sums_kernel<K_><<<grid, block, smem, st>>>(g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias,
+                                                                                              (size_t)ldb, N, C, n_chunk, stat, gamma, beta, ns,
+                                                                                              sums)));
+    }
+    FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_main_kernel<K_><<<grid, block, smem, st>>>(
+                            g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C, n_chunk, stat, gamma, beta, ns, sums, count,
+                            training, gx, (size_t)ldgx, gw, (size_t)ldgw, gbias, (size_t)ldgb)));
+    if (stat && gbeta) vnpcc_double_to_float(sums, gbeta, C, stream);
+    if (stat && ggamma) vnpcc_double_to_float(sums + C, ggamma, C, stream);
+    return last_error();
+}
+
+}  // extern "C"

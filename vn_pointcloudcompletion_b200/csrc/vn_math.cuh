@@ -1,0 +1,83 @@
+// vn_math.cuh -- per-lane device helpers shared by the vectorised Vector-Neuron kernels (vn_stream.cu, vn_fused.cu).
+// A thread owns four consecutive channels ("lanes" l = 0..3) of one point; V4x3 holds the 3 components x 4 lanes.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace vnpcc {
+
+constexpr float VS_EPS = 1e-6f;
+
+struct V4x3 {
+    float v[3][4];   // [component][channel lane]
+};
+
+__device__ __forceinline__ V4x3 ld43(const float* __restrict__ base, size_t ld) {
+    V4x3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + c * ld));
+        r.v[c][0] = t.x;
+        r.v[c][1] = t.y;
+        r.v[c][2] = t.z;
+        r.v[c][3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ V4x3 ld43_rw(const float* base, size_t ld) {
+    V4x3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(base + c * ld);
+        r.v[c][0] = t.x;
+        r.v[c][1] = t.y;
+        r.v[c][2] = t.z;
+        r.v[c][3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void st43(float* __restrict__ base, size_t ld, const V4x3& r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(base + c * ld) = make_float4(r.v[c][0], r.v[c][1], r.v[c][2], r.v[c][3]);
+}
+// (a*b).sum over the 3 components: three rounded products summed left to right, no contraction
+__device__ __forceinline__ float dot3l(const V4x3& a, const V4x3& b, int l) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.v[0][l], b.v[0][l]), __fmul_rn(a.v[1][l], b.v[1][l])), __fmul_rn(a.v[2][l], b.v[2][l]));
+}
+
+struct ChanParams {
+    float mean[4], invstd[4], gamma[4], beta[4];
+};
+__device__ __forceinline__ ChanParams load_params(const float* stat, const float* gamma, const float* beta, int C, int c0) {
+    ChanParams p;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        p.mean[l] = stat ? __ldg(stat + c0 + l) : 0.f;
+        p.invstd[l] = stat ? __ldg(stat + C + c0 + l) : 0.f;
+        p.gamma[l] = stat ? __ldg(gamma + c0 + l) : 0.f;
+        p.beta[l] = stat ? __ldg(beta + c0 + l) : 0.f;
+    }
+    return p;
+}
+
+__device__ __forceinline__ void bn_apply_lane(V4x3& v, int l, const ChanParams& cp, float& n_out, float& nhat_out, float& nb_out) {
+    const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v.v[0][l], v.v[0][l]), __fmul_rn(v.v[1][l], v.v[1][l])),
+                                    __fmul_rn(v.v[2][l], v.v[2][l])));
+    const float n = r + VS_EPS;
+    const float nhat = (n - cp.mean[l]) * cp.invstd[l];
+    const float nb = nhat * cp.gamma[l] + cp.beta[l];
+    v.v[0][l] = v.v[0][l] / n * nb;
+    v.v[1][l] = v.v[1][l] / n * nb;
+    v.v[2][l] = v.v[2][l] / n * nb;
+    n_out = n;
+    nhat_out = nhat;
+    nb_out = nb;
+}
+
+
+// approximate reciprocal / square root (MUFU, ~1 ulp): used by the BACKWARD kernels only -- gradients do not need the
+// op-by-op IEEE rounding the forward keeps for parity of masks and selections, and IEEE divisions (about ten per lane)
+// made those kernels instruction-bound
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.f, x); }
+__device__ __forceinline__ float fsqrt_fast(float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; }
+
+}  // namespace vnpcc

@@ -11,62 +11,9 @@
 #include <stdint.h>
 
 #include "vnpcc_internal.h"
+#include "vn_math.cuh"
 
 namespace vnpcc {
-
-constexpr float VS_EPS = 1e-6f;
-
-struct V4x3 {
-    float v[3][4];   // [component][channel lane]
-};
-
-__device__ __forceinline__ V4x3 ld43(const float* __restrict__ base, size_t ld) {
-    V4x3 r;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(base + c * ld));
-        r.v[c][0] = t.x;
-        r.v[c][1] = t.y;
-        r.v[c][2] = t.z;
-        r.v[c][3] = t.w;
-    }
-    return r;
-}
-__device__ __forceinline__ V4x3 ld43_rw(const float* base, size_t ld) {
-    V4x3 r;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float4 t = *reinterpret_cast<const float4*>(base + c * ld);
-        r.v[c][0] = t.x;
-        r.v[c][1] = t.y;
-        r.v[c][2] = t.z;
-        r.v[c][3] = t.w;
-    }
-    return r;
-}
-__device__ __forceinline__ void st43(float* __restrict__ base, size_t ld, const V4x3& r) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(base + c * ld) = make_float4(r.v[c][0], r.v[c][1], r.v[c][2], r.v[c][3]);
-}
-// (a*b).sum over the 3 components: three rounded products summed left to right, no contraction
-__device__ __forceinline__ float dot3l(const V4x3& a, const V4x3& b, int l) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(a.v[0][l], b.v[0][l]), __fmul_rn(a.v[1][l], b.v[1][l])), __fmul_rn(a.v[2][l], b.v[2][l]));
-}
-
-struct ChanParams {
-    float mean[4], invstd[4], gamma[4], beta[4];
-};
-__device__ __forceinline__ ChanParams load_params(const float* stat, const float* gamma, const float* beta, int C, int c0) {
-    ChanParams p;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        p.mean[l] = stat ? __ldg(stat + c0 + l) : 0.f;
-        p.invstd[l] = stat ? __ldg(stat + C + c0 + l) : 0.f;
-        p.gamma[l] = stat ? __ldg(gamma + c0 + l) : 0.f;
-        p.beta[l] = stat ? __ldg(beta + c0 + l) : 0.f;
-    }
-    return p;
-}
 
 // block (32, 8): lane -> channel quad, y -> point lane; grid.x tiles quads by 32, grid.y strides over points
 #define VS_BLOCK_REDUCE2(S1, S2, sums, C, c0)                                   \
@@ -109,20 +56,6 @@ __global__ void __launch_bounds__(256) norm_stats_v4_kernel(const float* __restr
         }
     }
     VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)
-}
-
-__device__ __forceinline__ void bn_apply_lane(V4x3& v, int l, const ChanParams& cp, float& n_out, float& nhat_out, float& nb_out) {
-    const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v.v[0][l], v.v[0][l]), __fmul_rn(v.v[1][l], v.v[1][l])),
-                                    __fmul_rn(v.v[2][l], v.v[2][l])));
-    const float n = r + VS_EPS;
-    const float nhat = (n - cp.mean[l]) * cp.invstd[l];
-    const float nb = nhat * cp.gamma[l] + cp.beta[l];
-    v.v[0][l] = v.v[0][l] / n * nb;
-    v.v[1][l] = v.v[1][l] / n * nb;
-    v.v[2][l] = v.v[2][l] / n * nb;
-    n_out = n;
-    nhat_out = nhat;
-    nb_out = nb;
 }
 
 template <bool HAS_BN, bool HAS_D>
@@ -211,12 +144,12 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
                 float n = 1.f, nhat = 0.f;
                 float pb0 = pr.v[0][l], pb1 = pr.v[1][l], pb2 = pr.v[2][l];      // BN(p), same op order as the forward
                 if (HAS_BN) {
-                    n = sqrtf(dot3l(pr, pr, l)) + VS_EPS;
+                    n = fsqrt_fast(dot3l(pr, pr, l)) + VS_EPS;
                     nhat = (n - cp.mean[l]) * cp.invstd[l];
-                    const float nb = nhat * cp.gamma[l] + cp.beta[l];
-                    pb0 = pb0 / n * nb;
-                    pb1 = pb1 / n * nb;
-                    pb2 = pb2 / n * nb;
+                    const float t = (nhat * cp.gamma[l] + cp.beta[l]) * frcp(n);
+                    pb0 *= t;
+                    pb1 *= t;
+                    pb2 *= t;
                 }
                 if (HAS_D) {
                     const float s = __fadd_rn(__fadd_rn(__fmul_rn(pb0, dv.v[0][l]), __fmul_rn(pb1, dv.v[1][l])), __fmul_rn(pb2, dv.v[2][l]));
@@ -229,9 +162,9 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
                         s3[l] += gy3[0] * o0 + gy3[1] * o1 + gy3[2] * o2;
                     }
                     if (s < 0.f) {
-                        const float q = dot3l(dv, dv, l) + VS_EPS;
-                        const float a = s / q;
-                        const float gdq = dot3l(gv, dv, l) / q;
+                        const float rq = frcp(dot3l(dv, dv, l) + VS_EPS);
+                        const float a = s * rq;
+                        const float gdq = dot3l(gv, dv, l) * rq;
                         const float pbv[3] = {pb0, pb1, pb2};
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
@@ -244,7 +177,7 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
                     }
                 }
                 if (HAS_BN) {
-                    const float dnb = dot3l(gv, pr, l) / n;
+                    const float dnb = dot3l(gv, pr, l) * frcp(n);
                     s1[l] += (double)dnb;
                     s2[l] = fma((double)dnb, (double)nhat, s2[l]);
                 }
@@ -353,17 +286,18 @@ __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp,
         V4x3 gv = ld43_rw(gptr, ldgp);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-            const float r = sqrtf(dot3l(pr, pr, l));
+            const float r = fsqrt_fast(dot3l(pr, pr, l));
             const float n = r + VS_EPS;
+            const float rn = frcp(n);
             const float nhat = (n - cp.mean[l]) * cp.invstd[l];
             const float nb = nhat * cp.gamma[l] + cp.beta[l];
             const float gx = dot3l(gv, pr, l);
-            const float dnb = gx / n;
+            const float dnb = gx * rn;
             float dn = cp.gamma[l] * dnb;
             if (training) dn = dn - m1[l] - nhat * m2[l];
-            dn = dn * cp.invstd[l] - gx * nb / (n * n);
-            const float sc = nb / n;
-            const float ur = r > 0.f ? dn / r : 0.f;
+            dn = dn * cp.invstd[l] - gx * nb * rn * rn;
+            const float sc = nb * rn;
+            const float ur = r > 0.f ? dn * frcp(r) : 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) gv.v[c][l] = gv.v[c][l] * sc + ur * pr.v[c][l];
         }

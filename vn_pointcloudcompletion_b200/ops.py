@@ -243,14 +243,18 @@ def linear_rows(x, w, bias=None, rows_per_sample=0):
 # ---------------------------------------------------------------------------------------------------------------
 # VNBatchNorm (+ leaky projection) on rows
 # ---------------------------------------------------------------------------------------------------------------
-def _bn_prepare(p, C, bn, training, count):
-    """returns stat [2C] (mean | invstd) and updates the running buffers in training mode"""
-    dev = p.device
+def _bn_prepare(p, C, bn, training, count, stats_fn=None):
+    """returns stat [2C] (mean | invstd) and updates the running buffers in training mode.  stats_fn(sums) may supply
+    the per-channel sums (sum n | sum n^2, fp64) itself; by default they are reduced from the rows p."""
+    dev = bn.weight.device if p is None else p.device
     stat = torch.empty(2 * C, device=dev, dtype=torch.float32)
     sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
     use_batch = training or bn.running_mean is None
     if use_batch:
-        call("vnpcc_vn_norm_stats", ptr(p), _ld(p), count, C, ptr(sums), stream())
+        if stats_fn is not None:
+            stats_fn(sums)
+        else:
+            call("vnpcc_vn_norm_stats", ptr(p), _ld(p), count, C, ptr(sums), stream())
     momentum = bn.momentum
     upd = training and bn.track_running_stats and bn.running_mean is not None
     if upd:
@@ -371,6 +375,61 @@ class _BNLeakyDot(torch.autograd.Function):
         gw2 = torch.empty(C, device=dev, dtype=torch.float32)
         call("vnpcc_double_to_float", ptr(gw2d), ptr(gw2), C, stream())
         return gpd, ggamma, gbeta, None, None, None, gw2.view(1, C), (gy if has_res else None)
+
+
+class _SmallKBNLeaky(torch.autograd.Function):
+    """out = leaky(BN(Wf x + b_p), Wd x + b_d) for x with <= 4 channels and per-sample bias rows, p / d never stored
+    (csrc/vn_fused.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gamma, beta, stat, use_batch, ns, B, N):
+        C = w.shape[0] // 2
+        K = x.shape[1]
+        out = torch.empty((x.shape[0], C), device=x.device, dtype=torch.float32)
+        call("vnpcc_fold_fwd", ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0, B, N, K, C, ptr(stat),
+             ptr(gamma), ptr(beta), float(ns), ptr(out), C, stream())
+        ctx.save_for_backward(x, w, bias, gamma, beta, stat)
+        ctx.cfg = (B, N, K, C, float(ns), bool(use_batch))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, bias, gamma, beta, stat = ctx.saved_tensors
+        B, N, K, C, ns, use_batch = ctx.cfg
+        g = _rows2d(g, "grad")
+        dev = x.device
+        gx = torch.empty((x.shape[0], K), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        gw = torch.empty((2 * C, K), device=dev, dtype=torch.float32)
+        gb = torch.empty((B * 3, 2 * C), device=dev, dtype=torch.float32) if bias is not None else None
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        ggamma = torch.empty(C, device=dev, dtype=torch.float32) if stat is not None else None
+        gbeta = torch.empty(C, device=dev, dtype=torch.float32) if stat is not None else None
+        call("vnpcc_fold_bwd", ptr(g), _ld(g), ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0, B, N, K, C,
+             ptr(stat), ptr(gamma), ptr(beta), ns, 1 if use_batch else 0, ptr(sums), ptr(gx), K, ptr(gw), K, ptr(gb), 2 * C,
+             ptr(ggamma), ptr(gbeta), stream())
+        return gx, gw, gb, ggamma, gbeta, None, None, None, None, None
+
+
+def smallk_bn_leaky_supported(K, C, bias):
+    return 1 <= K <= 4 and C % 128 == 0 and C <= 1024 and (bias is None or (bias.stride(0) % 4 == 0 and bias.stride(1) == 1))
+
+
+def smallk_bn_leaky(x, w, bias, bn, training, ns, B, N):
+    """VNLinearLeakyReLU on rows x [B*N*3, K<=4] with stacked weights w [2C, K] and per-sample bias rows [B*3, 2C]"""
+    x = _rows2d(x, "x")
+    _check(w, "weight")
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    C = w.shape[0] // 2
+    K = x.shape[1]
+    stat, use_batch, gamma, beta = None, False, None, None
+    if bn is not None:
+        def stats_fn(sums):
+            call("vnpcc_fold_stats", ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0, B, N, K, C,
+                 ptr(sums), stream())
+        stat, use_batch = _bn_prepare(None, C, bn, training, B * N, stats_fn)
+        gamma, beta = bn.weight, bn.bias
+    return _SmallKBNLeaky.apply(x, w, bias, gamma, beta, stat, use_batch, ns, B, N)
 
 
 def bn_leaky_dot_supported(C):

@@ -112,8 +112,13 @@ class VN_FoldingNet(nn.Module):
         l0, l1, l2 = self.final_conv[0], self.final_conv[1], self.final_conv[2]
         wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [512, Cg+2]
         bias = ops.linear_rows(fg_rows, wcat[:, :Cg])                                      # [B*3,512]
-        pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                            # [R,512]
-        h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
+        C0 = l0.map_to_feat.weight.shape[0]
+        if ops.smallk_bn_leaky_supported(2, C0, bias) and l0.batchnorm.bn.affine:
+            # p = W_feat x + b_p and d = W_dir x + b_d are two FMAs per component: recomputed in every pass, never stored
+            h = ops.smallk_bn_leaky(local, wcat[:, Cg:], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, B, nd)
+        else:
+            pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                        # [R,512]
+            h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
         C1 = l1.map_to_feat.weight.shape[0]
         if l1.map_to_dir.weight.shape[0] == C1 and ops.bn_leaky_dot_supported(C1):
             # final_conv[1] (BN + leaky) fused with final_conv[2] = VNLinear(256,1) and the residual: its [R,256] output
