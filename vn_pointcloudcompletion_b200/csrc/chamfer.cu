@@ -230,7 +230,214 @@ __global__ void __launch_bounds__(256) nn_grad_kernel(const float* __restrict__ 
     }
 }
 
-static int g_chamfer_packed = 1;
+
+// -------------------------------------------------------------------------------------------------------------
+// Pre-filtered search (default).  The reference formula costs 6 FP32-pipe slots per pair (3 FADD, FMUL, 2 FFMA) and
+// must be reproduced bit for bit -- but only for the WINNER.  The search therefore ranks candidates with the
+// expansion form  e(q,c) = |c|^2 - 2 q.c  (= d - |q|^2; three FFMA per pair, packed two pairs per instruction, |c|^2
+// computed once per candidate while staging the tile) and keeps, per query, the smallest and second-smallest
+// per-chunk minima and the winning chunk.  With u = 2^-24 and G = (|q| + max|c|)^2,
+//     |fl(e) + |q|^2 - d_ref| <= 11 u G      (3 FMA roundings + |c|^2 rounding + the reference's own rounding)
+// so if  second - best > 2 * 32 u G  no candidate outside the winning 32-candidate chunk can equal or beat its exact
+// minimum, and nn_resolve2_kernel rescans that one chunk with the reference arithmetic (strict <, lowest index).
+// Queries that fail the test (exact ties across chunks, duplicated candidates, near-equidistant neighbours: ~1e-3 of
+// uniform random clouds) are appended to a list and re-searched exactly over ALL candidates by nn_exact_list_kernel.
+// Results are therefore identical to the reference kernel's for every input; only the work per pair changes.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void cand_prepare_kernel(const float* __restrict__ xc, int B, int M, float* __restrict__ cmax2, int* __restrict__ count) {
+    // cmax2[b] = max_k |c_k|^2 (non-negative floats order like their bit patterns); resets the slow-path counter
+    const int b = blockIdx.y;
+    float m = 0.f;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x) {
+        const float* p = xc + ((size_t)b * M + k) * 3;
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        m = fmaxf(m, fmaf(z, z, fmaf(y, y, x * x)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(cmax2) + b, __float_as_int(m));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *count = 0;
+}
+
+__global__ void __launch_bounds__(CH_T) nn_prefilter_kernel(const float* __restrict__ xq, const float* __restrict__ xc, int B,
+                                                             int N, int M, float* __restrict__ best_out,
+                                                             float* __restrict__ second_out, int* __restrict__ chunk_out,
+                                                             int n_qblocks, int n_splits, int split_len) {
+    __shared__ float4 tile[CH_TC / 4 * 4];   // per 4 candidates: {x0..3},{y0..3},{z0..3},{|c|^2 0..3}
+    const int tid = threadIdx.x;
+    const float INF = __int_as_float(0x7f800000);
+    const long long total = (long long)B * n_qblocks * n_splits;
+    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+        const int cs = (int)(item % n_splits);
+        const int qb = (int)((item / n_splits) % n_qblocks);
+        const int b = (int)(item / ((long long)n_splits * n_qblocks));
+        const int k0 = cs * split_len;
+        const int k1 = min(M, k0 + split_len);
+        u64 ax[CH_Q], ay[CH_Q], az[CH_Q];   // (-2 q) broadcast into both halves of a packed pair
+        float best[CH_Q], second[CH_Q];
+        int bchunk[CH_Q];
+#pragma unroll
+        for (int i = 0; i < CH_Q; ++i) {
+            int j = qb * CH_QB + i * CH_T + tid;
+            if (j >= N) j = N - 1;
+            const float* p = xq + ((size_t)b * N + j) * 3;
+            const float qx = -2.f * __ldg(p + 0), qy = -2.f * __ldg(p + 1), qz = -2.f * __ldg(p + 2);
+            ax[i] = pack2(qx, qx);
+            ay[i] = pack2(qy, qy);
+            az[i] = pack2(qz, qz);
+            best[i] = INF;
+            second[i] = INF;
+            bchunk[i] = 0;
+        }
+        for (int t0 = k0; t0 < k1; t0 += CH_TC) {
+            const int cnt = min(CH_TC, k1 - t0);
+            const int nchunks = (cnt + CH_CH - 1) / CH_CH;
+            __syncthreads();
+            {
+                const float* src = xc + ((size_t)b * M + t0) * 3;
+                float* ts = reinterpret_cast<float*>(tile);
+                const int padded = nchunks * CH_CH;
+                for (int c = tid; c < padded; c += CH_T) {
+                    const int cs_ = min(c, cnt - 1);      // the last chunk is padded with copies of the last real candidate
+                    const float x = __ldg(src + cs_ * 3 + 0), y = __ldg(src + cs_ * 3 + 1), z = __ldg(src + cs_ * 3 + 2);
+                    float* g = ts + (c >> 2) * 16 + (c & 3);
+                    g[0] = x;
+                    g[4] = y;
+                    g[8] = z;
+                    g[12] = fmaf(z, z, fmaf(y, y, x * x));
+                }
+            }
+            __syncthreads();
+            const int chunk_base = t0 / CH_CH;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                float cmin[CH_Q];
+#pragma unroll
+                for (int i = 0; i < CH_Q; ++i) cmin[i] = INF;
+                const float4* g = tile + ch * (CH_CH / 4) * 4;
+#pragma unroll
+                for (int gi = 0; gi < CH_CH / 4; ++gi) {
+                    const float4 X = g[gi * 4 + 0], Y = g[gi * 4 + 1], Z = g[gi * 4 + 2], W = g[gi * 4 + 3];
+                    const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+                    const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+                    const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+                    const u64 w01 = pack2(W.x, W.y), w23 = pack2(W.z, W.w);
+#pragma unroll
+                    for (int i = 0; i < CH_Q; ++i) {
+                        const u64 e01 = fma2(ax[i], x01, fma2(ay[i], y01, fma2(az[i], z01, w01)));
+                        const u64 e23 = fma2(ax[i], x23, fma2(ay[i], y23, fma2(az[i], z23, w23)));
+                        cmin[i] = fminf(fminf(cmin[i], lo32(e01)), hi32(e01));
+                        cmin[i] = fminf(fminf(cmin[i], lo32(e23)), hi32(e23));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CH_Q; ++i) {
+                    const bool lt = cmin[i] < best[i];
+                    second[i] = lt ? best[i] : fminf(second[i], cmin[i]);
+                    bchunk[i] = lt ? (chunk_base + ch) : bchunk[i];
+                    best[i] = lt ? cmin[i] : best[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CH_Q; ++i) {
+            const int j = qb * CH_QB + i * CH_T + tid;
+            if (j < N) {
+                const size_t o = ((size_t)b * N + j) * n_splits + cs;
+                best_out[o] = best[i];
+                second_out[o] = second[i];
+                chunk_out[o] = bchunk[i];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) nn_resolve2_kernel(const float* __restrict__ xq, const float* __restrict__ xc, int B, int N,
+                                                           int M, const float* __restrict__ best_in,
+                                                           const float* __restrict__ second_in, const int* __restrict__ chunk_in,
+                                                           int n_splits, const float* __restrict__ cmax2,
+                                                           float* __restrict__ dist, int* __restrict__ idx, int* __restrict__ count,
+                                                           int* __restrict__ list) {
+    const size_t total = (size_t)B * N;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / N);
+        const float INF = __int_as_float(0x7f800000);
+        float gb = INF, gs = INF;
+        int chunk = 0;
+        for (int s = 0; s < n_splits; ++s) {
+            const float bs = best_in[t * n_splits + s], ss = second_in[t * n_splits + s];
+            if (bs < gb) {
+                gs = fminf(gb, ss);
+                gb = bs;
+                chunk = chunk_in[t * n_splits + s];
+            } else {
+                gs = fminf(gs, bs);
+            }
+        }
+        const float qx = __ldg(xq + t * 3 + 0), qy = __ldg(xq + t * 3 + 1), qz = __ldg(xq + t * 3 + 2);
+        const float qn = sqrtf(fmaf(qz, qz, fmaf(qy, qy, qx * qx)));
+        const float cm = sqrtf(__ldg(cmax2 + b));
+        const float G = (qn + cm) * (qn + cm);
+        const float thr = 3.8146973e-6f * G + 1e-37f;     // 2 * 32 u G = 2^-18 G  (u = 2^-24), see the derivation above
+        if (gs - gb > thr) {
+            const int c0 = chunk * CH_CH;
+            const int c1 = min(M, c0 + CH_CH);
+            const float* src = xc + ((size_t)b * M) * 3;
+            float bestd = 0.f;
+            int best_i = c0;
+            for (int k = c0; k < c1; ++k) {
+                const float d = sqdist_ref(__ldg(src + k * 3 + 0), __ldg(src + k * 3 + 1), __ldg(src + k * 3 + 2), qx, qy, qz);
+                if (k == c0 || d < bestd) {
+                    bestd = d;
+                    best_i = k;
+                }
+            }
+            dist[t] = bestd;
+            idx[t] = best_i;
+        } else {
+            list[atomicAdd(count, 1)] = (int)t;      // (NaN comparisons land here too)
+        }
+    }
+}
+
+// exact search over all candidates for the listed queries: one warp per query, reference arithmetic, lowest index wins
+__global__ void __launch_bounds__(256) nn_exact_list_kernel(const float* __restrict__ xq, const float* __restrict__ xc, int N, int M,
+                                                             const int* __restrict__ count, const int* __restrict__ list,
+                                                             float* __restrict__ dist, int* __restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = *count;
+    for (int e = warp; e < n; e += nwarps) {
+        const int t = list[e];
+        const int b = t / N;
+        const float qx = __ldg(xq + (size_t)t * 3 + 0), qy = __ldg(xq + (size_t)t * 3 + 1), qz = __ldg(xq + (size_t)t * 3 + 2);
+        const float* src = xc + ((size_t)b * M) * 3;
+        float best = __int_as_float(0x7f800000);
+        int bi = 0x7fffffff;
+        for (int k = lane; k < M; k += 32) {
+            const float d = sqdist_ref(__ldg(src + k * 3 + 0), __ldg(src + k * 3 + 1), __ldg(src + k * 3 + 2), qx, qy, qz);
+            if (d < best || bi == 0x7fffffff) {
+                best = d;
+                bi = k;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float d2 = __shfl_xor_sync(0xffffffffu, best, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (i2 != 0x7fffffff && (bi == 0x7fffffff || d2 < best || (d2 == best && i2 < bi))) {
+                best = d2;
+                bi = i2;
+            }
+        }
+        if (lane == 0) {
+            dist[t] = best;
+            idx[t] = bi;
+        }
+    }
+}
+
+static int g_chamfer_packed = 2;   // 0: exact scalar search, 1: exact packed search, 2: pre-filtered search (default)
 
 }  // namespace vnpcc
 
@@ -238,38 +445,82 @@ using namespace vnpcc;
 
 extern "C" {
 
-void vnpcc_chamfer_set_packed_math(int on) { g_chamfer_packed = on ? 1 : 0; }
+// 0: exact scalar search, 1: exact packed-fp32 search, 2 (default, any other value): pre-filtered search
+void vnpcc_chamfer_set_packed_math(int mode) { g_chamfer_packed = (mode == 0 || mode == 1) ? mode : 2; }
 
-size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M) {
-    return ((size_t)B * (size_t)N + (size_t)B * (size_t)M) * sizeof(u64);
+// candidate-range splits for one directed pass: enough (sample, query block, split) items to fill the machine
+static void plan_splits(int B, int N, int M, int* n_qblocks, int* n_splits, int* split_len) {
+    const int nq = (N + CH_QB - 1) / CH_QB;
+    const long long slots = (long long)sm_count() * 4;
+    const int max_splits = (M + CH_TC - 1) / CH_TC;
+    long long want = (slots * 8 + (long long)B * nq - 1) / ((long long)B * nq);
+    int ns = (int)(want < 1 ? 1 : (want > max_splits ? max_splits : want));
+    int sl = ((M + ns - 1) / ns + CH_TC - 1) / CH_TC * CH_TC;
+    ns = (M + sl - 1) / sl;
+    *n_qblocks = nq;
+    *n_splits = ns < 1 ? 1 : ns;
+    *split_len = sl;
 }
 
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// per directed pass: (best, second, chunk) per (query, split) + slow-path list + per-sample max |c|^2 + counter
+static size_t directed_ws_bytes(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return 256;
+    int nq, ns, sl;
+    plan_splits(B, N, M, &nq, &ns, &sl);
+    const size_t per = (size_t)B * N;
+    size_t packed = per * sizeof(u64);                       // exact modes
+    size_t pre = 3 * align256(per * ns * 4) + align256(per * 4) + align256((size_t)B * 4) + 256;
+    return align256(packed > pre ? packed : pre);
+}
+
+size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M) { return directed_ws_bytes(B, N, M) + directed_ws_bytes(B, M, N); }
+
 // One directed pass (queries xq[B,N,3] against candidates xc[B,M,3]).
-static int nn_directed(const float* xq, const float* xc, int B, int N, int M, float* dist, int* idx, u64* ws,
-                       cudaStream_t st) {
+static int nn_directed(const float* xq, const float* xc, int B, int N, int M, float* dist, int* idx, void* wsv, cudaStream_t st) {
     if (B <= 0 || N <= 0) return 0;
     if (M <= 0) return 0;   // reference leaves outputs untouched for m == 0 (chamfer3D.cu:16)
     const int sms = sm_count();
-    const int n_qblocks = (N + CH_QB - 1) / CH_QB;
-    // choose the candidate split so that there are >= ~8 items per resident CTA slot (4 CTAs/SM), splits aligned to tiles
+    int n_qblocks, n_splits, split_len;
+    plan_splits(B, N, M, &n_qblocks, &n_splits, &split_len);
     const long long slots = (long long)sms * 4;
-    const int max_splits = (M + CH_TC - 1) / CH_TC;
-    long long want = (slots * 8 + (long long)B * n_qblocks - 1) / ((long long)B * n_qblocks);
-    int n_splits = (int)(want < 1 ? 1 : (want > max_splits ? max_splits : want));
-    int split_len = ((M + n_splits - 1) / n_splits + CH_TC - 1) / CH_TC * CH_TC;
-    n_splits = (M + split_len - 1) / split_len;
     const long long items = (long long)B * n_qblocks * n_splits;
+    const int grid = (int)(items < slots ? items : slots);
+    const size_t total = (size_t)B * N;
+    int rgrid = (int)((total + 255) / 256);
+    if (rgrid > sms * 8) rgrid = sms * 8;
+    if (g_chamfer_packed == 2) {
+        char* w = (char*)wsv;
+        float* best = (float*)w;
+        w += align256(total * n_splits * 4);
+        float* second = (float*)w;
+        w += align256(total * n_splits * 4);
+        int* chunk = (int*)w;
+        w += align256(total * n_splits * 4);
+        int* list = (int*)w;
+        w += align256(total * 4);
+        float* cmax2 = (float*)w;
+        w += align256((size_t)B * 4);
+        int* count = (int*)w;
+        cudaMemsetAsync(cmax2, 0, (size_t)B * 4, st);
+        int pg = (M + 255) / 256;
+        if (pg > 32) pg = 32;
+        count_launch(), cand_prepare_kernel<<<dim3(pg, B), 256, 0, st>>>(xc, B, M, cmax2, count);
+        count_launch(), nn_prefilter_kernel<<<grid, CH_T, 0, st>>>(xq, xc, B, N, M, best, second, chunk, n_qblocks, n_splits, split_len);
+        count_launch(), nn_resolve2_kernel<<<rgrid, 256, 0, st>>>(xq, xc, B, N, M, best, second, chunk, n_splits, cmax2, dist, idx, count,
+                                                                 list);
+        count_launch(), nn_exact_list_kernel<<<sms * 4, 256, 0, st>>>(xq, xc, N, M, count, list, dist, idx);
+        return 0;
+    }
+    u64* ws = (u64*)wsv;
     if (n_splits > 1) {
         count_launch(), fill_u64_kernel<<<sms * 2, 256, 0, st>>>(ws, (size_t)B * N, ~0ull);
     }
-    const int grid = (int)(items < slots ? items : slots);
     if (g_chamfer_packed)
         count_launch(), nn_search_kernel<true><<<grid, CH_T, 0, st>>>(xq, xc, B, N, M, ws, n_qblocks, n_splits, split_len);
     else
         count_launch(), nn_search_kernel<false><<<grid, CH_T, 0, st>>>(xq, xc, B, N, M, ws, n_qblocks, n_splits, split_len);
-    const size_t total = (size_t)B * N;
-    int rgrid = (int)((total + 255) / 256);
-    if (rgrid > sms * 8) rgrid = sms * 8;
     count_launch(), nn_resolve_kernel<<<rgrid, 256, 0, st>>>(xq, xc, B, N, M, ws, dist, idx);
     return 0;
 }
@@ -278,9 +529,9 @@ int vnpcc_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, in
                           int* idx1, int* idx2, void* workspace, size_t workspace_bytes, void* stream) {
     if (workspace_bytes < vnpcc_chamfer_workspace_bytes(B, N, M)) return VNPCC_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    u64* ws = (u64*)workspace;
+    char* ws = (char*)workspace;
     nn_directed(xyz1, xyz2, B, N, M, dist1, idx1, ws, st);
-    nn_directed(xyz2, xyz1, B, M, N, dist2, idx2, ws + (size_t)B * N, st);
+    nn_directed(xyz2, xyz1, B, M, N, dist2, idx2, ws + directed_ws_bytes(B, N, M), st);
     return last_error();
 }
 

@@ -269,25 +269,25 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                 if (!o_ok) continue;
                 float* dst = Y + (size_t)r0 * ldy + o;
                 if (HAS_BIAS) {
-                    // per-sample bias row (b, v) of output row r = (b*N + n)*3 + v: one division per 32-row chunk,
-                    // then incremental (rows_per_sample is a multiple of 3)
-                    long long b = r0 / rows_per_sample;
-                    long long rem = r0 - b * rows_per_sample;
-                    int vv = (int)(rem % 3);
-                    const float* bp = bias + (size_t)(b * 3 + vv) * ldbias + o;
+                    // per-sample bias row (b, v) of output row r = (b*N + n)*3 + v.  A 32-row chunk lies inside one
+                    // sample except at sample boundaries, so only the sample's 3 bias rows are needed: load them once,
+                    // rotate by the chunk's first component and add with compile-time indices.
+                    const long long b = r0 / rows_per_sample;
+                    const long long rem = r0 - b * rows_per_sample;
+                    const int vv = (int)(rem % 3);
+                    if (rem + 32 <= rows_per_sample) {
+                        const float* bp = bias + (size_t)(b * 3) * ldbias + o;
+                        const float z0 = __ldg(bp), z1 = __ldg(bp + ldbias), z2 = __ldg(bp + 2 * ldbias);
+                        const float t0 = vv == 0 ? z0 : (vv == 1 ? z1 : z2);
+                        const float t1 = vv == 0 ? z1 : (vv == 1 ? z2 : z0);
+                        const float t2 = vv == 0 ? z2 : (vv == 1 ? z0 : z1);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (r0 + j < R) v[j] += __ldg(bp);
-                        ++rem;
-                        if (++vv == 3) {
-                            vv = 0;
-                            bp -= 2 * ldbias;
-                            if (rem == rows_per_sample) {
-                                rem = 0;
-                                bp += 3 * ldbias;
-                            }
-                        } else {
-                            bp += ldbias;
+                        for (int j = 0; j < 32; ++j) v[j] += (j % 3 == 0) ? t0 : ((j % 3 == 1) ? t1 : t2);
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 32; ++j) {
+                            const long long r = r0 + j;
+                            if (r < R) v[j] += __ldg(bias + (size_t)((r / rows_per_sample) * 3 + (r % 3)) * ldbias + o);
                         }
                     }
                 }
