@@ -31,7 +31,7 @@
 
 namespace vnpcc {
 
-constexpr int CH_Q = 4;        // queries per thread
+constexpr int CH_Q = 8;        // queries per thread
 constexpr int CH_T = 128;      // threads per CTA
 constexpr int CH_QB = CH_Q * CH_T;   // queries per work item
 constexpr int CH_TC = 2048;    // candidates staged per shared-memory tile
@@ -56,6 +56,15 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// one LDS.128 delivering two aligned packed pairs
+__device__ __forceinline__ void lds_2x64(uint32_t addr, u64& a, u64& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
 __device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
@@ -237,8 +246,9 @@ __global__ void __launch_bounds__(256) nn_grad_kernel(const float* __restrict__ 
 // expansion form  e(q,c) = |c|^2 - 2 q.c  (= d - |q|^2; three FFMA per pair, packed two pairs per instruction, |c|^2
 // computed once per candidate while staging the tile) and keeps, per query, the smallest and second-smallest
 // per-chunk minima and the winning chunk.  With u = 2^-24 and G = (|q| + max|c|)^2,
-//     |fl(e) + |q|^2 - d_ref| <= 11 u G      (3 FMA roundings + |c|^2 rounding + the reference's own rounding)
-// so if  second - best > 2 * 32 u G  no candidate outside the winning 32-candidate chunk can equal or beat its exact
+//     |fl(e) + |q|^2 - d_ref| <= 11 u G      (e: 3 FMA roundings on partial sums <= |c|^2 + 2|q||c| plus 3u|c|^2 from |c|^2
+//                                             -> 6uG;  d_ref: rounded differences (2u) + 3 roundings -> 5u d <= 5uG)
+// so if  second - best > 2 * 12 u G  no candidate outside the winning 32-candidate chunk can equal or beat its exact
 // minimum, and nn_resolve2_kernel rescans that one chunk with the reference arithmetic (strict <, lowest index).
 // Queries that fail the test (exact ties across chunks, duplicated candidates, near-equidistant neighbours: ~1e-3 of
 // uniform random clouds) are appended to a list and re-searched exactly over ALL candidates by nn_exact_list_kernel.
@@ -264,6 +274,7 @@ __global__ void __launch_bounds__(CH_T) nn_prefilter_kernel(const float* __restr
                                                              float* __restrict__ second_out, int* __restrict__ chunk_out,
                                                              int n_qblocks, int n_splits, int split_len) {
     __shared__ float4 tile[CH_TC / 4 * 4];   // per 4 candidates: {x0..3},{y0..3},{z0..3},{|c|^2 0..3}
+    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
     const int tid = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
     const long long total = (long long)B * n_qblocks * n_splits;
@@ -313,21 +324,33 @@ __global__ void __launch_bounds__(CH_T) nn_prefilter_kernel(const float* __restr
                 float cmin[CH_Q];
 #pragma unroll
                 for (int i = 0; i < CH_Q; ++i) cmin[i] = INF;
-                const float4* g = tile + ch * (CH_CH / 4) * 4;
+                const uint32_t gaddr = tile_addr + (uint32_t)(ch * (CH_CH / 4) * 64);
 #pragma unroll
                 for (int gi = 0; gi < CH_CH / 4; ++gi) {
-                    const float4 X = g[gi * 4 + 0], Y = g[gi * 4 + 1], Z = g[gi * 4 + 2], W = g[gi * 4 + 3];
-                    const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
-                    const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
-                    const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
-                    const u64 w01 = pack2(W.x, W.y), w23 = pack2(W.z, W.w);
+                    u64 x01, x23, y01, y23, z01, z23, w01, w23;
+                    lds_2x64(gaddr + gi * 64 + 0, x01, x23);
+                    lds_2x64(gaddr + gi * 64 + 16, y01, y23);
+                    lds_2x64(gaddr + gi * 64 + 32, z01, z23);
+                    lds_2x64(gaddr + gi * 64 + 48, w01, w23);
+                    // stage-ordered so that 2*CH_Q independent FMA chains are in flight (latency 4, issue every 2 cycles)
+                    u64 e0[CH_Q], e1[CH_Q];
 #pragma unroll
                     for (int i = 0; i < CH_Q; ++i) {
-                        const u64 e01 = fma2(ax[i], x01, fma2(ay[i], y01, fma2(az[i], z01, w01)));
-                        const u64 e23 = fma2(ax[i], x23, fma2(ay[i], y23, fma2(az[i], z23, w23)));
-                        cmin[i] = fminf(fminf(cmin[i], lo32(e01)), hi32(e01));
-                        cmin[i] = fminf(fminf(cmin[i], lo32(e23)), hi32(e23));
+                        e0[i] = fma2(az[i], z01, w01);
+                        e1[i] = fma2(az[i], z23, w23);
                     }
+#pragma unroll
+                    for (int i = 0; i < CH_Q; ++i) {
+                        e0[i] = fma2(ay[i], y01, e0[i]);
+                        e1[i] = fma2(ay[i], y23, e1[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CH_Q; ++i) {
+                        e0[i] = fma2(ax[i], x01, e0[i]);
+                        e1[i] = fma2(ax[i], x23, e1[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CH_Q; ++i) cmin[i] = fmin3(fmin3(cmin[i], lo32(e0[i]), hi32(e0[i])), lo32(e1[i]), hi32(e1[i]));
                 }
 #pragma unroll
                 for (int i = 0; i < CH_Q; ++i) {
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(256) nn_resolve2_kernel(const float* __restric
         const float qn = sqrtf(fmaf(qz, qz, fmaf(qy, qy, qx * qx)));
         const float cm = sqrtf(__ldg(cmax2 + b));
         const float G = (qn + cm) * (qn + cm);
-        const float thr = 3.8146973e-6f * G + 1e-37f;     // 2 * 32 u G = 2^-18 G  (u = 2^-24), see the derivation above
+        const float thr = 1.5e-6f * G + 1e-37f;     // > 2 * 12 u G = 1.43e-6 G  (u = 2^-24), see the derivation above
         if (gs - gb > thr) {
             const int c0 = chunk * CH_CH;
             const int c1 = min(M, c0 + CH_CH);
