@@ -107,9 +107,9 @@ class KernelTimer:
         e0.record()
         return (cls, work, e0, e1)
 
-    def stop(self, tok):
+    def stop(self, tok, cls=None):
         tok[3].record()
-        self.records.append(tok)
+        self.records.append((cls or tok[0],) + tok[1:])
 
     def summary(self):
         out = {}
@@ -287,25 +287,32 @@ def main():
         # dominant kernel class inside the timed region
         roof = None
         classes = {}
+        traffic = {}
+        tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
         for cls, d in ksum.items():
             sec = d["ms"] / 1e3
-            if cls == "gemm":
+            if cls in ("gemm_rows_tf32", "gemm_wgrad_tf32", "sgemm_fp32", "gemm"):
                 tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
                 # TF32 dense peak is half the bf16 one; the driver measures bf16 only
-                peak = (pk["bf16_sustained"] / 2.0) if args.mode == "tf32" else None
+                peak = (pk["bf16_sustained"] / 2.0) if cls.endswith("tf32") else None
                 classes[cls] = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
-                                "frac": (tf / peak) if peak else None, "traffic": None, "ms_per_step": d["ms"] / args.steps,
+                                "frac": (tf / peak) if peak else None, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
                                 "launches_per_step": d["launches"] / args.steps,
-                                "peak_note": f"bf16 sustained ({pk['source']}) / 2 for TF32 operands" if peak else
-                                             "fp32 SIMT parity mode: no tensor-core peak applies"}
+                                "flop_per_launch": d["work"] / max(d["launches"], 1),
+                                "peak_note": f"bf16 sustained ({pk['source']}) / 2 for TF32 operands; achieved = sum of 2*R*K*Cout "
+                                             "over the class's launches / their CUDA-event time" if peak else
+                                             "fp32 SIMT kernel: no tensor-core peak applies"}
             elif cls == "chamfer_fwd":
                 pairs = d["work"] / sec if sec > 0 else 0.0
                 fclk = (clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6
                 peak_inst = 148 * 128 * fclk                 # FP32 lane-instructions / s
                 classes[cls] = {"bound": "fp32", "achieved": pairs / 1e9, "peak": peak_inst / 6 / 1e9, "unit": "Gpairs/s",
-                                "frac": 6 * pairs / peak_inst, "traffic": None, "ms_per_step": d["ms"] / args.steps,
+                                "frac": 6 * pairs / peak_inst, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
                                 "launches_per_step": d["launches"] / args.steps,
-                                "peak_note": "148 SMs x 128 lanes x median SM clock under load / 6 FP32 instr per pair"}
+                                "peak_note": "148 SMs x 128 lanes x median SM clock under load / 6 FP32 instr per pair (the "
+                                             "reference arithmetic, SURVEY 8d); the pre-filtered search spends 3 per pair on ranking"}
         if classes:
             top = max(classes, key=lambda k: classes[k]["ms_per_step"])
             roof = dict(classes[top])

@@ -39,6 +39,9 @@ extern "C" {
 int vnpcc_abi_version(void);
 /* number of kernel launches enqueued by this library in this process (bench.py's gpu_launches) */
 unsigned long long vnpcc_launch_count(void);
+/* forward elementwise kernels: 0 (default) = IEEE sqrt / division with the reference's op-by-op rounding (parity mode),
+ * 1 = MUFU reciprocal / rsqrt (throughput mode; the host layer switches it together with the TF32 GEMMs) */
+void vnpcc_set_fast_math(int on);
 
 /* ---------------------------------------------------------------- Chamfer ---------------------------------------- */
 size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M);

@@ -17,6 +17,7 @@ _p, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_dou
 SIGNATURES = {
     "vnpcc_abi_version": (_i, []),
     "vnpcc_launch_count": (C.c_ulonglong, []),
+    "vnpcc_set_fast_math": (None, [_i]),
     "vnpcc_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "vnpcc_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "vnpcc_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

@@ -5,8 +5,12 @@
 #include <stdint.h>
 
 #include "vnpcc_internal.h"
+#include "vn_math.cuh"
 
 namespace vnpcc {
+
+static bool g_fast_math = false;
+bool fast_math_enabled() { return g_fast_math; }
 
 unsigned long long& launch_counter() {
     static unsigned long long n = 0;
@@ -99,6 +103,7 @@ using namespace vnpcc;
 extern "C" {
 
 int vnpcc_abi_version(void) { return 1; }
+void vnpcc_set_fast_math(int on) { g_fast_math = on != 0; }
 unsigned long long vnpcc_launch_count(void) { return launch_counter(); }
 
 int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M, int mode, double* scratch, float* out,

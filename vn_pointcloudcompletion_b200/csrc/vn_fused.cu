@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict
     fold_reduce_channels<2>(acc, sums, C, c0, fold_sh);
 }
 
-template <int KS>
+template <int KS, bool FAST>
 __global__ void __launch_bounds__(256) fold_fwd_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
                                                         const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
                                                         const float* __restrict__ stat, const float* __restrict__ gamma,
@@ -143,19 +143,9 @@ __global__ void __launch_bounds__(256) fold_fwd_kernel(const float* __restrict__
         for (int l = 0; l < 4; ++l) {
             if (stat) {
                 float nn, nhat, nb;
-                bn_apply_lane(v, l, cp, nn, nhat, nb);
+                bn_apply_lane_t<FAST>(v, l, cp, nn, nhat, nb);
             }
-            const float dot = dot3l(v, dv, l);
-            float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
-            if (!(dot >= 0.f)) {
-                const float a = dot / __fadd_rn(dot3l(dv, dv, l), VS_EPS);
-                in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
-                in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
-                in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
-            }
-            v.v[0][l] = __fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k1, in0));
-            v.v[1][l] = __fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k1, in1));
-            v.v[2][l] = __fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k1, in2));
+            leaky_lane_t<FAST>(v, dv, l, ns, k1);
         }
         st43(out + row * ldo + c0, ldo, v);
     }
@@ -196,7 +186,7 @@ __device__ __forceinline__ void fold_lane_bwd(const V4x3& pr, V4x3& dv, V4x3& gv
 }
 
 template <int KS>
-__global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+__global__ void __launch_bounds__(256, 2) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
                                                              const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
                                                              size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
@@ -238,7 +228,7 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
 
 // pass B: gW (2C x KS, fp32 atomics), gbias ([B*3, 2C], fp32 atomics), gx ([R, KS], plain stores)
 template <int KS>
-__global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+__global__ void __launch_bounds__(256, 2) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
                                                              const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
                                                              size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
@@ -424,8 +414,13 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
     int n_chunk;
     size_t smem;
     fold_geometry(B, N, C, grid, block, n_chunk, smem);
-    FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C,
-                                                                                  n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+    if (fast_math_enabled()) {
+        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, true><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
+                                                                                            C, n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+    } else {
+        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, false><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
+                                                                                             C, n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+    }
     return last_error();
 }
 

@@ -59,6 +59,57 @@ __device__ __forceinline__ ChanParams load_params(const float* stat, const float
     return p;
 }
 
+// process-wide switch (vnpcc_set_fast_math): forward kernels use MUFU reciprocal / rsqrt instead of IEEE division / sqrt.
+// Off in parity (fp32) mode, on in throughput (TF32) mode where GEMM operands are already rounded to 10 mantissa bits.
+bool fast_math_enabled();
+
+template <bool FAST>
+__device__ __forceinline__ float vdiv(float a, float b) {
+    return FAST ? __fdividef(a, b) : a / b;
+}
+template <bool FAST>
+__device__ __forceinline__ float vsqrt(float a) {
+    return FAST ? (a > 0.f ? a * rsqrtf(a) : 0.f) : sqrtf(a);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void bn_apply_lane_t(V4x3& v, int l, const ChanParams& cp, float& n_out, float& nhat_out, float& nb_out) {
+    const float r = vsqrt<FAST>(__fadd_rn(__fadd_rn(__fmul_rn(v.v[0][l], v.v[0][l]), __fmul_rn(v.v[1][l], v.v[1][l])),
+                                          __fmul_rn(v.v[2][l], v.v[2][l])));
+    const float n = r + VS_EPS;
+    const float nhat = (n - cp.mean[l]) * cp.invstd[l];
+    const float nb = nhat * cp.gamma[l] + cp.beta[l];
+    if (FAST) {
+        const float t = __fdividef(nb, n);
+        v.v[0][l] *= t;
+        v.v[1][l] *= t;
+        v.v[2][l] *= t;
+    } else {
+        v.v[0][l] = v.v[0][l] / n * nb;
+        v.v[1][l] = v.v[1][l] / n * nb;
+        v.v[2][l] = v.v[2][l] / n * nb;
+    }
+    n_out = n;
+    nhat_out = nhat;
+    nb_out = nb;
+}
+
+// leaky projection of lane l of v (post-BN) along dv, in place (op-by-op rounding of the eager expression unless FAST)
+template <bool FAST>
+__device__ __forceinline__ void leaky_lane_t(V4x3& v, const V4x3& dv, int l, float ns, float k) {
+    const float dot = dot3l(v, dv, l);
+    float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
+    if (!(dot >= 0.f)) {
+        const float a = vdiv<FAST>(dot, __fadd_rn(dot3l(dv, dv, l), VS_EPS));
+        in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
+        in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
+        in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
+    }
+    v.v[0][l] = __fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k, in0));
+    v.v[1][l] = __fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k, in1));
+    v.v[2][l] = __fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k, in2));
+}
+
 __device__ __forceinline__ void bn_apply_lane(V4x3& v, int l, const ChanParams& cp, float& n_out, float& nhat_out, float& nb_out) {
     const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v.v[0][l], v.v[0][l]), __fmul_rn(v.v[1][l], v.v[1][l])),
                                     __fmul_rn(v.v[2][l], v.v[2][l])));

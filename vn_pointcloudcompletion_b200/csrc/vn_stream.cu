@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) norm_stats_v4_kernel(const float* __restr
     VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)
 }
 
-template <bool HAS_BN, bool HAS_D>
+template <bool HAS_BN, bool HAS_D, bool FAST>
 __global__ void __launch_bounds__(256) bn_leaky_fwd_v4_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
                                                                size_t ldd, float* __restrict__ out, size_t ldo, long long P, int C,
                                                                const float* __restrict__ stat, const float* __restrict__ gamma,
@@ -77,22 +77,9 @@ __global__ void __launch_bounds__(256) bn_leaky_fwd_v4_kernel(const float* __res
         for (int l = 0; l < 4; ++l) {
             if (HAS_BN) {
                 float n, nhat, nb;
-                bn_apply_lane(v, l, cp, n, nhat, nb);
+                bn_apply_lane_t<FAST>(v, l, cp, n, nhat, nb);
             }
-            if (HAS_D) {
-                // op-by-op rounding of  ns*p + (1-ns)*(mask*p + (1-mask)*(p - (dot/(dsq+EPS))*d))
-                const float dot = dot3l(v, dv, l);
-                float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
-                if (!(dot >= 0.f)) {
-                    const float a = dot / __fadd_rn(dot3l(dv, dv, l), VS_EPS);
-                    in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
-                    in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
-                    in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
-                }
-                v.v[0][l] = __fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k, in0));
-                v.v[1][l] = __fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k, in1));
-                v.v[2][l] = __fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k, in2));
-            }
+            if (HAS_D) leaky_lane_t<FAST>(v, dv, l, ns, k);
         }
         st43(out + (size_t)pt * 3 * ldo + c0, ldo, v);
     }
@@ -204,7 +191,7 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
 }
 
 // fused forward tail: y[r] = sum_c leaky(BN(p), d)[r, c] * w2[c] (+ res[r]); block (C/4, 256/(C/4)): one point per block row
-template <bool HAS_BN>
+template <bool HAS_BN, bool FAST>
 __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
                                                                    size_t ldd, long long P, int C, const float* __restrict__ stat,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -230,19 +217,12 @@ __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* _
             for (int l = 0; l < 4; ++l) {
                 if (HAS_BN) {
                     float n, nhat, nb;
-                    bn_apply_lane(v, l, cp, n, nhat, nb);
+                    bn_apply_lane_t<FAST>(v, l, cp, n, nhat, nb);
                 }
-                const float dot = dot3l(v, dv, l);
-                float in0 = v.v[0][l], in1 = v.v[1][l], in2 = v.v[2][l];
-                if (!(dot >= 0.f)) {
-                    const float a = dot / __fadd_rn(dot3l(dv, dv, l), VS_EPS);
-                    in0 = __fsub_rn(in0, __fmul_rn(a, dv.v[0][l]));
-                    in1 = __fsub_rn(in1, __fmul_rn(a, dv.v[1][l]));
-                    in2 = __fsub_rn(in2, __fmul_rn(a, dv.v[2][l]));
-                }
-                acc[0] = fmaf(__fadd_rn(__fmul_rn(ns, v.v[0][l]), __fmul_rn(k, in0)), w2l[l], acc[0]);
-                acc[1] = fmaf(__fadd_rn(__fmul_rn(ns, v.v[1][l]), __fmul_rn(k, in1)), w2l[l], acc[1]);
-                acc[2] = fmaf(__fadd_rn(__fmul_rn(ns, v.v[2][l]), __fmul_rn(k, in2)), w2l[l], acc[2]);
+                leaky_lane_t<FAST>(v, dv, l, ns, k);
+                acc[0] = fmaf(v.v[0][l], w2l[l], acc[0]);
+                acc[1] = fmaf(v.v[1][l], w2l[l], acc[1]);
+                acc[2] = fmaf(v.v[2][l], w2l[l], acc[2]);
             }
         }
 #pragma unroll
@@ -327,13 +307,20 @@ bool try_bn_leaky_fwd_v4(const float* p, long long ldp, const float* d, long lon
                          const float* stat, const float* gamma, const float* beta, float ns, cudaStream_t st) {
     if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(out, ldo)) return false;
     const dim3 grid = stream_grid(P, C), block(32, 8);
-#define VS_FWD(BN_, D_)                                                                                                          \
-    count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, \
-                                                                             gamma, beta, ns)
-    if (stat && d) VS_FWD(true, true);
-    else if (stat) VS_FWD(true, false);
-    else if (d) VS_FWD(false, true);
-    else VS_FWD(false, false);
+    const bool fast = fast_math_enabled();
+#define VS_FWD(BN_, D_)                                                                                                                   \
+    {                                                                                                                                     \
+        if (fast)                                                                                                                         \
+            count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, true><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
+                                                                                           C, stat, gamma, beta, ns);                        \
+        else                                                                                                                              \
+            count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, false><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
+                                                                                            C, stat, gamma, beta, ns);                       \
+    }
+    if (stat && d) VS_FWD(true, true)
+    else if (stat) VS_FWD(true, false)
+    else if (d) VS_FWD(false, true)
+    else VS_FWD(false, false)
 #undef VS_FWD
     return true;
 }
@@ -371,12 +358,15 @@ bool try_bn_leaky_dot_fwd_v4(const float* p, long long ldp, const float* d, long
     long long g = (P + by - 1) / by;
     const long long cap = (long long)sm_count() * 8;
     if (g > cap) g = cap;
-    if (stat)
-        count_launch(), bn_leaky_dot_fwd_v4_kernel<true><<<(unsigned)g, dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma,
-                                                                                           beta, ns, w2, res, y);
-    else
-        count_launch(), bn_leaky_dot_fwd_v4_kernel<false><<<(unsigned)g, dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma,
-                                                                                            beta, ns, w2, res, y);
+    const bool fast = fast_math_enabled();
+#define VS_DOT(BN_, F_)                                                                                                                       \
+    count_launch(), bn_leaky_dot_fwd_v4_kernel<BN_, F_><<<(unsigned)g, dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma, \
+                                                                                              beta, ns, w2, res, y)
+    if (stat && fast) VS_DOT(true, true);
+    else if (stat) VS_DOT(true, false);
+    else if (fast) VS_DOT(false, true);
+    else VS_DOT(false, false);
+#undef VS_DOT
     return true;
 }
 

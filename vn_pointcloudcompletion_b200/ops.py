@@ -30,6 +30,7 @@ def set_gemm_mode(mode):
     if mode not in ("fp32", "tf32"):
         raise ValueError(mode)
     _GEMM_MODE = mode
+    _lib.load().vnpcc_set_fast_math(1 if mode == "tf32" else 0)
 
 
 def get_gemm_mode():
@@ -46,10 +47,15 @@ def set_timer(timer):
     _TIMER = timer
 
 
+_LAST_KERNEL = [None]     # name of the kernel family the most recent GEMM launch helper actually used
+
+
 class _Timed:
-    __slots__ = ("tok",)
+    __slots__ = ("tok", "cls")
 
     def __init__(self, cls, work):
+        self.cls = cls
+        _LAST_KERNEL[0] = None
         self.tok = _TIMER.start(cls, work) if _TIMER is not None else None
 
     def __enter__(self):
@@ -57,7 +63,7 @@ class _Timed:
 
     def __exit__(self, *a):
         if self.tok is not None:
-            _TIMER.stop(self.tok)
+            _TIMER.stop(self.tok, _LAST_KERNEL[0] or self.cls)
         return False
 
 
@@ -108,12 +114,14 @@ def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, 
         rc = _lib.raw("vnpcc_smallk_fwd", ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0,
                       rows_per_sample, ptr(out), _ld(out), R, K, Cout, stream())
         if rc == 0:
+            _LAST_KERNEL[0] = "smallk"
             return out
         if rc != 10003:
             raise _lib.VnpccError(f"vnpcc_smallk_fwd failed with code {rc}")
     if not accumulate and trans_w and Cout <= 4 and bias is None:
         rc = _lib.raw("vnpcc_smallk_dgrad", ptr(x), _ld(x), ptr(w), _ld(w), ptr(out), _ld(out), R, Cout, K, stream())
         if rc == 0:
+            _LAST_KERNEL[0] = "smallk"
             return out
         if rc != 10003:
             raise _lib.VnpccError(f"vnpcc_smallk_dgrad failed with code {rc}")
@@ -125,9 +133,11 @@ def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, 
         rc = _lib.raw("vnpcc_gemm_rows_tf32", ptr(x), _ld(x), ptr(wt), _ld(wt), ptr(out), _ld(out), R, K, Cout, ptr(bias),
                       _ld(bias) if bias is not None else 0, rows_per_sample, stream())
         if rc == 0:
+            _LAST_KERNEL[0] = "gemm_rows_tf32"
             return out
         if rc != 10003:   # VNPCC_ERR_UNSUPPORTED -> shape not taken by the tensor-core kernel
             raise _lib.VnpccError(f"vnpcc_gemm_rows_tf32 failed with code {rc}")
+    _LAST_KERNEL[0] = "sgemm_fp32"
     call("vnpcc_gemm_rows_fp32", ptr(x), _ld(x), ptr(w), _ld(w), 1 if trans_w else 0, ptr(out), _ld(out), R, K, Cout,
          ptr(bias), _ld(bias) if bias is not None else 0, rows_per_sample, 1 if accumulate else 0, stream())
     return out
@@ -170,6 +180,7 @@ def _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K):
     if not accumulate and K <= 4 and R % 3 == 0 and out.stride(0) == K:
         rc = _lib.raw("vnpcc_smallk_wgrad", ptr(dy), _ld(dy), ptr(x), _ld(x), 1, R // 3, K, Cout, ptr(out), K, None, 0, stream())
         if rc == 0:
+            _LAST_KERNEL[0] = "smallk"
             return out
         if rc != 10003:
             raise _lib.VnpccError(f"vnpcc_smallk_wgrad failed with code {rc}")
@@ -179,9 +190,11 @@ def _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K):
         rc = _lib.raw("vnpcc_gemm_wgrad_tf32", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(out), _ld(out), R, Cout, K, ptr(ws),
                       ws.numel(), stream())
         if rc == 0:
+            _LAST_KERNEL[0] = "gemm_wgrad_tf32"
             return out
         if rc != 10003:
             raise _lib.VnpccError(f"vnpcc_gemm_wgrad_tf32 failed with code {rc}")
+    _LAST_KERNEL[0] = "sgemm_fp32"
     call("vnpcc_gemm_wgrad_fp32", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(out), _ld(out), R, Cout, K, 1 if accumulate else 0,
          stream())
     return out
