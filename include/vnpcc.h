@@ -80,6 +80,14 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
 int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg,
                           long long R, int Cout, int K, float* workspace, size_t workspace_bytes, void* stream);
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long R, int Cout, int K);
+/* VNLinearLeakyReLU (models/vn_layers.py:60-74) with BatchNorm-on-norm + leaky projection fused into the tcgen05 GEMM epilogue
+ * (no-grad / inference forward: the linear outputs p, d never reach HBM).  Wcat [2C, K] = (W_feat ; W_dir); C % 128 == 0.
+ * _stats: per-channel (sum ||p||, sum ||p||^2) in fp64 for training-mode statistics; _apply: out [R, C]. */
+int vnpcc_gemm_vn_stats(const float* X, long long ldx, const float* Wcat, long long ldw, long long R, int K, int C, const float* bias,
+                        long long ldbias, long long rows_per_sample, double* sums, void* stream);
+int vnpcc_gemm_vn_apply(const float* X, long long ldx, const float* Wcat, long long ldw, float* out, long long ldo, long long R, int K,
+                        int C, const float* bias, long long ldbias, long long rows_per_sample, const float* stat, const float* gamma,
+                        const float* beta, float ns, void* stream);
 
 /* ---------------------------------------------------------------- VN elementwise / reductions ------------------- */
 int vnpcc_vn_norm_stats(const float* p, long long ldp, long long P, int C, double* sums, void* stream);

@@ -118,3 +118,53 @@ def test_pcn_train_step_tf32_close_to_fp32(tf32_mode):
     assert (a[1] - b[1]).abs().max() <= 2e-2 * a[1].abs().max()
     assert abs(a[2] - b[2]) <= 1e-2 * abs(a[2])
     assert (a[3] - b[3]).norm() <= 5e-2 * a[3].norm()
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_fused_epilogue_vn_gemm_matches_unfused(tf32_mode, train):
+    """VNLinearLeakyReLU no-grad forward with BN + leaky fused into the tcgen05 epilogue vs the unfused kernels on the same
+    TF32 GEMM: same MMA sequence -> the only differences are fp32 rounding of the elementwise tail"""
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import ops
+    torch.manual_seed(3)
+    B, N, K, C = 3, 100, 64, 256            # 300 points: exercises a partial last tile and sample boundaries inside tiles
+    m = V.VNLinearLeakyReLU(K, C, dim=4).cuda()
+    with torch.no_grad():
+        m.batchnorm.bn.weight.copy_(torch.randn(C))
+        m.batchnorm.bn.bias.copy_(torch.randn(C) * 0.3)
+        m.batchnorm.bn.running_mean.copy_(torch.rand(C) * 5)
+        m.batchnorm.bn.running_var.copy_(torch.rand(C) + 0.5)
+    m.train(train)
+    rows = torch.randn(B * N * 3, K, device="cuda")
+    bias = torch.randn(B * 3, 2 * C, device="cuda")
+    for b_rows, rps in ((None, 0), (bias, 3 * N)):
+        rm0 = m.batchnorm.bn.running_mean.clone()
+        with torch.enable_grad():
+            ref = m.forward_rows(rows, b_rows, rps).detach()
+        rm_ref = m.batchnorm.bn.running_mean.clone()
+        m.batchnorm.bn.running_mean.copy_(rm0)
+        with torch.no_grad():
+            w = torch.cat([m.map_to_feat.weight, m.map_to_dir.weight], 0)
+            fused = ops.linear_bn_leaky_fused_nograd(rows, w, b_rows, rps, m.batchnorm.bn, m.training, m.negative_slope)
+        assert fused is not None, "fused kernel refused the shape"
+        assert (fused - ref).abs().max() <= 2e-4 * ref.abs().max()
+        assert torch.allclose(m.batchnorm.bn.running_mean, rm_ref, rtol=1e-5, atol=1e-6)
+        m.batchnorm.bn.running_mean.copy_(rm0)
+
+
+def test_pcn_eval_forward_fused_vs_unfused(tf32_mode):
+    from types import SimpleNamespace
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200.synthetic import make_batch
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cuda", enc_pretrained="none")
+    torch.manual_seed(0)
+    net = V.PCNNet(cfg).eval()
+    p, c, R = (torch.from_numpy(a).cuda() for a in make_batch(3, 256, 2048, seed=5))
+    with torch.enable_grad():
+        c0, f0 = net(p, V.Rotate(R))
+        idx = (net.encoder.maxpool1.last_idx.clone(), net.encoder.maxpool2.last_idx.clone())
+    net.encoder.maxpool1.forced_idx, net.encoder.maxpool2.forced_idx = idx
+    with torch.no_grad():
+        c1, f1 = net(p, V.Rotate(R))
+    assert (c0.detach() - c1).abs().max() <= 1e-3 * c0.abs().max()
+    assert (f0.detach() - f1).abs().max() <= 1e-3 * f0.abs().max()

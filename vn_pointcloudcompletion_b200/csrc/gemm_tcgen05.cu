@@ -28,6 +28,7 @@
 #include "vnpcc_internal.h"
 
 namespace vnpcc {
+bool fast_math_enabled();
 namespace tc {
 
 constexpr int BM = 128;            // output channels per tile (TMEM lanes)
@@ -314,6 +315,263 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// VNLinearLeakyReLU with the Vector-Neuron tail fused into the GEMM epilogue (no-grad / inference forward):
+//     p = W_feat x (+ b_p),  d = W_dir x (+ b_d),  out = leaky(BN_vn(p), d)         models/vn_layers.py:60-74
+// One CTA tile = 128 output channels x 96 rows (= 32 points x 3 components).  Two accumulators per tile live in TMEM
+// (P for the feat rows of the stacked weight, D for the dir rows, same activation tile as B operand), double-buffered
+// (4 x 96 = 384 columns).  An epilogue thread owns one channel; the three components of a point are three consecutive
+// TMEM columns of the same thread, so the norm, the BatchNorm-on-norm scale, <p,d> and the projection are thread-local
+// and only `out` ever reaches HBM: the linear outputs make no HBM round trip at all.
+//   MODE_STATS : feat accumulator only; per-channel sum ||p||, sum ||p||^2 (fp64) for training-mode batch statistics
+//   MODE_APPLY : feat + dir accumulators; writes out [R, C]
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FBN = 96;            // rows per tile: multiple of 3 (whole points) and of 16 (UMMA N granularity)
+constexpr int MODE_STATS = 0, MODE_APPLY = 1;
+
+template <int STAGES, int MODE>
+struct FusedSmem {
+    static constexpr int A_BYTES = BM * BK * 4;                       // one weight tile (feat or dir)
+    static constexpr int NA = MODE == MODE_APPLY ? 2 : 1;
+    static constexpr int B_BYTES = 12 * 1024;                         // 96 x 32 fp32 (8-row swizzle groups: 96 = 12 x 8)
+    static constexpr int STAGE_BYTES = NA * A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int STAGES, int MODE, bool FAST>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ out,
+                     size_t ldo, long long R, int K, int C, const float* __restrict__ bias, size_t ldbias, long long rows_per_sample,
+                     const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
+                     double* __restrict__ sums, int num_m, long long num_tiles) {
+    using L = FusedSmem<STAGES, MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (K + BK - 1) / BK;
+    constexpr int ACC_COLS = 2 * FBN;   // P | D per accumulator stage
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            PipeState ps;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (int)(tile % num_m) * BM;
+                const long long n0 = (tile / num_m) * FBN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+                    uint8_t* sa = smem + ps.stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::NA * L::A_BYTES;
+                    mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
+                    tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
+                    if (MODE == MODE_APPLY) tma_load_2d(&map_w, &full_bar[ps.stage], sa + L::A_BYTES, kb * BK, C + m0);
+                    tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
+                    ps.advance<STAGES>();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, FBN, 0, 0);
+            PipeState ps;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t p_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                const uint32_t d_tmem = p_tmem + FBN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[ps.stage], ps.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ps.stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::NA * L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t bd = make_desc(sb + k * UMMA_K * 4, 16, 1024);
+                        umma_tf32(p_tmem, make_desc(sa + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (MODE == MODE_APPLY)
+                            umma_tf32(d_tmem, make_desc(sa + L::A_BYTES + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[ps.stage]);
+                    ps.advance<STAGES>();
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        double s1 = 0.0, s2 = 0.0;
+        int stat_c = -1;                 // channel whose statistics s1/s2 currently hold
+        const float k1 = 1.f - ns;
+        const long long pts_per_sample = rows_per_sample > 0 ? rows_per_sample / 3 : 1;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (int)(tile % num_m) * BM;
+            const long long n0 = (tile / num_m) * FBN;
+            const int c = m0 + quad * 32 + lane;             // C is a multiple of 128: always a valid channel
+            if (MODE == MODE_STATS && c != stat_c) {
+                if (stat_c >= 0) {
+                    atomicAdd(sums + stat_c, s1);
+                    atomicAdd(sums + C + stat_c, s2);
+                }
+                s1 = s2 = 0.0;
+                stat_c = c;
+            }
+            float mean = 0.f, invstd = 0.f, ga = 0.f, be = 0.f;
+            if (MODE == MODE_APPLY && stat) {
+                mean = __ldg(stat + c);
+                invstd = __ldg(stat + C + c);
+                ga = __ldg(gamma + c);
+                be = __ldg(beta + c);
+            }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+            for (int h = 0; h < FBN / 48; ++h) {             // 48 columns = 16 points per pass
+                const long long r0 = n0 + h * 48;
+                if (r0 >= R) break;                          // warp-uniform
+                float pv[48], dv[48];
+                tmem_ld16(t_base + h * 48 + 0, pv);
+                tmem_ld16(t_base + h * 48 + 16, pv + 16);
+                tmem_ld16(t_base + h * 48 + 32, pv + 32);
+                if (MODE == MODE_APPLY) {
+                    tmem_ld16(t_base + FBN + h * 48 + 0, dv);
+                    tmem_ld16(t_base + FBN + h * 48 + 16, dv + 16);
+                    tmem_ld16(t_base + FBN + h * 48 + 32, dv + 32);
+                }
+                tmem_ld_wait();
+                // per-sample bias rows of this pass (a pass of 16 points lies inside one sample unless it straddles a boundary)
+                float bp[3] = {0.f, 0.f, 0.f}, bd[3] = {0.f, 0.f, 0.f};
+                long long pt0 = r0 / 3;
+                long long b0 = 0;
+                bool uniform_sample = true;
+                if (bias) {
+                    b0 = pt0 / pts_per_sample;
+                    uniform_sample = (pt0 + 15) / pts_per_sample == b0;
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        bp[v] = __ldg(bias + (size_t)(b0 * 3 + v) * ldbias + c);
+                        if (MODE == MODE_APPLY) bd[v] = __ldg(bias + (size_t)(b0 * 3 + v) * ldbias + C + c);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const long long r = r0 + 3 * j;
+                    if (r >= R) break;
+                    if (bias && !uniform_sample) {
+                        const long long bb = (pt0 + j) / pts_per_sample;
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+                            bp[v] = __ldg(bias + (size_t)(bb * 3 + v) * ldbias + c);
+                            if (MODE == MODE_APPLY) bd[v] = __ldg(bias + (size_t)(bb * 3 + v) * ldbias + C + c);
+                        }
+                    }
+                    float p0 = pv[3 * j] + bp[0], p1 = pv[3 * j + 1] + bp[1], p2 = pv[3 * j + 2] + bp[2];
+                    const float nrm2 = __fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2));
+                    if (MODE == MODE_STATS) {
+                        const double n = (double)(sqrtf(nrm2) + 1e-6f);
+                        s1 += n;
+                        s2 = fma(n, n, s2);
+                    } else {
+                        if (stat) {
+                            const float n = (FAST ? (nrm2 > 0.f ? nrm2 * rsqrtf(nrm2) : 0.f) : sqrtf(nrm2)) + 1e-6f;
+                            const float nb = ((n - mean) * invstd) * ga + be;
+                            if (FAST) {
+                                const float t = __fdividef(nb, n);
+                                p0 *= t;
+                                p1 *= t;
+                                p2 *= t;
+                            } else {
+                                p0 = p0 / n * nb;
+                                p1 = p1 / n * nb;
+                                p2 = p2 / n * nb;
+                            }
+                        }
+                        const float d0 = dv[3 * j] + bd[0], d1 = dv[3 * j + 1] + bd[1], d2 = dv[3 * j + 2] + bd[2];
+                        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(p0, d0), __fmul_rn(p1, d1)), __fmul_rn(p2, d2));
+                        float i0 = p0, i1 = p1, i2 = p2;
+                        if (!(dot >= 0.f)) {
+                            const float dsq = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), 1e-6f);
+                            const float a = FAST ? __fdividef(dot, dsq) : dot / dsq;
+                            i0 = __fsub_rn(p0, __fmul_rn(a, d0));
+                            i1 = __fsub_rn(p1, __fmul_rn(a, d1));
+                            i2 = __fsub_rn(p2, __fmul_rn(a, d2));
+                        }
+                        float* dst = out + (size_t)r * ldo + c;
+                        dst[0] = __fadd_rn(__fmul_rn(ns, p0), __fmul_rn(k1, i0));
+                        dst[ldo] = __fadd_rn(__fmul_rn(ns, p1), __fmul_rn(k1, i1));
+                        dst[2 * ldo] = __fadd_rn(__fmul_rn(ns, p2), __fmul_rn(k1, i2));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (MODE == MODE_STATS && stat_c >= 0) {
+            atomicAdd(sums + stat_c, s1);
+            atomicAdd(sums + C + stat_c, s2);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // weight gradient:  G[o, k] += sum_{r in chunk} dY[r, o] X[r, k]      (both operands MN-major, split over r)
 //   A = dY^T : MN-major, 4 slabs of {32 o} x BR rows ; B = X : MN-major, BNW/32 slabs of {32 k} x BR rows
@@ -504,6 +762,31 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     return last_error();
 }
 
+
+template <int MODE, bool FAST>
+static int launch_fused(const float* X, long long ldx, const float* Wcat, long long ldw, float* out, long long ldo, long long R, int K,
+                        int C, const float* bias, long long ldbias, long long rps, const float* stat, const float* gamma,
+                        const float* beta, float ns, double* sums, cudaStream_t st) {
+    constexpr int STAGES = 4;
+    using L = FusedSmem<STAGES, MODE>;
+    CUtensorMap mw, mx;
+    if (!make_map(&mw, Wcat, MODE == MODE_APPLY ? 2 * C : C, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
+    if (!make_map(&mx, X, R, K, ldx, BK, FBN)) return VNPCC_ERR_DRIVER;
+    auto kern = gemm_vn_fused_kernel<STAGES, MODE, FAST>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
+        attr_done = true;
+    }
+    const int num_m = C / BM;
+    const long long num_n = (R + FBN - 1) / FBN;
+    const long long num_tiles = num_m * num_n;
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    count_launch(), kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(mw, mx, out, (size_t)ldo, R, K, C, bias, (size_t)ldbias, rps, stat, gamma, beta,
+                                                             ns, sums, num_m, num_tiles);
+    return last_error();
+}
+
 }  // namespace tc
 }  // namespace vnpcc
 
@@ -522,6 +805,36 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
     cudaStream_t st = (cudaStream_t)stream;
     if (R <= 128) return tc::launch_rows<128, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
     return tc::launch_rows<256, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
+}
+
+static bool fused_ok(const float* X, long long ldx, const float* W, long long ldw, long long R, int K, int C, const float* bias,
+                     long long rps) {
+    return R > 0 && R % 3 == 0 && R < (1ll << 31) && K >= 32 && (K & 3) == 0 && (ldx & 3) == 0 && (ldw & 3) == 0 && tc::aligned16(X) &&
+           tc::aligned16(W) && C >= 128 && (C % 128) == 0 && (!bias || (rps > 0 && rps % 3 == 0));
+}
+
+// VNLinearLeakyReLU forward with the VN tail fused into the tcgen05 GEMM epilogue (no-grad / inference path).
+//   Wcat [2C, K] = (W_feat ; W_dir) stacked, bias [B*3, 2C] per-sample rows or NULL, stat [2C] = (mean | invstd) or NULL (no BN).
+// vnpcc_gemm_vn_stats: batch statistics of ||W_feat x + b_p|| (sums: 2C doubles, zeroed here) without writing anything else.
+int vnpcc_gemm_vn_stats(const float* X, long long ldx, const float* Wcat, long long ldw, long long R, int K, int C, const float* bias,
+                        long long ldbias, long long rows_per_sample, double* sums, void* stream) {
+    if (!fused_ok(X, ldx, Wcat, ldw, R, K, C, bias, rows_per_sample)) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    return tc::launch_fused<tc::MODE_STATS, false>(X, ldx, Wcat, ldw, nullptr, 0, R, K, C, bias, ldbias, rows_per_sample, nullptr, nullptr,
+                                                   nullptr, 0.f, sums, st);
+}
+
+int vnpcc_gemm_vn_apply(const float* X, long long ldx, const float* Wcat, long long ldw, float* out, long long ldo, long long R, int K,
+                        int C, const float* bias, long long ldbias, long long rows_per_sample, const float* stat, const float* gamma,
+                        const float* beta, float ns, void* stream) {
+    if (!fused_ok(X, ldx, Wcat, ldw, R, K, C, bias, rows_per_sample)) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fast_math_enabled())
+        return tc::launch_fused<tc::MODE_APPLY, true>(X, ldx, Wcat, ldw, out, ldo, R, K, C, bias, ldbias, rows_per_sample, stat, gamma, beta,
+                                                      ns, nullptr, st);
+    return tc::launch_fused<tc::MODE_APPLY, false>(X, ldx, Wcat, ldw, out, ldo, R, K, C, bias, ldbias, rows_per_sample, stat, gamma, beta, ns,
+                                                   nullptr, st);
 }
 
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long, int, int) { return 0; }

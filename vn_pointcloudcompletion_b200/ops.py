@@ -390,6 +390,34 @@ class _BNLeakyDot(torch.autograd.Function):
         return gpd, ggamma, gbeta, None, None, None, gw2.view(1, C), (gy if has_res else None)
 
 
+def linear_bn_leaky_fused_nograd(x, wcat, bias, rows_per_sample, bn, training, ns):
+    """No-grad forward of VNLinearLeakyReLU with BatchNorm-on-norm + leaky projection fused into the tcgen05 GEMM epilogue
+    (csrc/gemm_tcgen05.cu, gemm_vn_fused_kernel): p and d never reach HBM.  Returns None when the shape is not taken (the
+    caller then uses the unfused kernels).  Only used with gradients disabled (validation / test loops, train.py:199-226,
+    test.py:54-72): the training backward needs p and d."""
+    if torch.is_grad_enabled() or _GEMM_MODE != "tf32":
+        return None
+    x = _rows2d(x, "x")
+    R, K = x.shape
+    C = wcat.shape[0] // 2
+    if wcat.stride(1) != 1:
+        wcat = wcat.contiguous()
+    if C % 128 != 0 or K < 32 or K % 4 != 0 or R % 3 != 0 or _ld(x) % 4 != 0 or _ld(wcat) % 4 != 0 or x.data_ptr() % 16 or wcat.data_ptr() % 16:
+        return None
+    ldb = _ld(bias) if bias is not None else 0
+    stat, gamma, beta = None, None, None
+    if bn is not None:
+        def stats_fn(sums):
+            call("vnpcc_gemm_vn_stats", ptr(x), _ld(x), ptr(wcat), _ld(wcat), R, K, C, ptr(bias), ldb, rows_per_sample, ptr(sums), stream())
+        stat, _ = _bn_prepare(None, C, bn, training, R // 3, stats_fn)
+        gamma, beta = bn.weight, bn.bias
+    out = torch.empty((R, C), device=x.device, dtype=torch.float32)
+    with _Timed("gemm_vn_fused", 2.0 * R * K * 2 * C):
+        call("vnpcc_gemm_vn_apply", ptr(x), _ld(x), ptr(wcat), _ld(wcat), ptr(out), C, R, K, C, ptr(bias), ldb, rows_per_sample,
+             ptr(stat), ptr(gamma), ptr(beta), float(ns), stream())
+    return out
+
+
 class _SmallKBNLeaky(torch.autograd.Function):
     """out = leaky(BN(Wf x + b_p), Wd x + b_d) for x with <= 4 channels and per-sample bias rows, p / d never stored
     (csrc/vn_fused.cu)."""

@@ -52,8 +52,10 @@ class VN_PointNet(nn.Module):
         l0 = self.second_conv[0]
         wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [2048,1024]
         bias = ops.linear_rows(g1, wcat[:, :Cg])                                          # [B*3,2048]
-        pd = ops.linear_rows(f1, wcat[:, Cg:], bias, 3 * N)                               # [R,2048]
-        f2 = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)   # [R,1024]
+        f2 = ops.linear_bn_leaky_fused_nograd(f1, wcat[:, Cg:], bias, 3 * N, l0.batchnorm.bn, l0.training, l0.negative_slope)
+        if f2 is None:
+            pd = ops.linear_rows(f1, wcat[:, Cg:], bias, 3 * N)                           # [R,2048]
+            f2 = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)   # [R,1024]
         # second_conv[1] feeds only maxpool2: fused, its [R,2048] output is transient and its backward is sparse
         fg, idx2 = ops.linear_maxpool_rows(f2, self.second_conv[1].map_to_feat.weight, self.maxpool2.map_to_dir.weight, B, N,
                                            self.maxpool2.forced_idx)                       # [B*3,2048]
@@ -120,12 +122,12 @@ class VN_FoldingNet(nn.Module):
             pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                        # [R,512]
             h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
         C1 = l1.map_to_feat.weight.shape[0]
-        if l1.map_to_dir.weight.shape[0] == C1 and ops.bn_leaky_dot_supported(C1):
+        if torch.is_grad_enabled() and l1.map_to_dir.weight.shape[0] == C1 and ops.bn_leaky_dot_supported(C1):
             # final_conv[1] (BN + leaky) fused with final_conv[2] = VNLinear(256,1) and the residual: its [R,256] output
             # and gradient never touch HBM
             pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0))
             fine = ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, local[:, 1])
         else:
-            h = l1.forward_rows(h)
+            h = l1.forward_rows(h)      # no-grad: BN + leaky fused into the tcgen05 GEMM epilogue (vn_layers.VNLinearLeakyReLU)
             fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                     # final VNLinear(256,1) + point_feat
         return fine.view(B, nd, 3)

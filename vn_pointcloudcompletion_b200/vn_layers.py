@@ -121,6 +121,11 @@ class VNLinearLeakyReLU(nn.Module):
         w = torch.cat([wf, wd], dim=0)       # one GEMM for feat and dir: the input rows are read once
         if w_slice is not None:
             w = w[:, w_slice]
+        if self.batchnorm.bn.affine:
+            fused = ops.linear_bn_leaky_fused_nograd(rows, w, bias_rows, rows_per_sample, self.batchnorm.bn, self.training,
+                                                     self.negative_slope)
+            if fused is not None:               # inference: BN + leaky in the GEMM epilogue, p / d never stored
+                return fused
         pd = ops.linear_rows(rows, w, bias_rows, rows_per_sample)
         return ops.bn_leaky(pd, None, self.batchnorm.bn, self.training, self.negative_slope, stacked=True)
 
