@@ -280,6 +280,29 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2.item())
 
+    # inference leg (validation loop of train.py:199-226): eval-mode forward + l1_cd metric under no_grad
+    net.eval()
+    from vn_pointcloudcompletion_b200.loss import l1_cd
+    def step_eval(i):
+        p, c, R = resident[i % pool]
+        with torch.no_grad():
+            coarse, dense = net(p, V.Rotate(R))
+            return l1_cd(dense, c)
+    for i in range(2):
+        step_eval(i)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for i in range(args.steps):
+        step_eval(i)
+    e5.record()
+    barrier()
+    ms3 = torch.tensor([e4.elapsed_time(e5)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+    eval_ms = float(ms3.item())
+    net.train()
+
     if rank == 0:
         pk = peaks()
         samples = B * world * args.steps
@@ -326,6 +349,8 @@ def main():
                            "l2": "per-step activations (>10 GB) exceed the 126 MB L2; inputs rotate over a pool"},
                 "e2e": {"value": (samples / (e2e_ms / 1e3)) if not args.no_e2e else None, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
+                "eval": {"value": B * world * args.steps / (eval_ms / 1e3), "unit": "samples/s",
+                         "what": "eval-mode forward + l1_cd under no_grad (fused VN GEMM epilogue)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_classes": classes,
                 "final_loss": final_loss}
         if world == 1 and not args.no_cpu_baseline:
