@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
+    ap.add_argument("--no-eval", action="store_true", help="skip the inference leg (profiling runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,15 +289,20 @@ def main():
         with torch.no_grad():
             coarse, dense = net(p, V.Rotate(R))
             return l1_cd(dense, c)
-    for i in range(2):
-        step_eval(i)
-    barrier()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for i in range(args.steps):
-        step_eval(i)
-    e5.record()
-    barrier()
+    if args.no_eval:
+        e4.record()
+        e5.record()
+        barrier()
+    else:
+        for i in range(2):
+            step_eval(i)
+        barrier()
+        e4.record()
+        for i in range(args.steps):
+            step_eval(i)
+        e5.record()
+        barrier()
     ms3 = torch.tensor([e4.elapsed_time(e5)], device=dev)
     if world > 1:
         dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
@@ -313,14 +319,14 @@ def main():
         traffic = {}
         tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath))
+            traffic = {k: v for k, v in json.load(open(tpath)).items() if not k.startswith("_")}
         for cls, d in ksum.items():
             sec = d["ms"] / 1e3
             if cls in ("gemm_rows_tf32", "gemm_wgrad_tf32", "sgemm_fp32", "gemm"):
                 tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
                 # TF32 dense peak is half the bf16 one; the driver measures bf16 only
                 peak = (pk["bf16_sustained"] / 2.0) if cls.endswith("tf32") else None
-                classes[cls] = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                classes[cls] = {"bound": "tensor" if peak else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                                 "frac": (tf / peak) if peak else None, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
                                 "launches_per_step": d["launches"] / args.steps,
                                 "flop_per_launch": d["work"] / max(d["launches"], 1),
@@ -349,7 +355,7 @@ def main():
                            "l2": "per-step activations (>10 GB) exceed the 126 MB L2; inputs rotate over a pool"},
                 "e2e": {"value": (samples / (e2e_ms / 1e3)) if not args.no_e2e else None, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
-                "eval": {"value": B * world * args.steps / (eval_ms / 1e3), "unit": "samples/s",
+                "eval": {"value": (B * world * args.steps / (eval_ms / 1e3)) if not args.no_eval else None, "unit": "samples/s",
                          "what": "eval-mode forward + l1_cd under no_grad (fused VN GEMM epilogue)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_classes": classes,
                 "final_loss": final_loss}
