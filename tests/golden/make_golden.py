@@ -14,6 +14,7 @@ Fixtures:
                         rand(4,200,3) through chamfer_python.distChamfer (the reference's CPU-capable Chamfer),
                         plus a ragged/edge set and autograd gradients of sum(dist1)+sum(dist2) and of CD-L1.
   vn_layers.npz         every class of models/vn_layers.py on small seeded inputs: forward, backward, BN buffers.
+  loss_variants.npz     utils/loss.py calc_cd / calc_dcd (+ fscore) of the reference run unmodified on CPU.
   pcn_b6.npz            same as pcn_small at B=6, N=128, GT 1024 (better-conditioned BatchNorm statistics).
   pcn_small.npz         VN_PointNet + VN_FoldingNet (models/pcn.py) at B=2, N=256 under torch.manual_seed(0):
                         inputs, rotation, VNMaxPool selections, coarse / fine, CD-L1 losses, gradient digests,
@@ -102,6 +103,39 @@ def gen_chamfer(out):
         out[f"ch_{name}_l2"] = npy(torch.mean(d1) + torch.mean(d2))                       # metrics/loss.py:42-43
         out[f"ch_{name}_l2cd"] = npy(torch.sum(d1.mean(1) + d2.mean(1)))                  # metrics/metric.py:12-16
         out[f"ch_{name}_l1cd"] = npy(torch.sum(torch.sqrt(d1).mean(1) + torch.sqrt(d2).mean(1)) / 2)  # :19-23
+
+
+def gen_loss_variants(out):
+    """utils/loss.py calc_cd / calc_dcd and fscore, run UNMODIFIED; their only CUDA dependency
+    (chamfer3D.dist_chamfer_3D.chamfer_3DDist) is served by the reference's own CPU Chamfer (chamfer_python.distChamfer)."""
+    import chamfer_python
+    stub = types.ModuleType("chamfer3D")
+    sub = types.ModuleType("chamfer3D.dist_chamfer_3D")
+
+    class chamfer_3DDist(torch.nn.Module):
+        def forward(self, a, b):
+            return chamfer_python.distChamfer(a, b)
+    sub.chamfer_3DDist = chamfer_3DDist
+    stub.dist_chamfer_3D = sub
+    sys.modules["chamfer3D"] = stub
+    sys.modules["chamfer3D.dist_chamfer_3D"] = sub
+    spec = importlib.util.spec_from_file_location("ref_utils_loss", os.path.join(REF, "utils", "loss.py"))
+    L = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(L)
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(3, 200, 3, generator=g) * 0.2
+    gt = torch.rand(3, 300, 3, generator=g) * 0.2
+    out["lv_x"], out["lv_gt"] = npy(x), npy(gt)
+    cd_p, cd_t, f1 = L.calc_cd(x, gt, calc_f1=True)
+    out["lv_cd_p"], out["lv_cd_t"], out["lv_f1"] = npy(cd_p), npy(cd_t), npy(f1)
+    sp, st = L.calc_cd(x, gt, separate=True)
+    out["lv_sep_p"], out["lv_sep_t"] = npy(sp), npy(st)
+    for name, kw in (("dcd", {}), ("dcd_nonreg", dict(non_reg=True, alpha=200, n_lambda=0.5))):
+        xr = x.clone().requires_grad_(True)
+        loss, cp, ct = L.calc_dcd(xr, gt, **kw)
+        loss.sum().backward()
+        out[f"lv_{name}_loss"], out[f"lv_{name}_cd_p"], out[f"lv_{name}_cd_t"] = npy(loss), npy(cp), npy(ct)
+        out[f"lv_{name}_gx"] = npy(xr.grad)
 
 
 def _sd(mod, out, key):
@@ -251,7 +285,7 @@ def main():
     # pcn_b6: same network at B=6 -- with more samples per batch the decoder's BatchNorm-on-norms is far better
     # conditioned than at B=2 (see DESIGN.md "conditioning"), so values can be compared at the north-star 1e-4.
     only = set(sys.argv[1:])
-    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn),
+    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants),
                      ("pcn_b6", lambda o: gen_pcn(o, B=6, n_partial=128, n_gt=1024, seed=17))):
         if only and name not in only:
             continue

@@ -156,3 +156,25 @@ def test_bit_exact_vs_reference_kernel(B, N, M):
     ((d1 * w1).sum() + (d2 * w2).sum()).backward()
     g1, g2 = RC.backward(a.detach(), b.detach(), w1, w2, j1, j2)
     assert torch.allclose(a.grad, g1, rtol=1e-4, atol=1e-5) and torch.allclose(b.grad, g2, rtol=1e-4, atol=1e-5)
+
+
+def test_loss_variants_vs_reference_golden(golden):
+    """calc_cd / calc_dcd / fscore against the reference's utils/loss.py run unmodified (golden fixture)"""
+    from vn_pointcloudcompletion_b200 import loss as L
+    g = golden("loss_variants")
+    x, gt = _dev(g["lv_x"]), _dev(g["lv_gt"])
+    cd_p, cd_t, f1 = L.calc_cd(x, gt, calc_f1=True)
+    np.testing.assert_allclose(cd_p.cpu().numpy(), g["lv_cd_p"], rtol=1e-5)
+    np.testing.assert_allclose(cd_t.cpu().numpy(), g["lv_cd_t"], rtol=1e-5)
+    np.testing.assert_allclose(f1.cpu().numpy(), g["lv_f1"], rtol=1e-5, atol=1e-6)
+    sp, st = L.calc_cd(x, gt, separate=True)
+    np.testing.assert_allclose(sp.cpu().numpy(), g["lv_sep_p"], rtol=1e-5)
+    np.testing.assert_allclose(st.cpu().numpy(), g["lv_sep_t"], rtol=1e-5)
+    for name, kw in (("dcd", {}), ("dcd_nonreg", dict(non_reg=True, alpha=200, n_lambda=0.5))):
+        xr = x.clone().requires_grad_(True)
+        loss, cp, ct = L.calc_dcd(xr, gt, **kw)
+        loss.sum().backward()
+        np.testing.assert_allclose(loss.cpu().detach().numpy(), g[f"lv_{name}_loss"], rtol=1e-5)
+        np.testing.assert_allclose(cp.cpu().detach().numpy(), g[f"lv_{name}_cd_p"], rtol=1e-5)
+        ref = g[f"lv_{name}_gx"]
+        np.testing.assert_allclose(xr.grad.cpu().numpy(), ref, rtol=1e-3, atol=1e-5 * np.abs(ref).max())
