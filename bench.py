@@ -322,10 +322,10 @@ def main():
             traffic = {k: v for k, v in json.load(open(tpath)).items() if not k.startswith("_")}
         for cls, d in ksum.items():
             sec = d["ms"] / 1e3
-            if cls in ("gemm_rows_tf32", "gemm_wgrad_tf32", "sgemm_fp32", "gemm"):
+            if cls in ("gemm_rows_tf32", "gemm_wgrad_tf32", "gemm_vn_fused", "sgemm_fp32", "gemm"):
                 tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
                 # TF32 dense peak is half the bf16 one; the driver measures bf16 only
-                peak = (pk["bf16_sustained"] / 2.0) if cls.endswith("tf32") else None
+                peak = (pk["bf16_sustained"] / 2.0) if (cls.endswith("tf32") or cls == "gemm_vn_fused") else None
                 classes[cls] = {"bound": "tensor" if peak else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                                 "frac": (tf / peak) if peak else None, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
                                 "launches_per_step": d["launches"] / args.steps,

@@ -136,6 +136,13 @@ int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx,
                    long long ldb, int B, int N, int K, int C, const float* stat, const float* gamma, const float* beta, float ns,
                    int training, double* sums, float* gx, long long ldgx, float* gw, long long ldgw, float* gbias, long long ldgb,
                    float* ggamma, float* gbeta, void* stream);
+/* fused VNLinear -> VNMaxPool forward (TF32): arg-max inside the tcgen05 GEMM epilogue, pooled rows recomputed from the
+ * selected inputs; the [R, C] layer output and its direction are never stored */
+int vnpcc_gemm_vn_pool(const float* X, long long ldx, const float* Wcat, long long ldw, long long R, int K, int C, long long N,
+                       unsigned long long* best, void* stream);
+int vnpcc_vn_maxpool_decode(const unsigned long long* best, long long total, long long* idx, void* stream);
+int vnpcc_pool_linear_gather(const float* x, long long ldx, const float* W, long long ldw, const long long* idx, int B, int N, int C, int K,
+                             float* out, long long ldo, void* stream);
 /* backward of VNLinear -> VNMaxPool without the dense gradient (gx zeroed + scattered, gW gathered; either may be NULL) */
 int vnpcc_pool_linear_bwd(const float* g, long long ldg, const long long* idx, const float* x, long long ldx, const float* W,
                           long long ldw, int B, int N, int C, int K, float* gx, long long ldgx, float* gW, long long ldgw,

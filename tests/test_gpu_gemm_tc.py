@@ -168,3 +168,30 @@ def test_pcn_eval_forward_fused_vs_unfused(tf32_mode):
         c1, f1 = net(p, V.Rotate(R))
     assert (c0.detach() - c1).abs().max() <= 1e-3 * c0.abs().max()
     assert (f0.detach() - f1).abs().max() <= 1e-3 * f0.abs().max()
+
+
+def test_fused_pool_gemm_selects_like_unfused(tf32_mode):
+    """VNLinear -> VNMaxPool with the arg-max inside the tcgen05 epilogue: same TF32 MMA sequence as the unfused GEMMs, so
+    the selections must be identical; pooled rows are recomputed in exact fp32 from the selected inputs"""
+    from vn_pointcloudcompletion_b200 import ops
+    torch.manual_seed(5)
+    G, N, K, C = 3, 100, 64, 256             # N not a multiple of 32: tiles straddle groups
+    x = torch.randn(G * N * 3, K, device="cuda")
+    w = torch.randn(C, K, device="cuda") / 8
+    wdir = torch.randn(C, C, device="cuda") / 16
+    out, idx = ops.linear_maxpool_rows(x, w, wdir, G, N)
+    wc = ops.gemm_rows(wdir, w, True)
+    f = ops.gemm_rows(x, w)
+    d = ops.gemm_rows(x, wc)
+    ref_idx = ops.maxpool_select(f, d, G, N)
+    assert torch.equal(idx, ref_idx)
+    xs = x.view(G, N, 3, K)
+    sel = torch.gather(xs, 1, idx.view(G, C, 1, 1).expand(G, C, 3, K).permute(0, 1, 2, 3).contiguous().view(G, C, 3, K)[:, :, :, :].permute(0, 1, 2, 3))
+    want = torch.einsum("gcvk,ck->gvc", sel.double(), w.double()).reshape(G * 3, C)
+    assert torch.allclose(out.double(), want, rtol=1e-4, atol=1e-4)
+    # gradient path (sparse backward) still works on the fused forward
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    o2, _ = ops.linear_maxpool_rows(x, w, wdir, G, N)
+    o2.sum().backward()
+    assert x.grad.abs().sum() > 0 and w.grad.abs().sum() > 0

@@ -32,6 +32,9 @@ SIGNATURES = {
     "vnpcc_gemm_wgrad_tf32_workspace_bytes": (_sz, [_ll, _i, _i]),
     "vnpcc_gemm_vn_stats": (_i, [_p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _p, _p]),
     "vnpcc_gemm_vn_apply": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _p, _p, _p, _f, _p]),
+    "vnpcc_gemm_vn_pool": (_i, [_p, _ll, _p, _ll, _ll, _i, _i, _ll, _p, _p]),
+    "vnpcc_vn_maxpool_decode": (_i, [_p, _ll, _p, _p]),
+    "vnpcc_pool_linear_gather": (_i, [_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p]),
     "vnpcc_vn_norm_stats": (_i, [_p, _ll, _ll, _i, _p, _p]),
     "vnpcc_bn_finalize": (_i, [_p, _d, _i, _i, _p, _p, _f, _f, _p, _p]),
     "vnpcc_vn_bn_leaky_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p]),

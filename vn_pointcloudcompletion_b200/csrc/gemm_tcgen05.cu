@@ -326,15 +326,20 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 // and only `out` ever reaches HBM: the linear outputs make no HBM round trip at all.
 //   MODE_STATS : feat accumulator only; per-channel sum ||p||, sum ||p||^2 (fp64) for training-mode batch statistics
 //   MODE_APPLY : feat + dir accumulators; writes out [R, C]
+//   MODE_POOL  : VNLinear -> VNMaxPool (models/vn_layers.py:158-167): P = W x (the pooled layer), D = W_dir' x (its direction);
+//                the epilogue forms score = <p, d> per point and keeps the per-channel arg-max (64-bit atomicMax on
+//                (orderable score << 32 | ~n), first maximum wins); neither P nor D is written
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FBN = 96;            // rows per tile: multiple of 3 (whole points) and of 16 (UMMA N granularity)
-constexpr int MODE_STATS = 0, MODE_APPLY = 1;
+constexpr int MODE_STATS = 0, MODE_APPLY = 1, MODE_POOL = 2;
 
-template <int STAGES, int MODE>
+// FBN rows per tile: a multiple of 3 (whole points) and of 16 (UMMA N granularity).  96 with two accumulator stages
+// (epilogue of tile i overlaps the MMAs of tile i+1: the store-heavy APPLY mode), 192 with one stage (light epilogues:
+// STATS / POOL; N = 192 keeps the shared-memory operand traffic per MMA cycle under the 128 B/clk limit).
+template <int STAGES, int MODE, int FBN>
 struct FusedSmem {
     static constexpr int A_BYTES = BM * BK * 4;                       // one weight tile (feat or dir)
-    static constexpr int NA = MODE == MODE_APPLY ? 2 : 1;
-    static constexpr int B_BYTES = 12 * 1024;                         // 96 x 32 fp32 (8-row swizzle groups: 96 = 12 x 8)
+    static constexpr int NA = MODE == MODE_STATS ? 1 : 2;
+    static constexpr int B_BYTES = FBN * BK * 4;
     static constexpr int STAGE_BYTES = NA * A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
@@ -355,13 +360,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int STAGES, int MODE, bool FAST>
+template <int STAGES, int MODE, bool FAST, int FBN, int NACC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ out,
                      size_t ldo, long long R, int K, int C, const float* __restrict__ bias, size_t ldbias, long long rows_per_sample,
                      const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
                      double* __restrict__ sums, int num_m, long long num_tiles) {
-    using L = FusedSmem<STAGES, MODE>;
+    using L = FusedSmem<STAGES, MODE, FBN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -383,7 +388,7 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NACC; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], 4);
         }
@@ -407,7 +412,7 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     uint8_t* sb = sa + L::NA * L::A_BYTES;
                     mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
                     tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
-                    if (MODE == MODE_APPLY) tma_load_2d(&map_w, &full_bar[ps.stage], sa + L::A_BYTES, kb * BK, C + m0);
+                    if (MODE != MODE_STATS) tma_load_2d(&map_w, &full_bar[ps.stage], sa + L::A_BYTES, kb * BK, C + m0);
                     tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
                     ps.advance<STAGES>();
                 }
@@ -433,14 +438,14 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t bd = make_desc(sb + k * UMMA_K * 4, 16, 1024);
                         umma_tf32(p_tmem, make_desc(sa + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (MODE == MODE_APPLY)
+                        if (MODE != MODE_STATS)
                             umma_tf32(d_tmem, make_desc(sa + L::A_BYTES + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[ps.stage]);
                     ps.advance<STAGES>();
                 }
                 umma_commit(&tfull_bar[acc]);
-                if (++acc == 2) {
+                if (++acc == NACC) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -452,6 +457,9 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         uint32_t acc_phase = 0;
         double s1 = 0.0, s2 = 0.0;
         int stat_c = -1;                 // channel whose statistics s1/s2 currently hold
+        long long pool_g = -1;           // MODE_POOL: group (sample) of the running winner
+        unsigned long long pool_key = 0;
+        unsigned long long* pool_best = reinterpret_cast<unsigned long long*>(sums);
         const float k1 = 1.f - ns;
         const long long pts_per_sample = rows_per_sample > 0 ? rows_per_sample / 3 : 1;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -484,7 +492,7 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 tmem_ld16(t_base + h * 48 + 0, pv);
                 tmem_ld16(t_base + h * 48 + 16, pv + 16);
                 tmem_ld16(t_base + h * 48 + 32, pv + 32);
-                if (MODE == MODE_APPLY) {
+                if (MODE != MODE_STATS) {
                     tmem_ld16(t_base + FBN + h * 48 + 0, dv);
                     tmem_ld16(t_base + FBN + h * 48 + 16, dv + 16);
                     tmem_ld16(t_base + FBN + h * 48 + 32, dv + 32);
@@ -493,6 +501,8 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 // per-sample bias rows of this pass (a pass of 16 points lies inside one sample unless it straddles a boundary)
                 float bp[3] = {0.f, 0.f, 0.f}, bd[3] = {0.f, 0.f, 0.f};
                 long long pt0 = r0 / 3;
+                const long long pool_g0 = MODE == MODE_POOL ? pt0 / pts_per_sample : 0;
+                const long long pool_n0 = MODE == MODE_POOL ? pt0 - pool_g0 * pts_per_sample : 0;
                 long long b0 = 0;
                 bool uniform_sample = true;
                 if (bias) {
@@ -515,6 +525,30 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             bp[v] = __ldg(bias + (size_t)(bb * 3 + v) * ldbias + c);
                             if (MODE == MODE_APPLY) bd[v] = __ldg(bias + (size_t)(bb * 3 + v) * ldbias + C + c);
                         }
+                    }
+                    if (MODE == MODE_POOL) {
+                        // score = (x*d).sum(2): three rounded products summed left to right (vn_layers.py:163)
+                        const float sc = __fadd_rn(__fadd_rn(__fmul_rn(pv[3 * j], dv[3 * j]), __fmul_rn(pv[3 * j + 1], dv[3 * j + 1])),
+                                                   __fmul_rn(pv[3 * j + 2], dv[3 * j + 2]));
+                        // group / index-in-group of point pt0 + j without a division per point
+                        long long g = pool_g0;
+                        long long nn = pool_n0 + j;
+                        while (nn >= pts_per_sample) {
+                            nn -= pts_per_sample;
+                            ++g;
+                        }
+                        const unsigned n = (unsigned)nn;
+                        unsigned u = __float_as_uint(sc);
+                        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                        const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - n);
+                        if (g != pool_g) {
+                            if (pool_g >= 0) atomicMax(pool_best + (size_t)pool_g * C + c, pool_key);
+                            pool_g = g;
+                            pool_key = key;
+                        } else {
+                            pool_key = key > pool_key ? key : pool_key;
+                        }
+                        continue;
                     }
                     float p0 = pv[3 * j] + bp[0], p1 = pv[3 * j + 1] + bp[1], p2 = pv[3 * j + 2] + bp[2];
                     const float nrm2 = __fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2));
@@ -554,10 +588,14 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     }
                 }
             }
+            if (MODE == MODE_POOL && pool_g >= 0) {      // flush this tile's winner (the next tile may belong to other channels)
+                atomicMax(pool_best + (size_t)pool_g * C + c, pool_key);
+                pool_g = -1;
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) {
+            if (++acc == NACC) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -767,12 +805,14 @@ template <int MODE, bool FAST>
 static int launch_fused(const float* X, long long ldx, const float* Wcat, long long ldw, float* out, long long ldo, long long R, int K,
                         int C, const float* bias, long long ldbias, long long rps, const float* stat, const float* gamma,
                         const float* beta, float ns, double* sums, cudaStream_t st) {
-    constexpr int STAGES = 4;
-    using L = FusedSmem<STAGES, MODE>;
+    constexpr int FBN = MODE == MODE_APPLY ? 96 : 192;
+    constexpr int NACC = MODE == MODE_APPLY ? 2 : 1;
+    constexpr int STAGES = MODE == MODE_POOL ? 3 : 4;
+    using L = FusedSmem<STAGES, MODE, FBN>;
     CUtensorMap mw, mx;
-    if (!make_map(&mw, Wcat, MODE == MODE_APPLY ? 2 * C : C, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
+    if (!make_map(&mw, Wcat, MODE == MODE_STATS ? C : 2 * C, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
     if (!make_map(&mx, X, R, K, ldx, BK, FBN)) return VNPCC_ERR_DRIVER;
-    auto kern = gemm_vn_fused_kernel<STAGES, MODE, FAST>;
+    auto kern = gemm_vn_fused_kernel<STAGES, MODE, FAST, FBN, NACC>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
@@ -835,6 +875,17 @@ int vnpcc_gemm_vn_apply(const float* X, long long ldx, const float* Wcat, long l
                                                       ns, nullptr, st);
     return tc::launch_fused<tc::MODE_APPLY, false>(X, ldx, Wcat, ldw, out, ldo, R, K, C, bias, ldbias, rows_per_sample, stat, gamma, beta, ns,
                                                    nullptr, st);
+}
+
+// VNLinear(K -> C) followed by VNMaxPool(C) over groups of N consecutive points, arg-max only: Wcat [2C, K] = (W ; W_dir W),
+// best: G*C u64 (zeroed here), decoded by vnpcc_vn_maxpool_decode.  Neither the [R, C] layer output nor its direction is stored.
+int vnpcc_gemm_vn_pool(const float* X, long long ldx, const float* Wcat, long long ldw, long long R, int K, int C, long long N,
+                       unsigned long long* best, void* stream) {
+    if (!fused_ok(X, ldx, Wcat, ldw, R, K, C, nullptr, 0) || N <= 0 || R % (3 * N) != 0 || N >= (1ll << 31)) return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)(R / (3 * N)) * C, st);
+    return tc::launch_fused<tc::MODE_POOL, false>(X, ldx, Wcat, ldw, nullptr, 0, R, K, C, nullptr, 0, 3 * N, nullptr, nullptr, nullptr, 0.f,
+                                                  reinterpret_cast<double*>(best), st);
 }
 
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long, int, int) { return 0; }

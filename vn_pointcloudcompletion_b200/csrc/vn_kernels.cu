@@ -697,6 +697,42 @@ __global__ void __launch_bounds__(256) pool_linear_bwd_w_kernel(const float* __r
     }
 }
 
+
+// pooled output of  VNLinear -> VNMaxPool  recomputed from the selected input rows (the layer output itself was never
+// stored by the fused pooling GEMM):  out[(b,v), c] = sum_k W[c,k] * x[(b, idx[b,c], v), k].  One warp per (b, c).
+__global__ void __launch_bounds__(256) pool_linear_gather_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ W,
+                                                                  size_t ldw, const long long* __restrict__ idx, int B, int N, int C,
+                                                                  int K, float* __restrict__ out, size_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (long long)B * C) return;
+    const int b = (int)(warp / C), c = (int)(warp - (long long)b * C);
+    const long long n = idx[warp];
+    const float* xr = x + (((size_t)b * N + n) * 3) * ldx;
+    const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)c * ldw);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int q = lane; q < (K >> 2); q += 32) {
+        const float4 w = __ldg(w4 + q);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(xr) + q);
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(xr + ldx) + q);
+        const float4 x2 = __ldg(reinterpret_cast<const float4*>(xr + 2 * ldx) + q);
+        a0 = fmaf(w.x, x0.x, fmaf(w.y, x0.y, fmaf(w.z, x0.z, fmaf(w.w, x0.w, a0))));
+        a1 = fmaf(w.x, x1.x, fmaf(w.y, x1.y, fmaf(w.z, x1.z, fmaf(w.w, x1.w, a1))));
+        a2 = fmaf(w.x, x2.x, fmaf(w.y, x2.y, fmaf(w.z, x2.z, fmaf(w.w, x2.w, a2))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        out[((size_t)b * 3 + 0) * ldo + c] = a0;
+        out[((size_t)b * 3 + 1) * ldo + c] = a1;
+        out[((size_t)b * 3 + 2) * ldo + c] = a2;
+    }
+}
+
 }  // namespace vnpcc
 
 using namespace vnpcc;
@@ -985,6 +1021,22 @@ int vnpcc_bn_leaky_dot_bwd1(const float* gy, const float* p, long long ldp, cons
 int vnpcc_double_to_float(const double* in, float* out, int n, void* stream) {
     if (n <= 0) return 0;
     count_launch(), double_to_float_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, out, n);
+    return last_error();
+}
+
+int vnpcc_vn_maxpool_decode(const unsigned long long* best, long long total, long long* idx, void* stream) {
+    if (total <= 0) return 0;
+    count_launch(), vn_maxpool_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(best, total, idx);
+    return last_error();
+}
+
+int vnpcc_pool_linear_gather(const float* x, long long ldx, const float* W, long long ldw, const long long* idx, int B, int N, int C, int K,
+                             float* out, long long ldo, void* stream) {
+    if (B <= 0 || C <= 0) return 0;
+    if ((K & 3) || (ldx & 3) || (ldw & 3) || ((uintptr_t)x & 15) || ((uintptr_t)W & 15)) return VNPCC_ERR_UNSUPPORTED;
+    const long long warps = (long long)B * C;
+    count_launch(), pool_linear_gather_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, (size_t)ldx, W, (size_t)ldw, idx, B, N, C, K, out, (size_t)ldo);
     return last_error();
 }
 

@@ -539,21 +539,34 @@ class _LinearMaxPool(torch.autograd.Function):
         x = _rows2d(x, "x")
         if w.stride(1) != 1:
             w = w.contiguous()
-        f = gemm_rows(x, w)
-        if forced_idx is None:
-            if _GEMM_MODE == "tf32":
-                # d = Wdir (W x) = (Wdir W) x : contract over K (the layer's input width) instead of C >= K
-                wc = gemm_rows(wdir, w, True)
-                d = gemm_rows(x, wc)
-            else:
-                d = gemm_rows(f, wdir)       # reference order of operations (parity mode)
-            idx = maxpool_select(f, d, G, N)
-            del d
-        else:
+        C, K = w.shape
+        idx = None
+        if forced_idx is not None:
             idx = forced_idx.reshape(G, -1).contiguous()
-        C = f.shape[1]
+        elif _GEMM_MODE == "tf32":
+            # d = Wdir (W x) = (Wdir W) x: contract over K (the layer's input width) instead of C >= K, and run both
+            # GEMMs as ONE tcgen05 kernel whose epilogue does the arg-max: neither f nor d is written to HBM
+            wc = gemm_rows(wdir, w, True)
+            wcat = torch.cat([w, wc], dim=0)
+            best = torch.empty(G * C, device=x.device, dtype=torch.int64)
+            with _Timed("gemm_vn_fused", 2.0 * x.shape[0] * K * 2 * C):
+                rc = _lib.raw("vnpcc_gemm_vn_pool", ptr(x), _ld(x), ptr(wcat), _ld(wcat), x.shape[0], K, C, N, ptr(best), stream())
+            if rc == 0:
+                idx = torch.empty((G, C), device=x.device, dtype=torch.int64)
+                call("vnpcc_vn_maxpool_decode", ptr(best), G * C, ptr(idx), stream())
+            elif rc != 10003:
+                raise _lib.VnpccError(f"vnpcc_gemm_vn_pool failed with code {rc}")
         out = torch.empty((G * 3, C), device=x.device, dtype=torch.float32)
-        call("vnpcc_vn_maxpool_gather", ptr(f), _ld(f), ptr(idx), G, N, C, ptr(out), C, stream())
+        if idx is not None and _GEMM_MODE == "tf32" and K % 4 == 0:
+            # pooled rows recomputed from the selected inputs (exact fp32 dot products)
+            call("vnpcc_pool_linear_gather", ptr(x), _ld(x), ptr(w), _ld(w), ptr(idx), G, N, C, K, ptr(out), C, stream())
+        else:
+            f = gemm_rows(x, w)
+            if idx is None:
+                d = gemm_rows(f, wdir)       # reference order of operations (parity mode)
+                idx = maxpool_select(f, d, G, N)
+                del d
+            call("vnpcc_vn_maxpool_gather", ptr(f), _ld(f), ptr(idx), G, N, C, ptr(out), C, stream())
         ctx.save_for_backward(x, w, idx)
         ctx.cfg = (G, N)
         ctx.mark_non_differentiable(idx)
