@@ -134,8 +134,8 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
                    void* stream);
 int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx, const float* w, long long ldw, const float* bias,
                    long long ldb, int B, int N, int K, int C, const float* stat, const float* gamma, const float* beta, float ns,
-                   int training, double* sums, float* gx, long long ldgx, float* gw, long long ldgw, float* gbias, long long ldgb,
-                   float* ggamma, float* gbeta, void* stream);
+                   int training, double* sums, float* gx, long long ldgx, int gx_first_col, float* gw, long long ldgw, float* gbias,
+                   long long ldgb, float* ggamma, float* gbeta, void* stream);
 /* fused VNLinear -> VNMaxPool forward (TF32): arg-max inside the tcgen05 GEMM epilogue, pooled rows recomputed from the
  * selected inputs; the [R, C] layer output and its direction are never stored */
 int vnpcc_gemm_vn_pool(const float* X, long long ldx, const float* Wcat, long long ldw, long long R, int K, int C, long long N,

@@ -52,7 +52,7 @@ SIGNATURES = {
     "vnpcc_double_to_float": (_i, [_p, _p, _i, _p]),
     "vnpcc_fold_stats": (_i, [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p]),
     "vnpcc_fold_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p, _p, _f, _p, _ll, _p]),
-    "vnpcc_fold_bwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p, _p, _f, _i, _p, _p, _ll, _p, _ll, _p, _ll,
+    "vnpcc_fold_bwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p, _p, _f, _i, _p, _p, _ll, _i, _p, _ll, _p, _ll,
                             _p, _p, _p]),
     "vnpcc_pool_linear_bwd": (_i, [_p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _ll, _p, _ll, _p]),
     "vnpcc_smallk_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _p]),

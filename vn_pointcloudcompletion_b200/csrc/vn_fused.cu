@@ -185,153 +185,308 @@ __device__ __forceinline__ void fold_lane_bwd(const V4x3& pr, V4x3& dv, V4x3& gv
     }
 }
 
+// ---- packed (fp32x2) backward: the four channel lanes of a thread are two pairs; the leaky / BatchNorm backward is
+// written in terms of five dot products per lane (p.p, p.d, d.d, g.p, g.d) so that no per-lane vector temporaries and
+// no divergent branches remain (the `s < 0` case only selects scalar coefficients):
+//     t = nb/n,  s = t (p.d);   if s < 0:  c1 = k (g.d)/q,  a = s/q  (q = d.d + eps)   else c1 = a = 0
+//     dL/dBN(p) = g - c1 d                      dL/dd = -k a g - c1 t p + 2 a c1 d
+//     <dL/dBN(p), p> = g.p - c1 (p.d)           d_nb = that / n
+//     dL/dp = t (g - c1 d) + (dn / r) p,  dn = (gamma d_nb - m1 - nhat m2) invstd - <.,p> nb / n^2       
 template <int KS>
-__global__ void __launch_bounds__(256, 2) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+struct FoldCtx2 {
+    f2 wf[2][KS], wd[2][KS];      // [pair][k]
+    f2 bp[3][2], bd[3][2];        // [component][pair]
+};
+
+template <int KS>
+__device__ __forceinline__ void fold_load_ctx2(FoldCtx2<KS>& cx, const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+                                               size_t ldb, int b, int C, int c0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            cx.wf[h][k] = mk2(__ldg(w + (size_t)(c0 + 2 * h) * ldw + k), __ldg(w + (size_t)(c0 + 2 * h + 1) * ldw + k));
+            cx.wd[h][k] = mk2(__ldg(w + (size_t)(C + c0 + 2 * h) * ldw + k), __ldg(w + (size_t)(C + c0 + 2 * h + 1) * ldw + k));
+        }
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const float4 p4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb + c0)) : make_float4(0, 0, 0, 0);
+        const float4 d4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb + C + c0)) : make_float4(0, 0, 0, 0);
+        cx.bp[v][0] = mk2(p4.x, p4.y);
+        cx.bp[v][1] = mk2(p4.z, p4.w);
+        cx.bd[v][0] = mk2(d4.x, d4.y);
+        cx.bd[v][1] = mk2(d4.z, d4.w);
+    }
+}
+
+struct ChanParams2 {
+    f2 mean[2], invstd[2], gamma[2], beta[2];
+};
+__device__ __forceinline__ ChanParams2 load_params2(const float* stat, const float* gamma, const float* beta, int C, int c0) {
+    ChanParams2 p;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = c0 + 2 * h;
+        p.mean[h] = stat ? mk2(__ldg(stat + c), __ldg(stat + c + 1)) : bc2(0.f);
+        p.invstd[h] = stat ? mk2(__ldg(stat + C + c), __ldg(stat + C + c + 1)) : bc2(0.f);
+        p.gamma[h] = stat ? mk2(__ldg(gamma + c), __ldg(gamma + c + 1)) : bc2(0.f);
+        p.beta[h] = stat ? mk2(__ldg(beta + c), __ldg(beta + c + 1)) : bc2(0.f);
+    }
+    return p;
+}
+
+// everything the two backward passes share for one lane pair
+struct PairBwd {
+    f2 p[3], d[3];       // raw linear outputs
+    f2 t;                // nb / n  (1 without BatchNorm)
+    f2 nhat, nb, rn, rs; // BatchNorm-on-norm pieces: rn = 1/n, rs = 1/r (0 where r == 0)
+    f2 c1, a;            // leaky coefficients (0 where <BN(p), d> >= 0)
+    f2 gxd;              // <dL/dBN(p), p>
+};
+
+template <int KS, bool HAS_BN>
+__device__ __forceinline__ void fold_pair_bwd(PairBwd& o, const FoldCtx2<KS>& cx, int h, const float (&xv)[3][KS], const f2 (&g)[3],
+                                              const ChanParams2& cp, float k1) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        f2 a = cx.bp[v][h], e = cx.bd[v][h];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const f2 xb = bc2(xv[v][k]);
+            a = fma2p(xb, cx.wf[h][k], a);
+            e = fma2p(xb, cx.wd[h][k], e);
+        }
+        o.p[v] = a;
+        o.d[v] = e;
+    }
+    const f2 pd = dot3p(o.p, o.d), dd = dot3p(o.d, o.d), gp = dot3p(g, o.p), gd = dot3p(g, o.d);
+    if (HAS_BN) {
+        const f2 pp = dot3p(o.p, o.p);
+        const f2 rs = rsqrt2(pp);
+        o.rs = mk2(pp.v.x > 0.f ? rs.v.x : 0.f, pp.v.y > 0.f ? rs.v.y : 0.f);
+        const f2 n = fma2p(pp, o.rs, bc2(VS_EPS));            // r + eps
+        o.rn = rcp2(n);
+        o.nhat = (n - cp.mean[h]) * cp.invstd[h];
+        o.nb = fma2p(o.nhat, cp.gamma[h], cp.beta[h]);
+        o.t = o.nb * o.rn;
+    } else {
+        o.t = bc2(1.f);
+        o.nhat = o.nb = o.rn = o.rs = bc2(0.f);
+    }
+    const f2 s = o.t * pd;
+    const f2 rq = rcp2(dd + bc2(VS_EPS));
+    const bool mx = s.v.x < 0.f, my = s.v.y < 0.f;
+    o.a = sel0(mx, my, s * rq);
+    o.c1 = sel0(mx, my, bc2(k1) * (gd * rq));
+    o.gxd = gp - o.c1 * pd;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
                                                              const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
                                                              size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
                                                              double* __restrict__ sums) {
     extern __shared__ double fold_sh[];
-    FOLD_PROLOGUE
-    const ChanParams cp = load_params(stat, gamma, beta, C, c0);
+    const int c0 = threadIdx.x * 4;
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);
+    FoldCtx2<KS> cx;
+    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
+    const ChanParams2 cp = load_params2(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
     double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    constexpr int U = 2;     // points in flight per thread: 6 independent 16-byte loads hide the HBM latency at 1 CTA / SM
-    for (int nb0 = n0 + threadIdx.y; nb0 < n1; nb0 += blockDim.y * U) {
-        V4x3 gvu[U];
+    float f1[4] = {0, 0, 0, 0}, f2s[4] = {0, 0, 0, 0};
+    int since_flush = 0;
+    // software pipeline: the gradient rows of the next point are in flight while this one is processed
+    float4 gnext[3];
+    float xnext[3][KS];
+    {
+        const int n = n0 + threadIdx.y;
+        if (n < n1) {
+            const size_t row = ((size_t)b * N + n) * 3;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int n = nb0 + u * blockDim.y;
-            if (n < n1) gvu[u] = ld43(g + (((size_t)b * N + n) * 3) * ldg + c0, ldg);
+            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (row + v) * ldg + c0));
+            fold_load_x<KS>(x, ldx, row, xnext);
+        }
+    }
+#pragma unroll 1
+    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+        float4 g4[3];
+        float xv[3][KS];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            g4[v] = gnext[v];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) xv[v][k] = xnext[v][k];
+        }
+        if (n + (int)blockDim.y < n1) {
+            const size_t rown = ((size_t)b * N + n + blockDim.y) * 3;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (rown + v) * ldg + c0));
+            fold_load_x<KS>(x, ldx, rown, xnext);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int n = nb0 + u * blockDim.y;
-            if (n >= n1) break;
-            const size_t row = ((size_t)b * N + n) * 3;
-            float xv[3][KS];
-            fold_load_x<KS>(x, ldx, row, xv);
-            V4x3 pr, dv;
-            fold_pd<KS, true>(cx, xv, pr, dv);
+        for (int h = 0; h < 2; ++h) {
+            f2 gg[3];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) gg[v] = h == 0 ? mk2(g4[v].x, g4[v].y) : mk2(g4[v].z, g4[v].w);
+            PairBwd o;
+            fold_pair_bwd<KS, true>(o, cx, h, xv, gg, cp, k1);
+            const f2 dnb = o.gxd * o.rn;
+            const f2 dn2 = dnb * o.nhat;
+            f1[2 * h] += dnb.v.x;
+            f1[2 * h + 1] += dnb.v.y;
+            f2s[2 * h] += dn2.v.x;
+            f2s[2 * h + 1] += dn2.v.y;
+        }
+        if (++since_flush == 32) {         // short fp32 partial sums, flushed to fp64 (the totals feed a mean subtraction)
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
-                float nn, nhat, nb;
-                fold_lane_bwd(pr, dv, gvu[u], l, cp, true, k1, nn, nhat, nb);
-                const float dnb = dot3l(gvu[u], pr, l) * frcp(nn);
-                acc[0][l] += (double)dnb;
-                acc[1][l] = fma((double)dnb, (double)nhat, acc[1][l]);
+                acc[0][l] += (double)f1[l];
+                acc[1][l] += (double)f2s[l];
+                f1[l] = f2s[l] = 0.f;
             }
+            since_flush = 0;
         }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        acc[0][l] += (double)f1[l];
+        acc[1][l] += (double)f2s[l];
     }
     fold_reduce_channels<2>(acc, sums, C, c0, fold_sh);
 }
 
-// pass B: gW (2C x KS, fp32 atomics), gbias ([B*3, 2C], fp32 atomics), gx ([R, KS], plain stores)
+// pass B: gW (2C x KS, fp32 atomics), gbias ([B*3, 2C], fp32 atomics), gx ([R, KS], red.add; only columns >= gx_k0)
 template <int KS>
-__global__ void __launch_bounds__(256, 2) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+__global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
                                                              const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
                                                              size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
                                                              const double* __restrict__ sums, double count, int training,
-                                                             float* __restrict__ gx, size_t ldgx, float* __restrict__ gw, size_t ldgw,
-                                                             float* __restrict__ gbias, size_t ldgb) {
+                                                             float* __restrict__ gx, size_t ldgx, int gx_k0, float* __restrict__ gw,
+                                                             size_t ldgw, float* __restrict__ gbias, size_t ldgb) {
     extern __shared__ double fold_sh[];
     float* shf = reinterpret_cast<float*>(fold_sh);
-    FOLD_PROLOGUE
+    const int c0 = threadIdx.x * 4;
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);
+    FoldCtx2<KS> cx;
+    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
     const bool has_bn = stat != nullptr;
-    const ChanParams cp = load_params(stat, gamma, beta, C, c0);
+    const ChanParams2 cp = load_params2(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
-    float m1[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
-    if (has_bn && training) {
+    f2 m1[2], m2[2];
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            m1[l] = (float)(sums[c0 + l] / count) * cp.gamma[l];
-            m2[l] = (float)(sums[C + c0 + l] / count) * cp.gamma[l];
+    for (int h = 0; h < 2; ++h) {
+        m1[h] = m2[h] = bc2(0.f);
+        if (has_bn && training) {
+            const int c = c0 + 2 * h;
+            m1[h] = mk2((float)(sums[c] / count), (float)(sums[c + 1] / count)) * cp.gamma[h];
+            m2[h] = mk2((float)(sums[C + c] / count), (float)(sums[C + c + 1] / count)) * cp.gamma[h];
         }
     }
-    float awf[KS][4], awd[KS][4], abp[3][4], abd[3][4];
+    f2 awf[KS][2], awd[KS][2], abp[3][2], abd[3][2];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int k = 0; k < KS; ++k) awf[k][l] = awd[k][l] = 0.f;
+        for (int k = 0; k < KS; ++k) awf[k][h] = awd[k][h] = bc2(0.f);
 #pragma unroll
-        for (int v = 0; v < 3; ++v) abp[v][l] = abd[v][l] = 0.f;
+        for (int v = 0; v < 3; ++v) abp[v][h] = abd[v][h] = bc2(0.f);
     }
     const int lane = threadIdx.x & 31;
-    constexpr int U = 2;     // points in flight per thread
-    for (int nb0 = n0 + threadIdx.y; nb0 < n1; nb0 += blockDim.y * U) {
-        V4x3 gvu[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int n = nb0 + u * blockDim.y;
-            if (n < n1) gvu[u] = ld43(g + (((size_t)b * N + n) * 3) * ldg + c0, ldg);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int n = nb0 + u * blockDim.y;
-            if (n >= n1) break;          // uniform within a warp (a block row spans whole warps)
-            V4x3& gv = gvu[u];
+    float4 gnext[3];
+    float xnext[3][KS];
+    {
+        const int n = n0 + threadIdx.y;
+        if (n < n1) {
             const size_t row = ((size_t)b * N + n) * 3;
-            float xv[3][KS];
-            fold_load_x<KS>(x, ldx, row, xv);
-            V4x3 pr, dv;
-            fold_pd<KS, true>(cx, xv, pr, dv);
-            float gxp[3][KS];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (row + v) * ldg + c0));
+            fold_load_x<KS>(x, ldx, row, xnext);
+        }
+    }
+#pragma unroll 1
+    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+        const size_t row = ((size_t)b * N + n) * 3;
+        float4 g4[3];
+        float xv[3][KS];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            g4[v] = gnext[v];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) xv[v][k] = xnext[v][k];
+        }
+        if (n + (int)blockDim.y < n1) {
+            const size_t rown = ((size_t)b * N + n + blockDim.y) * 3;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (rown + v) * ldg + c0));
+            fold_load_x<KS>(x, ldx, rown, xnext);
+        }
+        f2 gxp[3][KS];
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) gxp[v][k] = bc2(0.f);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            f2 gg[3];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) gg[v] = h == 0 ? mk2(g4[v].x, g4[v].y) : mk2(g4[v].z, g4[v].w);
+            PairBwd o;
+            if (has_bn) fold_pair_bwd<KS, true>(o, cx, h, xv, gg, cp, k1);
+            else fold_pair_bwd<KS, false>(o, cx, h, xv, gg, cp, k1);
+            // dL/dd = (-k a) g + (-c1 t) p + (2 a c1) d ;  dL/dp = t (g - c1 d) + ur p
+            const f2 ca = neg2(bc2(k1) * o.a), cb = neg2(o.c1 * o.t), cc = bc2(2.f) * (o.a * o.c1);
+            f2 ur = bc2(0.f);
+            if (has_bn) {
+                const f2 dnb = o.gxd * o.rn;
+                f2 dn = cp.gamma[h] * dnb;
+                if (training) dn = dn - m1[h] - o.nhat * m2[h];
+                dn = dn * cp.invstd[h] - o.gxd * (o.nb * (o.rn * o.rn));
+                ur = dn * o.rs;
+            }
+            const f2 tc1 = o.t * o.c1;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const f2 gdv = fma2p(cc, o.d[v], fma2p(cb, o.p[v], ca * gg[v]));
+                const f2 gpv = fma2p(ur, o.p[v], o.t * gg[v] - tc1 * o.d[v]);
+                abp[v][h] = abp[v][h] + gpv;
+                abd[v][h] = abd[v][h] + gdv;
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    const f2 xb = bc2(xv[v][k]);
+                    awf[k][h] = fma2p(gpv, xb, awf[k][h]);
+                    awd[k][h] = fma2p(gdv, xb, awd[k][h]);
+                    if (k >= gx_k0) gxp[v][k] = fma2p(gpv, cx.wf[h][k], fma2p(gdv, cx.wd[h][k], gxp[v][k]));
+                }
+            }
+        }
+        if (gx) {
+            // per-row reduction over channels: pair halves, warp shuffle, then one red.add per warp (gx zeroed by the launcher)
 #pragma unroll
             for (int v = 0; v < 3; ++v)
 #pragma unroll
-                for (int k = 0; k < KS; ++k) gxp[v][k] = 0.f;
+                for (int k = 0; k < KS; ++k) {
+                    if (k < gx_k0) continue;
+                    float t = gxp[v][k].v.x + gxp[v][k].v.y;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                float nn, nhat, nb;
-                fold_lane_bwd(pr, dv, gv, l, cp, has_bn, k1, nn, nhat, nb);
-                if (has_bn) {
-                    // BatchNorm-on-norm backward (vn_bn_bwd2): gv <- dL/dp
-                    const float r = nn - VS_EPS;
-                    const float rn = frcp(nn);
-                    const float gxd = dot3l(gv, pr, l);
-                    const float dnb = gxd * rn;
-                    float dn = cp.gamma[l] * dnb;
-                    if (training) dn = dn - m1[l] - nhat * m2[l];
-                    dn = dn * cp.invstd[l] - gxd * nb * rn * rn;
-                    const float sc = nb * rn;
-                    const float ur = r > 0.f ? dn * frcp(r) : 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) gv.v[c][l] = gv.v[c][l] * sc + ur * pr.v[c][l];
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0) atomicAdd(gx + (row + v) * ldgx + k, t);
                 }
-#pragma unroll
-                for (int v = 0; v < 3; ++v) {
-                    const float gpv = gv.v[v][l], gdv = dv.v[v][l];
-                    abp[v][l] += gpv;
-                    abd[v][l] += gdv;
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) {
-                        awf[k][l] = fmaf(gpv, xv[v][k], awf[k][l]);
-                        awd[k][l] = fmaf(gdv, xv[v][k], awd[k][l]);
-                        gxp[v][k] = fmaf(gpv, cx.wf[l][k], fmaf(gdv, cx.wd[l][k], gxp[v][k]));
-                    }
-                }
-            }
-            if (gx) {
-                // per-row reduction over channels: warp shuffle, then one red.add per warp (gx is zeroed by the launcher)
-#pragma unroll
-                for (int v = 0; v < 3; ++v)
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) {
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) gxp[v][k] += __shfl_xor_sync(0xffffffffu, gxp[v][k], o);
-                        if (lane == 0) atomicAdd(gx + (row + v) * ldgx + k, gxp[v][k]);
-                    }
-            }
         }
     }
     // per-channel reductions over the block rows
     __syncthreads();
     float* red = shf;   // [blockDim.y][blockDim.x][4]
-    auto reduce_store = [&](float (&a)[4], float* dst, size_t stride_lane) {
+    auto reduce_store = [&](const f2 (&a)[2], float* dst, size_t stride_lane) {
         __syncthreads();
-#pragma unroll
-        for (int l = 0; l < 4; ++l) red[((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4 + l] = a[l];
+        float* mine = red + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4;
+        mine[0] = a[0].v.x;
+        mine[1] = a[0].v.y;
+        mine[2] = a[1].v.x;
+        mine[3] = a[1].v.y;
         __syncthreads();
         if (threadIdx.y == 0) {
 #pragma unroll
@@ -424,12 +579,13 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
     return last_error();
 }
 
-// g [R, C] = dL/dout.  Outputs: gx [R, K] (may be NULL), gw [2C, K] and gbias [B*3, 2C] (zeroed here, gbias may be NULL),
+// g [R, C] = dL/dout.  Outputs: gx [R, K] (may be NULL; columns < gx_first_col are left zero: inputs that need no
+// gradient, e.g. the constant folding seed), gw [2C, K] and gbias [B*3, 2C] (zeroed here, gbias may be NULL),
 // ggamma / gbeta [C] (written when stat != NULL).  sums: workspace of 2C doubles.
 int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx, const float* w, long long ldw, const float* bias,
                    long long ldb, int B, int N, int K, int C, const float* stat, const float* gamma, const float* beta, float ns,
-                   int training, double* sums, float* gx, long long ldgx, float* gw, long long ldgw, float* gbias, long long ldgb,
-                   float* ggamma, float* gbeta, void* stream) {
+                   int training, double* sums, float* gx, long long ldgx, int gx_first_col, float* gw, long long ldgw, float* gbias,
+                   long long ldgb, float* ggamma, float* gbeta, void* stream) {
     if (!fold_ok(K, C, bias, ldb, g, ldg) || (gbias && ((ldgb & 3) || ((uintptr_t)gbias & 15)))) return VNPCC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemset2DAsync(gw, (size_t)ldgw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)2 * C, st);
@@ -449,7 +605,7 @@ int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx,
     }
     FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_main_kernel<K_><<<grid, block, smem, st>>>(
                             g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C, n_chunk, stat, gamma, beta, ns, sums, count,
-                            training, gx, (size_t)ldgx, gw, (size_t)ldgw, gbias, (size_t)ldgb)));
+                            training, gx, (size_t)ldgx, gx_first_col, gw, (size_t)ldgw, gbias, (size_t)ldgb)));
     if (stat && gbeta) vnpcc_double_to_float(sums, gbeta, C, stream);
     if (stat && ggamma) vnpcc_double_to_float(sums + C, ggamma, C, stream);
     return last_error();

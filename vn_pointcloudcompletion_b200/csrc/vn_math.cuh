@@ -125,6 +125,24 @@ __device__ __forceinline__ void bn_apply_lane(V4x3& v, int l, const ChanParams& 
 }
 
 
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per issue slot) ----
+// A thread's four channel lanes are handled as two pairs; all per-lane scalars of the backward formulas become pairs.
+struct f2 {
+    float2 v;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) { return {make_float2(a, b)}; }
+__device__ __forceinline__ f2 bc2(float a) { return {make_float2(a, a)}; }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { return {__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { return {__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f2 fma2p(f2 a, f2 b, f2 c) { return {__ffma2_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { return {__ffma2_rn(b.v, make_float2(-1.f, -1.f), a.v)}; }   // exact: a + (-1)*b
+__device__ __forceinline__ f2 neg2(f2 a) { return mk2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ f2 rcp2(f2 a) { return mk2(__fdividef(1.f, a.v.x), __fdividef(1.f, a.v.y)); }
+__device__ __forceinline__ f2 rsqrt2(f2 a) { return mk2(rsqrtf(a.v.x), rsqrtf(a.v.y)); }
+// a where the mask half is true, 0 elsewhere
+__device__ __forceinline__ f2 sel0(bool mx, bool my, f2 a) { return mk2(mx ? a.v.x : 0.f, my ? a.v.y : 0.f); }
+__device__ __forceinline__ f2 dot3p(const f2 (&a)[3], const f2 (&b)[3]) { return fma2p(a[2], b[2], fma2p(a[1], b[1], a[0] * b[0])); }
+
 // approximate reciprocal / square root (MUFU, ~1 ulp): used by the BACKWARD kernels only -- gradients do not need the
 // op-by-op IEEE rounding the forward keeps for parity of masks and selections, and IEEE divisions (about ten per lane)
 // made those kernels instruction-bound

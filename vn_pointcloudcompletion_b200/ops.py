@@ -423,20 +423,20 @@ class _SmallKBNLeaky(torch.autograd.Function):
     (csrc/vn_fused.cu)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, gamma, beta, stat, use_batch, ns, B, N):
+    def forward(ctx, x, w, bias, gamma, beta, stat, use_batch, ns, B, N, gx_first_col):
         C = w.shape[0] // 2
         K = x.shape[1]
         out = torch.empty((x.shape[0], C), device=x.device, dtype=torch.float32)
         call("vnpcc_fold_fwd", ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0, B, N, K, C, ptr(stat),
              ptr(gamma), ptr(beta), float(ns), ptr(out), C, stream())
         ctx.save_for_backward(x, w, bias, gamma, beta, stat)
-        ctx.cfg = (B, N, K, C, float(ns), bool(use_batch))
+        ctx.cfg = (B, N, K, C, float(ns), bool(use_batch), int(gx_first_col))
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, w, bias, gamma, beta, stat = ctx.saved_tensors
-        B, N, K, C, ns, use_batch = ctx.cfg
+        B, N, K, C, ns, use_batch, gx_first_col = ctx.cfg
         g = _rows2d(g, "grad")
         dev = x.device
         gx = torch.empty((x.shape[0], K), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
@@ -446,17 +446,18 @@ class _SmallKBNLeaky(torch.autograd.Function):
         ggamma = torch.empty(C, device=dev, dtype=torch.float32) if stat is not None else None
         gbeta = torch.empty(C, device=dev, dtype=torch.float32) if stat is not None else None
         call("vnpcc_fold_bwd", ptr(g), _ld(g), ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0, B, N, K, C,
-             ptr(stat), ptr(gamma), ptr(beta), ns, 1 if use_batch else 0, ptr(sums), ptr(gx), K, ptr(gw), K, ptr(gb), 2 * C,
-             ptr(ggamma), ptr(gbeta), stream())
-        return gx, gw, gb, ggamma, gbeta, None, None, None, None, None
+             ptr(stat), ptr(gamma), ptr(beta), ns, 1 if use_batch else 0, ptr(sums), ptr(gx), K, gx_first_col, ptr(gw), K, ptr(gb),
+             2 * C, ptr(ggamma), ptr(gbeta), stream())
+        return gx, gw, gb, ggamma, gbeta, None, None, None, None, None, None
 
 
 def smallk_bn_leaky_supported(K, C, bias):
     return 1 <= K <= 4 and C % 128 == 0 and C <= 1024 and (bias is None or (bias.stride(0) % 4 == 0 and bias.stride(1) == 1))
 
 
-def smallk_bn_leaky(x, w, bias, bn, training, ns, B, N):
-    """VNLinearLeakyReLU on rows x [B*N*3, K<=4] with stacked weights w [2C, K] and per-sample bias rows [B*3, 2C]"""
+def smallk_bn_leaky(x, w, bias, bn, training, ns, B, N, gx_first_col=0):
+    """VNLinearLeakyReLU on rows x [B*N*3, K<=4] with stacked weights w [2C, K] and per-sample bias rows [B*3, 2C].
+    Input columns < gx_first_col are treated as constants (their gradient is returned as zero and not computed)."""
     x = _rows2d(x, "x")
     _check(w, "weight")
     if w.stride(1) != 1:
@@ -470,7 +471,7 @@ def smallk_bn_leaky(x, w, bias, bn, training, ns, B, N):
                  ptr(sums), stream())
         stat, use_batch = _bn_prepare(None, C, bn, training, B * N, stats_fn)
         gamma, beta = bn.weight, bn.bias
-    return _SmallKBNLeaky.apply(x, w, bias, gamma, beta, stat, use_batch, ns, B, N)
+    return _SmallKBNLeaky.apply(x, w, bias, gamma, beta, stat, use_batch, ns, B, N, gx_first_col)
 
 
 def bn_leaky_dot_supported(C):

@@ -117,7 +117,9 @@ class VN_FoldingNet(nn.Module):
         C0 = l0.map_to_feat.weight.shape[0]
         if ops.smallk_bn_leaky_supported(2, C0, bias) and l0.batchnorm.bn.affine:
             # p = W_feat x + b_p and d = W_dir x + b_d are two FMAs per component: recomputed in every pass, never stored
-            h = ops.smallk_bn_leaky(local, wcat[:, Cg:], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, B, nd)
+            # column 0 of `local` is the folding seed: a constant unless the rotation itself is being differentiated
+            seed_const = 0 if seed_pts.requires_grad else 1
+            h = ops.smallk_bn_leaky(local, wcat[:, Cg:], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, B, nd, seed_const)
         else:
             pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                        # [R,512]
             h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
