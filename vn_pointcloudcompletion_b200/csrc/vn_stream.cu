@@ -190,6 +190,141 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
     }
 }
 
+// Packed (fp32x2) version of the pass above for the case with a direction (HAS_D): the four channel lanes are two pairs
+// and the backward is expressed through the dot products p.p, p.d, d.d, g.p, g.d (see vn_fused.cu for the formulas), so
+// the `s < 0` branch only selects two scalar coefficients and every vector update is a packed FMA.
+template <bool HAS_BN, bool TAIL>
+__global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_p2_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ p,
+                                                                   size_t ldp, const float* __restrict__ d, size_t ldd,
+                                                                   float* __restrict__ gp, size_t ldgp, float* __restrict__ gd,
+                                                                   size_t ldgd, long long P, int C, const float* __restrict__ stat,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float ns, double* __restrict__ sums,
+                                                                   const float* __restrict__ w2, double* __restrict__ gw2) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const bool active = c0 < C;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float s3[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        f2 mean[2], invstd[2], ga[2], be[2], w2p[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = c0 + 2 * h;
+            mean[h] = HAS_BN ? mk2(__ldg(stat + c), __ldg(stat + c + 1)) : bc2(0.f);
+            invstd[h] = HAS_BN ? mk2(__ldg(stat + C + c), __ldg(stat + C + c + 1)) : bc2(0.f);
+            ga[h] = HAS_BN ? mk2(__ldg(gamma + c), __ldg(gamma + c + 1)) : bc2(0.f);
+            be[h] = HAS_BN ? mk2(__ldg(beta + c), __ldg(beta + c + 1)) : bc2(0.f);
+            w2p[h] = TAIL ? mk2(__ldg(w2 + c), __ldg(w2 + c + 1)) : bc2(0.f);
+        }
+        const float k = 1.f - ns;
+        float f1[4] = {0, 0, 0, 0}, f2s[4] = {0, 0, 0, 0};
+        int since_flush = 0;
+        const long long stride = (long long)gridDim.y * 8;
+        for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+            float4 p4[3], d4[3], g4[3];
+            float gy3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                p4[v] = __ldg(reinterpret_cast<const float4*>(p + ((size_t)pt * 3 + v) * ldp + c0));
+                d4[v] = __ldg(reinterpret_cast<const float4*>(d + ((size_t)pt * 3 + v) * ldd + c0));
+                if (TAIL) gy3[v] = __ldg(g + (size_t)pt * 3 + v);
+                else g4[v] = __ldg(reinterpret_cast<const float4*>(g + ((size_t)pt * 3 + v) * ldg + c0));
+            }
+            float4 ogp[3], ogd[3];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                f2 pp_[3], dd_[3], gg[3];
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    pp_[v] = h == 0 ? mk2(p4[v].x, p4[v].y) : mk2(p4[v].z, p4[v].w);
+                    dd_[v] = h == 0 ? mk2(d4[v].x, d4[v].y) : mk2(d4[v].z, d4[v].w);
+                    if (TAIL) gg[v] = bc2(gy3[v]) * w2p[h];
+                    else gg[v] = h == 0 ? mk2(g4[v].x, g4[v].y) : mk2(g4[v].z, g4[v].w);
+                }
+                const f2 pd = dot3p(pp_, dd_), dq = dot3p(dd_, dd_), gpd = dot3p(gg, pp_), gdd = dot3p(gg, dd_);
+                f2 t = bc2(1.f), rn = bc2(0.f), nhat = bc2(0.f);
+                if (HAS_BN) {
+                    const f2 pp = dot3p(pp_, pp_);
+                    f2 rs = rsqrt2(pp);
+                    rs = mk2(pp.v.x > 0.f ? rs.v.x : 0.f, pp.v.y > 0.f ? rs.v.y : 0.f);
+                    const f2 n = fma2p(pp, rs, bc2(VS_EPS));
+                    rn = rcp2(n);
+                    nhat = (n - mean[h]) * invstd[h];
+                    t = fma2p(nhat, ga[h], be[h]) * rn;
+                }
+                const f2 sdot = t * pd;
+                const f2 rq = rcp2(dq + bc2(VS_EPS));
+                const bool mx = sdot.v.x < 0.f, my = sdot.v.y < 0.f;
+                const f2 a = sel0(mx, my, sdot * rq);
+                const f2 c1 = sel0(mx, my, bc2(k) * (gdd * rq));
+                const f2 ca = neg2(bc2(k) * a), cb = neg2(c1 * t), cc = bc2(2.f) * (a * c1);
+                f2 ogpv[3], ogdv[3];
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    ogpv[v] = gg[v] - c1 * dd_[v];                                          // dL/d BN(p)
+                    ogdv[v] = fma2p(cc, dd_[v], fma2p(cb, pp_[v], ca * gg[v]));             // dL/d d
+                    if (h == 0) {
+                        ogp[v].x = ogpv[v].v.x; ogp[v].y = ogpv[v].v.y;
+                        ogd[v].x = ogdv[v].v.x; ogd[v].y = ogdv[v].v.y;
+                    } else {
+                        ogp[v].z = ogpv[v].v.x; ogp[v].w = ogpv[v].v.y;
+                        ogd[v].z = ogdv[v].v.x; ogd[v].w = ogdv[v].v.y;
+                    }
+                }
+                if (HAS_BN) {
+                    const f2 dnb = (gpd - c1 * pd) * rn;
+                    const f2 dn2 = dnb * nhat;
+                    f1[2 * h] += dnb.v.x;
+                    f1[2 * h + 1] += dnb.v.y;
+                    f2s[2 * h] += dn2.v.x;
+                    f2s[2 * h + 1] += dn2.v.y;
+                }
+                if (TAIL) {
+                    // sum_v gy[v] out[v] with out = t p - k a d (the recomputed layer output)
+                    const f2 gyb[3] = {bc2(gy3[0]), bc2(gy3[1]), bc2(gy3[2])};
+                    const f2 q = t * dot3p(gyb, pp_) - (bc2(k) * a) * dot3p(gyb, dd_);
+                    s3[2 * h] += q.v.x;
+                    s3[2 * h + 1] += q.v.y;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                *reinterpret_cast<float4*>(gp + ((size_t)pt * 3 + v) * ldgp + c0) = ogp[v];
+                *reinterpret_cast<float4*>(gd + ((size_t)pt * 3 + v) * ldgd + c0) = ogd[v];
+            }
+            if (HAS_BN && ++since_flush == 32) {
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    s1[l] += (double)f1[l];
+                    s2[l] += (double)f2s[l];
+                    f1[l] = f2s[l] = 0.f;
+                }
+                since_flush = 0;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            s1[l] += (double)f1[l];
+            s2[l] += (double)f2s[l];
+        }
+    }
+    if (HAS_BN) VS_BLOCK_REDUCE2(s1, s2, sums, C, c0)
+    if (TAIL) {
+        __shared__ float sh3[8][32][4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) sh3[threadIdx.y][threadIdx.x][l] = s3[l];
+        __syncthreads();
+        if (threadIdx.y == 0 && active) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                double a = 0.0;
+                for (int i = 0; i < 8; ++i) a += (double)sh3[i][threadIdx.x][l];
+                atomicAdd(gw2 + c0 + l, a);
+            }
+        }
+    }
+}
+
 // fused forward tail: y[r] = sum_c leaky(BN(p), d)[r, c] * w2[c] (+ res[r]); block (C/4, 256/(C/4)): one point per block row
 template <bool HAS_BN, bool FAST>
 __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
@@ -334,9 +469,13 @@ bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long lo
     count_launch(), bn_leaky_bwd1_v4_kernel<BN_, D_, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp,    \
                                                                                      (size_t)ldgp, gd, (size_t)ldgd, P, C, stat, gamma, beta, \
                                                                                      ns, sums, nullptr, nullptr)
-    if (stat && d) VS_BWD(true, true);
+    if (stat && d)
+        count_launch(), bn_leaky_bwd1_p2_kernel<true, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
+                                                                                 gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, nullptr, nullptr);
     else if (stat) VS_BWD(true, false);
-    else if (d) VS_BWD(false, true);
+    else if (d)
+        count_launch(), bn_leaky_bwd1_p2_kernel<false, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
+                                                                                  gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, nullptr, nullptr);
     else VS_BWD(false, false);
 #undef VS_BWD
     return true;
@@ -376,11 +515,11 @@ bool try_bn_leaky_dot_bwd1_v4(const float* gy, const float* p, long long ldp, co
     if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(gp, ldgp) || !ok4(gd, ldgd) || d == nullptr) return false;
     const dim3 grid = stream_grid(P, C), block(32, 8);
     if (stat)
-        count_launch(), bn_leaky_bwd1_v4_kernel<true, true, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
-                                                                                      (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
+        count_launch(), bn_leaky_bwd1_p2_kernel<true, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
+                                                                                (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
     else
-        count_launch(), bn_leaky_bwd1_v4_kernel<false, true, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
-                                                                                       gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
+        count_launch(), bn_leaky_bwd1_p2_kernel<false, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
+                                                                                 (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
     return true;
 }
 
