@@ -511,6 +511,49 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
     }
 }
 
+// throughput-mode forward of the fused small-K layer, packed fp32x2
+template <int KS>
+__global__ void __launch_bounds__(256) fold_fwd_p2_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
+                                                           const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
+                                                           const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float ns, float* __restrict__ out, size_t ldo) {
+    const int c0 = threadIdx.x * 4;
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);
+    FoldCtx2<KS> cx;
+    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
+    const BNPair bn[2] = {load_bn_pair(stat, gamma, beta, C, c0), load_bn_pair(stat, gamma, beta, C, c0 + 2)};
+    const float k1 = 1.f - ns;
+#pragma unroll 2
+    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+        const size_t row = ((size_t)b * N + n) * 3;
+        float xv[3][KS];
+        fold_load_x<KS>(x, ldx, row, xv);
+        f2 o[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            f2 d[3];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                f2 a = cx.bp[v][h], e = cx.bd[v][h];
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    const f2 xb = bc2(xv[v][k]);
+                    a = fma2p(xb, cx.wf[h][k], a);
+                    e = fma2p(xb, cx.wd[h][k], e);
+                }
+                o[h][v] = a;
+                d[v] = e;
+            }
+            if (stat) leaky_bn_pair_fwd<true>(o[h], d, bn[h], k1);
+            else leaky_bn_pair_fwd<false>(o[h], d, bn[h], k1);
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+            *reinterpret_cast<float4*>(out + (row + v) * ldo + c0) = make_float4(o[0][v].v.x, o[0][v].v.y, o[1][v].v.x, o[1][v].v.y);
+    }
+}
+
 static bool fold_ok(int KS, int C, const void* bias, long long ldb, const void* big, long long ldbig) {
     return KS >= 1 && KS <= 4 && (C & 127) == 0 && C <= 1024 && (bias == nullptr || ((ldb & 3) == 0 && ((uintptr_t)bias & 15) == 0)) &&
            (big == nullptr || ((ldbig & 3) == 0 && ((uintptr_t)big & 15) == 0));
@@ -570,8 +613,8 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
     size_t smem;
     fold_geometry(B, N, C, grid, block, n_chunk, smem);
     if (fast_math_enabled()) {
-        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, true><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
-                                                                                            C, n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_p2_kernel<K_><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C,
+                                                                                         n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
     } else {
         FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, false><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
                                                                                              C, n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));

@@ -143,6 +143,37 @@ __device__ __forceinline__ f2 rsqrt2(f2 a) { return mk2(rsqrtf(a.v.x), rsqrtf(a.
 __device__ __forceinline__ f2 sel0(bool mx, bool my, f2 a) { return mk2(mx ? a.v.x : 0.f, my ? a.v.y : 0.f); }
 __device__ __forceinline__ f2 dot3p(const f2 (&a)[3], const f2 (&b)[3]) { return fma2p(a[2], b[2], fma2p(a[1], b[1], a[0] * b[0])); }
 
+// packed throughput-mode forward of one lane pair: out = leaky(BN(p), d) = t p - (k a) d  with  t = nb / n (1 without BN),
+// a = <BN(p), d> / (d.d + eps) where that is negative and 0 elsewhere.  p is overwritten with the output.
+struct BNPair {
+    f2 mean, invstd, gamma, beta;
+};
+template <bool HAS_BN>
+__device__ __forceinline__ void leaky_bn_pair_fwd(f2 (&p)[3], const f2 (&d)[3], const BNPair& bn, float k) {
+    f2 t = bc2(1.f);
+    if (HAS_BN) {
+        const f2 pp = dot3p(p, p);
+        f2 rs = rsqrt2(pp);
+        rs = mk2(pp.v.x > 0.f ? rs.v.x : 0.f, pp.v.y > 0.f ? rs.v.y : 0.f);
+        const f2 n = fma2p(pp, rs, bc2(VS_EPS));
+        const f2 nhat = (n - bn.mean) * bn.invstd;
+        t = fma2p(nhat, bn.gamma, bn.beta) * rcp2(n);
+    }
+    const f2 s = t * dot3p(p, d);
+    const f2 rq = rcp2(dot3p(d, d) + bc2(VS_EPS));
+    const f2 ka = sel0(s.v.x < 0.f, s.v.y < 0.f, bc2(k) * (s * rq));
+#pragma unroll
+    for (int v = 0; v < 3; ++v) p[v] = t * p[v] - ka * d[v];
+}
+__device__ __forceinline__ BNPair load_bn_pair(const float* stat, const float* gamma, const float* beta, int C, int c) {
+    BNPair b;
+    b.mean = stat ? mk2(__ldg(stat + c), __ldg(stat + c + 1)) : bc2(0.f);
+    b.invstd = stat ? mk2(__ldg(stat + C + c), __ldg(stat + C + c + 1)) : bc2(0.f);
+    b.gamma = stat ? mk2(__ldg(gamma + c), __ldg(gamma + c + 1)) : bc2(0.f);
+    b.beta = stat ? mk2(__ldg(beta + c), __ldg(beta + c + 1)) : bc2(0.f);
+    return b;
+}
+
 // approximate reciprocal / square root (MUFU, ~1 ulp): used by the BACKWARD kernels only -- gradients do not need the
 // op-by-op IEEE rounding the forward keeps for parity of masks and selections, and IEEE divisions (about ten per lane)
 // made those kernels instruction-bound

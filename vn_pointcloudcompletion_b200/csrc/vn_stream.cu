@@ -85,6 +85,37 @@ __global__ void __launch_bounds__(256) bn_leaky_fwd_v4_kernel(const float* __res
     }
 }
 
+// throughput-mode (fast math) forward with a direction, packed fp32x2: out = t p - (k a) d per lane pair
+template <bool HAS_BN>
+__global__ void __launch_bounds__(256) bn_leaky_fwd_p2_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
+                                                               size_t ldd, float* __restrict__ out, size_t ldo, long long P, int C,
+                                                               const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float ns) {
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (c0 >= C) return;
+    const BNPair bn[2] = {load_bn_pair(HAS_BN ? stat : nullptr, gamma, beta, C, c0), load_bn_pair(HAS_BN ? stat : nullptr, gamma, beta, C, c0 + 2)};
+    const float k = 1.f - ns;
+    const long long stride = (long long)gridDim.y * 8;
+#pragma unroll 2
+    for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+        float4 p4[3], d4[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            p4[v] = __ldg(reinterpret_cast<const float4*>(p + ((size_t)pt * 3 + v) * ldp + c0));
+            d4[v] = __ldg(reinterpret_cast<const float4*>(d + ((size_t)pt * 3 + v) * ldd + c0));
+        }
+        f2 a[3] = {mk2(p4[0].x, p4[0].y), mk2(p4[1].x, p4[1].y), mk2(p4[2].x, p4[2].y)};
+        f2 b[3] = {mk2(p4[0].z, p4[0].w), mk2(p4[1].z, p4[1].w), mk2(p4[2].z, p4[2].w)};
+        const f2 da[3] = {mk2(d4[0].x, d4[0].y), mk2(d4[1].x, d4[1].y), mk2(d4[2].x, d4[2].y)};
+        const f2 db[3] = {mk2(d4[0].z, d4[0].w), mk2(d4[1].z, d4[1].w), mk2(d4[2].z, d4[2].w)};
+        leaky_bn_pair_fwd<HAS_BN>(a, da, bn[0], k);
+        leaky_bn_pair_fwd<HAS_BN>(b, db, bn[1], k);
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+            *reinterpret_cast<float4*>(out + ((size_t)pt * 3 + v) * ldo + c0) = make_float4(a[v].v.x, a[v].v.y, b[v].v.x, b[v].v.y);
+    }
+}
+
 // TAIL: the consumer of this layer is VNLinear(C,1) (+ residual): its gradient is rank one, g[r,c] = gy[r]*w2[c], so it is
 // formed on the fly (g = gy, ldg unused) and the weight gradient gw2[c] = sum_r gy[r]*out[r,c] is accumulated from the
 // recomputed layer output -- the [R,C] activation and its gradient never exist in HBM.
@@ -335,6 +366,7 @@ __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* _
     __shared__ float part[8][8][3];     // [block row][warp within row][component]
     const int c0 = threadIdx.x * 4;
     const ChanParams cp = load_params(HAS_BN ? stat : nullptr, gamma, beta, C, c0);
+    const BNPair bnp[2] = {load_bn_pair(HAS_BN ? stat : nullptr, gamma, beta, C, c0), load_bn_pair(HAS_BN ? stat : nullptr, gamma, beta, C, c0 + 2)};
     float w2l[4];
 #pragma unroll
     for (int l = 0; l < 4; ++l) w2l[l] = __ldg(w2 + c0 + l);
@@ -348,16 +380,31 @@ __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* _
         if (pt < P) {
             V4x3 v = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
             const V4x3 dv = ld43(d + (size_t)pt * 3 * ldd + c0, ldd);
+            if (FAST) {
+                f2 a[3] = {mk2(v.v[0][0], v.v[0][1]), mk2(v.v[1][0], v.v[1][1]), mk2(v.v[2][0], v.v[2][1])};
+                f2 b[3] = {mk2(v.v[0][2], v.v[0][3]), mk2(v.v[1][2], v.v[1][3]), mk2(v.v[2][2], v.v[2][3])};
+                const f2 da[3] = {mk2(dv.v[0][0], dv.v[0][1]), mk2(dv.v[1][0], dv.v[1][1]), mk2(dv.v[2][0], dv.v[2][1])};
+                const f2 db[3] = {mk2(dv.v[0][2], dv.v[0][3]), mk2(dv.v[1][2], dv.v[1][3]), mk2(dv.v[2][2], dv.v[2][3])};
+                leaky_bn_pair_fwd<HAS_BN>(a, da, bnp[0], k);
+                leaky_bn_pair_fwd<HAS_BN>(b, db, bnp[1], k);
+                const f2 wa = mk2(w2l[0], w2l[1]), wb = mk2(w2l[2], w2l[3]);
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                if (HAS_BN) {
-                    float n, nhat, nb;
-                    bn_apply_lane_t<FAST>(v, l, cp, n, nhat, nb);
+                for (int c = 0; c < 3; ++c) {
+                    const f2 q = fma2p(b[c], wb, a[c] * wa);
+                    acc[c] = q.v.x + q.v.y;
                 }
-                leaky_lane_t<FAST>(v, dv, l, ns, k);
-                acc[0] = fmaf(v.v[0][l], w2l[l], acc[0]);
-                acc[1] = fmaf(v.v[1][l], w2l[l], acc[1]);
-                acc[2] = fmaf(v.v[2][l], w2l[l], acc[2]);
+            } else {
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    if (HAS_BN) {
+                        float n, nhat, nb;
+                        bn_apply_lane_t<FAST>(v, l, cp, n, nhat, nb);
+                    }
+                    leaky_lane_t<FAST>(v, dv, l, ns, k);
+                    acc[0] = fmaf(v.v[0][l], w2l[l], acc[0]);
+                    acc[1] = fmaf(v.v[1][l], w2l[l], acc[1]);
+                    acc[2] = fmaf(v.v[2][l], w2l[l], acc[2]);
+                }
             }
         }
 #pragma unroll
@@ -451,6 +498,15 @@ bool try_bn_leaky_fwd_v4(const float* p, long long ldp, const float* d, long lon
         else                                                                                                                              \
             count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, false><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
                                                                                             C, stat, gamma, beta, ns);                       \
+    }
+    if (fast && d) {
+        if (stat)
+            count_launch(), bn_leaky_fwd_p2_kernel<true><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma,
+                                                                             beta, ns);
+        else
+            count_launch(), bn_leaky_fwd_p2_kernel<false><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma,
+                                                                              beta, ns);
+        return true;
     }
     if (stat && d) VS_FWD(true, true)
     else if (stat) VS_FWD(true, false)
