@@ -155,6 +155,31 @@ int vnpcc_smallk_dgrad(const float* gy, long long ldgy, const float* W, long lon
 int vnpcc_smallk_wgrad(const float* gy, long long ldgy, const float* x, long long ldx, int B, int N, int K, int Cout, float* gW,
                        long long ldgw, float* gbias, long long ldgb, void* stream);
 
+/* ---------------------------------------------------------------- point-set graph ops (VN_DGCNN_fps) -- */
+/* k nearest neighbours of every query among the reference points of the same sample, 3-D (replaces knn_cuda.KNN(k,
+ * transpose_mode=False) at models/dgcnn.py:11,236,257-259).  ref [B,Nr,3], query [B,Nq,3] contiguous fp32 ->
+ * idx [B,k,Nq] int64 (knn_cuda's layout), dist [B,k,Nq] Euclidean distances (may be NULL).  Ordered by (distance, index);
+ * distance = fma(dz,dz,fma(dy,dy,dx*dx)) of fp32 differences.  1 <= k <= min(32, Nr). */
+int vnpcc_knn3d(const float* ref, const float* query, int B, int Nr, int Nq, int k, long long* idx, float* dist, void* stream);
+/* furthest point sampling (replaces pointnet2_utils.furthest_point_sample, models/dgcnn.py:15,210): xyz [B,N,3] ->
+ * idx [B,M] int32; starts at point 0, points with |p|^2 <= 1e-3 never compete, lowest index wins exact ties.  N <= 16384. */
+int vnpcc_fps(const float* xyz, int B, int N, int M, int* idx, void* stream);
+/* pointnet2_utils.gather_operation on the row layout: rows (b,n,v) x C -> rows (b,m,v) x C with n = idx[b,m]; and its adjoint
+ * (gx is zeroed, then accumulated) */
+int vnpcc_points_gather(const float* x, long long ldx, const int* idx, int B, int N, int M, int C, float* out, long long ldo,
+                        void* stream);
+int vnpcc_points_scatter_add(const float* g, long long ldg, const int* idx, int B, int N, int M, int C, float* gx, long long ldgx,
+                             void* stream);
+/* VN_DGCNN_fps.vn_get_graph_feature (models/dgcnn.py:251-278): x rows (b,n,v) x C, idx [B,k,N] -> rows ((b,n,j),v) x 2C =
+ * (x_j - x_i | x_i); adjoint: gx zeroed, then accumulated with fp32 atomics */
+int vnpcc_edge_feature_fwd(const float* x, long long ldx, const long long* idx, int B, int N, int k, int C, float* out, long long ldo,
+                           void* stream);
+int vnpcc_edge_feature_bwd(const float* g, long long ldg, const long long* idx, int B, int N, int k, int C, float* gx, long long ldgx,
+                           void* stream);
+/* mean_pool over the k neighbours (models/vn_layers.py:170-171): rows ((g,j),v) x C -> rows (g,v) x C; adjoint */
+int vnpcc_rows_group_mean(const float* x, long long ldx, long long G, int k, int C, float* out, long long ldo, void* stream);
+int vnpcc_rows_group_mean_bwd(const float* g, long long ldg, long long G, int k, int C, float* gx, long long ldgx, void* stream);
+
 /* ---------------------------------------------------------------- optimiser / misc ------------------------------ */
 /* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
 int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

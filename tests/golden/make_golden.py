@@ -15,6 +15,8 @@ Fixtures:
                         plus a ragged/edge set and autograd gradients of sum(dist1)+sum(dist2) and of CD-L1.
   vn_layers.npz         every class of models/vn_layers.py on small seeded inputs: forward, backward, BN buffers.
   loss_variants.npz     utils/loss.py calc_cd / calc_dcd (+ fscore) of the reference run unmodified on CPU.
+  dgcnn_small.npz       VN_DGCNN_fps (models/dgcnn.py:164-324) at B=3, N=640 with the oracle's kNN / FPS restatement plugged into
+                        its un-vendored knn_cuda / pointnet2_ops imports: searches, outputs, autograd gradients.
   pcn_b6.npz            same as pcn_small at B=6, N=128, GT 1024 (better-conditioned BatchNorm statistics).
   pcn_small.npz         VN_PointNet + VN_FoldingNet (models/pcn.py) at B=2, N=256 under torch.manual_seed(0):
                         inputs, rotation, VNMaxPool selections, coarse / fine, CD-L1 losses, gradient digests,
@@ -279,13 +281,95 @@ def gen_pcn(out, B=2, n_partial=256, n_gt=2048, seed=99):
     out["eval_coarse"], out["eval_fine"] = npy(coarse_e), npy(fine_e)
 
 
+def gen_dgcnn(out, B=3, N=640, seed=5):
+    """the reference's VN_DGCNN_fps (models/dgcnn.py:164-324) run UNMODIFIED on CPU.  Its two third-party
+    CUDA imports (knn_cuda.KNN, pointnet2_ops furthest_point_sample / gather_operation; neither is vendored) are served by the
+    oracle's restatement (oracle/graph_oracle.c); the hard-coded torch.device('cuda') of vn_get_graph_feature
+    (models/dgcnn.py:261) is redirected to the CPU."""
+    import models.dgcnn as D
+    from oracle import graph_oracle as GO
+    rec = {"knn": [], "fps": []}
+
+    def knn_stub(ref, query):                                   # [B,3,N] each -> (dist, idx) [B,k,N]
+        r = np.ascontiguousarray(ref.detach().transpose(1, 2).numpy())
+        q = np.ascontiguousarray(query.detach().transpose(1, 2).numpy())
+        idx, dist = GO.knn3d(r, q, 16)
+        rec["knn"].append(idx)
+        return torch.from_numpy(dist), torch.from_numpy(idx)
+
+    def fps_stub(xyz, m):
+        idx = GO.fps(np.ascontiguousarray(xyz.detach().numpy()), m)
+        rec["fps"].append(idx)
+        return torch.from_numpy(idx)
+
+    def gather_stub(feat, idx):                                  # [B,C,N], [B,M] -> [B,C,M]
+        return torch.gather(feat, 2, idx.long().unsqueeze(1).expand(-1, feat.shape[1], -1))
+
+    class TorchProxy:
+        def __getattr__(self, n):
+            return getattr(torch, n)
+
+        def device(self, *a, **k):
+            return torch.device("cpu")
+
+    D.knn = knn_stub
+    D.pointnet2_utils.furthest_point_sample = fps_stub
+    D.pointnet2_utils.gather_operation = gather_stub
+    D.torch = TorchProxy()
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=512, only_coarse=False, device="cpu", enc_pretrained="none")
+    torch.manual_seed(0)
+    enc = D.VN_DGCNN_fps(cfg)
+    enc.train()
+    for k, v in list(enc.state_dict().items()):
+        out["sd_digest.encoder." + k] = digest(v.float())
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand(B, N, 3, generator=g) - 0.5
+    sel = {}
+
+    def hook(mod, inp, outp):
+        x = inp[0]
+        with torch.no_grad():
+            d = mod.map_to_dir(x.transpose(1, -1)).transpose(1, -1)
+            dot = (x * d).sum(2, keepdims=True)
+            sel["idx"] = dot.max(dim=-1)[1]
+            top2 = dot.squeeze(2).topk(2, dim=-1)[0]
+            sel["gap"] = (top2[..., 0] - top2[..., 1]) / top2[..., 0].abs().clamp_min(1e-30)
+    enc.pool5.register_forward_hook(hook)
+    xin = xyz.clone().requires_grad_(True)
+    coarse, gf = enc(xin)
+    w1 = torch.randn(coarse.shape, generator=g)
+    w2 = torch.randn(gf.shape, generator=g)
+    ((coarse * w1).sum() + (gf * w2).sum()).backward()
+    out["xyz"], out["w1"], out["w2"] = npy(xyz), npy(w1), npy(w2)
+    out["knn0"], out["knn1"], out["knn1b"], out["knn2"] = rec["knn"]
+    out["fps1"], out["fps2"] = rec["fps"]
+    out["pool_idx"], out["pool_gap"] = npy(sel["idx"]), npy(sel["gap"])
+    out["coarse"], out["gf"] = npy(coarse), npy(gf)
+    out["gxyz"] = npy(xin.grad)
+    for n_, prm in enc.named_parameters():
+        if prm.grad is None:
+            out["grad_none.encoder." + n_] = np.zeros(0, np.float32)
+        elif prm.numel() <= 70000:
+            out["grad.encoder." + n_] = npy(prm.grad)
+        else:
+            out["grad_digest.encoder." + n_] = digest(prm.grad)
+            out["grad_head.encoder." + n_] = npy(prm.grad).ravel()[:256].copy()
+    for n_, buf in enc.named_buffers():
+        out["buf_post.encoder." + n_] = npy(buf)
+    enc.eval()
+    with torch.no_grad():
+        coarse_e, gf_e = enc(xyz)
+    out["eval_pool_idx"] = npy(sel["idx"])
+    out["eval_coarse"], out["eval_gf"] = npy(coarse_e), npy(gf_e)
+
+
 def main():
     install_shim()
     torch.set_num_threads(os.cpu_count())
     # pcn_b6: same network at B=6 -- with more samples per batch the decoder's BatchNorm-on-norms is far better
     # conditioned than at B=2 (see DESIGN.md "conditioning"), so values can be compared at the north-star 1e-4.
     only = set(sys.argv[1:])
-    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants),
+    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants), ("dgcnn_small", gen_dgcnn),
                      ("pcn_b6", lambda o: gen_pcn(o, B=6, n_partial=128, n_gt=1024, seed=17))):
         if only and name not in only:
             continue

@@ -1,0 +1,259 @@
+"""VN_DGCNN_fps encoder: oracle vs the reference golden on CPU, CUDA path vs oracle / golden on the GPU.
+
+Tolerances: kNN / FPS indices bit-exact against the oracle (graph_oracle.c); activations 1e-4 relative against the reference
+golden with the reference's VNMaxPool selections teacher-forced where the top-2 gap is below 1e-4; gradients relative L2
+<= 5e-3 (conftest.assert_grad_close)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from conftest import assert_grad_close
+from oracle import graph_oracle as GO
+
+
+def _digest(a):
+    a = np.asarray(a, np.float64).ravel()
+    return np.array([a.sum(), np.abs(a).sum(), (a * a).sum(), a[:: max(1, a.size // 97)][:64].sum()], np.float64)
+
+
+def _seeded_encoder(device="cpu"):
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=512, only_coarse=False, device=device, enc_pretrained="none")
+    torch.manual_seed(0)
+    return V.VN_DGCNN_fps(cfg)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle
+def test_state_dict_matches_reference(golden):
+    """same keys and (under the same seed) bit-identical initial weights as the reference's VN_DGCNN_fps"""
+    g = golden("dgcnn_small")
+    enc = _seeded_encoder()
+    sd = enc.state_dict()
+    ref_keys = sorted(k[len("sd_digest.encoder."):] for k in g.files if k.startswith("sd_digest.encoder."))
+    assert sorted(sd.keys()) == ref_keys
+    for k in ref_keys:
+        np.testing.assert_allclose(_digest(sd[k].float().numpy()), g["sd_digest.encoder." + k], rtol=1e-12, err_msg=k)
+
+
+def test_knn_fps_oracle_properties():
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-0.5, 0.5, (2, 300, 3)).astype(np.float32)
+    idx, dist = GO.knn3d(x, x, 16)
+    assert (idx[:, 0] == np.arange(300)[None]).all() and (dist[:, 0] == 0).all()     # self first
+    assert (np.diff(dist, axis=1) >= 0).all()                                         # ascending
+    d = np.sqrt(((x[:, :, None] - x[:, None]) ** 2).sum(-1))
+    ref = np.argsort(d, axis=-1, kind="stable")[:, :, :16]
+    assert (np.sort(ref, -1) == np.sort(np.swapaxes(idx, 1, 2), -1)).mean() > 0.999   # same neighbour sets (up to fp ties)
+    f = GO.fps(x, 64)
+    assert (f[:, 0] == 0).all()
+    for b in range(2):
+        assert len(set(f[b].tolist())) == 64
+        # greedy property: each pick maximises the distance to the already selected set
+        sel = [0]
+        for j in range(1, 8):
+            dm = d[b][:, sel].min(1)
+            dm[(x[b] ** 2).sum(1) <= 1e-3] = -1
+            assert abs(dm[f[b, j]] - dm.max()) < 1e-6
+            sel.append(int(f[b, j]))
+    # duplicated points: ties resolved towards the lower index, order stays (distance, index)
+    y = np.repeat(x[:, :40], 2, axis=1)
+    idx, dist = GO.knn3d(y, y, 4)
+    assert (idx[:, 0] == (np.arange(80) // 2 * 2)[None]).all() and (idx[:, 1] == (np.arange(80) // 2 * 2 + 1)[None]).all()
+
+
+def test_dgcnn_oracle_vs_reference_golden(golden):
+    """pins oracle.VNDGCNNOracle (forward and backward) against the reference's own VN_DGCNN_fps (make_golden.gen_dgcnn)"""
+    g = golden("dgcnn_small")
+    enc = _seeded_encoder()
+    P = {"encoder." + k: v.detach().numpy().copy() for k, v in enc.state_dict().items()}
+    orc = GO.VNDGCNNOracle(P)
+    orc.forward(g["xyz"], training=True, update_running=False)
+    for a, b in zip(orc.knn_idx, (g["knn0"], g["knn1"], g["knn2"])):
+        assert np.array_equal(a, b)
+    assert np.array_equal(g["knn1"], g["knn1b"])
+    for a, b in zip(orc.fps_idx, (g["fps1"], g["fps2"])):
+        assert np.array_equal(a, b)
+    bad = orc.pool_idx != g["pool_idx"]
+    assert (np.abs(g["pool_gap"]).reshape(bad.shape)[bad] < 1e-4).all() and bad.mean() < 0.05
+    coarse, gf = orc.forward(g["xyz"], training=True, forced_pool_idx=g["pool_idx"])
+    np.testing.assert_allclose(gf, g["gf"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(coarse, g["coarse"], rtol=1e-4, atol=1e-5)
+    G, gxyz = orc.backward(g["w1"], g["w2"])
+    assert_grad_close(gxyz, g["gxyz"], "gxyz")
+    for k in g.files:
+        if k.startswith("grad."):
+            assert_grad_close(G[k[5:]], g[k], k)
+        elif k.startswith("grad_head."):
+            assert_grad_close(G[k[10:]].ravel()[:256], g[k], k)
+        elif k.startswith("grad_none."):
+            assert k[10:] not in G
+        elif k.startswith("buf_post.") and not k.endswith("num_batches_tracked"):
+            np.testing.assert_allclose(P[k[9:]], g[k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+# ------------------------------------------------------------------------------------------------ GPU: CUDA path
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Nr,Nq,k", [(2, 300, 300, 16), (3, 1000, 77, 8), (1, 33, 5, 20), (32, 2048, 2048, 16), (2, 5000, 1500, 32)])
+def test_knn3d_bit_exact(B, Nr, Nq, k):
+    import torch
+
+    from vn_pointcloudcompletion_b200 import graph_ops as G
+    rng = np.random.RandomState(B * 1000 + Nr)
+    ref = rng.uniform(-0.5, 0.5, (B, Nr, 3)).astype(np.float32)
+    qry = ref if Nr == Nq else rng.uniform(-0.5, 0.5, (B, Nq, 3)).astype(np.float32)
+    if Nr == 300:
+        ref[:, 100:140] = ref[:, 0:40]          # duplicated points -> exact ties
+        qry = ref
+    idx, dist = G.knn3d(_dev(ref), _dev(qry), k, want_dist=True)
+    oi, od = GO.knn3d(ref, qry, k)
+    torch.cuda.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    assert np.array_equal(dist.cpu().numpy(), od)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,M", [(2, 640, 512), (3, 512, 128), (32, 2048, 512), (1, 5000, 300), (2, 100, 100), (2, 16384, 64)])
+def test_fps_bit_exact(B, N, M):
+    from vn_pointcloudcompletion_b200 import graph_ops as G
+    rng = np.random.RandomState(N + M)
+    x = rng.uniform(-0.5, 0.5, (B, N, 3)).astype(np.float32)
+    x[:, 5] = 0.001                                       # |p|^2 <= 1e-3: never competes
+    idx = G.fps(_dev(x), M).cpu().numpy()
+    assert np.array_equal(idx, GO.fps(x, M))
+
+
+@pytest.mark.gpu
+def test_graph_ops_vs_oracle():
+    """edge features / group mean / point gather, forward and adjoint, against the numpy oracle"""
+    import torch
+
+    from vn_pointcloudcompletion_b200 import graph_ops as G
+    from vn_pointcloudcompletion_b200.vn_layers import from_rows, to_rows
+    rng = np.random.RandomState(3)
+    B, C, N, k, M = 3, 12, 50, 7, 20
+    x = rng.standard_normal((B, C, 3, N)).astype(np.float32)
+    idx = rng.randint(0, N, (B, k, N)).astype(np.int64)
+    xt = _dev(x).requires_grad_(True)
+    rows, _, _ = to_rows(xt)
+    e = G.edge_feature(rows, _dev(idx), B, N)
+    el = from_rows(e, B, (N, k))
+    np.testing.assert_array_equal(el.detach().cpu().numpy(), GO.graph_feature(x, idx))
+    m = G.group_mean(e, k)
+    np.testing.assert_allclose(from_rows(m, B, (N,)).detach().cpu().numpy(), GO.graph_feature(x, idx).mean(-1), rtol=1e-6, atol=1e-6)
+    ge = rng.standard_normal(tuple(el.shape)).astype(np.float32)
+    gm = rng.standard_normal((B, 2 * C, 3, N)).astype(np.float32)
+    ((el * _dev(ge)).sum() + (from_rows(m, B, (N,)) * _dev(gm)).sum()).backward()
+    want = GO.graph_feature_bwd(x.shape, idx, ge + np.broadcast_to(gm[..., None] / k, ge.shape))
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    fi = np.stack([rng.permutation(N)[:M] for _ in range(B)]).astype(np.int32)
+    xt2 = _dev(x).requires_grad_(True)
+    rows2, _, _ = to_rows(xt2)
+    gsel = from_rows(G.points_gather(rows2, _dev(fi), B, N), B, (M,))
+    np.testing.assert_array_equal(gsel.detach().cpu().numpy(), GO.gather_points(x, fi))
+    gg = rng.standard_normal(tuple(gsel.shape)).astype(np.float32)
+    (gsel * _dev(gg)).sum().backward()
+    np.testing.assert_allclose(xt2.grad.cpu().numpy(), GO.gather_points_bwd(x.shape, fi, gg), rtol=1e-6, atol=1e-6)
+    # third-party call signatures
+    import vn_pointcloudcompletion_b200 as V
+    feat = _dev(rng.standard_normal((B, 9, N)).astype(np.float32))
+    got = V.gather_operation(feat, _dev(fi))
+    np.testing.assert_array_equal(got.cpu().numpy(), np.take_along_axis(feat.cpu().numpy(), fi[:, None, :].astype(np.int64).repeat(9, 1), 2))
+    pts = rng.uniform(-0.5, 0.5, (B, N, 3)).astype(np.float32)
+    dist, ki = V.KNN(k=5, transpose_mode=False)(_dev(pts).transpose(1, 2), _dev(pts).transpose(1, 2))
+    oi, od = GO.knn3d(pts, pts, 5)
+    assert np.array_equal(ki.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    dist_t, ki_t = V.KNN(k=5, transpose_mode=True)(_dev(pts), _dev(pts))
+    assert np.array_equal(ki_t.cpu().numpy(), np.swapaxes(oi, 1, 2))
+    assert np.array_equal(V.furthest_point_sample(_dev(pts), 10).cpu().numpy(), GO.fps(pts, 10))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_dgcnn_vs_reference_golden(golden, mode):
+    """the CUDA VN_DGCNN_fps against the reference's own outputs / autograd gradients (tests/golden/dgcnn_small.npz)"""
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    g = golden("dgcnn_small")
+    V.set_gemm_mode(mode)
+    try:
+        enc = _seeded_encoder("cuda").cuda().train()
+        # own searches: bit-exact; own arg-max: equal except at near-ties
+        xin = _dev(g["xyz"]).requires_grad_(True)
+        with torch.no_grad():
+            enc(xin)
+        for a, b in zip(enc.last_knn_idx, (g["knn0"], g["knn1"], g["knn2"])):
+            assert np.array_equal(a.cpu().numpy(), b)
+        for a, b in zip(enc.last_fps_idx, (g["fps1"], g["fps2"])):
+            assert np.array_equal(a.cpu().numpy(), b)
+        own = enc.pool5.last_idx.cpu().numpy().reshape(g["pool_idx"].shape)
+        bad = own != g["pool_idx"]
+        gap_lim = 1e-4 if mode == "fp32" else 2e-2
+        assert (np.abs(g["pool_gap"]).reshape(bad.shape)[bad] < gap_lim).all() and bad.mean() < (0.05 if mode == "fp32" else 0.3)
+        # values with the reference's selections teacher-forced; fresh BN buffers
+        enc = _seeded_encoder("cuda").cuda().train()
+        enc.pool5.forced_idx = _dev(g["pool_idx"]).reshape(g["pool_idx"].shape[0], -1)
+        coarse, gf = enc(xin)
+        ((coarse * _dev(g["w1"])).sum() + (gf * _dev(g["w2"])).sum()).backward()
+        torch.cuda.synchronize()
+        rt = 1e-4 if mode == "fp32" else 2e-2
+        # TF32 operands (10-bit mantissa) through 5 layers: error bounded relative to the tensor's largest entry
+        at_gf = 1e-6 if mode == "fp32" else rt * float(np.abs(g["gf"]).max())
+        at_c = 1e-5 if mode == "fp32" else rt * float(np.abs(g["coarse"]).max())
+        np.testing.assert_allclose(gf.detach().cpu().numpy(), g["gf"], rtol=rt, atol=at_gf)
+        np.testing.assert_allclose(coarse.detach().cpu().numpy(), g["coarse"], rtol=rt, atol=at_c)
+        l2, mx = (5e-3, 2e-2) if mode == "fp32" else (5e-2, 1e-1)
+        assert_grad_close(xin.grad.cpu().numpy(), g["gxyz"], "gxyz", l2, mx)
+        sd = dict(enc.named_parameters())
+        for k in g.files:
+            if k.startswith("grad.encoder."):
+                assert_grad_close(sd[k[13:]].grad.cpu().numpy(), g[k], k, l2, mx)
+            elif k.startswith("grad_head.encoder."):
+                assert_grad_close(sd[k[18:]].grad.cpu().numpy().ravel()[:256], g[k], k, l2, mx)
+            elif k.startswith("grad_none.encoder."):
+                assert sd[k[18:]].grad is None
+        if mode == "fp32":
+            bufs = dict(enc.named_buffers())
+            for k in g.files:
+                if k.startswith("buf_post.encoder.") and not k.endswith("num_batches_tracked"):
+                    np.testing.assert_allclose(bufs[k[17:]].cpu().numpy(), g[k], rtol=1e-4, atol=1e-6, err_msg=k)
+            enc.eval()
+            enc.pool5.forced_idx = _dev(g["eval_pool_idx"]).reshape(g["pool_idx"].shape[0], -1)
+            with torch.no_grad():
+                ce, ge = enc(xin)
+            np.testing.assert_allclose(ce.cpu().numpy(), g["eval_coarse"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(ge.cpu().numpy(), g["eval_gf"], rtol=1e-4, atol=1e-6)
+    finally:
+        V.set_gemm_mode("fp32")
+
+
+@pytest.mark.gpu
+def test_pcnnet_dgcnn_foldingnet_trains():
+    """PCNNet(enc_type='vn_dgcnn_fps', dec_type='vn_foldingnet') at latent_dim=512 (the pair that runs in the reference):
+    one train step end to end, finite loss and gradients for every trained parameter"""
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200.synthetic import make_batch
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=512, only_coarse=False, device="cuda", enc_pretrained="none")
+    torch.manual_seed(0)
+    net = V.PCNNet(cfg, enc_type="vn_dgcnn_fps", dec_type="vn_foldingnet").train()
+    p, c, R = make_batch(2, n_partial=2048, n_gt=4096, seed=11)
+    coarse, fine = net(_dev(p), V.Rotate(_dev(R)))
+    assert coarse.shape == (2, 1024, 3) and fine.shape == (2, 16384, 3)
+    loss = V.cd_loss_L1(coarse, _dev(c)) + V.cd_loss_L1(fine, _dev(c))
+    loss.backward()
+    assert np.isfinite(loss.item())
+    for n, prm in net.named_parameters():
+        if "pool5" in n:
+            assert prm.grad is None
+        else:
+            assert prm.grad is not None and torch.isfinite(prm.grad).all(), n

@@ -3,6 +3,8 @@ ChenBarryHu/VN_PointCloudCompletion: the Vector-Neuron layer stack (vn_pointnet 
 and the Chamfer loss/metric, behind the reference's own Python interfaces.  See DESIGN.md / INTEGRATION.md."""
 from . import _lib  # noqa: F401
 from .chamfer_distance import ChamferDistance, chamfer_3DDist, chamfer_3DFunction  # noqa: F401
+from .dgcnn import VN_DGCNN_fps  # noqa: F401
+from .graph_ops import KNN, furthest_point_sample, gather_operation  # noqa: F401
 from .loss import cd_loss_L1, cd_loss_L2, l1_cd, l2_cd  # noqa: F401
 from .model import PCNNet, Rotate, random_rotations  # noqa: F401
 from .ops import get_gemm_mode, set_gemm_mode  # noqa: F401

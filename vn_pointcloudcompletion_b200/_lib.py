@@ -58,6 +58,14 @@ SIGNATURES = {
     "vnpcc_smallk_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _p]),
     "vnpcc_smallk_dgrad": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p]),
     "vnpcc_smallk_wgrad": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _ll, _p, _ll, _p]),
+    "vnpcc_knn3d": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "vnpcc_fps": (_i, [_p, _i, _i, _i, _p, _p]),
+    "vnpcc_points_gather": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_points_scatter_add": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_edge_feature_fwd": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_edge_feature_bwd": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_rows_group_mean": (_i, [_p, _ll, _ll, _i, _i, _p, _ll, _p]),
+    "vnpcc_rows_group_mean_bwd": (_i, [_p, _ll, _ll, _i, _i, _p, _ll, _p]),
     "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
 }

@@ -1,11 +1,12 @@
 """Drop-in PCNNet (reference: models/model.py:9-64) for the north-star pair enc_type='vn_pointnet' +
-dec_type='vn_foldingnet'.  Same constructor (config namespace with num_coarse, latent_dim, only_coarse, device,
+dec_type='vn_foldingnet', plus enc_type='vn_dgcnn_fps' (pairs with vn_foldingnet at latent_dim=512).  Same constructor (config namespace with num_coarse, latent_dim, only_coarse, device,
 enc_pretrained), same forward(input, rot=None) -> (coarse, fine), same state_dict keys ('encoder.*', 'decoder.*')."""
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
+from .dgcnn import VN_DGCNN_fps
 from .pcn import VN_FoldingNet, VN_PointNet
 
 
@@ -16,8 +17,10 @@ class PCNNet(nn.Module):
         self.only_coarse = config.only_coarse
         if enc_type == "vn_pointnet":
             self.encoder = VN_PointNet(config).to(config.device)
+        elif enc_type == "vn_dgcnn_fps":
+            self.encoder = VN_DGCNN_fps(config, only_coarse=config.only_coarse).to(config.device)
         else:
-            raise Exception(f"encoder type {enc_type} not supported yet (B200 hot path covers vn_pointnet, SURVEY.md 8)")
+            raise Exception(f"encoder type {enc_type} not supported yet (B200 path covers vn_pointnet and vn_dgcnn_fps, SURVEY.md 8)")
         if config.enc_pretrained != "none":
             sd = torch.load(config.enc_pretrained)
             self.encoder.load_state_dict(sd, strict=False)
