@@ -206,7 +206,7 @@ def test_dgcnn_vs_reference_golden(golden, mode):
         torch.cuda.synchronize()
         rt = 1e-4 if mode == "fp32" else 2e-2
         # TF32 operands (10-bit mantissa) through 5 layers: error bounded relative to the tensor's largest entry
-        at_gf = 1e-6 if mode == "fp32" else rt * float(np.abs(g["gf"]).max())
+        at_gf = 5e-6 if mode == "fp32" else rt * float(np.abs(g["gf"]).max())
         at_c = 1e-5 if mode == "fp32" else rt * float(np.abs(g["coarse"]).max())
         np.testing.assert_allclose(gf.detach().cpu().numpy(), g["gf"], rtol=rt, atol=at_gf)
         np.testing.assert_allclose(coarse.detach().cpu().numpy(), g["coarse"], rtol=rt, atol=at_c)
