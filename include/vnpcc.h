@@ -180,6 +180,26 @@ int vnpcc_edge_feature_bwd(const float* g, long long ldg, const long long* idx, 
 int vnpcc_rows_group_mean(const float* x, long long ldx, long long G, int k, int C, float* out, long long ldo, void* stream);
 int vnpcc_rows_group_mean_bwd(const float* g, long long ldg, long long G, int k, int C, float* gx, long long ldgx, void* stream);
 
+/* ---------------------------------------------------------------- transformer-refined decoder (Attention_VN_FoldingNet) -- */
+/* VNLayerNorm (models/vn_layers.py:129-150): per token (3 rows) norm[c] = ||x[c,:]|| + 1e-6, nn.LayerNorm over the C channels
+ * (weight, bias, eps = ln_eps), y = x / norm * ln(norm).  P tokens, C <= 512.  stats [P,2] = (mean, rstd) for the backward
+ * (may be NULL in no-grad forwards).  _bwd zeroes gweight / gbias [C] and accumulates them with fp32 atomics. */
+int vnpcc_vn_layernorm_fwd(const float* x, long long ldx, long long P, int C, const float* weight, const float* bias, float ln_eps, float* y,
+                           long long ldy, float* stats, void* stream);
+int vnpcc_vn_layernorm_bwd(const float* g, long long ldg, const float* x, long long ldx, long long P, int C, const float* weight,
+                           const float* bias, const float* stats, float* gx, long long ldgx, float* gweight, float* gbias, void* stream);
+/* out = a + b on rows (residual additions of VN_Block, models/transformer.py:60,68) */
+int vnpcc_rows_add(const float* a, long long lda, const float* b, long long ldb, float* out, long long ldo, long long R, int C, void* stream);
+/* VN multi-head attention core (models/transformer.py:89-100): qkv [B*N*3, 3C] = (q | k | v) rows, C = H*D channels, head h =
+ * channels [h*D, (h+1)*D) of the 3 rows of a token (a 3D-dim feature); out[token] = softmax_m(scale * <q_n, k_m>) v_m per head, written
+ * in the same row layout [B*N*3, C]; lse [B,H,N] = log-sum-exp of the scaled scores (saved for the backward).  Exact fp32,
+ * flash-style (no [N,N] matrix in HBM).  D in {16, 32, 48}; ld % 4 == 0. */
+int vnpcc_vn_attention_fwd(const float* qkv, long long ld, int B, int N, int H, int D, float scale, float* out, long long ldo, float* lse,
+                           void* stream);
+/* dqkv [B*N*3, 3C] fully written (q part zeroed then accumulated with fp32 atomics); delta: workspace of B*H*N floats */
+int vnpcc_vn_attention_bwd(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo, const float* lse,
+                           int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta, void* stream);
+
 /* ---------------------------------------------------------------- optimiser / misc ------------------------------ */
 /* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
 int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

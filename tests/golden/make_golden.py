@@ -10,6 +10,8 @@ own classes on CPU with seeded inputs, and stores inputs, parameters, outputs an
 next to this script.  Nothing from the reference is copied: only its numerical outputs are stored.
 
 Fixtures:
+  attn_small.npz        VNLayerNorm, Attention, VN_Block (models/transformer.py) and Attention_VN_FoldingNet (models/pcn.py:392-520):
+                        forward, autograd gradients, BN buffers.
   chamfer_unit.npz      the reference's only test (ChamferDistancePytorch/unit_test.py:14-35): rand(4,100,3) vs
                         rand(4,200,3) through chamfer_python.distChamfer (the reference's CPU-capable Chamfer),
                         plus a ragged/edge set and autograd gradients of sum(dist1)+sum(dist2) and of CD-L1.
@@ -363,13 +365,80 @@ def gen_dgcnn(out, B=3, N=640, seed=5):
     out["eval_coarse"], out["eval_gf"] = npy(coarse_e), npy(gf_e)
 
 
+def gen_attn(out):
+    """VNLayerNorm, Attention, VN_Block (models/transformer.py) and Attention_VN_FoldingNet (models/pcn.py:392-520)
+    of the reference run UNMODIFIED on CPU (only the hard-coded .cuda() of the folding seed, pcn.py:454, is neutralised)."""
+    import models.pcn as P
+    import models.transformer as T
+    import models.vn_layers as V
+    g = torch.Generator().manual_seed(2468)
+
+    def rnd(*s):
+        return torch.randn(*s, generator=g)
+
+    def run(key, mod, x):
+        mod.train()
+        _sd(mod, out, key + ".pre")
+        xi = x.clone().requires_grad_(True)
+        y = mod(xi)
+        gy = rnd(*y.shape)
+        (y * gy).sum().backward()
+        out[key + ".x"], out[key + ".y"], out[key + ".gy"], out[key + ".gx"] = npy(x), npy(y), npy(gy), npy(xi.grad)
+        for n_, p in mod.named_parameters():
+            out[f"{key}.grad.{n_}"] = npy(p.grad) if p.grad is not None else np.zeros(0, np.float32)
+        _sd(mod, out, key + ".post")
+
+    torch.manual_seed(11)
+    ln = V.VNLayerNorm(48)
+    with torch.no_grad():
+        ln.layer_norm.weight.copy_(rnd(48))
+        ln.layer_norm.bias.copy_(rnd(48) * 0.3)
+    run("VNLayerNorm", ln, rnd(3, 48, 3, 37))
+    run("Attention", T.Attention(64, num_heads=4, qk_scale=1), rnd(2, 64, 3, 70))
+    run("Attention_defscale", T.Attention(96, num_heads=2), rnd(2, 96, 3, 33))
+    run("VN_Block", T.VN_Block(dim=64, num_heads=4, mlp_ratio=1, qkv_bias=False, qk_scale=1, drop=0, attn_drop=0), rnd(2, 70, 192))
+    # the decoder: B=2, 80 coarse points, global feature [2,2048,3,1]
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cpu", enc_pretrained="none")
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        torch.manual_seed(0)
+        dec = P.Attention_VN_FoldingNet(cfg)
+    finally:
+        torch.Tensor.cuda = _cuda
+    dec.train()
+    for k, v in list(dec.state_dict().items()):
+        out["sd_digest.decoder." + k] = digest(v.float())
+    coarse = (torch.rand(2, 80, 3, generator=g) - 0.5)
+    fg = rnd(2, 2048, 3, 1) * 0.5
+    ci, fi = coarse.clone().requires_grad_(True), fg.clone().requires_grad_(True)
+    pts = dec(ci, fi)
+    w = rnd(*pts.shape)
+    (pts * w).sum().backward()
+    out["dec.coarse"], out["dec.fg"], out["dec.w"], out["dec.pts"] = npy(coarse), npy(fg), npy(w), npy(pts)
+    out["dec.gcoarse"], out["dec.gfg"] = npy(ci.grad), npy(fi.grad)
+    for n_, prm in dec.named_parameters():
+        if prm.grad is None:
+            out["grad_none.decoder." + n_] = np.zeros(0, np.float32)
+        elif prm.numel() <= 70000:
+            out["grad.decoder." + n_] = npy(prm.grad)
+        else:
+            out["grad_digest.decoder." + n_] = digest(prm.grad)
+            out["grad_head.decoder." + n_] = npy(prm.grad).ravel()[:256].copy()
+    for n_, buf in dec.named_buffers():
+        out["buf_post.decoder." + n_] = npy(buf)
+    dec.eval()
+    with torch.no_grad():
+        out["dec.eval_pts"] = npy(dec(coarse, fg))
+
+
 def main():
     install_shim()
     torch.set_num_threads(os.cpu_count())
     # pcn_b6: same network at B=6 -- with more samples per batch the decoder's BatchNorm-on-norms is far better
     # conditioned than at B=2 (see DESIGN.md "conditioning"), so values can be compared at the north-star 1e-4.
     only = set(sys.argv[1:])
-    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants), ("dgcnn_small", gen_dgcnn),
+    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants), ("dgcnn_small", gen_dgcnn), ("attn_small", gen_attn),
                      ("pcn_b6", lambda o: gen_pcn(o, B=6, n_partial=128, n_gt=1024, seed=17))):
         if only and name not in only:
             continue

@@ -8,6 +8,7 @@ from .graph_ops import KNN, furthest_point_sample, gather_operation  # noqa: F40
 from .loss import cd_loss_L1, cd_loss_L2, l1_cd, l2_cd  # noqa: F401
 from .model import PCNNet, Rotate, random_rotations  # noqa: F401
 from .ops import get_gemm_mode, set_gemm_mode  # noqa: F401
-from .pcn import VN_FoldingNet, VN_PointNet  # noqa: F401
+from .pcn import Attention_VN_FoldingNet, VN_FoldingNet, VN_PointNet  # noqa: F401
 from .vn_layers import (VNBatchNorm, VNLeakyReLU, VNLinear, VNLinearAndLeakyReLU, VNLinearLeakyReLU,  # noqa: F401
-                        VNMaxPool, VNStdFeature, mean_pool)
+                        VNLayerNorm, VNMaxPool, VNStdFeature, mean_pool)
+from .transformer import Attention, VN_Block  # noqa: F401

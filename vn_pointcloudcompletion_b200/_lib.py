@@ -66,6 +66,11 @@ SIGNATURES = {
     "vnpcc_edge_feature_bwd": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p]),
     "vnpcc_rows_group_mean": (_i, [_p, _ll, _ll, _i, _i, _p, _ll, _p]),
     "vnpcc_rows_group_mean_bwd": (_i, [_p, _ll, _ll, _i, _i, _p, _ll, _p]),
+    "vnpcc_vn_layernorm_fwd": (_i, [_p, _ll, _ll, _i, _p, _p, _f, _p, _ll, _p, _p]),
+    "vnpcc_vn_layernorm_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _ll, _p, _p, _p]),
+    "vnpcc_rows_add": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _p]),
+    "vnpcc_vn_attention_fwd": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
+    "vnpcc_vn_attention_bwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
     "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
 }

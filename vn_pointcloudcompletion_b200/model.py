@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .dgcnn import VN_DGCNN_fps
-from .pcn import VN_FoldingNet, VN_PointNet
+from .pcn import Attention_VN_FoldingNet, VN_FoldingNet, VN_PointNet
 
 
 class PCNNet(nn.Module):
@@ -29,6 +29,8 @@ class PCNNet(nn.Module):
         if not config.only_coarse:
             if dec_type == "vn_foldingnet":
                 self.decoder = VN_FoldingNet(config).to(config.device)
+            elif dec_type == "attention_vn_foldingnet":
+                self.decoder = Attention_VN_FoldingNet(config).to(config.device)
             else:
                 raise Exception(f"decoder type {dec_type} not supported yet (B200 hot path covers vn_foldingnet, SURVEY.md 8)")
 

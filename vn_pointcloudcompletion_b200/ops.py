@@ -713,3 +713,92 @@ def cd_reduce(dist1, dist2, mode):
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     call("vnpcc_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
          float(weight_decay), int(step), float(grad_scale), stream())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# transformer-refined decoder: VNLayerNorm, residual add, VN multi-head attention core
+# ---------------------------------------------------------------------------------------------------------------
+class _VNLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _rows2d(x, "x")
+        R, C = x.shape
+        P = R // 3
+        y = torch.empty((R, C), device=x.device, dtype=torch.float32)
+        need = any(ctx.needs_input_grad[:3])
+        stats = torch.empty((P, 2), device=x.device, dtype=torch.float32) if need else None
+        call("vnpcc_vn_layernorm_fwd", ptr(x), _ld(x), P, C, ptr(weight), ptr(bias), float(eps), ptr(y), C, ptr(stats), stream())
+        ctx.save_for_backward(x, weight, bias, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, bias, stats = ctx.saved_tensors
+        g = _rows2d(g, "grad")
+        R, C = x.shape
+        gx = torch.empty((R, C), device=x.device, dtype=torch.float32)
+        gw = torch.empty(C, device=x.device, dtype=torch.float32)
+        gb = torch.empty(C, device=x.device, dtype=torch.float32)
+        call("vnpcc_vn_layernorm_bwd", ptr(g), _ld(g), ptr(x), _ld(x), R // 3, C, ptr(weight), ptr(bias), ptr(stats), ptr(gx), C, ptr(gw), ptr(gb),
+             stream())
+        return gx, gw, gb, None
+
+
+def vn_layernorm(x, ln):
+    """x rows [P*3, C]; ln: an nn.LayerNorm(C) module (parameter container) -> VNLayerNorm rows (models/vn_layers.py:140-150)"""
+    if not ln.elementwise_affine:
+        raise NotImplementedError("VNLayerNorm without affine parameters")
+    return _VNLayerNorm.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+class _RowsAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = _rows2d(a, "a")
+        b = _rows2d(b, "b")
+        out = torch.empty((a.shape[0], a.shape[1]), device=a.device, dtype=torch.float32)
+        call("vnpcc_rows_add", ptr(a), _ld(a), ptr(b), _ld(b), ptr(out), a.shape[1], a.shape[0], a.shape[1], stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def rows_add(a, b):
+    """a + b on rows (residual connections of VN_Block, models/transformer.py:60,68)"""
+    return _RowsAdd.apply(a, b)
+
+
+class _VNAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, B, N, H, scale):
+        qkv = _rows2d(qkv, "qkv")
+        C = qkv.shape[1] // 3
+        D = C // H
+        out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float32)
+        lse = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+        with _Timed("attention_fwd", 4.0 * B * H * N * N * 3 * D):
+            call("vnpcc_vn_attention_fwd", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), stream())
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (B, N, H, D, float(scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, out, lse = ctx.saved_tensors
+        B, N, H, D, scale = ctx.cfg
+        g = _rows2d(g, "grad")
+        if _ld(g) % 4 != 0 or g.data_ptr() % 16:
+            g = g.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+        with _Timed("attention_bwd", 10.0 * B * H * N * N * 3 * D):
+            call("vnpcc_vn_attention_bwd", ptr(qkv), _ld(qkv), ptr(g), _ld(g), ptr(out), _ld(out), ptr(lse), B, N, H, D, scale, ptr(dqkv),
+                 _ld(dqkv), ptr(delta), stream())
+        return dqkv, None, None, None, None
+
+
+def vn_attention(qkv, B, N, H, scale):
+    """qkv rows [B*N*3, 3C] = (q | k | v) -> attention output rows [B*N*3, C] (models/transformer.py:89-100)"""
+    return _VNAttention.apply(qkv, B, N, H, scale)

@@ -133,3 +133,92 @@ class VN_FoldingNet(nn.Module):
             h = l1.forward_rows(h)      # no-grad: BN + leaky fused into the tcgen05 GEMM epilogue (vn_layers.VNLinearLeakyReLU)
             fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                     # final VNLinear(256,1) + point_feat
         return fine.view(B, nd, 3)
+
+
+class Attention_VN_FoldingNet(nn.Module):
+    """models/pcn.py:392-520: two VN_Blocks over the 1024 coarse tokens (feature = down-sized global feature +
+    the token's own coordinates), then two folding MLPs per token over a 4x4 seed grid.
+
+    B200-first restructuring (same results up to fp32 rounding):
+      * the token tensor is built and kept in the row layout; the per-block [B,N,C*3] <-> [B,C,3,N] transposes disappear;
+      * cat([seed | fd1, features.expand(16)]) -> VNLinearLeakyReLU(385, 256) (pcn.py:487-491): the 384 broadcast channels are
+        applied once per token as a per-token bias ([B*N*3, 512] rows), only the 1 local channel is recomputed per folded
+        point, and its (p, d) are never stored (csrc/vn_fused.cu);
+      * VNLinearLeakyReLU(256,128) -> VNLinear(128,1) (+ the coarse-point residual, pcn.py:493) is one fused tail.
+    `final_conv` is constructed (and stays in the state_dict) but is not used by the reference's forward either."""
+
+    def __init__(self, config, grid_size=4):
+        super().__init__()
+        from .transformer import VN_Block
+        self.grid_size = grid_size
+        self.latent_dim = config.latent_dim
+        self.num_dense = 16384
+        if config.num_coarse == 448:
+            self.num_coarse = config.num_coarse // 2
+            self.num_dense = 14336
+            self.grid_size = 8
+        else:
+            self.num_coarse = config.num_coarse
+            self.num_dense = 16384
+            self.grid_size = 4
+        self.transformer = nn.ModuleList([VN_Block(dim=384, num_heads=8, mlp_ratio=1, qkv_bias=False, qk_scale=1, drop=0, attn_drop=0)
+                                          for _ in range(2)])
+        self.final_conv = nn.Sequential(VNLinearLeakyReLU(self.latent_dim + 1 + 1, 256, dim=4), VNLinearLeakyReLU(256, 256, dim=4),
+                                        VNLinear(256, 1))
+        self.downsize_global = VNLinear(2048, 384)
+        gs = self.grid_size
+        a = torch.linspace(-1., 1., steps=gs, dtype=torch.float).view(1, gs).expand(gs, gs).reshape(1, -1)
+        b = torch.linspace(-1., 1., steps=gs, dtype=torch.float).view(gs, 1).expand(gs, gs).reshape(1, -1)
+        c = torch.zeros_like(a, dtype=torch.float)
+        self.folding_seed = torch.cat([a, b, c], dim=0)              # [3, S]; plain attribute like the reference (pcn.py:454)
+        in_channel, hidden_dim = 384, 256
+        self.vn_folding1 = nn.Sequential(VNLinearLeakyReLU(in_channel + 1, hidden_dim, dim=4),
+                                         VNLinearLeakyReLU(hidden_dim, hidden_dim // 2, dim=4), VNLinear(hidden_dim // 2, 1))
+        self.vn_folding2 = nn.Sequential(VNLinearLeakyReLU(in_channel + 1, hidden_dim, dim=4),
+                                         VNLinearLeakyReLU(hidden_dim, hidden_dim // 2, dim=4), VNLinear(hidden_dim // 2, 1))
+
+    @staticmethod
+    def _fold(seq, local, feat_rows, T, S, const_local, res=None):
+        """one folding MLP: local rows ((token, s), v) x 1, feat_rows (token, v) x 384 -> rows ((token, s), v) [R]"""
+        l0, l1, l2 = seq[0], seq[1], seq[2]
+        wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)           # [512, 385]; column 0 = the local channel
+        bias = ops.linear_rows(feat_rows, wcat[:, 1:])                                    # [T*3, 512]
+        C0 = l0.map_to_feat.weight.shape[0]
+        if ops.smallk_bn_leaky_supported(1, C0, bias) and l0.batchnorm.bn.affine:
+            h = ops.smallk_bn_leaky(local, wcat[:, :1], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, T, S, 1 if const_local else 0)
+        else:
+            pd = ops.linear_rows(local, wcat[:, :1], bias, 3 * S)
+            h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
+        C1 = l1.map_to_feat.weight.shape[0]
+        if torch.is_grad_enabled() and ops.bn_leaky_dot_supported(C1):
+            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0))
+            return ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, res)
+        h = l1.forward_rows(h)
+        return ops.rows_dot(h, l2.map_to_feat.weight, res)
+
+    def forward(self, coarse, feature_global, rot=None):
+        dev = coarse.device
+        if self.folding_seed.device != dev:
+            self.folding_seed = self.folding_seed.to(dev)
+        B, N, _ = coarse.shape
+        S = self.grid_size ** 2
+        coarse = coarse.contiguous()
+        # tokens: rows (b, n, v) x 384 = downsize_global(fg)[(b, v), :] + centers[b, v, n]   (pcn.py:466-470).
+        # NOTE the reference builds `repeat_input_centers` with expand(-1,384,-1,-1).reshape(bs,-1,N) on a [B,384,N,3] tensor,
+        # which re-interprets each sample's [N,3] coordinate block as [3,N] (no transpose): token n receives the vector
+        # (flat[n], flat[N+n], flat[2N+n]) of coarse[b].flatten().  Reproduced as is -- parity with the reference's outputs.
+        centers = coarse.reshape(B, 3, N).transpose(1, 2).contiguous().view(B * N * 3, 1)
+        fg_rows = feature_global.squeeze(-1).transpose(1, 2).reshape(B * 3, -1)
+        dg = ops.linear_rows(fg_rows, self.downsize_global.map_to_feat.weight)            # [B*3, 384]
+        ones = torch.ones((dg.shape[1], 1), device=dev, dtype=torch.float32)
+        tok = ops.linear_rows(centers, ones, dg, 3 * N)                                   # broadcast add as a K=1 VNLinear + per-sample bias
+        for blk in self.transformer:
+            tok = blk.forward_rows(tok, B, N)
+        # folding (pcn.py:477-493): every token is a "sample" of S points
+        T = B * N
+        seed = self.folding_seed.t().contiguous()                                          # [S, 3] rows (s, v)
+        local1 = seed.unsqueeze(0).expand(T, S, 3).reshape(T * S * 3, 1)
+        fd1 = self._fold(self.vn_folding1, local1, tok, T, S, True)
+        res = coarse[:, :, None, :].expand(B, N, S, 3).reshape(-1)
+        fd2 = self._fold(self.vn_folding2, fd1.view(T * S * 3, 1), tok, T, S, False, res)  # + coarse.unsqueeze(-1)  (pcn.py:493)
+        return fd2.view(B, N * S, 3)

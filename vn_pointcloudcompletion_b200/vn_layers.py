@@ -225,3 +225,20 @@ class VNStdFeature(nn.Module):
         elif self.dim == 5:
             x_std = torch.einsum('bijmn,bjkmn->bikmn', x, z0)
         return x_std, z0
+
+
+class VNLayerNorm(nn.Module):
+    """models/vn_layers.py:129-150: LayerNorm over the channel axis of the vector norms, x [B, C, 3, N]"""
+
+    def __init__(self, num_features):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(num_features)
+
+    def forward_rows(self, rows):
+        return ops.vn_layernorm(rows, self.layer_norm)
+
+    def forward(self, x):
+        if x.dim() != 4:
+            raise ValueError(f"VNLayerNorm expects [B, C, 3, N] (the reference transposes a 3-D norm tensor), got {tuple(x.shape)}")
+        rows, B, sp = to_rows(x)
+        return from_rows(self.forward_rows(rows), B, sp)
