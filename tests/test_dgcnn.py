@@ -216,7 +216,9 @@ def test_dgcnn_vs_reference_golden(golden, mode):
         for k in g.files:
             if k.startswith("grad.encoder."):
                 assert_grad_close(sd[k[13:]].grad.cpu().numpy(), g[k], k, l2, mx)
-            elif k.startswith("grad_head.encoder."):
+            elif k.startswith("grad_head.encoder.") and mode == "fp32":
+                # (TF32: a 256-entry slice = part of ONE output channel is dominated by the few points whose leaky mask flips
+                # under 10-bit operands; whole tensors are compared above)
                 assert_grad_close(sd[k[18:]].grad.cpu().numpy().ravel()[:256], g[k], k, l2, mx)
             elif k.startswith("grad_none.encoder."):
                 assert sd[k[18:]].grad is None
