@@ -180,6 +180,17 @@ int vnpcc_edge_feature_bwd(const float* g, long long ldg, const long long* idx, 
 int vnpcc_rows_group_mean(const float* x, long long ldx, long long G, int k, int C, float* out, long long ldo, void* stream);
 int vnpcc_rows_group_mean_bwd(const float* g, long long ldg, long long G, int k, int C, float* gx, long long ldgx, void* stream);
 
+/* edge convolution without the edge tensor (csrc/edge_conv.cu): uw [B*N*3, 4C] = (U_p | U_d | W_p | W_d) with U = W1 x, W = (W2 - W1) x of
+ * the point GEMM; edge (i, j = idx[b, j, i]): p = U_p[j] + W_p[i], d = U_d[j] + W_d[i]; out[i] = mean_j leaky(BN(p), d).  BatchNorm
+ * statistics over the B*N*k edges.  C % 4 == 0, 256 % (C/4) == 0, C <= 1024.  _bwd writes guw [B*N*3, 4C] completely (U half zeroed +
+ * red.add, W half stored) and ggamma / gbeta [C]; sums: 2C doubles of workspace. */
+int vnpcc_edge_conv_stats(const float* uw, long long ld, const long long* idx, int B, int N, int k, int C, double* sums, void* stream);
+int vnpcc_edge_conv_fwd(const float* uw, long long ld, const long long* idx, int B, int N, int k, int C, const float* stat, const float* gamma,
+                        const float* beta, float ns, float* out, long long ldo, void* stream);
+int vnpcc_edge_conv_bwd(const float* g, long long ldg, const float* uw, long long ld, const long long* idx, int B, int N, int k, int C,
+                        const float* stat, const float* gamma, const float* beta, float ns, int training, double* sums, float* guw,
+                        long long ldgu, float* ggamma, float* gbeta, void* stream);
+
 /* ---------------------------------------------------------------- transformer-refined decoder (Attention_VN_FoldingNet) -- */
 /* VNLayerNorm (models/vn_layers.py:129-150): per token (3 rows) norm[c] = ||x[c,:]|| + 1e-6, nn.LayerNorm over the C channels
  * (weight, bias, eps = ln_eps), y = x / norm * ln(norm).  P tokens, C <= 512.  stats [P,2] = (mean, rstd) for the backward

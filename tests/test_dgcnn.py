@@ -259,3 +259,50 @@ def test_pcnnet_dgcnn_foldingnet_trains():
             assert prm.grad is None
         else:
             assert prm.grad is not None and torch.isfinite(prm.grad).all(), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Cin,Cout,N,k,train", [(2, 1, 32, 70, 16, True), (3, 16, 64, 45, 5, True), (2, 64, 128, 33, 16, False), (1, 8, 512, 20, 3, True)])
+def test_edge_conv_fused_vs_oracle(B, Cin, Cout, N, k, train):
+    """csrc/edge_conv.cu (point GEMM + gather-add, no edge tensor) against the materialised formulation of the oracle:
+    graph_feature -> VNLinearLeakyReLU(dim=5) -> mean over k, forward and backward"""
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import vn_oracle as O
+    from vn_pointcloudcompletion_b200.dgcnn import VN_DGCNN_fps
+    from vn_pointcloudcompletion_b200.vn_layers import from_rows, to_rows
+    rng = np.random.RandomState(Cin * 7 + Cout)
+    x = rng.standard_normal((B, Cin, 3, N)).astype(np.float32)
+    idx = rng.randint(0, N, (B, k, N)).astype(np.int64)
+    torch.manual_seed(Cout)
+    layer = V.VNLinearLeakyReLU(2 * Cin, Cout).cuda().train(train)
+    with torch.no_grad():
+        layer.batchnorm.bn.weight.copy_(torch.rand(Cout) + 0.5)
+        layer.batchnorm.bn.bias.copy_(torch.randn(Cout) * 0.2)
+        layer.batchnorm.bn.running_mean.copy_(torch.rand(Cout) + 0.5)
+        layer.batchnorm.bn.running_var.copy_(torch.rand(Cout) + 0.5)
+    Wf, Wd = layer.map_to_feat.weight.detach().cpu().numpy(), layer.map_to_dir.weight.detach().cpu().numpy()
+    bn = O.BNState(Cout)
+    bn.weight, bn.bias = layer.batchnorm.bn.weight.detach().cpu().numpy(), layer.batchnorm.bn.bias.detach().cpu().numpy()
+    bn.running_mean, bn.running_var = layer.batchnorm.bn.running_mean.cpu().numpy().copy(), layer.batchnorm.bn.running_var.cpu().numpy().copy()
+    e = GO.graph_feature(x, idx)
+    h, cache = O.vn_linear_leaky_relu(e, Wf, Wd, bn, training=train)
+    want = h.mean(-1)
+    gy = rng.standard_normal(want.shape).astype(np.float32)
+    r = O.vn_linear_leaky_relu_bwd(cache, Wf, Wd, np.broadcast_to(gy[..., None] / k, h.shape).astype(np.float32))
+    want_gx = GO.graph_feature_bwd(x.shape, idx, r["gx"])
+    xt = _dev(x).requires_grad_(True)
+    rows, _, _ = to_rows(xt)
+    out = from_rows(VN_DGCNN_fps._edge_conv(layer, rows, _dev(idx), B, N, k), B, (N,))
+    (out * _dev(gy)).sum().backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want, rtol=1e-4, atol=2e-5)
+    assert_grad_close(xt.grad.cpu().numpy(), want_gx, "gx")
+    assert_grad_close(layer.map_to_feat.weight.grad.cpu().numpy(), r["gWf"], "gWf")
+    assert_grad_close(layer.map_to_dir.weight.grad.cpu().numpy(), r["gWd"], "gWd")
+    assert_grad_close(layer.batchnorm.bn.weight.grad.cpu().numpy(), r["gweight"], "ggamma")
+    assert_grad_close(layer.batchnorm.bn.bias.grad.cpu().numpy(), r["gbias"], "gbeta")
+    if train:
+        np.testing.assert_allclose(layer.batchnorm.bn.running_mean.cpu().numpy(), bn.running_mean, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(layer.batchnorm.bn.running_var.cpu().numpy(), bn.running_var, rtol=1e-4, atol=1e-6)

@@ -71,6 +71,9 @@ SIGNATURES = {
     "vnpcc_rows_add": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _p]),
     "vnpcc_vn_attention_fwd": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
     "vnpcc_vn_attention_bwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
+    "vnpcc_edge_conv_stats": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _p]),
+    "vnpcc_edge_conv_fwd": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _ll, _p]),
+    "vnpcc_edge_conv_bwd": (_i, [_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _f, _i, _p, _p, _ll, _p, _p, _p]),
     "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
 }

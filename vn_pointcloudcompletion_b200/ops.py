@@ -95,8 +95,9 @@ def _ld(t):
 # ---------------------------------------------------------------------------------------------------------------
 # raw launch helpers (no autograd)
 # ---------------------------------------------------------------------------------------------------------------
-def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accumulate=False):
-    """y[r,o] = sum_k x[r,k] * (w[o,k] | w[k,o] if trans_w) (+ bias[(r // rows_per_sample)*3 + r%3, o])"""
+def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accumulate=False, exact=False):
+    """y[r,o] = sum_k x[r,k] * (w[o,k] | w[k,o] if trans_w) (+ bias[(r // rows_per_sample)*3 + r%3, o]); exact=True forces the
+    fp32 SIMT kernel even in TF32 mode (operands whose differences matter, e.g. the edge-convolution point GEMM)"""
     R, K = x.shape
     Cout = w.shape[1] if trans_w else w.shape[0]
     assert (w.shape[0] if trans_w else w.shape[1]) == K, (x.shape, w.shape, trans_w)
@@ -105,10 +106,10 @@ def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accum
     if R == 0 or Cout == 0:
         return out
     with _Timed("gemm", 2.0 * R * K * Cout):
-        return _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout)
+        return _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout, exact)
 
 
-def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout):
+def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout, exact=False):
     # <= 4 input (or, for the dgrad form, output) channels: HBM-bound streaming kernels, exact fp32 in both modes
     if not accumulate and not trans_w and K <= 4:
         rc = _lib.raw("vnpcc_smallk_fwd", ptr(x), _ld(x), ptr(w), _ld(w), ptr(bias), _ld(bias) if bias is not None else 0,
@@ -125,7 +126,7 @@ def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, 
             return out
         if rc != 10003:
             raise _lib.VnpccError(f"vnpcc_smallk_dgrad failed with code {rc}")
-    if _GEMM_MODE == "tf32" and not accumulate:
+    if _GEMM_MODE == "tf32" and not accumulate and not exact:
         wt = w
         if trans_w:   # the tensor-core kernel wants K-contiguous weights; weights are small, transpose them
             wt = torch.empty((Cout, K), device=w.device, dtype=torch.float32)
@@ -213,14 +214,14 @@ def rows_sample_sum(g, B, N):
 # ---------------------------------------------------------------------------------------------------------------
 class _LinearRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, rows_per_sample):
+    def forward(ctx, x, w, bias, rows_per_sample, exact=False):
         x = _rows2d(x, "x")
         _check(w, "weight")
         if w.stride(1) != 1:
             w = w.contiguous()
         if bias is not None:
             bias = _rows2d(bias, "bias")
-        y = gemm_rows(x, w, False, bias, rows_per_sample)
+        y = gemm_rows(x, w, False, bias, rows_per_sample, exact=exact)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.rps = rows_per_sample
@@ -237,20 +238,20 @@ class _LinearRows(torch.autograd.Function):
                 and gy.shape[1] % 4 == 0 and _ld(gy) % 4 == 0):
             R = gy.shape[0]
             gw, gb = smallk_wgrad(gy, x, R // ctx.rps, ctx.rps // 3, True)
-            return gx, gw, gb, None
+            return gx, gw, gb, None, None
         if ctx.needs_input_grad[1]:
             gw = gemm_wgrad(gy, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             R = gy.shape[0]
             B = R // ctx.rps
             gb = rows_sample_sum(gy, B, ctx.rps // 3)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def linear_rows(x, w, bias=None, rows_per_sample=0):
+def linear_rows(x, w, bias=None, rows_per_sample=0, exact=False):
     """x [R,K], w [Cout,K] -> [R,Cout]; optional per-sample bias rows [B*3, Cout] (row (b,v)) added to every point of
     sample b (the broadcast half of torch.cat([global.expand(N), local]) folded out of the GEMM, models/pcn.py:172,385)"""
-    return _LinearRows.apply(x, w, bias, rows_per_sample)
+    return _LinearRows.apply(x, w, bias, rows_per_sample, exact)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -802,3 +803,52 @@ class _VNAttention(torch.autograd.Function):
 def vn_attention(qkv, B, N, H, scale):
     """qkv rows [B*N*3, 3C] = (q | k | v) -> attention output rows [B*N*3, C] (models/transformer.py:89-100)"""
     return _VNAttention.apply(qkv, B, N, H, scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge convolution without the edge tensor (csrc/edge_conv.cu): VN_DGCNN_fps graph feature -> VNLinearLeakyReLU(dim=5) -> mean over k
+# ---------------------------------------------------------------------------------------------------------------
+class _EdgeConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uw, idx, gamma, beta, stat, use_batch, ns, B, N):
+        uw = _rows2d(uw, "uw")
+        C = uw.shape[1] // 4
+        k = idx.shape[1]
+        out = torch.empty((B * N * 3, C), device=uw.device, dtype=torch.float32)
+        call("vnpcc_edge_conv_fwd", ptr(uw), _ld(uw), ptr(idx), B, N, k, C, ptr(stat), ptr(gamma), ptr(beta), float(ns), ptr(out), C, stream())
+        ctx.save_for_backward(uw, idx, gamma, beta, stat)
+        ctx.cfg = (B, N, k, C, float(ns), bool(use_batch))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        uw, idx, gamma, beta, stat = ctx.saved_tensors
+        B, N, k, C, ns, use_batch = ctx.cfg
+        g = _rows2d(g, "grad")
+        if _ld(g) % 4 != 0 or g.data_ptr() % 16:
+            g = g.contiguous()
+        dev = uw.device
+        guw = torch.empty((B * N * 3, 4 * C), device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        ggamma = torch.empty(C, device=dev, dtype=torch.float32)
+        gbeta = torch.empty(C, device=dev, dtype=torch.float32)
+        call("vnpcc_edge_conv_bwd", ptr(g), _ld(g), ptr(uw), _ld(uw), ptr(idx), B, N, k, C, ptr(stat), ptr(gamma), ptr(beta), ns,
+             1 if use_batch else 0, ptr(sums), ptr(guw), 4 * C, ptr(ggamma), ptr(gbeta), stream())
+        return guw, None, ggamma, gbeta, None, None, None, None, None
+
+
+def edge_conv_supported(C, bn):
+    return C % 4 == 0 and 4 <= C <= 1024 and 256 % (C // 4) == 0 and bn is not None and bn.affine
+
+
+def edge_conv(uw, idx, bn, training, ns, B, N):
+    """uw rows (b,n,v) x 4C = (U_p | U_d | W_p | W_d) of the point GEMM, idx [B,k,N] int64 -> rows (b,n,v) x C =
+    mean_j leaky(BN(U_p[j] + W_p[i]), U_d[j] + W_d[i]); BatchNorm statistics over the B*N*k edges"""
+    uw = _rows2d(uw, "uw")
+    C = uw.shape[1] // 4
+    k = idx.shape[1]
+
+    def stats_fn(sums):
+        call("vnpcc_edge_conv_stats", ptr(uw), _ld(uw), ptr(idx), B, N, k, C, ptr(sums), stream())
+    stat, use_batch = _bn_prepare(None, C, bn, training, B * N * k, stats_fn)
+    return _EdgeConv.apply(uw, idx, bn.weight, bn.bias, stat, use_batch, ns, B, N)
