@@ -28,11 +28,23 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-enc", action="store_true", help="only 3 forward+backward passes of the encoder (for an ncu launch list)")
     a = ap.parse_args()
     B = a.batch
     p, c, R = make_batch(B, 2048, 16384, seed=1234)
     pt, ct, Rt = (torch.from_numpy(x).cuda() for x in (p, c, R))
     rows = []
+    if a.profile_enc:
+        V.set_gemm_mode("tf32")
+        cfg = SimpleNamespace(num_coarse=1024, latent_dim=512, only_coarse=False, device="cuda", enc_pretrained="none")
+        torch.manual_seed(0)
+        enc = V.VN_DGCNN_fps(cfg).cuda().train()
+        for _ in range(3):
+            for q in enc.parameters(): q.grad = None
+            co, gf = enc(pt)
+            (co.sum() + gf.sum()).backward()
+        torch.cuda.synchronize()
+        return
     t = timeit(lambda: G.knn3d(pt, pt, 16))
     pairs = B * 2048.0 * 2048
     rows.append(("knn3d k=16, 2048 x 2048", t, f"{pairs / t / 1e6:.0f} Gpairs/s"))

@@ -131,14 +131,15 @@ __global__ void __launch_bounds__(256) edge_fwd_kernel(const float* __restrict__
 // n / nhat / nb of the BatchNorm-on-norm, and gx_dot = <dL/dBN(p), p>.
 __device__ __forceinline__ void edge_lane_bwd(const V4x3& pr, V4x3& dv, V4x3& gv, int l, const ChanParams& cp, float k1, float& n, float& nhat,
                                               float& nb, float& gx_dot) {
-    n = sqrtf(dot3l(pr, pr, l)) + VS_EPS;
+    // MUFU reciprocal / rsqrt like the other backward kernels (vn_math.cuh): gradients do not need op-by-op IEEE rounding
+    n = fsqrt_fast(dot3l(pr, pr, l)) + VS_EPS;
     nhat = (n - cp.mean[l]) * cp.invstd[l];
     nb = nhat * cp.gamma[l] + cp.beta[l];
-    const float t = nb / n;
+    const float t = nb * frcp(n);
     const float pb[3] = {pr.v[0][l] * t, pr.v[1][l] * t, pr.v[2][l] * t};
     const float s = pb[0] * dv.v[0][l] + pb[1] * dv.v[1][l] + pb[2] * dv.v[2][l];
     if (s < 0.f) {
-        const float rq = 1.0f / (dot3l(dv, dv, l) + VS_EPS);
+        const float rq = frcp(dot3l(dv, dv, l) + VS_EPS);
         const float a = s * rq;
         const float gdq = dot3l(gv, dv, l) * rq;
 #pragma unroll
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) edge_bwd_sums_kernel(const float* __restr
             for (int l = 0; l < 4; ++l) {
                 float nn, nhat, nbv, gxd;
                 edge_lane_bwd(p, d, gv, l, cp, k1, nn, nhat, nbv, gxd);
-                const double dnb = (double)(gxd / nn);
+                const double dnb = (double)(gxd * frcp(nn));
                 acc[0][l] += dnb;
                 acc[1][l] = fma(dnb, (double)nhat, acc[1][l]);
             }
@@ -246,11 +247,12 @@ __global__ void __launch_bounds__(256) edge_bwd_main_kernel(const float* __restr
                 float nn, nhat, nbv, gxd;
                 edge_lane_bwd(p, d, gv, l, cp, k1, nn, nhat, nbv, gxd);
                 // BatchNorm-on-norm backward: gp = gpost * nb/n + dn * p / r
-                const float dnb = gxd / nn;
-                const float dn = (cp.gamma[l] * dnb - m1[l] - nhat * m2[l]) * cp.invstd[l] - gxd * nbv / (nn * nn);
+                const float rn = frcp(nn);
+                const float dnb = gxd * rn;
+                const float dn = (cp.gamma[l] * dnb - m1[l] - nhat * m2[l]) * cp.invstd[l] - gxd * nbv * rn * rn;
                 const float r = nn - VS_EPS;
-                const float dr = r > 0.f ? dn / r : 0.f;
-                const float t = nbv / nn;
+                const float dr = r > 0.f ? dn * frcp(r) : 0.f;
+                const float t = nbv * rn;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) gv.v[c][l] = fmaf(gv.v[c][l], t, dr * p.v[c][l]);
             }
