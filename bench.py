@@ -115,10 +115,13 @@ class KernelTimer:
         out = {}
         for cls, work, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            d = out.setdefault(cls, {"ms": 0.0, "work": 0.0, "launches": 0})
+            flops, nbytes = work if isinstance(work, tuple) else (work, 0.0)
+            d = out.setdefault(cls, {"ms": 0.0, "work": 0.0, "bytes": 0.0, "launches": 0, "per_launch": []})
             d["ms"] += ms
-            d["work"] += work
+            d["work"] += flops
+            d["bytes"] += nbytes
             d["launches"] += 1
+            d["per_launch"].append((flops, nbytes, ms))
         return out
 
 
@@ -152,7 +155,7 @@ def cpu_reference_step(batch, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--mode", default="tf32", choices=["tf32", "fp32"])
@@ -326,13 +329,22 @@ def main():
                 tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
                 # TF32 dense peak is half the bf16 one; the driver measures bf16 only
                 peak = (pk["bf16_sustained"] / 2.0) if (cls.endswith("tf32") or cls == "gemm_vn_fused") else None
-                classes[cls] = {"bound": "tensor" if peak else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
-                                "frac": (tf / peak) if peak else None, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
-                                "launches_per_step": d["launches"] / args.steps,
-                                "flop_per_launch": d["work"] / max(d["launches"], 1),
-                                "peak_note": f"bf16 sustained ({pk['source']}) / 2 for TF32 operands; achieved = sum of 2*R*K*Cout "
-                                             "over the class's launches / their CUDA-event time" if peak else
-                                             "fp32 SIMT kernel: no tensor-core peak applies"}
+                ent = {"bound": "tensor" if peak else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                       "frac": (tf / peak) if peak else None, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
+                       "launches_per_step": d["launches"] / args.steps,
+                       "flop_per_launch": d["work"] / max(d["launches"], 1),
+                       "peak_note": f"bf16 sustained ({pk['source']}) / 2 for TF32 operands; achieved = sum of 2*R*K*Cout "
+                                    "over the class's launches / their CUDA-event time" if peak else
+                                    "fp32 SIMT kernel: no tensor-core peak applies"}
+                if peak:
+                    # this kernel function runs both tensor-bound (K >= 512) and HBM-bound (K <= 256: arithmetic intensity below the
+                    # ridge peak_tensor / peak_hbm) shapes; per launch the attainable time is max(flops / tensor, bytes / hbm)
+                    t_roof = sum(max(f / (peak * 1e12), b / (pk["hbm"] * 1e9)) for f, b, _ in d["per_launch"])
+                    t_hbm = sum(b / (pk["hbm"] * 1e9) for f, b, _ in d["per_launch"] if b / (pk["hbm"] * 1e9) > f / (peak * 1e12))
+                    ent["roofline_model"] = {"frac": t_roof / sec if sec > 0 else None, "hbm_bound_share_of_attainable_time": t_hbm / t_roof if t_roof else None,
+                                             "bytes_per_launch": d["bytes"] / max(d["launches"], 1), "hbm_peak_gbs": pk["hbm"],
+                                             "note": "sum over launches of max(flops/peak_tensor, algorithmic bytes/peak_hbm) / measured time"}
+                classes[cls] = ent
             elif cls == "chamfer_fwd":
                 pairs = d["work"] / sec if sec > 0 else 0.0
                 fclk = (clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6

@@ -25,7 +25,20 @@ def timeit(fn, iters=10, warm=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--profile-step", action="store_true", help="only 2 train steps of the attention network (for an ncu launch list)")
     a = ap.parse_args()
+    if a.profile_step:
+        V.set_gemm_mode("tf32")
+        cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cuda", enc_pretrained="none")
+        torch.manual_seed(0)
+        net = V.PCNNet(cfg, enc_type="vn_pointnet", dec_type="attention_vn_foldingnet").train()
+        p, c, R = make_batch(a.batch, 2048, 16384, seed=1234)
+        pt, ct, Rt = (torch.from_numpy(z).cuda() for z in (p, c, R))
+        tr = DataParallelTrainer(net, lr=1e-4)
+        for _ in range(2):
+            tr.train_step(pt, ct, Rt)
+        torch.cuda.synchronize()
+        return
     B, N, H, D = a.batch, 1024, 8, 48
     C = H * D
     print(f"B = {B}, tokens N = {N}, heads = {H}, head features = 3 x {D}\n")

@@ -51,12 +51,14 @@ _LAST_KERNEL = [None]     # name of the kernel family the most recent GEMM launc
 
 
 class _Timed:
+    """work: algorithmic FLOPs (GEMMs, attention) or directed pairs (Chamfer) of the launch; nbytes: its algorithmic HBM bytes
+    (operands read once, result written once) -- together they place the launch on the roofline min(tensor, AI x HBM)"""
     __slots__ = ("tok", "cls")
 
-    def __init__(self, cls, work):
+    def __init__(self, cls, work, nbytes=0.0):
         self.cls = cls
         _LAST_KERNEL[0] = None
-        self.tok = _TIMER.start(cls, work) if _TIMER is not None else None
+        self.tok = _TIMER.start(cls, (work, nbytes)) if _TIMER is not None else None
 
     def __enter__(self):
         return self
@@ -105,7 +107,7 @@ def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accum
         out = torch.empty((R, Cout), device=x.device, dtype=torch.float32)
     if R == 0 or Cout == 0:
         return out
-    with _Timed("gemm", 2.0 * R * K * Cout):
+    with _Timed("gemm", 2.0 * R * K * Cout, 4.0 * (R * K + R * Cout + K * Cout)):
         return _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout, exact)
 
 
@@ -163,7 +165,7 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
     if out is None:
         out = torch.empty((Cout, K), device=x.device, dtype=torch.float32)
         accumulate = False
-    with _Timed("gemm", 2.0 * R * K * Cout):
+    with _Timed("gemm", 2.0 * R * K * Cout, 4.0 * (R * K + R * Cout + K * Cout)):
         return _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K)
 
 
@@ -413,7 +415,7 @@ def linear_bn_leaky_fused_nograd(x, wcat, bias, rows_per_sample, bn, training, n
         stat, _ = _bn_prepare(None, C, bn, training, R // 3, stats_fn)
         gamma, beta = bn.weight, bn.bias
     out = torch.empty((R, C), device=x.device, dtype=torch.float32)
-    with _Timed("gemm_vn_fused", 2.0 * R * K * 2 * C):
+    with _Timed("gemm_vn_fused", 2.0 * R * K * 2 * C, 4.0 * (R * K + R * C + 2 * C * K)):
         call("vnpcc_gemm_vn_apply", ptr(x), _ld(x), ptr(wcat), _ld(wcat), ptr(out), C, R, K, C, ptr(bias), ldb, rows_per_sample,
              ptr(stat), ptr(gamma), ptr(beta), float(ns), stream())
     return out
@@ -551,7 +553,7 @@ class _LinearMaxPool(torch.autograd.Function):
             wc = gemm_rows(wdir, w, True)
             wcat = torch.cat([w, wc], dim=0)
             best = torch.empty(G * C, device=x.device, dtype=torch.int64)
-            with _Timed("gemm_vn_fused", 2.0 * x.shape[0] * K * 2 * C):
+            with _Timed("gemm_vn_fused", 2.0 * x.shape[0] * K * 2 * C, 4.0 * (x.shape[0] * K + 2 * C * K)):
                 rc = _lib.raw("vnpcc_gemm_vn_pool", ptr(x), _ld(x), ptr(wcat), _ld(wcat), x.shape[0], K, C, N, ptr(best), stream())
             if rc == 0:
                 idx = torch.empty((G, C), device=x.device, dtype=torch.int64)
