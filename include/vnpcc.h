@@ -211,6 +211,15 @@ int vnpcc_vn_attention_fwd(const float* qkv, long long ld, int B, int N, int H, 
 int vnpcc_vn_attention_bwd(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo, const float* lse,
                            int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta, void* stream);
 
+/* ---------------------------------------------------------------- evaluation extras (test.py:73-78) ---------- */
+/* metrics/metric.py:31-48 f_score from the Chamfer search's SQUARED distances: out [B,3] = (precision, recall, F) with
+ * precision = #{sqrt(dist1) < th} / N, recall = #{sqrt(dist2) < th} / M */
+int vnpcc_fscore(const float* dist1, const float* dist2, int B, int N, int M, float th, float* out, void* stream);
+/* utils/voxel_util.py:89-105 points_to_voxels (pyntcloud VoxelGrid, regular bounding box of the cloud itself, size_grid^3 cells) as a bit
+ * mask: bits [B, ceil(size_grid^3 / 32)] (zeroed here), voxel (x,y,z) -> bit (x*n + y)*n + z; and utils/voxel_util.py:5-14 iou -> out [B] */
+int vnpcc_voxel_occupancy(const float* xyz, int B, int N, int size_grid, unsigned* bits, void* stream);
+int vnpcc_voxel_iou(const unsigned* bits_a, const unsigned* bits_b, int B, int words, float* out, void* stream);
+
 /* ---------------------------------------------------------------- optimiser / misc ------------------------------ */
 /* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
 int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

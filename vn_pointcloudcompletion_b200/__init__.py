@@ -4,6 +4,7 @@ and the Chamfer loss/metric, behind the reference's own Python interfaces.  See 
 from . import _lib  # noqa: F401
 from .chamfer_distance import ChamferDistance, chamfer_3DDist, chamfer_3DFunction  # noqa: F401
 from .dgcnn import VN_DGCNN_fps  # noqa: F401
+from .eval_metrics import RotateAxisAngle, evaluate_iou, f_score, points_to_voxels, random_sample, read_point_cloud  # noqa: F401
 from .graph_ops import KNN, furthest_point_sample, gather_operation  # noqa: F401
 from .loss import cd_loss_L1, cd_loss_L2, l1_cd, l2_cd  # noqa: F401
 from .model import PCNNet, Rotate, random_rotations  # noqa: F401

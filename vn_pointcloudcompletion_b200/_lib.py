@@ -74,6 +74,9 @@ SIGNATURES = {
     "vnpcc_edge_conv_stats": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _p]),
     "vnpcc_edge_conv_fwd": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _ll, _p]),
     "vnpcc_edge_conv_bwd": (_i, [_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _f, _i, _p, _p, _ll, _p, _p, _p]),
+    "vnpcc_fscore": (_i, [_p, _p, _i, _i, _i, _f, _p, _p]),
+    "vnpcc_voxel_occupancy": (_i, [_p, _i, _i, _i, _p, _p]),
+    "vnpcc_voxel_iou": (_i, [_p, _p, _i, _i, _p, _p]),
     "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
 }
