@@ -207,6 +207,10 @@ int vnpcc_rows_add(const float* a, long long lda, const float* b, long long ldb,
  * flash-style (no [N,N] matrix in HBM).  D in {16, 32, 48}; ld % 4 == 0. */
 int vnpcc_vn_attention_fwd(const float* qkv, long long ld, int B, int N, int H, int D, float scale, float* out, long long ldo, float* lse,
                            void* stream);
+/* tensor-core twin of the forward (csrc/attention_tc.cu): tcgen05 / TMEM, TF32 operands, fp32 accumulation, two-pass softmax with the
+ * output accumulator resident in TMEM.  Same arguments; D == 48 only, returns VNPCC_ERR_UNSUPPORTED otherwise. */
+int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, int H, int D, float scale, float* out, long long ldo, float* lse,
+                                void* stream);
 /* dqkv [B*N*3, 3C] fully written (q part zeroed then accumulated with fp32 atomics); delta: workspace of B*H*N floats */
 int vnpcc_vn_attention_bwd(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo, const float* lse,
                            int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta, void* stream);

@@ -266,3 +266,30 @@ def test_pcnnet_pointnet_attention_decoder_trains():
                 assert torch.isfinite(prm.grad).all(), n
     finally:
         V.set_gemm_mode("fp32")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,H", [(1, 64, 1), (2, 130, 2), (1, 1024, 8), (2, 200, 3)])
+def test_attention_core_tf32_tensor_core_forward(B, N, H):
+    """csrc/attention_tc.cu (tcgen05 / TMEM, TF32 operands) against the numpy oracle.  Stated TF32 tolerance: operands carry a 10-bit
+    mantissa, scores are sums of 144 products of O(1) features -> |dS| <~ 3e-3, i.e. a few 1e-3 relative error on softmax weights;
+    outputs are compared at 1e-2 of the largest entry (rel-L2 5e-3), lse at 5e-3 absolute."""
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import ops
+    D = 48
+    rng = np.random.RandomState(B * 100 + N)
+    C = H * D
+    q, k, v = (rng.standard_normal((B, C, 3, N)).astype(np.float32) * 0.3 for _ in range(3))
+    o, c = AO.attention_core(q, k, v, H, 0.7)
+    rows = lambda a: np.ascontiguousarray(a.transpose(0, 3, 2, 1)).reshape(B * N * 3, -1)      # noqa: E731
+    qkv = _dev(np.concatenate([rows(q), rows(k), rows(v)], 1))
+    V.set_gemm_mode("tf32")
+    try:
+        out = ops.vn_attention(qkv, B, N, H, 0.7)
+        torch.cuda.synchronize()
+        assert ops._LAST_KERNEL[0] == "attention_fwd_tf32"
+    finally:
+        V.set_gemm_mode("fp32")
+    assert_grad_close(out.cpu().numpy(), rows(o), "out", 5e-3, 1e-2)

@@ -48,6 +48,10 @@ def main():
     fl = 4.0 * B * H * N * N * 3 * D
     t = timeit(lambda: ops.vn_attention(qkv.detach(), B, N, H, 1.0))
     print(f"| vn_attention forward (fp32 SIMT, flash-style) | {t:.3f} | {fl / t / 1e9:.1f} TFLOP/s |")
+    V.set_gemm_mode("tf32")
+    t = timeit(lambda: ops.vn_attention(qkv.detach(), B, N, H, 1.0))
+    V.set_gemm_mode("fp32")
+    print(f"| vn_attention forward (tcgen05 / TMEM, TF32 operands, two-pass softmax) | {t:.3f} | {fl / t / 1e9:.1f} TFLOP/s algorithmic ({1.5 * fl / t / 1e9:.1f} executed: Q K^T runs twice) |")
     go = torch.randn(B * N * 3, C, device="cuda")
     def fb():
         qkv.grad = None

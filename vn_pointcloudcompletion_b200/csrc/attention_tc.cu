@@ -1,0 +1,312 @@
+// attention_tc.cu -- tensor-core (tcgen05 / TMEM, TF32 operands, fp32 accumulation) forward of the VN multi-head attention core
+// (models/transformer.py:89-100), throughput mode.  Same contract and ROW layout as vnpcc_vn_attention_fwd (attention.cu).
+//
+// One CTA = 128 query tokens of one (sample, head) = the 128 TMEM lanes; keys / values stream through in tiles of 64.
+//   S [128 q x 64 keys]  = Q K^T     tcgen05.mma kind::tf32, M128 N64,  K = 3 x 64 (a head's [48, 3] feature, each component's
+//                                    48 channels zero-padded to 64 so that it fills two 128-byte swizzle rows)
+//   O [128 q x 192]     += P V       M128 N192, K = 64 keys; P is written by the softmax threads (one thread = one query row = one
+//                                    TMEM lane, so the row maximum and row sum are thread-local) into shared memory in the
+//                                    K-major SWIZZLE_128B operand layout, V is staged transposed ([feature, key]) in the same layout
+// Softmax is two-pass (pass 1: row maxima from S alone; pass 2: P = exp(S - m), O += P V with the accumulator resident in TMEM),
+// which costs a second Q K^T but needs no accumulator rescaling.  Operand tiles are filled with ordinary vector loads / st.shared
+// (the head feature is three 192-byte segments of a token's rows: not a TMA-swizzlable box) followed by fence.proxy.async.
+// Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "vnpcc.h"
+#include "vnpcc_internal.h"
+
+namespace vnpcc {
+namespace atc {
+
+constexpr int BQ = 128;         // queries per CTA (TMEM lanes)
+constexpr int BKEY = 64;        // keys per tile
+constexpr int DP = 64;          // padded channels per component
+constexpr int KD = 3 * DP;      // padded head feature = MMA K of S, MMA N of O
+constexpr int NT = 128;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
+
+constexpr int Q_BYTES = (KD / 32) * BQ * 128;        // 98304
+constexpr int K_BYTES = (KD / 32) * BKEY * 128;      // 49152
+constexpr int VT_BYTES = (BKEY / 32) * KD * 128;     // 49152
+constexpr int P_BYTES = (BKEY / 32) * BQ * 128;      // 32768
+constexpr int TILE_BYTES = Q_BYTES + K_BYTES + VT_BYTES + P_BYTES;
+constexpr int SMEM_BYTES = TILE_BYTES + 64 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t of the warp gets lane (quadrant*32 + t), v[j] = column (col0 + j)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): LBO 16 B, SBO 1024 B (8 rows x 128 B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(16 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: c_format F32 [4,6), a/b format TF32 [7,10)/[10,13), K-major A and B, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of element (row r, k index kappa) inside a K-major SWIZZLE_128B tile of `rows` rows: k-blocks of 32 floats (one 128-byte
+// swizzle row each), 8-row groups of 1024 bytes, 16-byte chunk index XOR (row mod 8)
+__device__ __forceinline__ uint32_t sw128(int rows, int r, int kappa) {
+    return (uint32_t)((kappa >> 5) * (rows * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((((kappa & 31) >> 2) ^ (r & 7)) << 4) + (kappa & 3) * 4);
+}
+
+// rows tile of `rows` tokens starting at n0: element (token t, component v, channel c) -> (r = t, kappa = v*64 + c); zeros beyond N
+template <int D>
+__device__ __forceinline__ void fill_rows_tile(uint8_t* tile, int rows, const float* __restrict__ g, size_t ld, int n0, int N) {
+    constexpr int Q4 = D / 4;
+    for (int i = threadIdx.x; i < rows * 3 * Q4; i += NT) {
+        const int t = i / (3 * Q4);
+        const int rem = i - t * (3 * Q4);
+        const int v = rem / Q4, c4 = rem - v * Q4;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + t < N) val = __ldg(reinterpret_cast<const float4*>(g + ((size_t)(n0 + t) * 3 + v) * ld + c4 * 4));
+        *reinterpret_cast<float4*>(tile + sw128(rows, t, v * DP + c4 * 4)) = val;
+    }
+}
+
+// transposed tile: element (token t, component v, channel c) -> (r = v*64 + c, kappa = t); 32 consecutive lanes = 32 consecutive tokens
+template <int D>
+__device__ __forceinline__ void fill_transposed_tile(uint8_t* tile, const float* __restrict__ g, size_t ld, int n0, int N) {
+    constexpr int Q4 = D / 4;
+    for (int i = threadIdx.x; i < BKEY * 3 * Q4; i += NT) {
+        const int grp = i / BKEY;
+        const int t = i - grp * BKEY;
+        const int v = grp / Q4, c4 = grp - v * Q4;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + t < N) val = __ldg(reinterpret_cast<const float4*>(g + ((size_t)(n0 + t) * 3 + v) * ld + c4 * 4));
+        const int f = v * DP + c4 * 4;
+        *reinterpret_cast<float*>(tile + sw128(KD, f, t)) = val.x;
+        *reinterpret_cast<float*>(tile + sw128(KD, f + 1, t)) = val.y;
+        *reinterpret_cast<float*>(tile + sw128(KD, f + 2, t)) = val.z;
+        *reinterpret_cast<float*>(tile + sw128(KD, f + 3, t)) = val.w;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const float* __restrict__ qkv, size_t ld, int N, int H, int C, float scale,
+                                                           float* __restrict__ out, size_t ldo, float* __restrict__ lse) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* Qs = smem;
+    uint8_t* Ks = Qs + Q_BYTES;
+    uint8_t* Vt = Ks + K_BYTES;
+    uint8_t* Ps = Vt + VT_BYTES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TILE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int q0 = blockIdx.x * BQ;
+    const float* base = qkv + (size_t)b * N * 3 * ld + (size_t)h * D;
+
+    // zero all operand tiles once: the padding chunks (channels 48..63 of every component) stay zero for the whole kernel
+    for (int i = tid; i < TILE_BYTES / 16; i += NT) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    __syncthreads();
+    fill_rows_tile<D>(Qs, BQ, base, ld, q0, N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);      // this thread's TMEM lane = its query row
+    const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64;
+    constexpr uint32_t idesc_s = make_idesc(BQ, BKEY);
+    constexpr uint32_t idesc_o = make_idesc(BQ, KD);
+    uint32_t phase = 0;
+
+    auto issue_s = [&]() {
+        const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
+#pragma unroll
+        for (int ks = 0; ks < KD / 8; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            umma_tf32(s_tmem, make_desc(qa + kb * (BQ * 128) + kk * 32), make_desc(ka + kb * (BKEY * 128) + kk * 32), idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+    };
+
+    // ---- pass 1: row maxima of the scaled scores
+    float m = -INFINITY;
+    for (int k0 = 0; k0 < N; k0 += BKEY) {
+        fill_rows_tile<D>(Ks, BKEY, base + C, ld, k0, N);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_s();
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float s[32];
+            tmem_ld32(t_row + half * 32, s);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (k0 + half * 32 + j < N) m = fmaxf(m, s[j] * scale);
+        }
+    }
+
+    // ---- pass 2: P = exp(S - m), l = sum P, O += P V
+    float l = 0.f;
+    int tile = 0;
+    for (int k0 = 0; k0 < N; k0 += BKEY, ++tile) {
+        fill_rows_tile<D>(Ks, BKEY, base + C, ld, k0, N);
+        fill_transposed_tile<D>(Vt, base + 2 * C, ld, k0, N);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_s();
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float s[32];
+            tmem_ld32(t_row + half * 32, s);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = (k0 + half * 32 + j < N) ? expf(s[j] * scale - m) : 0.f;
+                s[j] = p;
+                l += p;
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(Ps + sw128(BQ, tid, half * 32 + j4 * 4)) = make_float4(s[j4 * 4], s[j4 * 4 + 1], s[j4 * 4 + 2], s[j4 * 4 + 3]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t pa = smem_u32(Ps), va = smem_u32(Vt);
+#pragma unroll
+            for (int ks = 0; ks < BKEY / 8; ++ks) {
+                const int kb = ks >> 2, kk = ks & 3;
+                umma_tf32(o_tmem, make_desc(pa + kb * (BQ * 128) + kk * 32), make_desc(va + kb * (KD * 128) + kk * 32), idesc_o,
+                          (tile | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);      // the operand tiles may be refilled and S overwritten only after these MMAs have completed
+        phase ^= 1;
+        tc_fence_after();
+    }
+
+    // ---- epilogue: out = O / l, lse = m + log l
+    const int n = q0 + tid;
+    const float inv = 1.0f / l;
+#pragma unroll 1
+    for (int i = 0; i < KD / 32; ++i) {
+        float o[32];
+        tmem_ld32(t_row + 64 + i * 32, o);
+        if (n < N) {
+            const int v = i >> 1, c0 = (i & 1) * 32;
+            float* dst = out + ((size_t)(b * (size_t)N + n) * 3 + v) * ldo + (size_t)h * D + c0;
+            const int cnt = (c0 + 32 <= D) ? 32 : (D - c0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+        }
+    }
+    if (n < N) lse[(size_t)bh * N + n] = m + logf(l);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace atc
+}  // namespace vnpcc
+
+using namespace vnpcc;
+
+extern "C" {
+
+// tensor-core twin of vnpcc_vn_attention_fwd (same arguments).  D == 48 only; returns VNPCC_ERR_UNSUPPORTED otherwise.
+int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, int H, int D, float scale, float* out, long long ldo, float* lse,
+                                void* stream) {
+    if (B <= 0 || N <= 0) return 0;
+    if (D != 48 || H <= 0 || ld % 4 != 0 || ldo % 4 != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || !(scale > 0.f))
+        return VNPCC_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(atc::attn_fwd_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES) != cudaSuccess)
+        return VNPCC_ERR_DRIVER;
+    dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
+    count_launch(), atc::attn_fwd_tc_kernel<48><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(qkv, (size_t)ld, N, H, H * D, scale, out,
+                                                                                                     (size_t)ldo, lse);
+    return last_error();
+}
+
+}  // extern "C"

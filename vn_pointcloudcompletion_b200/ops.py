@@ -782,7 +782,15 @@ class _VNAttention(torch.autograd.Function):
         out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float32)
         lse = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
         with _Timed("attention_fwd", 4.0 * B * H * N * N * 3 * D):
-            call("vnpcc_vn_attention_fwd", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), stream())
+            rc = 10003
+            if _GEMM_MODE == "tf32":      # tcgen05 / TMEM forward (csrc/attention_tc.cu); shapes it does not take fall through
+                rc = _lib.raw("vnpcc_vn_attention_fwd_tf32", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), stream())
+                if rc not in (0, 10003):
+                    raise _lib.VnpccError(f"vnpcc_vn_attention_fwd_tf32 failed with code {rc}")
+                if rc == 0:
+                    _LAST_KERNEL[0] = "attention_fwd_tf32"
+            if rc != 0:
+                call("vnpcc_vn_attention_fwd", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), stream())
         ctx.save_for_backward(qkv, out, lse)
         ctx.cfg = (B, N, H, D, float(scale))
         return out
