@@ -8,9 +8,16 @@
 //                                    TMEM lane, so the row maximum and row sum are thread-local) into shared memory in the
 //                                    K-major SWIZZLE_128B operand layout, V is staged transposed ([feature, key]) in the same layout
 // Softmax is two-pass (pass 1: row maxima from S alone; pass 2: P = exp(S - m), O += P V with the accumulator resident in TMEM),
-// which costs a second Q K^T but needs no accumulator rescaling.  Operand tiles are filled with ordinary vector loads / st.shared
-// (the head feature is three 192-byte segments of a token's rows: not a TMA-swizzlable box) followed by fence.proxy.async.
+// which costs a second Q K^T but needs no accumulator rescaling.
+// Operand staging: TMA, 3-D tensor maps over qkv viewed as [token][component][column].  A box of 32 columns x 1 component x T tokens is
+// exactly one k-block (T rows x 128 bytes) of the K-major SWIZZLE_128B layout; the second box of a component covers channels 32..63
+// of the head, i.e. 16 real channels and 16 that belong to the NEXT head.  Q's copies of those 16 columns are zeroed after its (single)
+// load, so whatever K holds there is multiplied by zero; V's extra columns only produce output columns that are never read.  V is the
+// MN-major B operand of the second MMA (feature contiguous): boxes with the 128B_ATOM_32B swizzle <-> UMMA SWIZZLE_128B_BASE32B, the
+// pairing the weight-gradient GEMM (gemm_tcgen05.cu) uses.  One thread issues TMA and MMA; the K tile of the next step is fetched while
+// the softmax threads work, the V tile while the next Q K^T runs.
 // Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -54,6 +61,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (done) return;
     }
     __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -104,9 +123,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: c_format F32 [4,6), a/b format TF32 [7,10)/[10,13), K-major A and B, N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major SWIZZLE_128B_BASE32B descriptor: slabs of {32 MN elements = 128 B} x rows (reduction index); the swizzle atom is 4 rows, one
+// K = 8 instruction spans two atoms (SBO = 512 B); LBO = bytes between consecutive 32-element slabs along M / N
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+// instruction descriptor: c_format F32 [4,6), a/b format TF32 [7,10)/[10,13), a_major [15], b_major [16] (0 = K-major, 1 = MN-major),
+// N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // byte offset of element (row r, k index kappa) inside a K-major SWIZZLE_128B tile of `rows` rows: k-blocks of 32 floats (one 128-byte
@@ -115,74 +146,54 @@ __device__ __forceinline__ uint32_t sw128(int rows, int r, int kappa) {
     return (uint32_t)((kappa >> 5) * (rows * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((((kappa & 31) >> 2) ^ (r & 7)) << 4) + (kappa & 3) * 4);
 }
 
-// rows tile of `rows` tokens starting at n0: element (token t, component v, channel c) -> (r = t, kappa = v*64 + c); zeros beyond N
 template <int D>
-__device__ __forceinline__ void fill_rows_tile(uint8_t* tile, int rows, const float* __restrict__ g, size_t ld, int n0, int N) {
-    constexpr int Q4 = D / 4;
-    for (int i = threadIdx.x; i < rows * 3 * Q4; i += NT) {
-        const int t = i / (3 * Q4);
-        const int rem = i - t * (3 * Q4);
-        const int v = rem / Q4, c4 = rem - v * Q4;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n0 + t < N) val = __ldg(reinterpret_cast<const float4*>(g + ((size_t)(n0 + t) * 3 + v) * ld + c4 * 4));
-        *reinterpret_cast<float4*>(tile + sw128(rows, t, v * DP + c4 * 4)) = val;
-    }
-}
-
-// transposed tile: element (token t, component v, channel c) -> (r = v*64 + c, kappa = t); 32 consecutive lanes = 32 consecutive tokens
-template <int D>
-__device__ __forceinline__ void fill_transposed_tile(uint8_t* tile, const float* __restrict__ g, size_t ld, int n0, int N) {
-    constexpr int Q4 = D / 4;
-    for (int i = threadIdx.x; i < BKEY * 3 * Q4; i += NT) {
-        const int grp = i / BKEY;
-        const int t = i - grp * BKEY;
-        const int v = grp / Q4, c4 = grp - v * Q4;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n0 + t < N) val = __ldg(reinterpret_cast<const float4*>(g + ((size_t)(n0 + t) * 3 + v) * ld + c4 * 4));
-        const int f = v * DP + c4 * 4;
-        *reinterpret_cast<float*>(tile + sw128(KD, f, t)) = val.x;
-        *reinterpret_cast<float*>(tile + sw128(KD, f + 1, t)) = val.y;
-        *reinterpret_cast<float*>(tile + sw128(KD, f + 2, t)) = val.z;
-        *reinterpret_cast<float*>(tile + sw128(KD, f + 3, t)) = val.w;
-    }
-}
-
-template <int D>
-__global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const float* __restrict__ qkv, size_t ld, int N, int H, int C, float scale,
+__global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_q,
+                                                           const __grid_constant__ CUtensorMap map_v, int N, int H, int C, float scale,
                                                            float* __restrict__ out, size_t ldo, float* __restrict__ lse) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
     uint8_t* Ks = Qs + Q_BYTES;
-    uint8_t* Vt = Ks + K_BYTES;
-    uint8_t* Ps = Vt + VT_BYTES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TILE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint8_t* Vs = Ks + K_BYTES;
+    uint8_t* Ps = Vs + VT_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TILE_BYTES);
+    uint64_t* qfull = bars, *kfull = bars + 1, *vfull = bars + 2, *s_done = bars + 3, *o_done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
     const int q0 = blockIdx.x * BQ;
-    const float* base = qkv + (size_t)b * N * 3 * ld + (size_t)h * D;
+    const int tok0 = b * N;                       // first token of the sample in the [B*N]-token tensor maps
+    const int colq = h * D, colk = C + h * D, colv = 2 * C + h * D;
+    const int T = (N + BKEY - 1) / BKEY;
 
-    // zero all operand tiles once: the padding chunks (channels 48..63 of every component) stay zero for the whole kernel
-    for (int i = tid; i < TILE_BYTES / 16; i += NT) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
-        mbar_init(bar, 1);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_v);
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 256);
-    __syncthreads();
-    fill_rows_tile<D>(Qs, BQ, base, ld, q0, N);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);      // this thread's TMEM lane = its query row
     const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64;
-    constexpr uint32_t idesc_s = make_idesc(BQ, BKEY);
-    constexpr uint32_t idesc_o = make_idesc(BQ, KD);
-    uint32_t phase = 0;
+    constexpr uint32_t idesc_s = make_idesc(BQ, BKEY, 0);
+    constexpr uint32_t idesc_o = make_idesc(BQ, KD, 1);
 
+    auto load_k = [&](int k0) {      // 6 boxes {32 cols, 1 component, 64 tokens} -> 6 k-blocks of 8 KB
+        mbar_expect_tx(kfull, K_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_k, kfull, Ks + kb * (BKEY * 128), colk + (kb & 1) * 32, kb >> 1, tok0 + k0);
+    };
+    auto load_v = [&](int k0) {      // 6 slabs {32 features, 64 keys}
+        mbar_expect_tx(vfull, VT_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < KD / 32; ++sl) tma_load_3d(&map_v, vfull, Vs + sl * (BKEY * 128), colv + (sl & 1) * 32, sl >> 1, tok0 + k0);
+    };
     auto issue_s = [&]() {
         const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
 #pragma unroll
@@ -190,23 +201,41 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const float* __restr
             const int kb = ks >> 2, kk = ks & 3;
             umma_tf32(s_tmem, make_desc(qa + kb * (BQ * 128) + kk * 32), make_desc(ka + kb * (BKEY * 128) + kk * 32), idesc_s, ks != 0 ? 1u : 0u);
         }
-        umma_commit(bar);
+        umma_commit(s_done);
     };
+
+    // ---- Q tile: one TMA load, then zero the 16 padding columns of every component (chunks 4..7 of the odd k-blocks)
+    if (tid == 0) {
+        mbar_expect_tx(qfull, Q_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_q, qfull, Qs + kb * (BQ * 128), colq + (kb & 1) * 32, kb >> 1, tok0 + q0);
+        load_k(0);
+    }
+    mbar_wait(qfull, 0);
+    for (int i = tid; i < 3 * BQ * 4; i += NT) {
+        const int v = i / (BQ * 4), rem = i - v * (BQ * 4);
+        const int r = rem >> 2, j = 4 + (rem & 3);
+        *reinterpret_cast<float4*>(Qs + (2 * v + 1) * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    uint32_t kph = 0, vph = 0, sph = 0, oph = 0;
 
     // ---- pass 1: row maxima of the scaled scores
     float m = -INFINITY;
-    for (int k0 = 0; k0 < N; k0 += BKEY) {
-        fill_rows_tile<D>(Ks, BKEY, base + C, ld, k0, N);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
+    for (int i = 0; i < T; ++i) {
+        const int k0 = i * BKEY;
         if (tid == 0) {
+            mbar_wait(kfull, kph);
             tc_fence_after();
             issue_s();
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
+        kph ^= 1;
+        mbar_wait(s_done, sph);
+        sph ^= 1;
         tc_fence_after();
+        if (tid == 0) load_k(i + 1 < T ? k0 + BKEY : 0);      // the K buffer is free; the last prefetch is tile 0 for pass 2
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float s[32];
@@ -215,24 +244,25 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const float* __restr
             for (int j = 0; j < 32; ++j)
                 if (k0 + half * 32 + j < N) m = fmaxf(m, s[j] * scale);
         }
+        tc_fence_before();
+        __syncthreads();      // every thread has read S before the next Q K^T overwrites it
     }
 
     // ---- pass 2: P = exp(S - m), l = sum P, O += P V
     float l = 0.f;
-    int tile = 0;
-    for (int k0 = 0; k0 < N; k0 += BKEY, ++tile) {
-        fill_rows_tile<D>(Ks, BKEY, base + C, ld, k0, N);
-        fill_transposed_tile<D>(Vt, base + 2 * C, ld, k0, N);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
+    if (tid == 0) load_v(0);
+    for (int i = 0; i < T; ++i) {
+        const int k0 = i * BKEY;
         if (tid == 0) {
+            mbar_wait(kfull, kph);
             tc_fence_after();
             issue_s();
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
+        kph ^= 1;
+        mbar_wait(s_done, sph);
+        sph ^= 1;
         tc_fence_after();
+        if (tid == 0 && i + 1 < T) load_k(k0 + BKEY);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float s[32];
@@ -249,22 +279,29 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const float* __restr
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();      // P complete (and S consumed)
         if (tid == 0) {
+            mbar_wait(vfull, vph);
             tc_fence_after();
-            const uint32_t pa = smem_u32(Ps), va = smem_u32(Vt);
+            const uint32_t pa = smem_u32(Ps), va = smem_u32(Vs);
 #pragma unroll
             for (int ks = 0; ks < BKEY / 8; ++ks) {
                 const int kb = ks >> 2, kk = ks & 3;
-                umma_tf32(o_tmem, make_desc(pa + kb * (BQ * 128) + kk * 32), make_desc(va + kb * (KD * 128) + kk * 32), idesc_o,
-                          (tile | ks) != 0 ? 1u : 0u);
+                umma_tf32(o_tmem, make_desc(pa + kb * (BQ * 128) + kk * 32), make_desc_mn(va + ks * 1024, BKEY * 128), idesc_o, (i | ks) != 0 ? 1u : 0u);
             }
-            umma_commit(bar);
+            umma_commit(o_done);
+            // V and P may be overwritten only after these MMAs have read them.  The next Q K^T is issued behind them (tcgen05 MMAs of
+            // one thread execute in order), so the softmax threads, which wait for it before touching P, need no extra wait.
+            mbar_wait(o_done, oph);
+            if (i + 1 < T) load_v(k0 + BKEY);
         }
-        mbar_wait(bar, phase);      // the operand tiles may be refilled and S overwritten only after these MMAs have completed
-        phase ^= 1;
-        tc_fence_after();
+        vph ^= 1;
+        oph ^= 1;
     }
+    // all MMAs are complete for thread 0; make that visible to everyone before the accumulator is read
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     // ---- epilogue: out = O / l, lse = m + log l
     const int n = q0 + tid;
@@ -288,6 +325,35 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const float* __restr
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// qkv [tokens*3, cols] (leading dimension ld) viewed as a 3-D tensor {cols, 3 components, tokens}; box = {32 cols, 1, box_tokens}
+static bool make_map3(CUtensorMap* m, const float* base, long long tokens, long long cols, long long ld, int box_tokens, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, 3, (cuuint64_t)tokens};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)ld * 3 * sizeof(float)};
+    cuuint32_t box[3] = {32, 1, (cuuint32_t)box_tokens};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace atc
 }  // namespace vnpcc
 
@@ -301,10 +367,16 @@ int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, in
     if (B <= 0 || N <= 0) return 0;
     if (D != 48 || H <= 0 || ld % 4 != 0 || ldo % 4 != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || !(scale > 0.f))
         return VNPCC_ERR_UNSUPPORTED;
+    CUtensorMap mk, mq, mv;
+    const long long tokens = (long long)B * N, cols = 3LL * H * D;
+    if (!atc::make_map3(&mk, qkv, tokens, cols, ld, atc::BKEY, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&mq, qkv, tokens, cols, ld, atc::BQ, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&mv, qkv, tokens, cols, ld, atc::BKEY, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return VNPCC_ERR_DRIVER;
     if (cudaFuncSetAttribute(atc::attn_fwd_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES) != cudaSuccess)
         return VNPCC_ERR_DRIVER;
     dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
-    count_launch(), atc::attn_fwd_tc_kernel<48><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(qkv, (size_t)ld, N, H, H * D, scale, out,
+    count_launch(), atc::attn_fwd_tc_kernel<48><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(mk, mq, mv, N, H, H * D, scale, out,
                                                                                                      (size_t)ldo, lse);
     return last_error();
 }
