@@ -215,6 +215,15 @@ int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, in
 int vnpcc_vn_attention_bwd(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo, const float* lse,
                            int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta, void* stream);
 
+/* delta[b,h,n] = <dout, out> over head h's features (first step of both attention backwards); and the tensor-core twin of the backward
+ * (csrc/attention_tc.cu): dV / dQ / dK by tcgen05 kernels with the accumulators resident in TMEM, dqkv fully written with plain stores
+ * (no atomics).  D == 48 only, VNPCC_ERR_UNSUPPORTED otherwise. */
+int vnpcc_vn_attention_delta(const float* dout, long long lddo, const float* out, long long ldo, int B, int N, int H, int D, float* delta,
+                             void* stream);
+int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo,
+                                const float* lse, int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta,
+                                void* stream);
+
 /* ---------------------------------------------------------------- evaluation extras (test.py:73-78) ---------- */
 /* metrics/metric.py:31-48 f_score from the Chamfer search's SQUARED distances: out [B,3] = (precision, recall, F) with
  * precision = #{sqrt(dist1) < th} / N, recall = #{sqrt(dist2) < th} / M */

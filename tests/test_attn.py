@@ -270,7 +270,7 @@ def test_pcnnet_pointnet_attention_decoder_trains():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,N,H", [(1, 64, 1), (2, 130, 2), (1, 1024, 8), (2, 200, 3)])
-def test_attention_core_tf32_tensor_core_forward(B, N, H):
+def test_attention_core_tf32_tensor_core(B, N, H):
     """csrc/attention_tc.cu (tcgen05 / TMEM, TF32 operands) against the numpy oracle.  Stated TF32 tolerance: operands carry a 10-bit
     mantissa, scores are sums of 144 products of O(1) features -> |dS| <~ 3e-3, i.e. a few 1e-3 relative error on softmax weights;
     outputs are compared at 1e-2 of the largest entry (rel-L2 5e-3), lse at 5e-3 absolute."""
@@ -285,11 +285,21 @@ def test_attention_core_tf32_tensor_core_forward(B, N, H):
     o, c = AO.attention_core(q, k, v, H, 0.7)
     rows = lambda a: np.ascontiguousarray(a.transpose(0, 3, 2, 1)).reshape(B * N * 3, -1)      # noqa: E731
     qkv = _dev(np.concatenate([rows(q), rows(k), rows(v)], 1))
+    gy = rng.standard_normal((B, C, 3, N)).astype(np.float32)
+    gq, gk, gv = AO.attention_core_bwd(c, gy)
+    qkv.requires_grad_(True)
     V.set_gemm_mode("tf32")
     try:
         out = ops.vn_attention(qkv, B, N, H, 0.7)
         torch.cuda.synchronize()
         assert ops._LAST_KERNEL[0] == "attention_fwd_tf32"
+        out.backward(_dev(rows(gy)))
+        torch.cuda.synchronize()
+        assert ops._LAST_KERNEL[0] == "attention_bwd_tf32"
     finally:
         V.set_gemm_mode("fp32")
-    assert_grad_close(out.cpu().numpy(), rows(o), "out", 5e-3, 1e-2)
+    assert_grad_close(out.detach().cpu().numpy(), rows(o), "out", 5e-3, 1e-2)
+    got = qkv.grad.cpu().numpy()
+    assert_grad_close(got[:, 2 * C:], rows(gv), "gv", 1e-2, 2e-2)
+    assert_grad_close(got[:, :C], rows(gq), "gq", 1e-2, 2e-2)
+    assert_grad_close(got[:, C:2 * C], rows(gk), "gk", 1e-2, 2e-2)

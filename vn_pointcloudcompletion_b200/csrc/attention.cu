@@ -537,4 +537,15 @@ int vnpcc_vn_attention_bwd(const float* qkv, long long ld, const float* dout, lo
     }
 }
 
+// delta[b, h, n] = sum over head h's features of dout * out  (shared by the SIMT and the tensor-core backward)
+int vnpcc_vn_attention_delta(const float* dout, long long lddo, const float* out, long long ldo, int B, int N, int H, int D, float* delta,
+                             void* stream) {
+    const long long total = (long long)B * N * H;
+    if (total <= 0) return 0;
+    if (D % 4 != 0 || lddo % 4 != 0 || ldo % 4 != 0 || ((uintptr_t)dout & 15) || ((uintptr_t)out & 15)) return VNPCC_ERR_UNSUPPORTED;
+    count_launch(), att::attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, (size_t)lddo, out, (size_t)ldo, B, N,
+                                                                                                     H, D, delta);
+    return last_error();
+}
+
 }  // extern "C"

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "vnpcc.h"
 #include "vnpcc_internal.h"
@@ -146,10 +147,15 @@ __device__ __forceinline__ uint32_t sw128(int rows, int r, int kappa) {
     return (uint32_t)((kappa >> 5) * (rows * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((((kappa & 31) >> 2) ^ (r & 7)) << 4) + (kappa & 3) * 4);
 }
 
-template <int D>
+// MODE_FWD: rows = queries (resident Q), streamed K / V:   out = softmax(scale Q K^T) V, lse written
+// MODE_DV : rows = keys (resident K), streamed Q / dO:      dV = P^T dO with P^T[key, q] = exp(scale K Q^T - lse[q]) (lse read); the
+//           same skeleton with the operands' roles swapped, one pass, no normalisation
+constexpr int MODE_FWD = 0, MODE_DV = 1;
+
+template <int D, int MODE>
 __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_q,
-                                                           const __grid_constant__ CUtensorMap map_v, int N, int H, int C, float scale,
-                                                           float* __restrict__ out, size_t ldo, float* __restrict__ lse) {
+                                                           const __grid_constant__ CUtensorMap map_v, int N, int H, int cx, int cy, int cz,
+                                                           float scale, float* __restrict__ out, size_t ldo, float* __restrict__ lse) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
     const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
     const int q0 = blockIdx.x * BQ;
     const int tok0 = b * N;                       // first token of the sample in the [B*N]-token tensor maps
-    const int colq = h * D, colk = C + h * D, colv = 2 * C + h * D;
+    const int colq = cx + h * D, colk = cy + h * D, colv = cz + h * D;      // resident rows / streamed K-major tile / streamed MN-major tile
     const int T = (N + BKEY - 1) / BKEY;
 
     if (tid == 0) {
@@ -199,32 +205,26 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
 #pragma unroll
         for (int ks = 0; ks < KD / 8; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
+            if ((kb & 1) && kk * 8 + 32 >= D) continue;      // columns D..63 of a component belong to the next head: those k-steps are skipped
             umma_tf32(s_tmem, make_desc(qa + kb * (BQ * 128) + kk * 32), make_desc(ka + kb * (BKEY * 128) + kk * 32), idesc_s, ks != 0 ? 1u : 0u);
         }
         umma_commit(s_done);
     };
 
-    // ---- Q tile: one TMA load, then zero the 16 padding columns of every component (chunks 4..7 of the odd k-blocks)
+    // ---- resident tile: one TMA load (its padding columns are never multiplied: see issue_s)
     if (tid == 0) {
         mbar_expect_tx(qfull, Q_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_q, qfull, Qs + kb * (BQ * 128), colq + (kb & 1) * 32, kb >> 1, tok0 + q0);
         load_k(0);
+        mbar_wait(qfull, 0);
     }
-    mbar_wait(qfull, 0);
-    for (int i = tid; i < 3 * BQ * 4; i += NT) {
-        const int v = i / (BQ * 4), rem = i - v * (BQ * 4);
-        const int r = rem >> 2, j = 4 + (rem & 3);
-        *reinterpret_cast<float4*>(Qs + (2 * v + 1) * (BQ * 128) + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    fence_async_smem();
-    __syncthreads();
 
     uint32_t kph = 0, vph = 0, sph = 0, oph = 0;
 
     // ---- pass 1: row maxima of the scaled scores
     float m = -INFINITY;
-    for (int i = 0; i < T; ++i) {
+    for (int i = 0; MODE == MODE_FWD && i < T; ++i) {
         const int k0 = i * BKEY;
         if (tid == 0) {
             mbar_wait(kfull, kph);
@@ -269,7 +269,9 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
             tmem_ld32(t_row + half * 32, s);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float p = (k0 + half * 32 + j < N) ? expf(s[j] * scale - m) : 0.f;
+                const int col = k0 + half * 32 + j;
+                float p = 0.f;
+                if (col < N) p = expf(s[j] * scale - (MODE == MODE_FWD ? m : __ldg(lse + (size_t)bh * N + col)));
                 s[j] = p;
                 l += p;
             }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
 
     // ---- epilogue: out = O / l, lse = m + log l
     const int n = q0 + tid;
-    const float inv = 1.0f / l;
+    const float inv = MODE == MODE_FWD ? 1.0f / l : 1.0f;
 #pragma unroll 1
     for (int i = 0; i < KD / 32; ++i) {
         float o[32];
@@ -319,7 +321,226 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
                 if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
         }
     }
-    if (n < N) lse[(size_t)bh * N + n] = m + logf(l);
+    if (MODE == MODE_FWD && n < N) lse[(size_t)bh * N + n] = m + logf(l);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// -------------------------------------------------------------------------------------------------------------------------------
+// backward, dQ and dK:  dS = P o (dP - delta) scale,  dQ = dS K,  dK = dS^T Q       (P = exp(scale Q K^T - lse), dP = dO V^T)
+// One kernel, two orientations (BMODE):
+//   BMODE_DQ: lanes = 128 queries.  resident X = Q, streamed tiles of 32 keys Y = K;  dP = G H^T with G = dO (rows = the queries), H = V
+//   BMODE_DK: lanes = 128 keys.     resident X = K, streamed tiles of 32 queries Y = Q; dP^T = G H^T with G = V (rows = the keys), H = dO
+// Per tile:  S = X Y^T (M128 N32) and dP = G H^T (M128 N32; G and H stream through a ring of 32-column k-blocks because a second resident
+// 96 KB tile does not fit) -> the threads (one per lane) form dS row-locally and store it as the K-major A operand -> acc[128 x 192] +=
+// dS Y with Y re-staged MN-major (M128 N192).  The accumulator stays in TMEM for the whole kernel and is stored once: no atomics.
+// -------------------------------------------------------------------------------------------------------------------------------
+constexpr int BMODE_DQ = 0, BMODE_DK = 1;
+constexpr int BT = 32;                               // streamed tokens per tile
+constexpr int NS = 3;                                // ring stages of the dP operands
+constexpr int BX_BYTES = (KD / 32) * BQ * 128;       // 98304  resident
+constexpr int BY_BYTES = (KD / 32) * BT * 128;       // 24576  streamed, K-major
+constexpr int BYM_BYTES = (KD / 32) * BT * 128;      // 24576  streamed, MN-major
+constexpr int BDS_BYTES = BQ * 128;                  // 16384  dS tile (one k-block of 32 tokens)
+constexpr int BG_BYTES = BQ * 128;                   // 16384  one k-block of G
+constexpr int BH_BYTES = BT * 128;                   // 4096   one k-block of H
+constexpr int BSTAGE_BYTES = BG_BYTES + BH_BYTES;
+constexpr int BTILE_BYTES = BX_BYTES + BY_BYTES + BYM_BYTES + BDS_BYTES + NS * BSTAGE_BYTES;
+constexpr int BSMEM_BYTES = BTILE_BYTES + 256 + 1024;
+
+template <int D, int BMODE>
+__global__ void __launch_bounds__(NT, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-major SW128, box 128 tokens  (resident X; G = V in BMODE_DK)
+                   const __grid_constant__ CUtensorMap map_y,      // qkv, K-major SW128, box 32 tokens   (Y; H = V in BMODE_DQ)
+                   const __grid_constant__ CUtensorMap map_ym,     // qkv, MN-major ATOM_32B, box 32 tokens (Y for the last product)
+                   const __grid_constant__ CUtensorMap map_do128,  // dO, K-major SW128, box 128 tokens   (G = dO in BMODE_DQ)
+                   const __grid_constant__ CUtensorMap map_do32,   // dO, K-major SW128, box 32 tokens    (H = dO in BMODE_DK)
+                   int N, int H, int C, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
+                   float* __restrict__ dqkv, size_t lddq) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* Xs = smem;
+    uint8_t* Ys = Xs + BX_BYTES;
+    uint8_t* Ym = Ys + BY_BYTES;
+    uint8_t* dSs = Ym + BYM_BYTES;
+    uint8_t* ring = dSs + BDS_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BTILE_BYTES);
+    uint64_t* xfull = bars, *yfull = bars + 1, *ymfull = bars + 2, *sdp_done = bars + 3, *acc_done = bars + 4;
+    uint64_t* sfull = bars + 5, *sfree = bars + 5 + NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NS);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int r0 = blockIdx.x * BQ;               // first resident token (query or key) of this CTA
+    const int tok0 = b * N;
+    const int colq = h * D, colk = C + h * D, colv = 2 * C + h * D, coldo = h * D;
+    const int colx = BMODE == BMODE_DQ ? colq : colk;      // resident
+    const int coly = BMODE == BMODE_DQ ? colk : colq;      // streamed
+    const int T = (N + BT - 1) / BT;
+    constexpr int KBLK = KD / 32;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_y);
+        tma_prefetch_desc(&map_ym);
+        tma_prefetch_desc(&map_do128);
+        tma_prefetch_desc(&map_do32);
+        for (int i = 0; i < 5 + 2 * NS; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t s_tmem = tmem_base, dp_tmem = tmem_base + 32, acc_tmem = tmem_base + 64;
+    constexpr uint32_t idesc_s = make_idesc(BQ, BT, 0);
+    constexpr uint32_t idesc_acc = make_idesc(BQ, KD, 1);
+
+    // producer / consumer state of the ring (thread 0 only)
+    int n_loaded = 0, n_used = 0;
+    auto ring_load = [&](int tile, int kb) {      // k-block kb of G (128 resident rows) and of H (the tile's 32 tokens)
+        const int st = n_loaded % NS;
+        if (n_loaded >= NS) mbar_wait(&sfree[st], (uint32_t)((n_loaded / NS - 1) & 1));
+        uint8_t* g = ring + st * BSTAGE_BYTES;
+        mbar_expect_tx(&sfull[st], BSTAGE_BYTES);
+        if (BMODE == BMODE_DQ) {
+            tma_load_3d(&map_do128, &sfull[st], g, coldo + (kb & 1) * 32, kb >> 1, tok0 + r0);
+            tma_load_3d(&map_y, &sfull[st], g + BG_BYTES, colv + (kb & 1) * 32, kb >> 1, tok0 + tile * BT);
+        } else {
+            tma_load_3d(&map_x, &sfull[st], g, colv + (kb & 1) * 32, kb >> 1, tok0 + r0);
+            tma_load_3d(&map_do32, &sfull[st], g + BG_BYTES, coldo + (kb & 1) * 32, kb >> 1, tok0 + tile * BT);
+        }
+        ++n_loaded;
+    };
+    auto load_y = [&](int tile) {
+        mbar_expect_tx(yfull, BY_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KBLK; ++kb) tma_load_3d(&map_y, yfull, Ys + kb * (BT * 128), coly + (kb & 1) * 32, kb >> 1, tok0 + tile * BT);
+    };
+    auto load_ym = [&](int tile) {
+        mbar_expect_tx(ymfull, BYM_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < KBLK; ++sl) tma_load_3d(&map_ym, ymfull, Ym + sl * (BT * 128), coly + (sl & 1) * 32, sl >> 1, tok0 + tile * BT);
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(xfull, BX_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KBLK; ++kb) tma_load_3d(&map_x, xfull, Xs + kb * (BQ * 128), colx + (kb & 1) * 32, kb >> 1, tok0 + r0);
+        load_y(0);
+        load_ym(0);
+        for (int kb = 0; kb < NS; ++kb) ring_load(0, kb);
+        mbar_wait(xfull, 0);
+    }
+
+    // per-lane scalars (BMODE_DQ: this lane's query)
+    const int n_row = r0 + tid;
+    float lse_r = 0.f, del_r = 0.f;
+    if (BMODE == BMODE_DQ && n_row < N) {
+        lse_r = __ldg(lse + (size_t)bh * N + n_row);
+        del_r = __ldg(delta + (size_t)bh * N + n_row);
+    }
+
+    uint32_t yph = 0, ymph = 0, sdph = 0, accph = 0;
+    for (int i = 0; i < T; ++i) {
+        const int c0 = i * BT;
+        if (tid == 0) {
+            // S = X Y^T
+            mbar_wait(yfull, yph);
+            tc_fence_after();
+            const uint32_t xa = smem_u32(Xs), ya = smem_u32(Ys);
+#pragma unroll
+            for (int ks = 0; ks < KD / 8; ++ks) {
+                const int kb = ks >> 2, kk = ks & 3;
+                if ((kb & 1) && kk * 8 + 32 >= D) continue;
+                umma_tf32(s_tmem, make_desc(xa + kb * (BQ * 128) + kk * 32), make_desc(ya + kb * (BT * 128) + kk * 32), idesc_s, ks != 0 ? 1u : 0u);
+            }
+            // dP = G H^T through the ring
+            for (int kb = 0; kb < KBLK; ++kb) {
+                const int st = n_used % NS;
+                mbar_wait(&sfull[st], (uint32_t)((n_used / NS) & 1));
+                tc_fence_after();
+                const uint32_t ga = smem_u32(ring + st * BSTAGE_BYTES), ha = ga + BG_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if ((kb & 1) && kk * 8 + 32 >= D) continue;
+                    umma_tf32(dp_tmem, make_desc(ga + kk * 32), make_desc(ha + kk * 32), idesc_s, (kb | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&sfree[st]);
+                ++n_used;
+                // keep the ring full: the next k-blocks of this tile, then the first ones of the next tile
+                const int nxt = kb + NS;
+                if (nxt < KBLK)
+                    ring_load(i, nxt);
+                else if (i + 1 < T)
+                    ring_load(i + 1, nxt - KBLK);
+            }
+            umma_commit(sdp_done);
+        }
+        yph ^= 1;
+        mbar_wait(sdp_done, sdph);
+        sdph ^= 1;
+        tc_fence_after();
+        if (tid == 0 && i + 1 < T) load_y(i + 1);      // the K-major Y buffer is free: S is complete
+        {
+            float sv[32], dv[32];
+            tmem_ld32(t_row, sv);
+            tmem_ld32(t_row + 32, dv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c0 + j;
+                float ds = 0.f;
+                if (col < N) {
+                    const float L = BMODE == BMODE_DQ ? lse_r : __ldg(lse + (size_t)bh * N + col);
+                    const float dl = BMODE == BMODE_DQ ? del_r : __ldg(delta + (size_t)bh * N + col);
+                    const float p = expf(sv[j] * scale - L);
+                    ds = p * (dv[j] - dl) * scale;
+                }
+                sv[j] = ds;
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(dSs + sw128(BQ, tid, j4 * 4)) = make_float4(sv[j4 * 4], sv[j4 * 4 + 1], sv[j4 * 4 + 2], sv[j4 * 4 + 3]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();      // dS complete, S / dP consumed
+        if (tid == 0) {
+            mbar_wait(ymfull, ymph);
+            tc_fence_after();
+            const uint32_t da = smem_u32(dSs), ma = smem_u32(Ym);
+#pragma unroll
+            for (int ks = 0; ks < BT / 8; ++ks)
+                umma_tf32(acc_tmem, make_desc(da + ks * 32), make_desc_mn(ma + ks * 1024, BT * 128), idesc_acc, (i | ks) != 0 ? 1u : 0u);
+            umma_commit(acc_done);
+            mbar_wait(acc_done, accph);      // dS and the MN-major Y buffer are free again
+            if (i + 1 < T) load_ym(i + 1);
+        }
+        ymph ^= 1;
+        accph ^= 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- epilogue: the accumulator rows are this lane's dQ (or dK)
+    const int part = BMODE == BMODE_DQ ? 0 : C;
+#pragma unroll 1
+    for (int i = 0; i < KD / 32; ++i) {
+        float o[32];
+        tmem_ld32(t_row + 64 + i * 32, o);
+        if (n_row < N) {
+            const int v = i >> 1, cc = (i & 1) * 32;
+            float* dst = dqkv + ((size_t)(b * (size_t)N + n_row) * 3 + v) * lddq + part + (size_t)h * D + cc;
+            const int cnt = (cc + 32 <= D) ? 32 : (D - cc);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -350,8 +571,11 @@ static bool make_map3(CUtensorMap* m, const float* base, long long tokens, long 
     cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)ld * 3 * sizeof(float)};
     cuuint32_t box[3] = {32, 1, (cuuint32_t)box_tokens};
     cuuint32_t estr[3] = {1, 1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    // the L2 promotion size must not exceed a row of the tensor (a 48-column dO has 192-byte rows)
+    const CUtensorMapL2promotion promo = cols * 4 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                          : (cols * 4 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace atc
@@ -373,11 +597,56 @@ int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, in
         !atc::make_map3(&mq, qkv, tokens, cols, ld, atc::BQ, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !atc::make_map3(&mv, qkv, tokens, cols, ld, atc::BKEY, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
         return VNPCC_ERR_DRIVER;
-    if (cudaFuncSetAttribute(atc::attn_fwd_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(atc::attn_fwd_tc_kernel<48, atc::MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES) !=
+        cudaSuccess)
         return VNPCC_ERR_DRIVER;
     dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
-    count_launch(), atc::attn_fwd_tc_kernel<48><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(mk, mq, mv, N, H, H * D, scale, out,
-                                                                                                     (size_t)ldo, lse);
+    const int C = H * D;
+    count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_FWD><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(mk, mq, mv, N, H, 0, C, 2 * C,
+                                                                                                                    scale, out, (size_t)ldo, lse);
+    return last_error();
+}
+
+// tensor-core twin of vnpcc_vn_attention_bwd (same arguments): dV by the forward skeleton with swapped roles, dK and dQ by the two
+// orientations of attn_bwd_tc_kernel.  dqkv is fully written with plain stores (no pre-zeroing, no atomics).  D == 48 only.
+int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo,
+                                const float* lse, int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta,
+                                void* stream) {
+    if (B <= 0 || N <= 0) return 0;
+    if (D != 48 || H <= 0 || ld % 4 != 0 || lddo % 4 != 0 || ldo % 4 != 0 || lddq % 4 != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) ||
+        ((uintptr_t)out & 15) || ((uintptr_t)dqkv & 15) || !(scale > 0.f))
+        return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = H * D;
+    const long long tokens = (long long)B * N;
+    CUtensorMap q128, q64, q32, qm32, do128, do32, dom64;
+    if (!atc::make_map3(&q128, qkv, tokens, 3LL * C, ld, 128, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&q64, qkv, tokens, 3LL * C, ld, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&q32, qkv, tokens, 3LL * C, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&qm32, qkv, tokens, 3LL * C, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !atc::make_map3(&do128, dout, tokens, C, lddo, 128, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&do32, dout, tokens, C, lddo, 32, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !atc::make_map3(&dom64, dout, tokens, C, lddo, 64, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+        fprintf(stderr, "[vnpcc] attention_bwd_tf32: tensor map encode failed (tokens %lld C %d ld %lld lddo %lld qkv %p dout %p)\n", tokens, C, ld, lddo,
+                (const void*)qkv, (const void*)dout);
+        return VNPCC_ERR_DRIVER;
+    }
+    if (cudaFuncSetAttribute(atc::attn_fwd_tc_kernel<48, atc::MODE_DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(atc::attn_bwd_tc_kernel<48, atc::BMODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::BSMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(atc::attn_bwd_tc_kernel<48, atc::BMODE_DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::BSMEM_BYTES) != cudaSuccess) {
+        fprintf(stderr, "[vnpcc] attention_bwd_tf32: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return VNPCC_ERR_DRIVER;
+    }
+    int rc = vnpcc_vn_attention_delta(dout, lddo, out, ldo, B, N, H, D, delta, stream);
+    if (rc) return rc;
+    dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
+    // dV: resident K (columns C..), streamed Q (columns 0..) K-major, streamed dO MN-major; writes the v part of dqkv
+    count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_DV><<<grid, atc::NT, atc::SMEM_BYTES, st>>>(q64, q128, dom64, N, H, C, 0, 0, scale, dqkv + 2 * C,
+                                                                                                 (size_t)lddq, const_cast<float*>(lse));
+    count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DQ><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale, lse,
+                                                                                                   delta, dqkv, (size_t)lddq);
+    count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DK><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale, lse,
+                                                                                                   delta, dqkv, (size_t)lddq);
     return last_error();
 }
 

@@ -805,8 +805,17 @@ class _VNAttention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         delta = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
         with _Timed("attention_bwd", 10.0 * B * H * N * N * 3 * D):
-            call("vnpcc_vn_attention_bwd", ptr(qkv), _ld(qkv), ptr(g), _ld(g), ptr(out), _ld(out), ptr(lse), B, N, H, D, scale, ptr(dqkv),
-                 _ld(dqkv), ptr(delta), stream())
+            rc = 10003
+            if _GEMM_MODE == "tf32":      # tcgen05 / TMEM backward (csrc/attention_tc.cu)
+                rc = _lib.raw("vnpcc_vn_attention_bwd_tf32", ptr(qkv), _ld(qkv), ptr(g), _ld(g), ptr(out), _ld(out), ptr(lse), B, N, H, D, scale,
+                              ptr(dqkv), _ld(dqkv), ptr(delta), stream())
+                if rc not in (0, 10003):
+                    raise _lib.VnpccError(f"vnpcc_vn_attention_bwd_tf32 failed with code {rc}")
+                if rc == 0:
+                    _LAST_KERNEL[0] = "attention_bwd_tf32"
+            if rc != 0:
+                call("vnpcc_vn_attention_bwd", ptr(qkv), _ld(qkv), ptr(g), _ld(g), ptr(out), _ld(out), ptr(lse), B, N, H, D, scale, ptr(dqkv),
+                     _ld(dqkv), ptr(delta), stream())
         return dqkv, None, None, None, None
 
 
