@@ -57,7 +57,11 @@ def main():
         qkv.grad = None
         ops.vn_attention(qkv, B, N, H, 1.0).backward(go)
     t2 = timeit(fb)
-    print(f"| vn_attention forward + backward | {t2:.3f} | {3.5 * fl / t2 / 1e9:.1f} TFLOP/s (7 tile products) |")
+    print(f"| vn_attention forward + backward (fp32 SIMT) | {t2:.3f} | {3.5 * fl / t2 / 1e9:.1f} TFLOP/s (7 tile products) |")
+    V.set_gemm_mode("tf32")
+    t3 = timeit(fb)
+    V.set_gemm_mode("fp32")
+    print(f"| vn_attention forward + backward (tcgen05: fwd, dV, dQ, dK kernels) | {t3:.3f} | {3.5 * fl / t3 / 1e9:.1f} TFLOP/s algorithmic |")
     x = torch.randn(B * N * 3, C, device="cuda")
     ln = torch.nn.LayerNorm(C).cuda()
     with torch.no_grad():
@@ -71,7 +75,7 @@ def main():
     pt, ct, Rt = (torch.from_numpy(z).cuda() for z in (p, c, R))
     tr = DataParallelTrainer(net, lr=1e-4)
     t = timeit(lambda: tr.train_step(pt, ct, Rt), 5)
-    print(f"| PCNNet(vn_pointnet + attention_vn_foldingnet) train step, TF32 GEMMs + fp32 attention | {t:.3f} | {B / t * 1e3:.0f} samples/s |")
+    print(f"| PCNNet(vn_pointnet + attention_vn_foldingnet) train step, TF32 mode (tcgen05 GEMMs and attention) | {t:.3f} | {B / t * 1e3:.0f} samples/s |")
 
 
 if __name__ == "__main__":
