@@ -160,6 +160,10 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--mode", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--enc", default="vn_pointnet", choices=["vn_pointnet", "vn_dgcnn_fps"],
+                    help="encoder (default = BASELINE configs[1]; vn_dgcnn_fps is the SURVEY 8f row f1 network, paired with latent_dim 512)")
+    ap.add_argument("--dec", default="vn_foldingnet", choices=["vn_foldingnet", "attention_vn_foldingnet"],
+                    help="decoder (attention_vn_foldingnet is the SURVEY 8f row f2 network; needs the vn_pointnet encoder)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
     ap.add_argument("--no-eval", action="store_true", help="skip the inference leg (profiling runs)")
@@ -205,9 +209,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     V.set_gemm_mode(args.mode)
     B = args.batch
-    cfg = SimpleNamespace(num_coarse=N_COARSE, latent_dim=2048, only_coarse=False, device=dev, enc_pretrained="none")
+    headline = args.enc == "vn_pointnet" and args.dec == "vn_foldingnet"
+    if args.enc == "vn_dgcnn_fps" and args.dec != "vn_foldingnet":
+        raise SystemExit("vn_dgcnn_fps (512-channel global feature) pairs with vn_foldingnet only: Attention_VN_FoldingNet hard-codes "
+                         "VNLinear(2048, 384) (models/pcn.py:438, SURVEY 8f)")
+    cfg = SimpleNamespace(num_coarse=N_COARSE, latent_dim=512 if args.enc == "vn_dgcnn_fps" else 2048, only_coarse=False, device=dev,
+                          enc_pretrained="none")
     torch.manual_seed(0)             # identical initial weights on every rank
-    net = V.PCNNet(cfg).train()
+    net = V.PCNNet(cfg, enc_type=args.enc, dec_type=args.dec).train()
     trainer = DataParallelTrainer(net, lr=1e-4, world_size=world)
 
     # synthetic data: a pool of distinct batches per rank (seed = 1234 + rank), staged in pinned host memory
@@ -345,6 +354,14 @@ def main():
                                              "bytes_per_launch": d["bytes"] / max(d["launches"], 1), "hbm_peak_gbs": pk["hbm"],
                                              "note": "sum over launches of max(flops/peak_tensor, algorithmic bytes/peak_hbm) / measured time"}
                 classes[cls] = ent
+            elif cls.startswith("attention"):
+                tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
+                tc_cls = cls.endswith("tf32")
+                peak = pk["bf16_sustained"] / 2.0 if tc_cls else 2 * 148 * 128 * ((clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6) / 1e12
+                classes[cls] = {"bound": "tensor" if tc_cls else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                "traffic": None, "ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] / args.steps,
+                                "peak_note": "algorithmic attention FLOPs (4 N^2 d forward, 10 N^2 d backward per head) / CUDA-event time vs "
+                                             + ("bf16 sustained / 2 (TF32 tcgen05)" if tc_cls else "148 SMs x 128 lanes x 2 x SM clock (fp32 FMA)")}
             elif cls == "chamfer_fwd":
                 pairs = d["work"] / sec if sec > 0 else 0.0
                 fclk = (clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6
@@ -361,7 +378,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if args.mode == "tf32" else "f32", "data": "synthetic",
-                "config": {"workload": "vn_pointnet_1024+vn_foldingnet train step (fwd + L1-CD coarse/dense + bwd + Adam), so3",
+                "config": {"workload": (f"{args.enc}_1024+{args.dec} train step (fwd + L1-CD coarse/dense + bwd + Adam), so3"
+                                        + ("" if headline else " [SURVEY 8f next-row network, not the BASELINE headline]")),
                            "batch_per_gpu": B, "global_batch": B * world, "n_partial": N_PARTIAL, "n_coarse": N_COARSE,
                            "n_dense": N_DENSE, "n_gt": N_GT, "parallelism": f"dp{world}", "gemm_mode": args.mode,
                            "l2": "per-step activations (>10 GB) exceed the 126 MB L2; inputs rotate over a pool"},
@@ -371,7 +389,7 @@ def main():
                          "what": "eval-mode forward + l1_cd under no_grad (fused VN GEMM epilogue)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_classes": classes,
                 "final_loss": final_loss}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and headline:
             cb = 2
             sps, sec = cpu_reference_step(cb, 1, 0)
             line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",

@@ -222,7 +222,9 @@ int vnpcc_vn_attention_delta(const float* dout, long long lddo, const float* out
                              void* stream);
 int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo,
                                 const float* lse, int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta,
-                                void* stream);
+                                float* ds_workspace, size_t ds_workspace_bytes, void* stream);
+/* ds_workspace (optional, B*H*N*N floats, used when N % 32 == 0): the dQ kernel writes dS there and dK = dS^T Q runs as a streaming
+ * tcgen05 GEMM; without it dK recomputes S and dP in the key orientation */
 
 /* ---------------------------------------------------------------- evaluation extras (test.py:73-78) ---------- */
 /* metrics/metric.py:31-48 f_score from the Chamfer search's SQUARED distances: out [B,3] = (precision, recall, F) with

@@ -269,8 +269,8 @@ def test_pcnnet_pointnet_attention_decoder_trains():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,N,H", [(1, 64, 1), (2, 130, 2), (1, 1024, 8), (2, 200, 3)])
-def test_attention_core_tf32_tensor_core(B, N, H):
+@pytest.mark.parametrize("B,N,H,ds_ws", [(1, 64, 1, True), (2, 130, 2, True), (1, 1024, 8, True), (2, 200, 3, True), (2, 256, 2, False)])
+def test_attention_core_tf32_tensor_core(B, N, H, ds_ws):
     """csrc/attention_tc.cu (tcgen05 / TMEM, TF32 operands) against the numpy oracle.  Stated TF32 tolerance: operands carry a 10-bit
     mantissa, scores are sums of 144 products of O(1) features -> |dS| <~ 3e-3, i.e. a few 1e-3 relative error on softmax weights;
     outputs are compared at 1e-2 of the largest entry (rel-L2 5e-3), lse at 5e-3 absolute."""
@@ -289,6 +289,7 @@ def test_attention_core_tf32_tensor_core(B, N, H):
     gq, gk, gv = AO.attention_core_bwd(c, gy)
     qkv.requires_grad_(True)
     V.set_gemm_mode("tf32")
+    ops._ATTN_DS_WORKSPACE = ds_ws       # N % 32 == 0 and ds_ws: dK from the stored dS (streaming GEMM); otherwise the recomputing kernel
     try:
         out = ops.vn_attention(qkv, B, N, H, 0.7)
         torch.cuda.synchronize()
@@ -297,6 +298,7 @@ def test_attention_core_tf32_tensor_core(B, N, H):
         torch.cuda.synchronize()
         assert ops._LAST_KERNEL[0] == "attention_bwd_tf32"
     finally:
+        ops._ATTN_DS_WORKSPACE = True
         V.set_gemm_mode("fp32")
     assert_grad_close(out.detach().cpu().numpy(), rows(o), "out", 5e-3, 1e-2)
     got = qkv.grad.cpu().numpy()

@@ -72,6 +72,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -137,8 +143,9 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_by
 }
 // instruction descriptor: c_format F32 [4,6), a/b format TF32 [7,10)/[10,13), a_major [15], b_major [16] (0 = K-major, 1 = MN-major),
 // N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major = 0) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major = 0, int a_mn_major = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 // byte offset of element (row r, k index kappa) inside a K-major SWIZZLE_128B tile of `rows` rows: k-blocks of 32 floats (one 128-byte
@@ -357,7 +364,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-maj
                    const __grid_constant__ CUtensorMap map_do128,  // dO, K-major SW128, box 128 tokens   (G = dO in BMODE_DQ)
                    const __grid_constant__ CUtensorMap map_do32,   // dO, K-major SW128, box 32 tokens    (H = dO in BMODE_DK)
                    int N, int H, int C, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
-                   float* __restrict__ dqkv, size_t lddq) {
+                   float* __restrict__ dqkv, size_t lddq, float* __restrict__ ds_out) {
+    // ds_out (BMODE_DQ only, may be NULL): dS [B*H*N, N] row-major, written tile by tile so that dK = dS^T Q can run as a plain streaming
+    // GEMM (attn_dk_gemm_kernel) instead of recomputing S and dP in the other orientation
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Xs = smem;
@@ -504,6 +513,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-maj
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
                 *reinterpret_cast<float4*>(dSs + sw128(BQ, tid, j4 * 4)) = make_float4(sv[j4 * 4], sv[j4 * 4 + 1], sv[j4 * 4 + 2], sv[j4 * 4 + 3]);
+            if (BMODE == BMODE_DQ && ds_out != nullptr && n_row < N) {      // host guarantees N % 32 == 0 on this path
+                float4* dst = reinterpret_cast<float4*>(ds_out + ((size_t)bh * N + n_row) * N + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) dst[j4] = make_float4(sv[j4 * 4], sv[j4 * 4 + 1], sv[j4 * 4 + 2], sv[j4 * 4 + 3]);
+            }
         }
         fence_async_smem();
         tc_fence_before();
@@ -535,6 +549,94 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-maj
         if (n_row < N) {
             const int v = i >> 1, cc = (i & 1) * 32;
             float* dst = dqkv + ((size_t)(b * (size_t)N + n_row) * 3 + v) * lddq + part + (size_t)h * D + cc;
+            const int cnt = (cc + 32 <= D) ? 32 : (D - cc);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// -------------------------------------------------------------------------------------------------------------------------------
+// dK = dS^T Q as a streaming GEMM over the dS matrix the dQ kernel wrote: lanes = 128 keys; per 32-query tile the A operand is the
+// MN-major [32 q x 128 keys] block of dS (keys contiguous; 4 TMA boxes with the 128B_ATOM_32B swizzle), the B operand the MN-major Q tile.
+// A 4-stage TMA ring keeps 160 KB in flight; one thread issues TMA and MMA.  N % 32 == 0.
+// -------------------------------------------------------------------------------------------------------------------------------
+constexpr int GK_NS = 4;
+constexpr int GK_A_BYTES = 4 * BT * 128;             // 16384: 4 slabs of {32 keys} x 32 q rows
+constexpr int GK_B_BYTES = (KD / 32) * BT * 128;     // 24576: 6 slabs of {32 features} x 32 q rows
+constexpr int GK_STAGE_BYTES = GK_A_BYTES + GK_B_BYTES;
+constexpr int GK_SMEM_BYTES = GK_NS * GK_STAGE_BYTES + 256 + 1024;
+
+template <int D>
+__global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_constant__ CUtensorMap map_ds,     // dS [B*H*N, N], ATOM_32B, box {32, 32}
+                                                            const __grid_constant__ CUtensorMap map_qm,     // qkv, MN-major ATOM_32B, box 32 tokens
+                                                            int N, int H, int C, float* __restrict__ dqkv, size_t lddq) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GK_NS * GK_STAGE_BYTES);
+    uint64_t* full = bars, *empty = bars + GK_NS, *done = bars + 2 * GK_NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GK_NS + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int r0 = blockIdx.x * BQ;               // first key of this CTA
+    const int tok0 = b * N;
+    const int colq = h * D;
+    const int T = N / BT;
+    if (tid == 0) {
+        tma_prefetch_desc(&map_ds);
+        tma_prefetch_desc(&map_qm);
+        for (int i = 0; i < 2 * GK_NS + 1; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc(BQ, KD, 1, 1);
+        auto load = [&](int tile) {
+            const int st = tile % GK_NS;
+            if (tile >= GK_NS) mbar_wait(&empty[st], (uint32_t)((tile / GK_NS - 1) & 1));
+            uint8_t* a = smem + st * GK_STAGE_BYTES;
+            mbar_expect_tx(&full[st], GK_STAGE_BYTES);
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) tma_load_2d(&map_ds, &full[st], a + sl * (BT * 128), r0 + sl * 32, bh * N + tile * BT);
+#pragma unroll
+            for (int sl = 0; sl < KD / 32; ++sl)
+                tma_load_3d(&map_qm, &full[st], a + GK_A_BYTES + sl * (BT * 128), colq + (sl & 1) * 32, sl >> 1, tok0 + tile * BT);
+        };
+        for (int i = 0; i < GK_NS && i < T; ++i) load(i);
+        for (int i = 0; i < T; ++i) {
+            const int st = i % GK_NS;
+            mbar_wait(&full[st], (uint32_t)((i / GK_NS) & 1));
+            tc_fence_after();
+            const uint32_t aa = smem_u32(smem + st * GK_STAGE_BYTES), ba = aa + GK_A_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BT / 8; ++ks)
+                umma_tf32(tmem_base, make_desc_mn(aa + ks * 1024, BT * 128), make_desc_mn(ba + ks * 1024, BT * 128), idesc, (i | ks) != 0 ? 1u : 0u);
+            umma_commit(&empty[st]);
+            if (i + GK_NS < T) load(i + GK_NS);
+        }
+        umma_commit(done);
+        mbar_wait(done, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int n_row = r0 + tid;
+#pragma unroll 1
+    for (int i = 0; i < KD / 32; ++i) {
+        float o[32];
+        tmem_ld32(t_row + i * 32, o);
+        if (n_row < N) {
+            const int v = i >> 1, cc = (i & 1) * 32;
+            float* dst = dqkv + ((size_t)(b * (size_t)N + n_row) * 3 + v) * lddq + C + (size_t)h * D + cc;
             const int cnt = (cc + 32 <= D) ? 32 : (D - cc);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -578,6 +680,19 @@ static bool make_map3(CUtensorMap* m, const float* base, long long tokens, long 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// row-major fp32 matrix [rows, cols] (leading dimension = cols); box = {32 cols, box_rows}
+static bool make_map2(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              cols * 4 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+           CUDA_SUCCESS;
+}
+
 }  // namespace atc
 }  // namespace vnpcc
 
@@ -611,7 +726,7 @@ int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, in
 // orientations of attn_bwd_tc_kernel.  dqkv is fully written with plain stores (no pre-zeroing, no atomics).  D == 48 only.
 int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo,
                                 const float* lse, int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta,
-                                void* stream) {
+                                float* ds_workspace, size_t ds_workspace_bytes, void* stream) {
     if (B <= 0 || N <= 0) return 0;
     if (D != 48 || H <= 0 || ld % 4 != 0 || lddo % 4 != 0 || ldo % 4 != 0 || lddq % 4 != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) ||
         ((uintptr_t)out & 15) || ((uintptr_t)dqkv & 15) || !(scale > 0.f))
@@ -643,10 +758,20 @@ int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dou
     // dV: resident K (columns C..), streamed Q (columns 0..) K-major, streamed dO MN-major; writes the v part of dqkv
     count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_DV><<<grid, atc::NT, atc::SMEM_BYTES, st>>>(q64, q128, dom64, N, H, C, 0, 0, scale, dqkv + 2 * C,
                                                                                                  (size_t)lddq, const_cast<float*>(lse));
+    // dQ (and, when the caller provides B*H*N*N floats of workspace and N % 32 == 0, the dS matrix for the dK GEMM)
+    const size_t ds_need = (size_t)B * H * N * N * sizeof(float);
+    CUtensorMap mds;
+    const bool use_ds = ds_workspace != nullptr && ds_workspace_bytes >= ds_need && N % 32 == 0 && !((uintptr_t)ds_workspace & 15) &&
+                        atc::make_map2(&mds, ds_workspace, (long long)B * H * N, N, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+                        cudaFuncSetAttribute(atc::attn_dk_gemm_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::GK_SMEM_BYTES) == cudaSuccess;
     count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DQ><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale, lse,
-                                                                                                   delta, dqkv, (size_t)lddq);
-    count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DK><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale, lse,
-                                                                                                   delta, dqkv, (size_t)lddq);
+                                                                                                   delta, dqkv, (size_t)lddq,
+                                                                                                   use_ds ? ds_workspace : nullptr);
+    if (use_ds)
+        count_launch(), atc::attn_dk_gemm_kernel<48><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mds, qm32, N, H, C, dqkv, (size_t)lddq);
+    else
+        count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DK><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale,
+                                                                                                       lse, delta, dqkv, (size_t)lddq, nullptr);
     return last_error();
 }
 

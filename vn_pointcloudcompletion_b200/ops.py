@@ -773,6 +773,9 @@ def rows_add(a, b):
     return _RowsAdd.apply(a, b)
 
 
+_ATTN_DS_WORKSPACE = True      # tests switch it off to exercise the recomputing dK kernel
+
+
 class _VNAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, B, N, H, scale):
@@ -807,8 +810,11 @@ class _VNAttention(torch.autograd.Function):
         with _Timed("attention_bwd", 10.0 * B * H * N * N * 3 * D):
             rc = 10003
             if _GEMM_MODE == "tf32":      # tcgen05 / TMEM backward (csrc/attention_tc.cu)
+                ws = None
+                if N % 32 == 0 and _ATTN_DS_WORKSPACE:      # dS [B*H*N, N]: lets dK run as a plain streaming GEMM
+                    ws = _workspace(4 * B * H * N * N, qkv.device, "attn_ds")
                 rc = _lib.raw("vnpcc_vn_attention_bwd_tf32", ptr(qkv), _ld(qkv), ptr(g), _ld(g), ptr(out), _ld(out), ptr(lse), B, N, H, D, scale,
-                              ptr(dqkv), _ld(dqkv), ptr(delta), stream())
+                              ptr(dqkv), _ld(dqkv), ptr(delta), ptr(ws), ws.numel() if ws is not None else 0, stream())
                 if rc not in (0, 10003):
                     raise _lib.VnpccError(f"vnpcc_vn_attention_bwd_tf32 failed with code {rc}")
                 if rc == 0:
