@@ -14,6 +14,9 @@
 //
 // Thread layout: block (C/4, 256/(C/4)); threadIdx.x owns 4 consecutive channels (weights + the sample's bias rows in
 // registers), each block row walks over a chunk of points of ONE sample.  grid = (chunks per sample, B).
+// Row mode (many small samples, e.g. the folding MLPs of Attention_VN_FoldingNet: 32768 tokens x 16 points): every block ROW owns whole
+// samples and loops over them, so the per-block prologue, shared-memory reductions and atomics are paid once per block instead of once
+// per 16 points, and the per-sample bias gradient is a plain store from registers.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -75,12 +78,16 @@ __device__ __forceinline__ void fold_load_x(const float* __restrict__ x, size_t 
         for (int k = 0; k < KS; ++k) xv[v][k] = __ldg(x + (row + v) * ldx + k);
 }
 
-#define FOLD_PROLOGUE                                                        \
-    const int c0 = threadIdx.x * 4;                                          \
-    const int b = blockIdx.y;                                                \
-    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);          \
-    FoldCtx<KS> cx;                                                          \
-    fold_load_ctx<KS>(cx, w, ldw, bias, ldb, b, C, c0);
+// sample loop shared by all fold kernels.  Block mode (row_mode == 0): one sample per blockIdx.y, the rows split its chunk of points.
+// Row mode: row threadIdx.y of block blockIdx.y owns samples b = blockIdx.y * blockDim.y + threadIdx.y, + gridDim.y * blockDim.y, ...
+#define FOLD_SAMPLES_BEGIN                                                                                   \
+    const int fs_step = row_mode ? (int)(gridDim.y * blockDim.y) : B;                                        \
+    for (int b = row_mode ? (int)(blockIdx.y * blockDim.y + threadIdx.y) : (int)blockIdx.y; b < B; b += fs_step) { \
+        const int n0 = row_mode ? 0 : (int)blockIdx.x * n_chunk;                                             \
+        const int n1 = row_mode ? N : min(N, n0 + n_chunk);                                                  \
+        const int nbeg = row_mode ? 0 : n0 + (int)threadIdx.y;                                               \
+        const int nstep = row_mode ? 1 : (int)blockDim.y;
+#define FOLD_SAMPLES_END }
 
 // per-channel reduction of NRED double values per lane over the block rows, then one atomicAdd per channel
 template <int NRED>
@@ -104,12 +111,15 @@ __device__ __forceinline__ void fold_reduce_channels(double (&acc)[NRED][4], dou
 
 template <int KS>
 __global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
-                                                          const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
-                                                          double* __restrict__ sums) {
+                                                          const float* __restrict__ bias, size_t ldb, int B, int N, int C, int n_chunk,
+                                                          int row_mode, double* __restrict__ sums) {
     extern __shared__ double fold_sh[];
-    FOLD_PROLOGUE
+    const int c0 = threadIdx.x * 4;
     double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+    FOLD_SAMPLES_BEGIN
+    FoldCtx<KS> cx;
+    fold_load_ctx<KS>(cx, w, ldw, bias, ldb, b, C, c0);
+    for (int n = nbeg; n < n1; n += nstep) {
         float xv[3][KS];
         fold_load_x<KS>(x, ldx, ((size_t)b * N + n) * 3, xv);
         V4x3 p, d;
@@ -121,19 +131,23 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict
             acc[1][l] = fma(nn, nn, acc[1][l]);
         }
     }
+    FOLD_SAMPLES_END
     fold_reduce_channels<2>(acc, sums, C, c0, fold_sh);
 }
 
 template <int KS, bool FAST>
 __global__ void __launch_bounds__(256) fold_fwd_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
-                                                        const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
+                                                        const float* __restrict__ bias, size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
                                                         const float* __restrict__ stat, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float ns, float* __restrict__ out, size_t ldo) {
-    FOLD_PROLOGUE
+    const int c0 = threadIdx.x * 4;
     const ChanParams cp = load_params(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
+    FOLD_SAMPLES_BEGIN
+    FoldCtx<KS> cx;
+    fold_load_ctx<KS>(cx, w, ldw, bias, ldb, b, C, c0);
 #pragma unroll 2
-    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+    for (int n = nbeg; n < n1; n += nstep) {
         const size_t row = ((size_t)b * N + n) * 3;
         float xv[3][KS];
         fold_load_x<KS>(x, ldx, row, xv);
@@ -149,6 +163,7 @@ __global__ void __launch_bounds__(256) fold_fwd_kernel(const float* __restrict__
         }
         st43(out + row * ldo + c0, ldo, v);
     }
+    FOLD_SAMPLES_END
 }
 
 // shared lane math of the two backward passes: given raw p (pr), d (dv) and g (gv, dL/dout) of one lane, turn gv into
@@ -284,25 +299,24 @@ __device__ __forceinline__ void fold_pair_bwd(PairBwd& o, const FoldCtx2<KS>& cx
 template <int KS>
 __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
                                                              const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
-                                                             size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
-                                                             double* __restrict__ sums) {
+                                                             size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
+                                                             const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float ns, double* __restrict__ sums) {
     extern __shared__ double fold_sh[];
     const int c0 = threadIdx.x * 4;
-    const int b = blockIdx.y;
-    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);
-    FoldCtx2<KS> cx;
-    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
     const ChanParams2 cp = load_params2(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
     double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     float f1[4] = {0, 0, 0, 0}, f2s[4] = {0, 0, 0, 0};
     int since_flush = 0;
+    FOLD_SAMPLES_BEGIN
+    FoldCtx2<KS> cx;
+    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
     // software pipeline: the gradient rows of the next point are in flight while this one is processed
     float4 gnext[3];
     float xnext[3][KS];
     {
-        const int n = n0 + threadIdx.y;
+        const int n = nbeg;
         if (n < n1) {
             const size_t row = ((size_t)b * N + n) * 3;
 #pragma unroll
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
         }
     }
 #pragma unroll 1
-    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+    for (int n = nbeg; n < n1; n += nstep) {
         float4 g4[3];
         float xv[3][KS];
 #pragma unroll
@@ -320,8 +334,8 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
 #pragma unroll
             for (int k = 0; k < KS; ++k) xv[v][k] = xnext[v][k];
         }
-        if (n + (int)blockDim.y < n1) {
-            const size_t rown = ((size_t)b * N + n + blockDim.y) * 3;
+        if (n + nstep < n1) {
+            const size_t rown = ((size_t)b * N + n + nstep) * 3;
 #pragma unroll
             for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (rown + v) * ldg + c0));
             fold_load_x<KS>(x, ldx, rown, xnext);
@@ -350,6 +364,7 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
             since_flush = 0;
         }
     }
+    FOLD_SAMPLES_END
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         acc[0][l] += (double)f1[l];
@@ -362,18 +377,15 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
 template <int KS>
 __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
                                                              const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
-                                                             size_t ldb, int N, int C, int n_chunk, const float* __restrict__ stat,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
-                                                             const double* __restrict__ sums, double count, int training,
+                                                             size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
+                                                             const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float ns, const double* __restrict__ sums,
+                                                             double count, int training,
                                                              float* __restrict__ gx, size_t ldgx, int gx_k0, float* __restrict__ gw,
                                                              size_t ldgw, float* __restrict__ gbias, size_t ldgb) {
     extern __shared__ double fold_sh[];
     float* shf = reinterpret_cast<float*>(fold_sh);
     const int c0 = threadIdx.x * 4;
-    const int b = blockIdx.y;
-    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);
-    FoldCtx2<KS> cx;
-    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
     const bool has_bn = stat != nullptr;
     const ChanParams2 cp = load_params2(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
@@ -396,10 +408,13 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
         for (int v = 0; v < 3; ++v) abp[v][h] = abd[v][h] = bc2(0.f);
     }
     const int lane = threadIdx.x & 31;
+    FOLD_SAMPLES_BEGIN
+    FoldCtx2<KS> cx;
+    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
     float4 gnext[3];
     float xnext[3][KS];
     {
-        const int n = n0 + threadIdx.y;
+        const int n = nbeg;
         if (n < n1) {
             const size_t row = ((size_t)b * N + n) * 3;
 #pragma unroll
@@ -408,7 +423,7 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
         }
     }
 #pragma unroll 1
-    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+    for (int n = nbeg; n < n1; n += nstep) {
         const size_t row = ((size_t)b * N + n) * 3;
         float4 g4[3];
         float xv[3][KS];
@@ -418,8 +433,8 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
 #pragma unroll
             for (int k = 0; k < KS; ++k) xv[v][k] = xnext[v][k];
         }
-        if (n + (int)blockDim.y < n1) {
-            const size_t rown = ((size_t)b * N + n + blockDim.y) * 3;
+        if (n + nstep < n1) {
+            const size_t rown = ((size_t)b * N + n + nstep) * 3;
 #pragma unroll
             for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (rown + v) * ldg + c0));
             fold_load_x<KS>(x, ldx, rown, xnext);
@@ -477,6 +492,16 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
                 }
         }
     }
+    if (row_mode && gbias) {      // this row owned the whole sample: its bias gradient is complete in registers
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            *reinterpret_cast<float4*>(gbias + (size_t)(b * 3 + v) * ldgb + c0) = make_float4(abp[v][0].v.x, abp[v][0].v.y, abp[v][1].v.x, abp[v][1].v.y);
+            *reinterpret_cast<float4*>(gbias + (size_t)(b * 3 + v) * ldgb + C + c0) =
+                make_float4(abd[v][0].v.x, abd[v][0].v.y, abd[v][1].v.x, abd[v][1].v.y);
+            abp[v][0] = abp[v][1] = abd[v][0] = abd[v][1] = bc2(0.f);
+        }
+    }
+    FOLD_SAMPLES_END
     // per-channel reductions over the block rows
     __syncthreads();
     float* red = shf;   // [blockDim.y][blockDim.x][4]
@@ -502,7 +527,8 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
         reduce_store(awf[k], gw + (size_t)c0 * ldgw + k, ldgw);
         reduce_store(awd[k], gw + (size_t)(C + c0) * ldgw + k, ldgw);
     }
-    if (gbias) {
+    if (gbias && !row_mode) {
+        const int b = blockIdx.y;
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
             reduce_store(abp[v], gbias + (size_t)(b * 3 + v) * ldgb + c0, 1);
@@ -514,18 +540,17 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
 // throughput-mode forward of the fused small-K layer, packed fp32x2
 template <int KS>
 __global__ void __launch_bounds__(256) fold_fwd_p2_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
-                                                           const float* __restrict__ bias, size_t ldb, int N, int C, int n_chunk,
-                                                           const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                           const float* __restrict__ bias, size_t ldb, int B, int N, int C, int n_chunk,
+                                                           int row_mode, const float* __restrict__ stat, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float ns, float* __restrict__ out, size_t ldo) {
     const int c0 = threadIdx.x * 4;
-    const int b = blockIdx.y;
-    const int n0 = blockIdx.x * n_chunk, n1 = min(N, n0 + n_chunk);
-    FoldCtx2<KS> cx;
-    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
     const BNPair bn[2] = {load_bn_pair(stat, gamma, beta, C, c0), load_bn_pair(stat, gamma, beta, C, c0 + 2)};
     const float k1 = 1.f - ns;
+    FOLD_SAMPLES_BEGIN
+    FoldCtx2<KS> cx;
+    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
 #pragma unroll 2
-    for (int n = n0 + threadIdx.y; n < n1; n += blockDim.y) {
+    for (int n = nbeg; n < n1; n += nstep) {
         const size_t row = ((size_t)b * N + n) * 3;
         float xv[3][KS];
         fold_load_x<KS>(x, ldx, row, xv);
@@ -552,6 +577,7 @@ __global__ void __launch_bounds__(256) fold_fwd_p2_kernel(const float* __restric
         for (int v = 0; v < 3; ++v)
             *reinterpret_cast<float4*>(out + (row + v) * ldo + c0) = make_float4(o[0][v].v.x, o[0][v].v.y, o[1][v].v.x, o[1][v].v.y);
     }
+    FOLD_SAMPLES_END
 }
 
 static bool fold_ok(int KS, int C, const void* bias, long long ldb, const void* big, long long ldbig) {
@@ -559,8 +585,20 @@ static bool fold_ok(int KS, int C, const void* bias, long long ldb, const void* 
            (big == nullptr || ((ldbig & 3) == 0 && ((uintptr_t)big & 15) == 0));
 }
 
-static void fold_geometry(int B, int N, int C, dim3& grid, dim3& block, int& n_chunk, size_t& smem) {
+static void fold_geometry(int B, int N, int C, dim3& grid, dim3& block, int& n_chunk, size_t& smem, int& row_mode) {
     const int bx = C / 4, by = 256 / bx;
+    row_mode = 0;
+    if (N <= 64 && B >= 4 * by) {      // many small samples: every block row owns whole samples and loops over them
+        row_mode = 1;
+        long long blocks = ((long long)B + by - 1) / by;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        grid = dim3(1, (unsigned)blocks);
+        block = dim3(bx, by);
+        n_chunk = N;
+        smem = sizeof(double) * 256 * 4;
+        return;
+    }
     int chunks = (int)(((long long)sm_count() * 4 + B - 1) / B);
     if (chunks < 1) chunks = 1;
     n_chunk = (N + chunks - 1) / chunks;
@@ -594,11 +632,11 @@ int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ld
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (B <= 0 || N <= 0) return last_error();
     dim3 grid, block;
-    int n_chunk;
+    int n_chunk, row_mode;
     size_t smem;
-    fold_geometry(B, N, C, grid, block, n_chunk, smem);
-    FOLD_KS_DISPATCH(K, (count_launch(), fold_stats_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
-                                                                                       C, n_chunk, sums)));
+    fold_geometry(B, N, C, grid, block, n_chunk, smem, row_mode);
+    FOLD_KS_DISPATCH(K, (count_launch(), fold_stats_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N,
+                                                                                       C, n_chunk, row_mode, sums)));
     return last_error();
 }
 
@@ -609,15 +647,15 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
     if (B <= 0 || N <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid, block;
-    int n_chunk;
+    int n_chunk, row_mode;
     size_t smem;
-    fold_geometry(B, N, C, grid, block, n_chunk, smem);
+    fold_geometry(B, N, C, grid, block, n_chunk, smem, row_mode);
     if (fast_math_enabled()) {
-        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_p2_kernel<K_><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C,
-                                                                                         n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_p2_kernel<K_><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C,
+                                                                                         n_chunk, row_mode, stat, gamma, beta, ns, out, (size_t)ldo)));
     } else {
-        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, false><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N,
-                                                                                             C, n_chunk, stat, gamma, beta, ns, out, (size_t)ldo)));
+        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, false><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N,
+                                                                                             C, n_chunk, row_mode, stat, gamma, beta, ns, out, (size_t)ldo)));
     }
     return last_error();
 }
@@ -637,17 +675,17 @@ int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx,
     if (gx) cudaMemset2DAsync(gx, (size_t)ldgx * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)B * N * 3, st);
     if (B <= 0 || N <= 0) return last_error();
     dim3 grid, block;
-    int n_chunk;
+    int n_chunk, row_mode;
     size_t smem;
-    fold_geometry(B, N, C, grid, block, n_chunk, smem);
+    fold_geometry(B, N, C, grid, block, n_chunk, smem, row_mode);
     const double count = (double)B * (double)N;
     if (stat) {
         FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_sums_kernel<K_><<<grid, block, smem, st>>>(g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias,
-                                                                                              (size_t)ldb, N, C, n_chunk, stat, gamma, beta, ns,
-                                                                                              sums)));
+                                                                                              (size_t)ldb, B, N, C, n_chunk, row_mode, stat, gamma, beta,
+                                                                                              ns, sums)));
     }
     FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_main_kernel<K_><<<grid, block, smem, st>>>(
-                            g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, N, C, n_chunk, stat, gamma, beta, ns, sums, count,
+                            g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, stat, gamma, beta, ns, sums, count,
                             training, gx, (size_t)ldgx, gx_first_col, gw, (size_t)ldgw, gbias, (size_t)ldgb)));
     if (stat && gbeta) vnpcc_double_to_float(sums, gbeta, C, stream);
     if (stat && ggamma) vnpcc_double_to_float(sums + C, ggamma, C, stream);
