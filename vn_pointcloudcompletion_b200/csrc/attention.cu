@@ -150,6 +150,168 @@ __global__ void __launch_bounds__(256) vn_layernorm_bwd_kernel(const float* __re
     }
 }
 
+// ---- vectorised VNLayerNorm (C % 4 == 0, 16-byte aligned rows): a lane owns float4 groups of channels {4 (lane + 32 i) .. + 3}
+constexpr int LN_V4 = 4;            // float4 groups per lane (C <= 512)
+
+__global__ void __launch_bounds__(256) vn_layernorm_fwd_v4_kernel(const float* __restrict__ x, size_t ldx, long long P, int C,
+                                                                 const float* __restrict__ w, const float* __restrict__ bvec, float ln_eps,
+                                                                 float* __restrict__ y, size_t ldy, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int G = C >> 2;
+    float4 wv[LN_V4], bv[LN_V4];
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+        const int gi = lane + 32 * i;
+        if (gi < G) {
+            wv[i] = __ldg(reinterpret_cast<const float4*>(w) + gi);
+            bv[i] = __ldg(reinterpret_cast<const float4*>(bvec) + gi);
+        }
+    }
+    for (long long t = warp; t < P; t += nwarps) {
+        const float* xp = x + (size_t)t * 3 * ldx;
+        float4 xv[LN_V4][3], nr[LN_V4];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int gi = lane + 32 * i;
+            if (gi < G) {
+#pragma unroll
+                for (int v = 0; v < 3; ++v) xv[i][v] = __ldg(reinterpret_cast<const float4*>(xp + v * ldx) + gi);
+#define LN_NORM(f) (sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xv[i][0].f, xv[i][0].f), __fmul_rn(xv[i][1].f, xv[i][1].f)), __fmul_rn(xv[i][2].f, xv[i][2].f))) + LN_VEPS)
+                nr[i] = make_float4(LN_NORM(x), LN_NORM(y), LN_NORM(z), LN_NORM(w));
+#undef LN_NORM
+                sum += (nr[i].x + nr[i].y) + (nr[i].z + nr[i].w);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)C;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int gi = lane + 32 * i;
+            if (gi < G) {
+                const float dx = nr[i].x - mean, dy = nr[i].y - mean, dz = nr[i].z - mean, dw = nr[i].w - mean;
+                var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, var))));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float rstd = 1.0f / sqrtf(var / (float)C + ln_eps);
+        if (stats && lane == 0) {
+            stats[2 * t] = mean;
+            stats[2 * t + 1] = rstd;
+        }
+        float* yp = y + (size_t)t * 3 * ldy;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int gi = lane + 32 * i;
+            if (gi < G) {
+                const float4 l = make_float4((nr[i].x - mean) * rstd * wv[i].x + bv[i].x, (nr[i].y - mean) * rstd * wv[i].y + bv[i].y,
+                                             (nr[i].z - mean) * rstd * wv[i].z + bv[i].z, (nr[i].w - mean) * rstd * wv[i].w + bv[i].w);
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                    reinterpret_cast<float4*>(yp + v * ldy)[gi] = make_float4(xv[i][v].x / nr[i].x * l.x, xv[i][v].y / nr[i].y * l.y,
+                                                                              xv[i][v].z / nr[i].z * l.z, xv[i][v].w / nr[i].w * l.w);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vn_layernorm_bwd_v4_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+                                                                 long long P, int C, const float* __restrict__ w, const float* __restrict__ bvec,
+                                                                 const float* __restrict__ stats, float* __restrict__ gx, size_t ldgx,
+                                                                 float* __restrict__ gw, float* __restrict__ gb) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int G = C >> 2;
+    float wv[LN_V4][4], bv[LN_V4][4], aw[LN_V4][4], ab[LN_V4][4];
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+        const int gi = lane + 32 * i;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) aw[i][e] = ab[i][e] = wv[i][e] = bv[i][e] = 0.f;
+        if (gi < G) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(w) + gi), b4 = __ldg(reinterpret_cast<const float4*>(bvec) + gi);
+            wv[i][0] = a.x, wv[i][1] = a.y, wv[i][2] = a.z, wv[i][3] = a.w;
+            bv[i][0] = b4.x, bv[i][1] = b4.y, bv[i][2] = b4.z, bv[i][3] = b4.w;
+        }
+    }
+    for (long long t = warp; t < P; t += nwarps) {
+        const float* xp = x + (size_t)t * 3 * ldx;
+        const float* gp = g + (size_t)t * 3 * ldg;
+        const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
+        float xs[LN_V4][3][4], gs[LN_V4][3][4], n[LN_V4][4], nh[LN_V4][4], a[LN_V4][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int gi = lane + 32 * i;
+            if (gi < G) {
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(xp + v * ldx) + gi), g4 = __ldg(reinterpret_cast<const float4*>(gp + v * ldg) + gi);
+                    xs[i][v][0] = a4.x, xs[i][v][1] = a4.y, xs[i][v][2] = a4.z, xs[i][v][3] = a4.w;
+                    gs[i][v][0] = g4.x, gs[i][v][1] = g4.y, gs[i][v][2] = g4.z, gs[i][v][3] = g4.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs[i][0][e], xs[i][0][e]), __fmul_rn(xs[i][1][e], xs[i][1][e])),
+                                                    __fmul_rn(xs[i][2][e], xs[i][2][e])));
+                    n[i][e] = r + LN_VEPS;
+                    nh[i][e] = (n[i][e] - mean) * rstd;
+                    a[i][e] = (gs[i][0][e] * xs[i][0][e] + gs[i][1][e] * xs[i][1][e] + gs[i][2][e] * xs[i][2][e]) / n[i][e];
+                    const float dnh = a[i][e] * wv[i][e];
+                    s1 += dnh;
+                    s2 = fmaf(dnh, nh[i][e], s2);
+                    aw[i][e] = fmaf(a[i][e], nh[i][e], aw[i][e]);
+                    ab[i][e] += a[i][e];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float m1 = s1 / (float)C, m2 = s2 / (float)C;
+        float* op = gx + (size_t)t * 3 * ldgx;
+#pragma unroll
+        for (int i = 0; i < LN_V4; ++i) {
+            const int gi = lane + 32 * i;
+            if (gi < G) {
+                float sc[4], dr[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float l = nh[i][e] * wv[i][e] + bv[i][e];
+                    const float dn = rstd * (a[i][e] * wv[i][e] - m1 - nh[i][e] * m2) - a[i][e] * l / n[i][e];
+                    const float r = n[i][e] - LN_VEPS;
+                    dr[e] = r > 0.f ? dn / r : 0.f;
+                    sc[e] = l / n[i][e];
+                }
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                    reinterpret_cast<float4*>(op + v * ldgx)[gi] =
+                        make_float4(fmaf(gs[i][v][0], sc[0], dr[0] * xs[i][v][0]), fmaf(gs[i][v][1], sc[1], dr[1] * xs[i][v][1]),
+                                    fmaf(gs[i][v][2], sc[2], dr[2] * xs[i][v][2]), fmaf(gs[i][v][3], sc[3], dr[3] * xs[i][v][3]));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+        const int gi = lane + 32 * i;
+        if (gi < G) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                atomicAdd(gw + gi * 4 + e, aw[i][e]);
+                atomicAdd(gb + gi * 4 + e, ab[i][e]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) rows_add_kernel(const float* __restrict__ a, size_t lda, const float* __restrict__ b, size_t ldb,
                                                       float* __restrict__ out, size_t ldo, long long R, int C) {
     const long long total = R * C;
@@ -478,7 +640,14 @@ int vnpcc_vn_layernorm_fwd(const float* x, long long ldx, long long P, int C, co
     if (C <= 0 || C > 32 * LN_CPL) return VNPCC_ERR_UNSUPPORTED;
     if (P <= 0) return 0;
     const int grid = grid_for((size_t)P * 32, 256, 8);
-    count_launch(), vn_layernorm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)ldx, P, C, weight, bias, ln_eps, y, (size_t)ldy, stats);
+    const bool v4 = C % 4 == 0 && C <= 128 * LN_V4 && ldx % 4 == 0 && ldy % 4 == 0 &&
+                    !(((uintptr_t)x | (uintptr_t)y | (uintptr_t)weight | (uintptr_t)bias) & 15);
+    if (v4)
+        count_launch(), vn_layernorm_fwd_v4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)ldx, P, C, weight, bias, ln_eps, y, (size_t)ldy,
+                                                                                        stats);
+    else
+        count_launch(), vn_layernorm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (size_t)ldx, P, C, weight, bias, ln_eps, y, (size_t)ldy,
+                                                                                     stats);
     return last_error();
 }
 
@@ -491,8 +660,14 @@ int vnpcc_vn_layernorm_bwd(const float* g, long long ldg, const float* x, long l
     cudaMemsetAsync(gbias, 0, sizeof(float) * C, st);
     if (P <= 0) return last_error();
     const int grid = grid_for((size_t)P * 32, 256, 4);
-    count_launch(), vn_layernorm_bwd_kernel<<<grid, 256, 0, st>>>(g, (size_t)ldg, x, (size_t)ldx, P, C, weight, bias, stats, gx, (size_t)ldgx, gweight,
-                                                                 gbias);
+    const bool v4 = C % 4 == 0 && C <= 128 * LN_V4 && ldx % 4 == 0 && ldg % 4 == 0 && ldgx % 4 == 0 &&
+                    !(((uintptr_t)x | (uintptr_t)g | (uintptr_t)gx | (uintptr_t)weight | (uintptr_t)bias) & 15);
+    if (v4)
+        count_launch(), vn_layernorm_bwd_v4_kernel<<<grid, 256, 0, st>>>(g, (size_t)ldg, x, (size_t)ldx, P, C, weight, bias, stats, gx, (size_t)ldgx,
+                                                                        gweight, gbias);
+    else
+        count_launch(), vn_layernorm_bwd_kernel<<<grid, 256, 0, st>>>(g, (size_t)ldg, x, (size_t)ldx, P, C, weight, bias, stats, gx, (size_t)ldgx,
+                                                                     gweight, gbias);
     return last_error();
 }
 

@@ -182,7 +182,9 @@ class Attention_VN_FoldingNet(nn.Module):
         """one folding MLP: local rows ((token, s), v) x 1, feat_rows (token, v) x 384 -> rows ((token, s), v) [R]"""
         l0, l1, l2 = seq[0], seq[1], seq[2]
         wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)           # [512, 385]; column 0 = the local channel
-        bias = ops.linear_rows(feat_rows, wcat[:, 1:])                                    # [T*3, 512]
+        # (a contiguous copy of the 384 broadcast columns: the [512, 385] view starts one float off 16-byte alignment, which would push this
+        # 98304 x 384 x 512 GEMM and its gradients off the tensor-core kernels)
+        bias = ops.linear_rows(feat_rows, wcat[:, 1:].contiguous())                       # [T*3, 512]
         C0 = l0.map_to_feat.weight.shape[0]
         if ops.smallk_bn_leaky_supported(1, C0, bias) and l0.batchnorm.bn.affine:
             h = ops.smallk_bn_leaky(local, wcat[:, :1], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, T, S, 1 if const_local else 0)
