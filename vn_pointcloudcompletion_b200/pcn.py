@@ -41,8 +41,6 @@ class VN_PointNet(nn.Module):
 
     def forward(self, xyz):
         B, N, _ = xyz.shape
-        if self.num_coarse == 224:
-            raise NotImplementedError("the 448-coarse variant needs pointnet2 furthest-point sampling (out of scope, SURVEY 8f)")
         # xyz.transpose(2,1).unsqueeze(1) is logical [B,1,3,N]; its rows (b,n,v) x 1 channel are xyz itself
         x0 = xyz.contiguous().view(B * N * 3, 1)
         f0 = self.first_conv[0].forward_rows(x0)                                          # [R,128]
@@ -66,6 +64,13 @@ class VN_PointNet(nn.Module):
         # reference: mlp(...)[B,nc,3,1].reshape(-1,nc,3)
         coarse = m.view(B, 3, self.num_coarse).transpose(1, 2).contiguous()
         feature_global = fg.view(B, 3, -1).transpose(1, 2).unsqueeze(-1)                   # logical [B,2048,3,1]
+        if self.num_coarse == 224:
+            # the 448-coarse variant (pcn.py:179-182): 224 predicted points + 224 furthest-point samples of the input (csrc/graph.cu)
+            from . import graph_ops as G
+            xyz_c = xyz.contiguous()
+            inp_sparse = G.points_gather(xyz_c.view(B * N * 3, 1), G.fps(xyz_c, 224), B, N).view(B, 224, 3)
+            coarse_cat = torch.cat([coarse, inp_sparse], dim=1).contiguous()
+            return (coarse, coarse_cat), feature_global
         return coarse, feature_global
 
 
