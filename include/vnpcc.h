@@ -210,7 +210,8 @@ int vnpcc_vn_attention_fwd(const float* qkv, long long ld, int B, int N, int H, 
 /* tensor-core twin of the forward (csrc/attention_tc.cu): tcgen05 / TMEM, TF32 operands, fp32 accumulation, two-pass softmax with the
  * output accumulator resident in TMEM.  Same arguments; D == 48 only, returns VNPCC_ERR_UNSUPPORTED otherwise. */
 int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, int H, int D, float scale, float* out, long long ldo, float* lse,
-                                void* stream);
+                                float* p_out, void* stream);
+/* p_out (optional, B*H*N*N floats, N % 32 == 0): the normalised attention weights, stored for the GEMM-shaped backward */
 /* dqkv [B*N*3, 3C] fully written (q part zeroed then accumulated with fp32 atomics); delta: workspace of B*H*N floats */
 int vnpcc_vn_attention_bwd(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo, const float* lse,
                            int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta, void* stream);
@@ -222,9 +223,10 @@ int vnpcc_vn_attention_delta(const float* dout, long long lddo, const float* out
                              void* stream);
 int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo,
                                 const float* lse, int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta,
-                                float* ds_workspace, size_t ds_workspace_bytes, void* stream);
-/* ds_workspace (optional, B*H*N*N floats, used when N % 32 == 0): the dQ kernel writes dS there and dK = dS^T Q runs as a streaming
- * tcgen05 GEMM; without it dK recomputes S and dP in the key orientation */
+                                float* ds_workspace, size_t ds_workspace_bytes, float* p_buf, void* stream);
+/* p_buf (optional: the P the forward stored; DESTROYED, it is turned into dS in place): dV = P^T dO, dQ = dS K and dK = dS^T Q all run as
+ * streaming tcgen05 GEMMs and only dP = dO V^T is recomputed.  Else ds_workspace (optional, B*H*N*N floats, N % 32 == 0): the dQ kernel
+ * writes dS there and dK = dS^T Q runs as a streaming GEMM; without either dK recomputes S and dP in the key orientation. */
 
 /* ---------------------------------------------------------------- evaluation extras (test.py:73-78) ---------- */
 /* metrics/metric.py:31-48 f_score from the Chamfer search's SQUARED distances: out [B,3] = (precision, recall, F) with

@@ -269,8 +269,9 @@ def test_pcnnet_pointnet_attention_decoder_trains():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,N,H,ds_ws", [(1, 64, 1, True), (2, 130, 2, True), (1, 1024, 8, True), (2, 200, 3, True), (2, 256, 2, False)])
-def test_attention_core_tf32_tensor_core(B, N, H, ds_ws):
+@pytest.mark.parametrize("B,N,H,ds_ws,store_p", [(1, 64, 1, True, True), (2, 130, 2, True, True), (1, 1024, 8, True, True), (2, 200, 3, True, True),
+                                                 (2, 256, 2, False, False), (2, 256, 2, True, False), (1, 1024, 8, True, False)])
+def test_attention_core_tf32_tensor_core(B, N, H, ds_ws, store_p):
     """csrc/attention_tc.cu (tcgen05 / TMEM, TF32 operands) against the numpy oracle.  Stated TF32 tolerance: operands carry a 10-bit
     mantissa, scores are sums of 144 products of O(1) features -> |dS| <~ 3e-3, i.e. a few 1e-3 relative error on softmax weights;
     outputs are compared at 1e-2 of the largest entry (rel-L2 5e-3), lse at 5e-3 absolute."""
@@ -289,7 +290,9 @@ def test_attention_core_tf32_tensor_core(B, N, H, ds_ws):
     gq, gk, gv = AO.attention_core_bwd(c, gy)
     qkv.requires_grad_(True)
     V.set_gemm_mode("tf32")
-    ops._ATTN_DS_WORKSPACE = ds_ws       # N % 32 == 0 and ds_ws: dK from the stored dS (streaming GEMM); otherwise the recomputing kernel
+    # backward routes: store_p (N % 32 == 0): P kept by the forward, dV / dQ / dK as streaming GEMMs; else ds_ws: dK from the stored dS;
+    # else the recomputing kernels
+    ops._ATTN_DS_WORKSPACE, ops._ATTN_STORE_P = ds_ws, store_p
     try:
         out = ops.vn_attention(qkv, B, N, H, 0.7)
         torch.cuda.synchronize()
@@ -298,7 +301,7 @@ def test_attention_core_tf32_tensor_core(B, N, H, ds_ws):
         torch.cuda.synchronize()
         assert ops._LAST_KERNEL[0] == "attention_bwd_tf32"
     finally:
-        ops._ATTN_DS_WORKSPACE = True
+        ops._ATTN_DS_WORKSPACE, ops._ATTN_STORE_P = True, True
         V.set_gemm_mode("fp32")
     assert_grad_close(out.detach().cpu().numpy(), rows(o), "out", 5e-3, 1e-2)
     got = qkv.grad.cpu().numpy()

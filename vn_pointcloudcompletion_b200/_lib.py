@@ -70,9 +70,9 @@ SIGNATURES = {
     "vnpcc_vn_layernorm_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _ll, _p, _p, _p]),
     "vnpcc_rows_add": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _p]),
     "vnpcc_vn_attention_fwd": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
-    "vnpcc_vn_attention_fwd_tf32": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
+    "vnpcc_vn_attention_fwd_tf32": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _ll, _p, _p, _p]),
     "vnpcc_vn_attention_delta": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p]),
-    "vnpcc_vn_attention_bwd_tf32": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _i, _f, _p, _ll, _p, _p, _sz, _p]),
+    "vnpcc_vn_attention_bwd_tf32": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _i, _f, _p, _ll, _p, _p, _sz, _p, _p]),
     "vnpcc_vn_attention_bwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _i, _i, _i, _i, _f, _p, _ll, _p, _p]),
     "vnpcc_edge_conv_stats": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _p]),
     "vnpcc_edge_conv_fwd": (_i, [_p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _ll, _p]),

@@ -162,7 +162,9 @@ constexpr int MODE_FWD = 0, MODE_DV = 1;
 template <int D, int MODE>
 __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_q,
                                                            const __grid_constant__ CUtensorMap map_v, int N, int H, int cx, int cy, int cz,
-                                                           float scale, float* __restrict__ out, size_t ldo, float* __restrict__ lse) {
+                                                           float scale, float* __restrict__ out, size_t ldo, float* __restrict__ lse,
+                                                           float* __restrict__ p_out) {
+    // p_out (MODE_FWD, may be NULL; N % 4 == 0): the normalised attention weights P [B*H*N, N], stored for the GEMM-shaped backward
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
 
     uint32_t kph = 0, vph = 0, sph = 0, oph = 0;
 
-    // ---- pass 1: row maxima of the scaled scores
-    float m = -INFINITY;
+    // ---- pass 1: row maxima and row sums of the scaled scores
+    float m = -INFINITY, l1 = 0.f;
     for (int i = 0; MODE == MODE_FWD && i < T; ++i) {
         const int k0 = i * BKEY;
         if (tid == 0) {
@@ -247,15 +249,27 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
         for (int half = 0; half < 2; ++half) {
             float s[32];
             tmem_ld32(t_row + half * 32, s);
+            float hm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (k0 + half * 32 + j < N) m = fmaxf(m, s[j] * scale);
+            for (int j = 0; j < 32; ++j) {
+                s[j] = (k0 + half * 32 + j < N) ? s[j] * scale : -INFINITY;
+                hm = fmaxf(hm, s[j]);
+            }
+            if (hm > -INFINITY) {      // online (max, sum): only the scalar l is rescaled
+                const float mn = fmaxf(m, hm);
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += expf(s[j] - mn);
+                l1 = fmaf(l1, expf(m - mn), acc);
+                m = mn;
+            }
         }
         tc_fence_before();
         __syncthreads();      // every thread has read S before the next Q K^T overwrites it
     }
+    const float lse_row = m + logf(l1);      // MODE_FWD: P = exp(S - lse) is normalised, O needs no final division
 
-    // ---- pass 2: P = exp(S - m), l = sum P, O += P V
+    // ---- pass 2: P = exp(S - lse), O += P V
     float l = 0.f;
     if (tid == 0) load_v(0);
     for (int i = 0; i < T; ++i) {
@@ -278,9 +292,15 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
             for (int j = 0; j < 32; ++j) {
                 const int col = k0 + half * 32 + j;
                 float p = 0.f;
-                if (col < N) p = expf(s[j] * scale - (MODE == MODE_FWD ? m : __ldg(lse + (size_t)bh * N + col)));
+                if (col < N) p = expf(s[j] * scale - (MODE == MODE_FWD ? lse_row : __ldg(lse + (size_t)bh * N + col)));
                 s[j] = p;
                 l += p;
+            }
+            if (MODE == MODE_FWD && p_out != nullptr && q0 + tid < N) {
+                float4* dst = reinterpret_cast<float4*>(p_out + ((size_t)bh * N + q0 + tid) * N + k0 + half * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    if (k0 + half * 32 + j4 * 4 < N) dst[j4] = make_float4(s[j4 * 4], s[j4 * 4 + 1], s[j4 * 4 + 2], s[j4 * 4 + 3]);
             }
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
@@ -314,7 +334,8 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
 
     // ---- epilogue: out = O / l, lse = m + log l
     const int n = q0 + tid;
-    const float inv = MODE == MODE_FWD ? 1.0f / l : 1.0f;
+    const float inv = 1.0f;      // P is normalised (MODE_FWD) or must not be (MODE_DV)
+    (void)l;
 #pragma unroll 1
     for (int i = 0; i < KD / 32; ++i) {
         float o[32];
@@ -328,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
                 if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
         }
     }
-    if (MODE == MODE_FWD && n < N) lse[(size_t)bh * N + n] = m + logf(l);
+    if (MODE == MODE_FWD && n < N) lse[(size_t)bh * N + n] = lse_row;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -366,7 +387,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-maj
                    int N, int H, int C, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
                    float* __restrict__ dqkv, size_t lddq, float* __restrict__ ds_out) {
     // ds_out (BMODE_DQ only, may be NULL): dS [B*H*N, N] row-major, written tile by tile so that dK = dS^T Q can run as a plain streaming
-    // GEMM (attn_dk_gemm_kernel) instead of recomputing S and dP in the other orientation
+    // GEMM (attn_acc_gemm_kernel) instead of recomputing S and dP in the other orientation
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Xs = smem;
@@ -561,20 +582,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-maj
 }
 
 // -------------------------------------------------------------------------------------------------------------------------------
-// dK = dS^T Q as a streaming GEMM over the dS matrix the dQ kernel wrote: lanes = 128 keys; per 32-query tile the A operand is the
-// MN-major [32 q x 128 keys] block of dS (keys contiguous; 4 TMA boxes with the 128B_ATOM_32B swizzle), the B operand the MN-major Q tile.
-// A 4-stage TMA ring keeps 160 KB in flight; one thread issues TMA and MMA.  N % 32 == 0.
+// Streaming GEMMs over a stored [B*H*N, N] score-shaped matrix M (P or dS), accumulator [128 lanes x 192] resident in TMEM, 4-stage TMA
+// ring (160 KB in flight), one thread issues TMA and MMA.  N % 32 == 0.
+//   A_MN = 1: lanes = 128 COLUMNS of M (keys):  acc[key] = sum_q M[q, key] * Z[q]     dK = dS^T Q,  dV = P^T dO
+//             A = the MN-major [32 q x 128 keys] block of M (keys contiguous; 4 TMA boxes, 128B_ATOM_32B)
+//   A_MN = 0: lanes = 128 ROWS of M (queries):  acc[q] = sum_k M[q, k] * Z[k]         dQ = dS K
+//             A = the K-major [128 q x 32 keys] block of M (one SWIZZLE_128B k-block)
+//   B = the MN-major tile of Z (32 tokens x 192 features, 6 TMA boxes out of the row layout): Z = Q, dO or K.
 // -------------------------------------------------------------------------------------------------------------------------------
 constexpr int GK_NS = 4;
-constexpr int GK_A_BYTES = 4 * BT * 128;             // 16384: 4 slabs of {32 keys} x 32 q rows
-constexpr int GK_B_BYTES = (KD / 32) * BT * 128;     // 24576: 6 slabs of {32 features} x 32 q rows
+constexpr int GK_A_BYTES = 4 * BT * 128;             // 16384 in both orientations
+constexpr int GK_B_BYTES = (KD / 32) * BT * 128;     // 24576: 6 slabs of {32 features} x 32 tokens
 constexpr int GK_STAGE_BYTES = GK_A_BYTES + GK_B_BYTES;
 constexpr int GK_SMEM_BYTES = GK_NS * GK_STAGE_BYTES + 256 + 1024;
 
-template <int D>
-__global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_constant__ CUtensorMap map_ds,     // dS [B*H*N, N], ATOM_32B, box {32, 32}
-                                                            const __grid_constant__ CUtensorMap map_qm,     // qkv, MN-major ATOM_32B, box 32 tokens
-                                                            int N, int H, int C, float* __restrict__ dqkv, size_t lddq) {
+template <int D, int A_MN>
+__global__ void __launch_bounds__(NT, 1) attn_acc_gemm_kernel(const __grid_constant__ CUtensorMap map_m,      // M: A_MN ? ATOM_32B box {32,32} : SW128 box {32,128}
+                                                             const __grid_constant__ CUtensorMap map_z,      // Z rows, MN-major ATOM_32B, box 32 tokens
+                                                             int N, int H, int colz0, float* __restrict__ outp, size_t ldo) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GK_NS * GK_STAGE_BYTES);
@@ -582,13 +607,13 @@ __global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GK_NS + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-    const int r0 = blockIdx.x * BQ;               // first key of this CTA
+    const int r0 = blockIdx.x * BQ;               // first lane token (key or query) of this CTA
     const int tok0 = b * N;
-    const int colq = h * D;
+    const int colz = colz0 + h * D;
     const int T = N / BT;
     if (tid == 0) {
-        tma_prefetch_desc(&map_ds);
-        tma_prefetch_desc(&map_qm);
+        tma_prefetch_desc(&map_m);
+        tma_prefetch_desc(&map_z);
         for (int i = 0; i < 2 * GK_NS + 1; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
@@ -599,17 +624,21 @@ __global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     if (tid == 0) {
-        constexpr uint32_t idesc = make_idesc(BQ, KD, 1, 1);
+        constexpr uint32_t idesc = make_idesc(BQ, KD, 1, A_MN);
         auto load = [&](int tile) {
             const int st = tile % GK_NS;
             if (tile >= GK_NS) mbar_wait(&empty[st], (uint32_t)((tile / GK_NS - 1) & 1));
             uint8_t* a = smem + st * GK_STAGE_BYTES;
             mbar_expect_tx(&full[st], GK_STAGE_BYTES);
+            if (A_MN) {
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) tma_load_2d(&map_ds, &full[st], a + sl * (BT * 128), r0 + sl * 32, bh * N + tile * BT);
+                for (int sl = 0; sl < 4; ++sl) tma_load_2d(&map_m, &full[st], a + sl * (BT * 128), r0 + sl * 32, bh * N + tile * BT);
+            } else {
+                tma_load_2d(&map_m, &full[st], a, tile * BT, bh * N + r0);
+            }
 #pragma unroll
             for (int sl = 0; sl < KD / 32; ++sl)
-                tma_load_3d(&map_qm, &full[st], a + GK_A_BYTES + sl * (BT * 128), colq + (sl & 1) * 32, sl >> 1, tok0 + tile * BT);
+                tma_load_3d(&map_z, &full[st], a + GK_A_BYTES + sl * (BT * 128), colz + (sl & 1) * 32, sl >> 1, tok0 + tile * BT);
         };
         for (int i = 0; i < GK_NS && i < T; ++i) load(i);
         for (int i = 0; i < T; ++i) {
@@ -619,7 +648,8 @@ __global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_consta
             const uint32_t aa = smem_u32(smem + st * GK_STAGE_BYTES), ba = aa + GK_A_BYTES;
 #pragma unroll
             for (int ks = 0; ks < BT / 8; ++ks)
-                umma_tf32(tmem_base, make_desc_mn(aa + ks * 1024, BT * 128), make_desc_mn(ba + ks * 1024, BT * 128), idesc, (i | ks) != 0 ? 1u : 0u);
+                umma_tf32(tmem_base, A_MN ? make_desc_mn(aa + ks * 1024, BT * 128) : make_desc(aa + ks * 32), make_desc_mn(ba + ks * 1024, BT * 128),
+                          idesc, (i | ks) != 0 ? 1u : 0u);
             umma_commit(&empty[st]);
             if (i + GK_NS < T) load(i + GK_NS);
         }
@@ -636,7 +666,7 @@ __global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_consta
         tmem_ld32(t_row + i * 32, o);
         if (n_row < N) {
             const int v = i >> 1, cc = (i & 1) * 32;
-            float* dst = dqkv + ((size_t)(b * (size_t)N + n_row) * 3 + v) * lddq + C + (size_t)h * D + cc;
+            float* dst = outp + ((size_t)(b * (size_t)N + n_row) * 3 + v) * ldo + (size_t)h * D + cc;
             const int cnt = (cc + 32 <= D) ? 32 : (D - cc);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -646,6 +676,105 @@ __global__ void __launch_bounds__(NT, 1) attn_dk_gemm_kernel(const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// -------------------------------------------------------------------------------------------------------------------------------
+// dS = P o (dP - delta) scale, IN PLACE over the stored P:  dP = dO V^T with dO (this CTA's 128 queries) resident and V streaming
+// in double-buffered 64-key tiles; the dP accumulator is double-buffered in TMEM so that the MMAs of tile i+1 run while the
+// lane threads turn tile i into dS.
+// -------------------------------------------------------------------------------------------------------------------------------
+constexpr int DSK_SMEM_BYTES = Q_BYTES + 2 * K_BYTES + 128 + 1024;
+
+template <int D>
+__global__ void __launch_bounds__(NT, 1) attn_ds_kernel(const __grid_constant__ CUtensorMap map_do,      // dO, K-major SW128, box 128 tokens
+                                                       const __grid_constant__ CUtensorMap map_v,       // qkv, K-major SW128, box 64 tokens
+                                                       int N, int H, int C, float scale, const float* __restrict__ delta, float* __restrict__ pds) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* dOs = smem;
+    uint8_t* Vs = dOs + Q_BYTES;      // two buffers of K_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + 2 * K_BYTES);
+    uint64_t* xfull = bars, *vfull = bars + 1, *dp_done = bars + 3;      // vfull[2], dp_done[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int q0 = blockIdx.x * BQ;
+    const int tok0 = b * N;
+    const int coldo = h * D, colv = 2 * C + h * D;
+    const int T = (N + BKEY - 1) / BKEY;
+    if (tid == 0) {
+        tma_prefetch_desc(&map_do);
+        tma_prefetch_desc(&map_v);
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t idesc = make_idesc(BQ, BKEY, 0);
+    auto load_v = [&](int tile) {
+        const int bf = tile & 1;
+        mbar_expect_tx(&vfull[bf], K_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KD / 32; ++kb)
+            tma_load_3d(&map_v, &vfull[bf], Vs + bf * K_BYTES + kb * (BKEY * 128), colv + (kb & 1) * 32, kb >> 1, tok0 + tile * BKEY);
+    };
+    auto issue_dp = [&](int tile) {
+        const int bf = tile & 1;
+        mbar_wait(&vfull[bf], (uint32_t)((tile >> 1) & 1));
+        tc_fence_after();
+        const uint32_t da = smem_u32(dOs), va = smem_u32(Vs + bf * K_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KD / 8; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            if ((kb & 1) && kk * 8 + 32 >= D) continue;
+            umma_tf32(tmem_base + bf * BKEY, make_desc(da + kb * (BQ * 128) + kk * 32), make_desc(va + kb * (BKEY * 128) + kk * 32), idesc,
+                      ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&dp_done[bf]);
+    };
+    if (tid == 0) {
+        mbar_expect_tx(xfull, Q_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_do, xfull, dOs + kb * (BQ * 128), coldo + (kb & 1) * 32, kb >> 1, tok0 + q0);
+        load_v(0);
+        if (T > 1) load_v(1);
+        mbar_wait(xfull, 0);
+        issue_dp(0);
+    }
+    const int n_row = q0 + tid;
+    const float del = n_row < N ? __ldg(delta + (size_t)bh * N + n_row) : 0.f;
+    for (int i = 0; i < T; ++i) {
+        const int bf = i & 1;
+        if (tid == 0 && i + 1 < T) issue_dp(i + 1);      // its TMEM buffer was released by the __syncthreads of iteration i - 1
+        mbar_wait(&dp_done[bf], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        if (tid == 0 && i + 2 < T) load_v(i + 2);        // V buffer bf is free: the MMAs that read it are complete
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float dp[32];
+            tmem_ld32(t_row + bf * BKEY + half * 32, dp);
+            if (n_row < N) {
+                float4* row = reinterpret_cast<float4*>(pds + ((size_t)bh * N + n_row) * N + i * BKEY + half * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    if (i * BKEY + half * 32 + j4 * 4 >= N) break;
+                    float4 p = row[j4];
+                    p.x = p.x * (dp[j4 * 4] - del) * scale;
+                    p.y = p.y * (dp[j4 * 4 + 1] - del) * scale;
+                    p.z = p.z * (dp[j4 * 4 + 2] - del) * scale;
+                    p.w = p.w * (dp[j4 * 4 + 3] - del) * scale;
+                    row[j4] = p;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -700,12 +829,14 @@ using namespace vnpcc;
 
 extern "C" {
 
-// tensor-core twin of vnpcc_vn_attention_fwd (same arguments).  D == 48 only; returns VNPCC_ERR_UNSUPPORTED otherwise.
+// tensor-core twin of vnpcc_vn_attention_fwd.  p_out (may be NULL; needs N % 32 == 0): the normalised attention weights P [B*H*N, N],
+// stored for the GEMM-shaped backward.  D == 48 only; returns VNPCC_ERR_UNSUPPORTED otherwise.
 int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, int H, int D, float scale, float* out, long long ldo, float* lse,
-                                void* stream) {
+                                float* p_out, void* stream) {
     if (B <= 0 || N <= 0) return 0;
     if (D != 48 || H <= 0 || ld % 4 != 0 || ldo % 4 != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || !(scale > 0.f))
         return VNPCC_ERR_UNSUPPORTED;
+    if (p_out != nullptr && (N % 32 != 0 || ((uintptr_t)p_out & 15))) return VNPCC_ERR_BAD_ARG;
     CUtensorMap mk, mq, mv;
     const long long tokens = (long long)B * N, cols = 3LL * H * D;
     if (!atc::make_map3(&mk, qkv, tokens, cols, ld, atc::BKEY, CU_TENSOR_MAP_SWIZZLE_128B) ||
@@ -717,16 +848,21 @@ int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, in
         return VNPCC_ERR_DRIVER;
     dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
     const int C = H * D;
-    count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_FWD><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(mk, mq, mv, N, H, 0, C, 2 * C,
-                                                                                                                    scale, out, (size_t)ldo, lse);
+    count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_FWD><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
+                        mk, mq, mv, N, H, 0, C, 2 * C, scale, out, (size_t)ldo, lse, p_out);
     return last_error();
 }
 
-// tensor-core twin of vnpcc_vn_attention_bwd (same arguments): dV by the forward skeleton with swapped roles, dK and dQ by the two
-// orientations of attn_bwd_tc_kernel.  dqkv is fully written with plain stores (no pre-zeroing, no atomics).  D == 48 only.
+// tensor-core twin of vnpcc_vn_attention_bwd.  dqkv is fully written with plain stores (no pre-zeroing, no atomics).  D == 48 only.
+// Three routes, fastest first:
+//   p_buf != NULL (the P the forward stored; N % 32 == 0; DESTROYED: it is turned into dS in place):
+//        dV = P^T dO (streaming GEMM) -> dS = P o (dO V^T - delta) scale in place -> dQ = dS K, dK = dS^T Q (streaming GEMMs)
+//   ds_workspace (B*H*N*N floats, N % 32 == 0): dV by the forward skeleton with swapped roles, dQ by the recomputing kernel which also
+//        stores dS, dK = dS^T Q as a streaming GEMM
+//   neither: dV as above, dQ and dK by the two orientations of the recomputing kernel
 int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dout, long long lddo, const float* out, long long ldo,
                                 const float* lse, int B, int N, int H, int D, float scale, float* dqkv, long long lddq, float* delta,
-                                float* ds_workspace, size_t ds_workspace_bytes, void* stream) {
+                                float* ds_workspace, size_t ds_workspace_bytes, float* p_buf, void* stream) {
     if (B <= 0 || N <= 0) return 0;
     if (D != 48 || H <= 0 || ld % 4 != 0 || lddo % 4 != 0 || ldo % 4 != 0 || lddq % 4 != 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) ||
         ((uintptr_t)out & 15) || ((uintptr_t)dqkv & 15) || !(scale > 0.f))
@@ -734,41 +870,61 @@ int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dou
     cudaStream_t st = (cudaStream_t)stream;
     const int C = H * D;
     const long long tokens = (long long)B * N;
-    CUtensorMap q128, q64, q32, qm32, do128, do32, dom64;
+    CUtensorMap q128, q64, q32, qm32, do128, do32, dom64, dom32;
     if (!atc::make_map3(&q128, qkv, tokens, 3LL * C, ld, 128, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !atc::make_map3(&q64, qkv, tokens, 3LL * C, ld, 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !atc::make_map3(&q32, qkv, tokens, 3LL * C, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !atc::make_map3(&qm32, qkv, tokens, 3LL * C, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
         !atc::make_map3(&do128, dout, tokens, C, lddo, 128, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !atc::make_map3(&do32, dout, tokens, C, lddo, 32, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !atc::make_map3(&dom64, dout, tokens, C, lddo, 64, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+        !atc::make_map3(&dom64, dout, tokens, C, lddo, 64, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !atc::make_map3(&dom32, dout, tokens, C, lddo, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
         fprintf(stderr, "[vnpcc] attention_bwd_tf32: tensor map encode failed (tokens %lld C %d ld %lld lddo %lld qkv %p dout %p)\n", tokens, C, ld, lddo,
                 (const void*)qkv, (const void*)dout);
         return VNPCC_ERR_DRIVER;
     }
     if (cudaFuncSetAttribute(atc::attn_fwd_tc_kernel<48, atc::MODE_DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(atc::attn_bwd_tc_kernel<48, atc::BMODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::BSMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(atc::attn_bwd_tc_kernel<48, atc::BMODE_DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::BSMEM_BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(atc::attn_bwd_tc_kernel<48, atc::BMODE_DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::BSMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(atc::attn_acc_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::GK_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(atc::attn_acc_gemm_kernel<48, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::GK_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(atc::attn_ds_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::DSK_SMEM_BYTES) != cudaSuccess) {
         fprintf(stderr, "[vnpcc] attention_bwd_tf32: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return VNPCC_ERR_DRIVER;
     }
     int rc = vnpcc_vn_attention_delta(dout, lddo, out, ldo, B, N, H, D, delta, stream);
     if (rc) return rc;
     dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
+    const long long mrows = (long long)B * H * N;
+
+    if (p_buf != nullptr && N % 32 == 0 && !((uintptr_t)p_buf & 15)) {
+        CUtensorMap mp_mn, mp_k;
+        if (!atc::make_map2(&mp_mn, p_buf, mrows, N, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+            !atc::make_map2(&mp_k, p_buf, mrows, N, 128, CU_TENSOR_MAP_SWIZZLE_128B))
+            return VNPCC_ERR_DRIVER;
+        // dV = P^T dO
+        count_launch(), atc::attn_acc_gemm_kernel<48, 1><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mp_mn, dom32, N, H, 0, dqkv + 2 * C, (size_t)lddq);
+        // P -> dS in place
+        count_launch(), atc::attn_ds_kernel<48><<<grid, atc::NT, atc::DSK_SMEM_BYTES, st>>>(do128, q64, N, H, C, scale, delta, p_buf);
+        // dQ = dS K ; dK = dS^T Q
+        count_launch(), atc::attn_acc_gemm_kernel<48, 0><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mp_k, qm32, N, H, C, dqkv, (size_t)lddq);
+        count_launch(), atc::attn_acc_gemm_kernel<48, 1><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mp_mn, qm32, N, H, 0, dqkv + C, (size_t)lddq);
+        return last_error();
+    }
+
     // dV: resident K (columns C..), streamed Q (columns 0..) K-major, streamed dO MN-major; writes the v part of dqkv
     count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_DV><<<grid, atc::NT, atc::SMEM_BYTES, st>>>(q64, q128, dom64, N, H, C, 0, 0, scale, dqkv + 2 * C,
-                                                                                                 (size_t)lddq, const_cast<float*>(lse));
+                                                                                                 (size_t)lddq, const_cast<float*>(lse), nullptr);
     // dQ (and, when the caller provides B*H*N*N floats of workspace and N % 32 == 0, the dS matrix for the dK GEMM)
     const size_t ds_need = (size_t)B * H * N * N * sizeof(float);
     CUtensorMap mds;
     const bool use_ds = ds_workspace != nullptr && ds_workspace_bytes >= ds_need && N % 32 == 0 && !((uintptr_t)ds_workspace & 15) &&
-                        atc::make_map2(&mds, ds_workspace, (long long)B * H * N, N, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
-                        cudaFuncSetAttribute(atc::attn_dk_gemm_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::GK_SMEM_BYTES) == cudaSuccess;
+                        atc::make_map2(&mds, ds_workspace, mrows, N, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DQ><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale, lse,
                                                                                                    delta, dqkv, (size_t)lddq,
                                                                                                    use_ds ? ds_workspace : nullptr);
     if (use_ds)
-        count_launch(), atc::attn_dk_gemm_kernel<48><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mds, qm32, N, H, C, dqkv, (size_t)lddq);
+        count_launch(), atc::attn_acc_gemm_kernel<48, 1><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mds, qm32, N, H, 0, dqkv + C, (size_t)lddq);
     else
         count_launch(), atc::attn_bwd_tc_kernel<48, atc::BMODE_DK><<<grid, atc::NT, atc::BSMEM_BYTES, st>>>(q128, q32, qm32, do128, do32, N, H, C, scale,
                                                                                                        lse, delta, dqkv, (size_t)lddq, nullptr);

@@ -773,7 +773,8 @@ def rows_add(a, b):
     return _RowsAdd.apply(a, b)
 
 
-_ATTN_DS_WORKSPACE = True      # tests switch it off to exercise the recomputing dK kernel
+_ATTN_DS_WORKSPACE = True      # tests switch these off to exercise the other backward routes
+_ATTN_STORE_P = True
 
 
 class _VNAttention(torch.autograd.Function):
@@ -784,17 +785,24 @@ class _VNAttention(torch.autograd.Function):
         D = C // H
         out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float32)
         lse = torch.empty((B, H, N), device=qkv.device, dtype=torch.float32)
+        pbuf = None
         with _Timed("attention_fwd", 4.0 * B * H * N * N * 3 * D):
             rc = 10003
             if _GEMM_MODE == "tf32":      # tcgen05 / TMEM forward (csrc/attention_tc.cu); shapes it does not take fall through
-                rc = _lib.raw("vnpcc_vn_attention_fwd_tf32", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), stream())
+                if _ATTN_STORE_P and ctx.needs_input_grad[0] and N % 32 == 0 and D == 48:
+                    # the attention weights P (B*H*N*N floats) are kept for the backward, which then consists of streaming GEMMs
+                    pbuf = torch.empty(B * H * N * N, device=qkv.device, dtype=torch.float32)
+                rc = _lib.raw("vnpcc_vn_attention_fwd_tf32", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), ptr(pbuf), stream())
                 if rc not in (0, 10003):
                     raise _lib.VnpccError(f"vnpcc_vn_attention_fwd_tf32 failed with code {rc}")
                 if rc == 0:
                     _LAST_KERNEL[0] = "attention_fwd_tf32"
+                else:
+                    pbuf = None
             if rc != 0:
                 call("vnpcc_vn_attention_fwd", ptr(qkv), _ld(qkv), B, N, H, D, float(scale), ptr(out), C, ptr(lse), stream())
         ctx.save_for_backward(qkv, out, lse)
+        ctx.pbuf = pbuf
         ctx.cfg = (B, N, H, D, float(scale))
         return out
 
@@ -810,11 +818,12 @@ class _VNAttention(torch.autograd.Function):
         with _Timed("attention_bwd", 10.0 * B * H * N * N * 3 * D):
             rc = 10003
             if _GEMM_MODE == "tf32":      # tcgen05 / TMEM backward (csrc/attention_tc.cu)
+                pbuf, ctx.pbuf = ctx.pbuf, None      # consumed: the backward turns P into dS in place
                 ws = None
-                if N % 32 == 0 and _ATTN_DS_WORKSPACE:      # dS [B*H*N, N]: lets dK run as a plain streaming GEMM
+                if pbuf is None and N % 32 == 0 and _ATTN_DS_WORKSPACE:      # dS [B*H*N, N]: lets dK run as a plain streaming GEMM
                     ws = _workspace(4 * B * H * N * N, qkv.device, "attn_ds")
                 rc = _lib.raw("vnpcc_vn_attention_bwd_tf32", ptr(qkv), _ld(qkv), ptr(g), _ld(g), ptr(out), _ld(out), ptr(lse), B, N, H, D, scale,
-                              ptr(dqkv), _ld(dqkv), ptr(delta), ptr(ws), ws.numel() if ws is not None else 0, stream())
+                              ptr(dqkv), _ld(dqkv), ptr(delta), ptr(ws), ws.numel() if ws is not None else 0, ptr(pbuf), stream())
                 if rc not in (0, 10003):
                     raise _lib.VnpccError(f"vnpcc_vn_attention_bwd_tf32 failed with code {rc}")
                 if rc == 0:
