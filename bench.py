@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
     ap.add_argument("--no-eval", action="store_true", help="skip the inference leg (profiling runs)")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
+                    help="development A/B knob of the kernel library (vnpcc_set_tuning); recorded in config.tuning")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,6 +210,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     V.set_gemm_mode(args.mode)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        _lib.raw("vnpcc_set_tuning", int(k), int(v))
     B = args.batch
     headline = args.enc == "vn_pointnet" and args.dec == "vn_foldingnet"
     if args.enc == "vn_dgcnn_fps" and args.dec != "vn_foldingnet":

@@ -42,6 +42,9 @@ unsigned long long vnpcc_launch_count(void);
 /* forward elementwise kernels: 0 (default) = IEEE sqrt / division with the reference's op-by-op rounding (parity mode),
  * 1 = MUFU reciprocal / rsqrt (throughput mode; the host layer switches it together with the TF32 GEMMs) */
 void vnpcc_set_fast_math(int on);
+/* development knobs for A/B measurements (tools/stream_bench.py); every knob defaults to 0 = the shipped behaviour.
+ * knob 0: 1 = legacy fixed grids instead of occupancy-sized single-wave grids;  knob 1: fused small-K backward register budget */
+void vnpcc_set_tuning(int knob, int value);
 
 /* ---------------------------------------------------------------- Chamfer ---------------------------------------- */
 size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M);

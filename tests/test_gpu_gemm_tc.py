@@ -46,10 +46,13 @@ def test_rows_gemm_tf32_exact_on_truncated_operands(tf32_mode, R, K, Cout):
     np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=1e-4 * np.sqrt(K / 64))
 
 
-def test_rows_gemm_tf32_bias_and_strides(tf32_mode):
+@pytest.mark.parametrize("B,N", [(3, 100), (40, 5), (6, 16), (2, 700), (5, 86)])
+def test_rows_gemm_tf32_bias_and_strides(tf32_mode, B, N):
+    """per-sample bias rows in the epilogue: tiles inside one sample, tiles over two samples (rows_per_sample >= 256), chunks that straddle
+    a sample boundary, and samples shorter than a 32-row chunk (row-by-row walk)"""
     from vn_pointcloudcompletion_b200 import ops
     rng = np.random.RandomState(1)
-    B, N, K, Cout = 3, 100, 64, 256
+    K, Cout = 64, 256
     R = B * N * 3
     xfull = _tf32(rng.standard_normal((R, K + 32)).astype(np.float32))
     wfull = _tf32(rng.standard_normal((Cout, 2 * K)).astype(np.float32))

@@ -18,6 +18,7 @@ SIGNATURES = {
     "vnpcc_abi_version": (_i, []),
     "vnpcc_launch_count": (C.c_ulonglong, []),
     "vnpcc_set_fast_math": (None, [_i]),
+    "vnpcc_set_tuning": (None, [_i, _i]),
     "vnpcc_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "vnpcc_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "vnpcc_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

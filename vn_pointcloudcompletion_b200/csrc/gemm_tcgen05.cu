@@ -258,6 +258,24 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             const long long n0 = (tile / num_m) * BN;
             const int o = m0 + quad * 32 + lane;
             const bool o_ok = o < Cout;
+            // per-sample bias row (b, v) of output row r = (b*N + n)*3 + v.  A tile of BN rows touches at most two samples when
+            // rows_per_sample >= BN: the 3 bias rows of the tile's first sample (za) and of the next one (zb) are fetched here, BEFORE
+            // the accumulator wait, so their latency and the 64-bit division are paid once per tile and hidden behind the MMAs.
+            long long tile_b = 0, tile_rem = 0;
+            float za[3] = {0.f, 0.f, 0.f}, zb[3] = {0.f, 0.f, 0.f};
+            if (HAS_BIAS) {
+                tile_b = n0 / rows_per_sample;
+                tile_rem = n0 - tile_b * rows_per_sample;
+                if (o_ok) {
+                    const float* bp = bias + (size_t)(tile_b * 3) * ldbias + o;
+                    const bool next_ok = (tile_b + 1) * rows_per_sample < R;
+#pragma unroll
+                    for (int v3 = 0; v3 < 3; ++v3) {
+                        za[v3] = __ldg(bp + (size_t)v3 * ldbias);
+                        zb[v3] = next_ok ? __ldg(bp + (size_t)(3 + v3) * ldbias) : 0.f;
+                    }
+                }
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
@@ -270,25 +288,31 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                 if (!o_ok) continue;
                 float* dst = Y + (size_t)r0 * ldy + o;
                 if (HAS_BIAS) {
-                    // per-sample bias row (b, v) of output row r = (b*N + n)*3 + v.  A 32-row chunk lies inside one
-                    // sample except at sample boundaries, so only the sample's 3 bias rows are needed: load them once,
-                    // rotate by the chunk's first component and add with compile-time indices.
-                    const long long b = r0 / rows_per_sample;
-                    const long long rem = r0 - b * rows_per_sample;
-                    const int vv = (int)(rem % 3);
-                    if (rem + 32 <= rows_per_sample) {
-                        const float* bp = bias + (size_t)(b * 3) * ldbias + o;
-                        const float z0 = __ldg(bp), z1 = __ldg(bp + ldbias), z2 = __ldg(bp + 2 * ldbias);
+                    // a 32-row chunk lies inside one sample except at sample boundaries: rotate that sample's 3 bias values by the
+                    // chunk's first component and add with compile-time indices
+                    const long long remc = tile_rem + c0;
+                    const bool in_a = remc + 32 <= rows_per_sample;
+                    const bool in_b = remc >= rows_per_sample && remc + 32 <= 2 * rows_per_sample;
+                    if (in_a || in_b) {
+                        const int vv = (int)((in_a ? remc : remc - rows_per_sample) % 3);
+                        const float z0 = in_a ? za[0] : zb[0], z1 = in_a ? za[1] : zb[1], z2 = in_a ? za[2] : zb[2];
                         const float t0 = vv == 0 ? z0 : (vv == 1 ? z1 : z2);
                         const float t1 = vv == 0 ? z1 : (vv == 1 ? z2 : z0);
                         const float t2 = vv == 0 ? z2 : (vv == 1 ? z0 : z1);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += (j % 3 == 0) ? t0 : ((j % 3 == 1) ? t1 : t2);
-                    } else {
-#pragma unroll 1
+                    } else {        // the chunk straddles a sample boundary, or rows_per_sample < BN: walk (sample, component) row by row
+                        long long bc = r0 / rows_per_sample;                 // (compile-time indices into v: it stays in registers)
+                        long long rc = r0 - bc * rows_per_sample;
+                        int vc = (int)(rc % 3);
+#pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const long long r = r0 + j;
-                            if (r < R) v[j] += __ldg(bias + (size_t)((r / rows_per_sample) * 3 + (r % 3)) * ldbias + o);
+                            if (r0 + j < R) v[j] += __ldg(bias + (size_t)(bc * 3 + vc) * ldbias + o);
+                            vc = vc == 2 ? 0 : vc + 1;
+                            if (++rc == rows_per_sample) {
+                                rc = 0;
+                                ++bc;
+                            }
                         }
                     }
                 }
@@ -841,7 +865,7 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
     if (K < 32 || (K & 3) || (ldx & 3) || (ldw & 3) || !tc::aligned16(X) || !tc::aligned16(W) || R >= (1ll << 31))
         return VNPCC_ERR_UNSUPPORTED;
     if (Cout < 64 || R < 64) return VNPCC_ERR_UNSUPPORTED;
-    if (bias && rows_per_sample <= 0) return VNPCC_ERR_BAD_ARG;
+    if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;   // a sample is whole points (3 rows each)
     cudaStream_t st = (cudaStream_t)stream;
     if (R <= 128) return tc::launch_rows<128, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
     return tc::launch_rows<256, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);

@@ -17,6 +17,36 @@ unsigned long long& launch_counter() {
     return n;
 }
 
+static int g_tuning[TUNE_N] = {0};
+int tuning(int knob) { return knob >= 0 && knob < TUNE_N ? g_tuning[knob] : 0; }
+
+int resident_ctas_impl(const void* fn, int threads, size_t smem) {
+    // small open-addressed cache keyed by (function, block size, shared memory); the Python caller is single-threaded and a
+    // racing duplicate insert would only recompute the same value
+    struct Entry { const void* fn; int threads; size_t smem; int n; };
+    static Entry cache[256] = {};
+    size_t h = (reinterpret_cast<uintptr_t>(fn) >> 4) * 2654435761u + (size_t)threads * 97u + smem;
+    for (int probe = 0; probe < 256; ++probe) {
+        Entry& e = cache[(h + probe) & 255];
+        if (e.fn == fn && e.threads == threads && e.smem == smem) return e.n;
+        if (e.fn == nullptr) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem) != cudaSuccess || n < 1) {
+                cudaGetLastError();
+                n = 1;
+            }
+            e.threads = threads;
+            e.smem = smem;
+            e.n = n;
+            e.fn = fn;
+            return n;
+        }
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
 // ---- CD reductions ------------------------------------------------------------------------------------------
 // All four entry points are  sum_b [ w1 * sum_j f(dist1[b,j]) + w2 * sum_k f(dist2[b,k]) ]  with f = sqrt or id:
 //   cd_loss_L1: f=sqrt, w1 = 1/(2 B N), w2 = 1/(2 B M)      cd_loss_L2: f=id, w1 = 1/(B N), w2 = 1/(B M)
@@ -104,6 +134,9 @@ extern "C" {
 
 int vnpcc_abi_version(void) { return 1; }
 void vnpcc_set_fast_math(int on) { g_fast_math = on != 0; }
+void vnpcc_set_tuning(int knob, int value) {
+    if (knob >= 0 && knob < TUNE_N) g_tuning[knob] = value;
+}
 unsigned long long vnpcc_launch_count(void) { return launch_counter(); }
 
 int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M, int mode, double* scratch, float* out,

@@ -90,19 +90,19 @@ __device__ __forceinline__ void fold_load_x(const float* __restrict__ x, size_t 
 #define FOLD_SAMPLES_END }
 
 // per-channel reduction of NRED double values per lane over the block rows, then one atomicAdd per channel
-template <int NRED>
-__device__ __forceinline__ void fold_reduce_channels(double (&acc)[NRED][4], double* __restrict__ out, int C, int c0, double* sh) {
-    // sh: [blockDim.y][blockDim.x][4] doubles, reused NRED times
+template <int NRED, int NL = 4>
+__device__ __forceinline__ void fold_reduce_channels(double (&acc)[NRED][NL], double* __restrict__ out, int C, int c0, double* sh) {
+    // sh: [blockDim.y][blockDim.x][NL] doubles, reused NRED times
     for (int i = 0; i < NRED; ++i) {
         __syncthreads();
 #pragma unroll
-        for (int l = 0; l < 4; ++l) sh[((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4 + l] = acc[i][l];
+        for (int l = 0; l < NL; ++l) sh[((size_t)threadIdx.y * blockDim.x + threadIdx.x) * NL + l] = acc[i][l];
         __syncthreads();
         if (threadIdx.y == 0) {
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
+            for (int l = 0; l < NL; ++l) {
                 double a = 0.0;
-                for (int y = 0; y < (int)blockDim.y; ++y) a += sh[((size_t)y * blockDim.x + threadIdx.x) * 4 + l];
+                for (int y = 0; y < (int)blockDim.y; ++y) a += sh[((size_t)y * blockDim.x + threadIdx.x) * NL + l];
                 atomicAdd(out + (size_t)i * C + c0 + l, a);
             }
         }
@@ -207,17 +207,37 @@ __device__ __forceinline__ void fold_lane_bwd(const V4x3& pr, V4x3& dv, V4x3& gv
 //     dL/dBN(p) = g - c1 d                      dL/dd = -k a g - c1 t p + 2 a c1 d
 //     <dL/dBN(p), p> = g.p - c1 (p.d)           d_nb = that / n
 //     dL/dp = t (g - c1 d) + (dn / r) p,  dn = (gamma d_nb - m1 - nhat m2) invstd - <.,p> nb / n^2       
-template <int KS>
+// NP = channel pairs per thread: 2 (four channels, float4 gradient loads) or 1 (two channels: half the accumulators and context,
+// so that the backward kernels fit twice as many warps on an SM)
+template <int KS, int NP = 2>
 struct FoldCtx2 {
-    f2 wf[2][KS], wd[2][KS];      // [pair][k]
-    f2 bp[3][2], bd[3][2];        // [component][pair]
+    f2 wf[NP][KS], wd[NP][KS];    // [pair][k]
+    f2 bp[3][NP], bd[3][NP];      // [component][pair]
 };
 
-template <int KS>
-__device__ __forceinline__ void fold_load_ctx2(FoldCtx2<KS>& cx, const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+// NP consecutive channel pairs starting at p (8- or 16-byte aligned)
+template <int NP>
+__device__ __forceinline__ void ld_pairs(const float* __restrict__ p, f2 (&o)[NP]) {
+    if constexpr (NP == 2) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        o[0] = mk2(t.x, t.y);
+        o[1] = mk2(t.z, t.w);
+    } else {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        o[0] = mk2(t.x, t.y);
+    }
+}
+template <int NP>
+__device__ __forceinline__ void st_pairs(float* __restrict__ p, const f2 (&o)[NP]) {
+    if constexpr (NP == 2) *reinterpret_cast<float4*>(p) = make_float4(o[0].v.x, o[0].v.y, o[1].v.x, o[1].v.y);
+    else *reinterpret_cast<float2*>(p) = make_float2(o[0].v.x, o[0].v.y);
+}
+
+template <int KS, int NP>
+__device__ __forceinline__ void fold_load_ctx2(FoldCtx2<KS, NP>& cx, const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
                                                size_t ldb, int b, int C, int c0) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < NP; ++h)
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
             cx.wf[h][k] = mk2(__ldg(w + (size_t)(c0 + 2 * h) * ldw + k), __ldg(w + (size_t)(c0 + 2 * h + 1) * ldw + k));
@@ -225,22 +245,25 @@ __device__ __forceinline__ void fold_load_ctx2(FoldCtx2<KS>& cx, const float* __
         }
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-        const float4 p4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb + c0)) : make_float4(0, 0, 0, 0);
-        const float4 d4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(b * 3 + v) * ldb + C + c0)) : make_float4(0, 0, 0, 0);
-        cx.bp[v][0] = mk2(p4.x, p4.y);
-        cx.bp[v][1] = mk2(p4.z, p4.w);
-        cx.bd[v][0] = mk2(d4.x, d4.y);
-        cx.bd[v][1] = mk2(d4.z, d4.w);
+        if (bias) {
+            ld_pairs<NP>(bias + (size_t)(b * 3 + v) * ldb + c0, cx.bp[v]);
+            ld_pairs<NP>(bias + (size_t)(b * 3 + v) * ldb + C + c0, cx.bd[v]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < NP; ++h) cx.bp[v][h] = cx.bd[v][h] = bc2(0.f);
+        }
     }
 }
 
+template <int NP = 2>
 struct ChanParams2 {
-    f2 mean[2], invstd[2], gamma[2], beta[2];
+    f2 mean[NP], invstd[NP], gamma[NP], beta[NP];
 };
-__device__ __forceinline__ ChanParams2 load_params2(const float* stat, const float* gamma, const float* beta, int C, int c0) {
-    ChanParams2 p;
+template <int NP = 2>
+__device__ __forceinline__ ChanParams2<NP> load_params2(const float* stat, const float* gamma, const float* beta, int C, int c0) {
+    ChanParams2<NP> p;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NP; ++h) {
         const int c = c0 + 2 * h;
         p.mean[h] = stat ? mk2(__ldg(stat + c), __ldg(stat + c + 1)) : bc2(0.f);
         p.invstd[h] = stat ? mk2(__ldg(stat + C + c), __ldg(stat + C + c + 1)) : bc2(0.f);
@@ -259,9 +282,9 @@ struct PairBwd {
     f2 gxd;              // <dL/dBN(p), p>
 };
 
-template <int KS, bool HAS_BN>
-__device__ __forceinline__ void fold_pair_bwd(PairBwd& o, const FoldCtx2<KS>& cx, int h, const float (&xv)[3][KS], const f2 (&g)[3],
-                                              const ChanParams2& cp, float k1) {
+template <int KS, bool HAS_BN, int NP>
+__device__ __forceinline__ void fold_pair_bwd(PairBwd& o, const FoldCtx2<KS, NP>& cx, int h, const float (&xv)[3][KS], const f2 (&g)[3],
+                                              const ChanParams2<NP>& cp, float k1) {
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
         f2 a = cx.bp[v][h], e = cx.bd[v][h];
@@ -296,57 +319,80 @@ __device__ __forceinline__ void fold_pair_bwd(PairBwd& o, const FoldCtx2<KS>& cx
     o.gxd = gp - o.c1 * pd;
 }
 
-template <int KS>
-__global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
-                                                             const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
-                                                             size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
-                                                             const float* __restrict__ stat, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float ns, double* __restrict__ sums) {
+// per-channel reduction of fp32 lane values over the block rows, then one atomicAdd per channel
+template <int NL>
+__device__ __forceinline__ void fold_reduce_store(const float (&a)[NL], float* red, float* dst, size_t stride_lane) {
+    __syncthreads();
+    float* mine = red + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * NL;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) mine[l] = a[l];
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            float t = 0.f;
+            for (int y = 0; y < (int)blockDim.y; ++y) t += red[((size_t)y * blockDim.x + threadIdx.x) * NL + l];
+            atomicAdd(dst + (size_t)l * stride_lane, t);
+        }
+    }
+}
+
+template <int KS, int NP, int MINB>
+__global__ void __launch_bounds__(256, MINB) fold_bwd_sums_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+                                                                   const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+                                                                   size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
+                                                                   const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float ns, double* __restrict__ sums) {
     extern __shared__ double fold_sh[];
-    const int c0 = threadIdx.x * 4;
-    const ChanParams2 cp = load_params2(stat, gamma, beta, C, c0);
+    constexpr int NL = 2 * NP;
+    const int c0 = threadIdx.x * NL;
+    const ChanParams2<NP> cp = load_params2<NP>(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
-    double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    float f1[4] = {0, 0, 0, 0}, f2s[4] = {0, 0, 0, 0};
+    double acc[2][NL];
+    float f1[NL], f2s[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        acc[0][l] = acc[1][l] = 0.0;
+        f1[l] = f2s[l] = 0.f;
+    }
     int since_flush = 0;
     FOLD_SAMPLES_BEGIN
-    FoldCtx2<KS> cx;
-    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
+    FoldCtx2<KS, NP> cx;
+    fold_load_ctx2<KS, NP>(cx, w, ldw, bias, ldb, b, C, c0);
     // software pipeline: the gradient rows of the next point are in flight while this one is processed
-    float4 gnext[3];
+    f2 gnext[3][NP];
     float xnext[3][KS];
     {
         const int n = nbeg;
         if (n < n1) {
             const size_t row = ((size_t)b * N + n) * 3;
 #pragma unroll
-            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (row + v) * ldg + c0));
+            for (int v = 0; v < 3; ++v) ld_pairs<NP>(g + (row + v) * ldg + c0, gnext[v]);
             fold_load_x<KS>(x, ldx, row, xnext);
         }
     }
 #pragma unroll 1
     for (int n = nbeg; n < n1; n += nstep) {
-        float4 g4[3];
+        f2 g4[3][NP];
         float xv[3][KS];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            g4[v] = gnext[v];
+#pragma unroll
+            for (int h = 0; h < NP; ++h) g4[v][h] = gnext[v][h];
 #pragma unroll
             for (int k = 0; k < KS; ++k) xv[v][k] = xnext[v][k];
         }
         if (n + nstep < n1) {
             const size_t rown = ((size_t)b * N + n + nstep) * 3;
 #pragma unroll
-            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (rown + v) * ldg + c0));
+            for (int v = 0; v < 3; ++v) ld_pairs<NP>(g + (rown + v) * ldg + c0, gnext[v]);
             fold_load_x<KS>(x, ldx, rown, xnext);
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            f2 gg[3];
-#pragma unroll
-            for (int v = 0; v < 3; ++v) gg[v] = h == 0 ? mk2(g4[v].x, g4[v].y) : mk2(g4[v].z, g4[v].w);
+        for (int h = 0; h < NP; ++h) {
+            const f2 gg[3] = {g4[0][h], g4[1][h], g4[2][h]};
             PairBwd o;
-            fold_pair_bwd<KS, true>(o, cx, h, xv, gg, cp, k1);
+            fold_pair_bwd<KS, true, NP>(o, cx, h, xv, gg, cp, k1);
             const f2 dnb = o.gxd * o.rn;
             const f2 dn2 = dnb * o.nhat;
             f1[2 * h] += dnb.v.x;
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
         }
         if (++since_flush == 32) {         // short fp32 partial sums, flushed to fp64 (the totals feed a mean subtraction)
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
+            for (int l = 0; l < NL; ++l) {
                 acc[0][l] += (double)f1[l];
                 acc[1][l] += (double)f2s[l];
                 f1[l] = f2s[l] = 0.f;
@@ -366,32 +412,33 @@ __global__ void __launch_bounds__(256) fold_bwd_sums_kernel(const float* __restr
     }
     FOLD_SAMPLES_END
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
+    for (int l = 0; l < NL; ++l) {
         acc[0][l] += (double)f1[l];
         acc[1][l] += (double)f2s[l];
     }
-    fold_reduce_channels<2>(acc, sums, C, c0, fold_sh);
+    fold_reduce_channels<2, NL>(acc, sums, C, c0, fold_sh);
 }
 
 // pass B: gW (2C x KS, fp32 atomics), gbias ([B*3, 2C], fp32 atomics), gx ([R, KS], red.add; only columns >= gx_k0)
-template <int KS>
-__global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
-                                                             const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
-                                                             size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
-                                                             const float* __restrict__ stat, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float ns, const double* __restrict__ sums,
-                                                             double count, int training,
-                                                             float* __restrict__ gx, size_t ldgx, int gx_k0, float* __restrict__ gw,
-                                                             size_t ldgw, float* __restrict__ gbias, size_t ldgb) {
+template <int KS, int NP, int MINB>
+__global__ void __launch_bounds__(256, MINB) fold_bwd_main_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ x, size_t ldx,
+                                                                   const float* __restrict__ w, size_t ldw, const float* __restrict__ bias,
+                                                                   size_t ldb, int B, int N, int C, int n_chunk, int row_mode,
+                                                                   const float* __restrict__ stat, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float ns, const double* __restrict__ sums,
+                                                                   double count, int training,
+                                                                   float* __restrict__ gx, size_t ldgx, int gx_k0, float* __restrict__ gw,
+                                                                   size_t ldgw, float* __restrict__ gbias, size_t ldgb) {
     extern __shared__ double fold_sh[];
     float* shf = reinterpret_cast<float*>(fold_sh);
-    const int c0 = threadIdx.x * 4;
+    constexpr int NL = 2 * NP;
+    const int c0 = threadIdx.x * NL;
     const bool has_bn = stat != nullptr;
-    const ChanParams2 cp = load_params2(stat, gamma, beta, C, c0);
+    const ChanParams2<NP> cp = load_params2<NP>(stat, gamma, beta, C, c0);
     const float k1 = 1.f - ns;
-    f2 m1[2], m2[2];
+    f2 m1[NP], m2[NP];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NP; ++h) {
         m1[h] = m2[h] = bc2(0.f);
         if (has_bn && training) {
             const int c = c0 + 2 * h;
@@ -399,9 +446,9 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
             m2[h] = mk2((float)(sums[C + c] / count), (float)(sums[C + c + 1] / count)) * cp.gamma[h];
         }
     }
-    f2 awf[KS][2], awd[KS][2], abp[3][2], abd[3][2];
+    f2 awf[KS][NP], awd[KS][NP], abp[3][NP], abd[3][NP];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NP; ++h) {
 #pragma unroll
         for (int k = 0; k < KS; ++k) awf[k][h] = awd[k][h] = bc2(0.f);
 #pragma unroll
@@ -409,34 +456,35 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
     }
     const int lane = threadIdx.x & 31;
     FOLD_SAMPLES_BEGIN
-    FoldCtx2<KS> cx;
-    fold_load_ctx2<KS>(cx, w, ldw, bias, ldb, b, C, c0);
-    float4 gnext[3];
+    FoldCtx2<KS, NP> cx;
+    fold_load_ctx2<KS, NP>(cx, w, ldw, bias, ldb, b, C, c0);
+    f2 gnext[3][NP];
     float xnext[3][KS];
     {
         const int n = nbeg;
         if (n < n1) {
             const size_t row = ((size_t)b * N + n) * 3;
 #pragma unroll
-            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (row + v) * ldg + c0));
+            for (int v = 0; v < 3; ++v) ld_pairs<NP>(g + (row + v) * ldg + c0, gnext[v]);
             fold_load_x<KS>(x, ldx, row, xnext);
         }
     }
 #pragma unroll 1
     for (int n = nbeg; n < n1; n += nstep) {
         const size_t row = ((size_t)b * N + n) * 3;
-        float4 g4[3];
+        f2 g4[3][NP];
         float xv[3][KS];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            g4[v] = gnext[v];
+#pragma unroll
+            for (int h = 0; h < NP; ++h) g4[v][h] = gnext[v][h];
 #pragma unroll
             for (int k = 0; k < KS; ++k) xv[v][k] = xnext[v][k];
         }
         if (n + nstep < n1) {
             const size_t rown = ((size_t)b * N + n + nstep) * 3;
 #pragma unroll
-            for (int v = 0; v < 3; ++v) gnext[v] = __ldg(reinterpret_cast<const float4*>(g + (rown + v) * ldg + c0));
+            for (int v = 0; v < 3; ++v) ld_pairs<NP>(g + (rown + v) * ldg + c0, gnext[v]);
             fold_load_x<KS>(x, ldx, rown, xnext);
         }
         f2 gxp[3][KS];
@@ -445,13 +493,11 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
 #pragma unroll
             for (int k = 0; k < KS; ++k) gxp[v][k] = bc2(0.f);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            f2 gg[3];
-#pragma unroll
-            for (int v = 0; v < 3; ++v) gg[v] = h == 0 ? mk2(g4[v].x, g4[v].y) : mk2(g4[v].z, g4[v].w);
+        for (int h = 0; h < NP; ++h) {
+            const f2 gg[3] = {g4[0][h], g4[1][h], g4[2][h]};
             PairBwd o;
-            if (has_bn) fold_pair_bwd<KS, true>(o, cx, h, xv, gg, cp, k1);
-            else fold_pair_bwd<KS, false>(o, cx, h, xv, gg, cp, k1);
+            if (has_bn) fold_pair_bwd<KS, true, NP>(o, cx, h, xv, gg, cp, k1);
+            else fold_pair_bwd<KS, false, NP>(o, cx, h, xv, gg, cp, k1);
             // dL/dd = (-k a) g + (-c1 t) p + (2 a c1) d ;  dL/dp = t (g - c1 d) + ur p
             const f2 ca = neg2(bc2(k1) * o.a), cb = neg2(o.c1 * o.t), cc = bc2(2.f) * (o.a * o.c1);
             f2 ur = bc2(0.f);
@@ -495,44 +541,39 @@ __global__ void __launch_bounds__(256) fold_bwd_main_kernel(const float* __restr
     if (row_mode && gbias) {      // this row owned the whole sample: its bias gradient is complete in registers
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            *reinterpret_cast<float4*>(gbias + (size_t)(b * 3 + v) * ldgb + c0) = make_float4(abp[v][0].v.x, abp[v][0].v.y, abp[v][1].v.x, abp[v][1].v.y);
-            *reinterpret_cast<float4*>(gbias + (size_t)(b * 3 + v) * ldgb + C + c0) =
-                make_float4(abd[v][0].v.x, abd[v][0].v.y, abd[v][1].v.x, abd[v][1].v.y);
-            abp[v][0] = abp[v][1] = abd[v][0] = abd[v][1] = bc2(0.f);
+            st_pairs<NP>(gbias + (size_t)(b * 3 + v) * ldgb + c0, abp[v]);
+            st_pairs<NP>(gbias + (size_t)(b * 3 + v) * ldgb + C + c0, abd[v]);
+#pragma unroll
+            for (int h = 0; h < NP; ++h) abp[v][h] = abd[v][h] = bc2(0.f);
         }
     }
     FOLD_SAMPLES_END
     // per-channel reductions over the block rows
     __syncthreads();
-    float* red = shf;   // [blockDim.y][blockDim.x][4]
-    auto reduce_store = [&](const f2 (&a)[2], float* dst, size_t stride_lane) {
-        __syncthreads();
-        float* mine = red + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 4;
-        mine[0] = a[0].v.x;
-        mine[1] = a[0].v.y;
-        mine[2] = a[1].v.x;
-        mine[3] = a[1].v.y;
-        __syncthreads();
-        if (threadIdx.y == 0) {
+    float* red = shf;   // [blockDim.y][blockDim.x][NL]
+    auto lanes = [](const f2 (&a)[NP], float (&o)[NL]) {
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                float t = 0.f;
-                for (int y = 0; y < (int)blockDim.y; ++y) t += red[((size_t)y * blockDim.x + threadIdx.x) * 4 + l];
-                atomicAdd(dst + (size_t)l * stride_lane, t);
-            }
+        for (int h = 0; h < NP; ++h) {
+            o[2 * h] = a[h].v.x;
+            o[2 * h + 1] = a[h].v.y;
         }
     };
+    float tmp[NL];
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-        reduce_store(awf[k], gw + (size_t)c0 * ldgw + k, ldgw);
-        reduce_store(awd[k], gw + (size_t)(C + c0) * ldgw + k, ldgw);
+        lanes(awf[k], tmp);
+        fold_reduce_store<NL>(tmp, red, gw + (size_t)c0 * ldgw + k, ldgw);
+        lanes(awd[k], tmp);
+        fold_reduce_store<NL>(tmp, red, gw + (size_t)(C + c0) * ldgw + k, ldgw);
     }
     if (gbias && !row_mode) {
         const int b = blockIdx.y;
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            reduce_store(abp[v], gbias + (size_t)(b * 3 + v) * ldgb + c0, 1);
-            reduce_store(abd[v], gbias + (size_t)(b * 3 + v) * ldgb + C + c0, 1);
+            lanes(abp[v], tmp);
+            fold_reduce_store<NL>(tmp, red, gbias + (size_t)(b * 3 + v) * ldgb + c0, 1);
+            lanes(abd[v], tmp);
+            fold_reduce_store<NL>(tmp, red, gbias + (size_t)(b * 3 + v) * ldgb + C + c0, 1);
         }
     }
 }
@@ -585,43 +626,80 @@ static bool fold_ok(int KS, int C, const void* bias, long long ldb, const void* 
            (big == nullptr || ((ldbig & 3) == 0 && ((uintptr_t)big & 15) == 0));
 }
 
-static void fold_geometry(int B, int N, int C, dim3& grid, dim3& block, int& n_chunk, size_t& smem, int& row_mode) {
-    const int bx = C / 4, by = 256 / bx;
+// `resident` = CTAs of THIS kernel that fit on one SM (resident_ctas): in block mode the chunk count is chosen so that the grid is a
+// whole number of waves of sm_count() * resident CTAs (a 608-CTA grid on 148 one-CTA SMs would run 5 waves for 4.1 waves of work).
+static void fold_geometry(int B, int N, int C, int resident, dim3& grid, dim3& block, int& n_chunk, size_t& smem, int& row_mode, int lanes = 4) {
+    const int bx = C / lanes, by = 256 / bx;
     row_mode = 0;
+    block = dim3(bx, by);
+    smem = sizeof(double) * 256 * 4;
     if (N <= 64 && B >= 4 * by) {      // many small samples: every block row owns whole samples and loops over them
         row_mode = 1;
         long long blocks = ((long long)B + by - 1) / by;
-        const long long cap = (long long)sm_count() * 8;
+        const long long cap = (long long)sm_count() * (tuning(TUNE_GRID_LEGACY) ? 8 : resident);
         if (blocks > cap) blocks = cap;
         grid = dim3(1, (unsigned)blocks);
-        block = dim3(bx, by);
         n_chunk = N;
-        smem = sizeof(double) * 256 * 4;
         return;
     }
-    int chunks = (int)(((long long)sm_count() * 4 + B - 1) / B);
-    if (chunks < 1) chunks = 1;
-    n_chunk = (N + chunks - 1) / chunks;
-    if (n_chunk < by * 8) n_chunk = by * 8;
-    chunks = (N + n_chunk - 1) / n_chunk;
-    grid = dim3((unsigned)chunks, (unsigned)B);
-    block = dim3(bx, by);
-    smem = sizeof(double) * 256 * 4;
+    if (tuning(TUNE_GRID_LEGACY)) {
+        int chunks = (int)(((long long)sm_count() * 4 + B - 1) / B);
+        if (chunks < 1) chunks = 1;
+        n_chunk = (N + chunks - 1) / chunks;
+        if (n_chunk < by * 8) n_chunk = by * 8;
+        chunks = (N + n_chunk - 1) / n_chunk;
+        grid = dim3((unsigned)chunks, (unsigned)B);
+        return;
+    }
+    // cost model: waves x (points per block row + a fixed per-block prologue / reduction cost of ~6 points per row)
+    const long long slots = (long long)sm_count() * resident;
+    const int min_chunk = by * 8;
+    const int max_chunks = N / min_chunk > 1 ? N / min_chunk : 1;
+    long long lo = (slots + B - 1) / B, hi = (8 * slots + B - 1) / B;
+    if (lo > max_chunks) lo = max_chunks;
+    if (hi > max_chunks) hi = max_chunks;
+    if (lo < 1) lo = 1;
+    int best_chunks = (int)lo;
+    long long best_cost = -1;
+    for (long long c = lo; c <= hi; ++c) {
+        const int nc = (int)((N + c - 1) / c);
+        const long long chunks = (N + nc - 1) / nc;
+        const long long waves = (chunks * B + slots - 1) / slots;
+        const long long cost = waves * ((nc + by - 1) / by + 6);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best_chunks = (int)chunks;
+        }
+    }
+    n_chunk = (N + best_chunks - 1) / best_chunks;
+    grid = dim3((unsigned)((N + n_chunk - 1) / n_chunk), (unsigned)B);
 }
 
 }  // namespace vnpcc
 
 using namespace vnpcc;
 
-#define FOLD_KS_DISPATCH(KS, CALL)                        \
-    switch (KS) {                                         \
-        case 1: { constexpr int K_ = 1; CALL; } break;    \
-        case 2: { constexpr int K_ = 2; CALL; } break;    \
-        case 3: { constexpr int K_ = 3; CALL; } break;    \
-        default: { constexpr int K_ = 4; CALL; } break;   \
+static constexpr size_t FOLD_SMEM = sizeof(double) * 256 * 4;
+static constexpr int FOLD_BWD_DEFAULT_VARIANT = 3;   // two channels per thread, 2 CTAs / SM (tools/stream_bench.py: 2.39 -> 2.27 ms forward + backward)
+
+#define FOLD_KS_DISPATCH(KS, ...)                                \
+    switch (KS) {                                                \
+        case 1: { constexpr int K_ = 1; __VA_ARGS__; } break;    \
+        case 2: { constexpr int K_ = 2; __VA_ARGS__; } break;    \
+        case 3: { constexpr int K_ = 3; __VA_ARGS__; } break;    \
+        default: { constexpr int K_ = 4; __VA_ARGS__; } break;   \
     }
 
 extern "C" {
+
+// geometry of one launch of KERNEL (a concrete instantiation): dynamic shared memory SMEM_ bytes
+#define FOLD_GEOM_L(KERNEL, SMEM_, LANES_)                                                                        \
+    dim3 grid, block;                                                                                             \
+    int n_chunk, row_mode;                                                                                        \
+    size_t smem;                                                                                                  \
+    fold_geometry(B, N, C, resident_ctas(KERNEL, 256, (SMEM_)), grid, block, n_chunk, smem, row_mode, (LANES_)); \
+    if ((SMEM_) == 0) smem = 0;
+#define FOLD_GEOM(KERNEL, SMEM_) FOLD_GEOM_L(KERNEL, SMEM_, 4)
 
 // x [B*N*3, K] local rows, w [2C, K] stacked (feat | dir) weights of the local channels, bias [B*3, 2C] per-sample rows
 // (may be NULL).  sums: 2C doubles (zeroed here).
@@ -631,12 +709,10 @@ int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ld
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (B <= 0 || N <= 0) return last_error();
-    dim3 grid, block;
-    int n_chunk, row_mode;
-    size_t smem;
-    fold_geometry(B, N, C, grid, block, n_chunk, smem, row_mode);
-    FOLD_KS_DISPATCH(K, (count_launch(), fold_stats_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N,
-                                                                                       C, n_chunk, row_mode, sums)));
+    FOLD_KS_DISPATCH(K, {
+        FOLD_GEOM(fold_stats_kernel<K_>, FOLD_SMEM);
+        count_launch(), fold_stats_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, sums);
+    });
     return last_error();
 }
 
@@ -646,16 +722,19 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
     if (!fold_ok(K, C, bias, ldb, out, ldo)) return VNPCC_ERR_UNSUPPORTED;
     if (B <= 0 || N <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid, block;
-    int n_chunk, row_mode;
-    size_t smem;
-    fold_geometry(B, N, C, grid, block, n_chunk, smem, row_mode);
     if (fast_math_enabled()) {
-        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_p2_kernel<K_><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C,
-                                                                                         n_chunk, row_mode, stat, gamma, beta, ns, out, (size_t)ldo)));
+        FOLD_KS_DISPATCH(K, {
+            FOLD_GEOM(fold_fwd_p2_kernel<K_>, 0);
+            count_launch(), fold_fwd_p2_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode,
+                                                                             stat, gamma, beta, ns, out, (size_t)ldo);
+        });
     } else {
-        FOLD_KS_DISPATCH(K, (count_launch(), fold_fwd_kernel<K_, false><<<grid, block, 0, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N,
-                                                                                             C, n_chunk, row_mode, stat, gamma, beta, ns, out, (size_t)ldo)));
+        FOLD_KS_DISPATCH(K, {
+            auto kern = fold_fwd_kernel<K_, false>;
+            FOLD_GEOM(kern, 0);
+            count_launch(), kern<<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, stat, gamma, beta,
+                                                           ns, out, (size_t)ldo);
+        });
     }
     return last_error();
 }
@@ -674,19 +753,42 @@ int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx,
     if (stat) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (gx) cudaMemset2DAsync(gx, (size_t)ldgx * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)B * N * 3, st);
     if (B <= 0 || N <= 0) return last_error();
-    dim3 grid, block;
-    int n_chunk, row_mode;
-    size_t smem;
-    fold_geometry(B, N, C, grid, block, n_chunk, smem, row_mode);
     const double count = (double)B * (double)N;
-    if (stat) {
-        FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_sums_kernel<K_><<<grid, block, smem, st>>>(g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias,
-                                                                                              (size_t)ldb, B, N, C, n_chunk, row_mode, stat, gamma, beta,
-                                                                                              ns, sums)));
+    // register budget / channels per thread of the two backward kernels (vnpcc_set_tuning knob 1):
+    //   1 = four channels per thread, 1 CTA / SM (no spills)      2 = four channels, 2 CTAs / SM (<= 128 registers)
+    //   3 = two channels per thread, 2 CTAs / SM                   0 = default
+    int variant = tuning(TUNE_FOLD_MINB);
+    if (variant == 0) variant = FOLD_BWD_DEFAULT_VARIANT;
+    if (variant == 3 && C > 512) variant = 1;
+#define FOLD_SUMS_LAUNCH(NP_, MINB_)                                                                                                             \
+    {                                                                                                                                            \
+        auto kern = fold_bwd_sums_kernel<K_, NP_, MINB_>;                                                                                       \
+        FOLD_GEOM_L(kern, FOLD_SMEM, 2 * NP_);                                                                                                   \
+        count_launch(), kern<<<grid, block, smem, st>>>(g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, \
+                                                       stat, gamma, beta, ns, sums);                                                            \
     }
-    FOLD_KS_DISPATCH(K, (count_launch(), fold_bwd_main_kernel<K_><<<grid, block, smem, st>>>(
-                            g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, stat, gamma, beta, ns, sums, count,
-                            training, gx, (size_t)ldgx, gx_first_col, gw, (size_t)ldgw, gbias, (size_t)ldgb)));
+#define FOLD_MAIN_LAUNCH(NP_, MINB_)                                                                                                             \
+    {                                                                                                                                            \
+        auto kern = fold_bwd_main_kernel<K_, NP_, MINB_>;                                                                                       \
+        FOLD_GEOM_L(kern, FOLD_SMEM, 2 * NP_);                                                                                                   \
+        count_launch(), kern<<<grid, block, smem, st>>>(g, (size_t)ldg, x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, \
+                                                       stat, gamma, beta, ns, sums, count, training, gx, (size_t)ldgx, gx_first_col, gw,        \
+                                                       (size_t)ldgw, gbias, (size_t)ldgb);                                                      \
+    }
+    if (stat) {
+        FOLD_KS_DISPATCH(K, {
+            if (variant == 3) FOLD_SUMS_LAUNCH(1, 2)
+            else if (variant == 2) FOLD_SUMS_LAUNCH(2, 2)
+            else FOLD_SUMS_LAUNCH(2, 1)
+        });
+    }
+    FOLD_KS_DISPATCH(K, {
+        if (variant == 3) FOLD_MAIN_LAUNCH(1, 2)
+        else if (variant == 2) FOLD_MAIN_LAUNCH(2, 2)
+        else FOLD_MAIN_LAUNCH(2, 1)
+    });
+#undef FOLD_SUMS_LAUNCH
+#undef FOLD_MAIN_LAUNCH
     if (stat && gbeta) vnpcc_double_to_float(sums, gbeta, C, stream);
     if (stat && ggamma) vnpcc_double_to_float(sums + C, ggamma, C, stream);
     return last_error();

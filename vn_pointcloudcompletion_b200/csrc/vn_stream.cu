@@ -470,41 +470,46 @@ __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp,
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline bool ok4(const void* p, long long ld) { return p == nullptr || (al16(p) && (ld & 3) == 0); }
 
-static dim3 stream_grid(long long P, int C) {
+// grid-stride over points: ONE wave of sm_count() * resident CTAs (resident = what fits of this kernel on an SM), so that every
+// CTA streams an equal share and no partial last wave runs at reduced bandwidth
+static dim3 stream_grid(long long P, int C, int resident) {
     const int gx = (C / 4 + 31) / 32;
     long long gy = (P + 7) / 8;
-    const long long cap = ((long long)sm_count() * 8 + gx - 1) / gx;   // ~8 CTAs of 256 threads per SM in total
+    const long long slots = (long long)sm_count() * (tuning(TUNE_GRID_LEGACY) ? 8 : resident);
+    long long cap = tuning(TUNE_GRID_LEGACY) ? (slots + gx - 1) / gx : slots / gx;
+    if (cap < 1) cap = 1;
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
     return dim3((unsigned)gx, (unsigned)gy);
 }
+#define STREAM_GRID(KERNEL) stream_grid(P, C, resident_ctas(KERNEL, 256))
 
 bool try_norm_stats_v4(const float* p, long long ldp, long long P, int C, double* sums, cudaStream_t st) {
     if ((C & 3) || !ok4(p, ldp)) return false;
-    count_launch(), norm_stats_v4_kernel<<<stream_grid(P, C), dim3(32, 8), 0, st>>>(p, (size_t)ldp, P, C, sums);
+    count_launch(), norm_stats_v4_kernel<<<STREAM_GRID(norm_stats_v4_kernel), dim3(32, 8), 0, st>>>(p, (size_t)ldp, P, C, sums);
     return true;
 }
 
 bool try_bn_leaky_fwd_v4(const float* p, long long ldp, const float* d, long long ldd, float* out, long long ldo, long long P, int C,
                          const float* stat, const float* gamma, const float* beta, float ns, cudaStream_t st) {
     if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(out, ldo)) return false;
-    const dim3 grid = stream_grid(P, C), block(32, 8);
+    const dim3 block(32, 8);
     const bool fast = fast_math_enabled();
 #define VS_FWD(BN_, D_)                                                                                                                   \
     {                                                                                                                                     \
         if (fast)                                                                                                                         \
-            count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, true><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
+            count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, true><<<STREAM_GRID((bn_leaky_fwd_v4_kernel<BN_, D_, true>)), block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
                                                                                            C, stat, gamma, beta, ns);                        \
         else                                                                                                                              \
-            count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, false><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
+            count_launch(), bn_leaky_fwd_v4_kernel<BN_, D_, false><<<STREAM_GRID((bn_leaky_fwd_v4_kernel<BN_, D_, false>)), block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, \
                                                                                             C, stat, gamma, beta, ns);                       \
     }
     if (fast && d) {
         if (stat)
-            count_launch(), bn_leaky_fwd_p2_kernel<true><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma,
+            count_launch(), bn_leaky_fwd_p2_kernel<true><<<STREAM_GRID(bn_leaky_fwd_p2_kernel<true>), block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma,
                                                                              beta, ns);
         else
-            count_launch(), bn_leaky_fwd_p2_kernel<false><<<grid, block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma,
+            count_launch(), bn_leaky_fwd_p2_kernel<false><<<STREAM_GRID(bn_leaky_fwd_p2_kernel<false>), block, 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, out, (size_t)ldo, P, C, stat, gamma,
                                                                               beta, ns);
         return true;
     }
@@ -520,17 +525,17 @@ bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long lo
                           long long ldgp, float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma,
                           const float* beta, float ns, double* sums, cudaStream_t st) {
     if ((C & 3) || !ok4(g, ldg) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(gp, ldgp) || !ok4(gd, ldgd)) return false;
-    const dim3 grid = stream_grid(P, C), block(32, 8);
+    const dim3 block(32, 8);
 #define VS_BWD(BN_, D_)                                                                                                            \
-    count_launch(), bn_leaky_bwd1_v4_kernel<BN_, D_, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp,    \
+    count_launch(), bn_leaky_bwd1_v4_kernel<BN_, D_, false><<<STREAM_GRID((bn_leaky_bwd1_v4_kernel<BN_, D_, false>)), block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp,    \
                                                                                      (size_t)ldgp, gd, (size_t)ldgd, P, C, stat, gamma, beta, \
                                                                                      ns, sums, nullptr, nullptr)
     if (stat && d)
-        count_launch(), bn_leaky_bwd1_p2_kernel<true, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
+        count_launch(), bn_leaky_bwd1_p2_kernel<true, false><<<STREAM_GRID((bn_leaky_bwd1_p2_kernel<true, false>)), block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
                                                                                  gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, nullptr, nullptr);
     else if (stat) VS_BWD(true, false);
     else if (d)
-        count_launch(), bn_leaky_bwd1_p2_kernel<false, false><<<grid, block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
+        count_launch(), bn_leaky_bwd1_p2_kernel<false, false><<<STREAM_GRID((bn_leaky_bwd1_p2_kernel<false, false>)), block, 0, st>>>(g, (size_t)ldg, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp,
                                                                                   gd, (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, nullptr, nullptr);
     else VS_BWD(false, false);
 #undef VS_BWD
@@ -540,7 +545,7 @@ bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long lo
 bool try_bn_bwd2_v4(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
                     const float* beta, const double* sums, double count, int training, cudaStream_t st) {
     if ((C & 3) || !ok4(gp, ldgp) || !ok4(p, ldp)) return false;
-    count_launch(), bn_bwd2_v4_kernel<<<stream_grid(P, C), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
+    count_launch(), bn_bwd2_v4_kernel<<<STREAM_GRID(bn_bwd2_v4_kernel), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
                                                                              sums, count, training);
     return true;
 }
@@ -550,12 +555,14 @@ bool try_bn_leaky_dot_fwd_v4(const float* p, long long ldp, const float* d, long
                              cudaStream_t st) {
     if ((C & 127) || C > 1024 || !ok4(p, ldp) || !ok4(d, ldd) || d == nullptr) return false;
     const int bx = C / 4, by = 256 / bx;
-    long long g = (P + by - 1) / by;
-    const long long cap = (long long)sm_count() * 8;
-    if (g > cap) g = cap;
     const bool fast = fast_math_enabled();
+    auto dot_grid = [&](int resident) {
+        long long g = (P + by - 1) / by;
+        const long long cap = (long long)sm_count() * (tuning(TUNE_GRID_LEGACY) ? 8 : resident);
+        return (unsigned)(g > cap ? cap : g);
+    };
 #define VS_DOT(BN_, F_)                                                                                                                       \
-    count_launch(), bn_leaky_dot_fwd_v4_kernel<BN_, F_><<<(unsigned)g, dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma, \
+    count_launch(), bn_leaky_dot_fwd_v4_kernel<BN_, F_><<<dot_grid(resident_ctas(bn_leaky_dot_fwd_v4_kernel<BN_, F_>, 256)), dim3(bx, by), 0, st>>>(p, (size_t)ldp, d, (size_t)ldd, P, C, stat, gamma, \
                                                                                               beta, ns, w2, res, y)
     if (stat && fast) VS_DOT(true, true);
     else if (stat) VS_DOT(true, false);
@@ -569,12 +576,12 @@ bool try_bn_leaky_dot_bwd1_v4(const float* gy, const float* p, long long ldp, co
                               float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
                               float ns, double* sums, const float* w2, double* gw2, cudaStream_t st) {
     if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || !ok4(gp, ldgp) || !ok4(gd, ldgd) || d == nullptr) return false;
-    const dim3 grid = stream_grid(P, C), block(32, 8);
+    const dim3 block(32, 8);
     if (stat)
-        count_launch(), bn_leaky_bwd1_p2_kernel<true, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
+        count_launch(), bn_leaky_bwd1_p2_kernel<true, true><<<STREAM_GRID((bn_leaky_bwd1_p2_kernel<true, true>)), block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
                                                                                 (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
     else
-        count_launch(), bn_leaky_bwd1_p2_kernel<false, true><<<grid, block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
+        count_launch(), bn_leaky_bwd1_p2_kernel<false, true><<<STREAM_GRID((bn_leaky_bwd1_p2_kernel<false, true>)), block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
                                                                                  (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
     return true;
 }

@@ -36,6 +36,17 @@ inline int count_launch() {
     return 0;
 }
 
+// resident CTAs per SM of one kernel at a block size / dynamic shared-memory size (occupancy calculator; cached per kernel).
+// Launchers size persistent / grid-stride grids as sm_count() * resident so that the whole grid is ONE wave of equal shares.
+int resident_ctas_impl(const void* fn, int threads, size_t smem);
+template <class K>
+inline int resident_ctas(K* kernel, int threads, size_t smem = 0) {
+    return resident_ctas_impl(reinterpret_cast<const void*>(kernel), threads, smem);
+}
+// development knobs (vnpcc_set_tuning): 0 = default behaviour
+enum { TUNE_GRID_LEGACY = 0, TUNE_FOLD_MINB = 1, TUNE_N = 8 };
+int tuning(int knob);
+
 inline int grid_for(size_t total, int block, int per_sm) {
     size_t g = (total + block - 1) / block;
     size_t cap = (size_t)sm_count() * per_sm;
