@@ -936,10 +936,31 @@ int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long 
         attr_done = true;
     }
     const int gm = (Cout + tc::BM - 1) / tc::BM, gn = (K + BNW - 1) / BNW;
-    long long splits = ((long long)sm_count() * 2 + (long long)gm * gn - 1) / ((long long)gm * gn);
+    // split of the reduction over CTAs: one CTA per SM is resident (192 KB of operand stages), so the grid should be a whole number of
+    // waves of sm_count() CTAs -- 32 output tiles x 10 splits = 320 CTAs would run 3 waves for 2.16 waves of work.  Cost model per
+    // candidate split count: waves x (rows per split + ~512 rows' worth of prologue / red.add epilogue).
+    const long long tiles = (long long)gm * gn, slots = sm_count();
     const long long max_splits = (R + 1023) / 1024;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    long long splits = 1, best_cost = -1;
+    if (tuning(TUNE_GRID_LEGACY)) {
+        splits = (slots * 2 + tiles - 1) / tiles;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    } else {
+        long long hi = (4 * slots + tiles - 1) / tiles;
+        if (hi > max_splits) hi = max_splits;
+        if (hi < 1) hi = 1;
+        for (long long c = 1; c <= hi; ++c) {
+            const long long rps = ((R + c - 1) / c + tc::BR - 1) / tc::BR * tc::BR;
+            const long long actual = (R + rps - 1) / rps;
+            const long long waves = (tiles * actual + slots - 1) / slots;
+            const long long cost = waves * (rps + 512);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                splits = actual;
+            }
+        }
+    }
     long long rows_per_split = ((R + splits - 1) / splits + tc::BR - 1) / tc::BR * tc::BR;
     splits = (R + rows_per_split - 1) / rows_per_split;
     // G is accumulated with atomics: clear it first (rows of K floats with pitch ldg)

@@ -526,11 +526,46 @@ class _MaxPoolGather(torch.autograd.Function):
         return gx, None, None, None
 
 
-def maxpool_rows(x, d, G, N, forced_idx=None):
-    """x, d rows [G*N*3, C] -> (pooled rows [G*3, C], idx [G, C]).  d carries no gradient (argmax), SURVEY B.3."""
+class _MaxPoolGatherTap(torch.autograd.Function):
+    """_MaxPoolGather that also hands its input through (an alias): for an activation that feeds the pool AND a dense consumer
+    (models/pcn.py:168-173: feature -> maxpool1 and -> cat -> second_conv).  The pooled gradient touches one point per (group, channel);
+    the backward scatters it IN PLACE into the dense consumer's gradient instead of materialising a second dense tensor of zeros and
+    summing the two (a 400 MB fill + a 1.2 GB add per step at B = 32)."""
+
+    @staticmethod
+    def forward(ctx, x, idx, G, N):
+        x = _rows2d(x, "x")
+        C = x.shape[1]
+        out = torch.empty((G * 3, C), device=x.device, dtype=torch.float32)
+        call("vnpcc_vn_maxpool_gather", ptr(x), _ld(x), ptr(idx), G, N, C, ptr(out), C, stream())
+        ctx.save_for_backward(idx)
+        ctx.cfg = (G, N, C)
+        return out, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g, gpass):
+        (idx,) = ctx.saved_tensors
+        G, N, C = ctx.cfg
+        if gpass is None:
+            gx = torch.zeros((G * N * 3, C), device=idx.device, dtype=torch.float32)
+        else:
+            gx = _rows2d(gpass, "grad")      # the dense consumer's gradient: a fresh tensor owned by this backward pass
+            if gx.stride(1) != 1 or gx.stride(0) < C:      # a broadcast / strided gradient is not ours to write into
+                gx = gx.contiguous()
+        if g is not None:
+            g = _rows2d(g, "grad")
+            call("vnpcc_vn_maxpool_scatter_add", ptr(g), _ld(g), ptr(idx), G, N, C, ptr(gx), _ld(gx), stream())
+        return gx, None, None, None
+
+
+def maxpool_rows(x, d, G, N, forced_idx=None, tap=False):
+    """x, d rows [G*N*3, C] -> (pooled rows [G*3, C], idx [G, C]).  d carries no gradient (argmax), SURVEY B.3.
+    tap=True: the pooled rows come with a pass-through alias of x for the dense consumer of the same activation, (pooled, x_alias)."""
     x = _rows2d(x, "x")
     with torch.no_grad():
         idx = maxpool_select(x, _rows2d(d.detach(), "d"), G, N) if forced_idx is None else forced_idx.reshape(G, -1).contiguous()
+    if tap:
+        return _MaxPoolGatherTap.apply(x, idx, G, N), idx
     return _MaxPoolGather.apply(x, idx, G, N), idx
 
 

@@ -45,7 +45,8 @@ class VN_PointNet(nn.Module):
         x0 = xyz.contiguous().view(B * N * 3, 1)
         f0 = self.first_conv[0].forward_rows(x0)                                          # [R,128]
         f1 = ops.linear_rows(f0, self.first_conv[1].map_to_feat.weight)                  # [R,512]
-        g1 = self.maxpool1.forward_rows(f1, B, N)                                         # [B*3,512]
+        # f1 feeds the pool and (through the concatenation) second_conv: the pool's sparse gradient is scattered into the dense one
+        g1, f1 = self.maxpool1.forward_rows(f1, B, N, tap=True)                           # [B*3,512]
         Cg = g1.shape[1]
         l0 = self.second_conv[0]
         wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [2048,1024]
@@ -118,7 +119,12 @@ class VN_FoldingNet(nn.Module):
         Cg = fg_rows.shape[1]
         l0, l1, l2 = self.final_conv[0], self.final_conv[1], self.final_conv[2]
         wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [512, Cg+2]
-        bias = ops.linear_rows(fg_rows, wcat[:, :Cg])                                      # [B*3,512]
+        # (a contiguous copy of the Cg broadcast columns when the [512, Cg+2] rows are not 16-byte aligned: 2050 floats per row would push
+        # this 96 x 2048 x 512 GEMM and its gradients onto the fp32 SIMT kernel -- 0.25 ms on four CTAs)
+        wg = wcat[:, :Cg]
+        if (wcat.stride(0) * 4) % 16 != 0:
+            wg = wg.contiguous()
+        bias = ops.linear_rows(fg_rows, wg)                                                # [B*3,512]
         C0 = l0.map_to_feat.weight.shape[0]
         if ops.smallk_bn_leaky_supported(2, C0, bias) and l0.batchnorm.bn.affine:
             # p = W_feat x + b_p and d = W_dir x + b_d are two FMAs per component: recomputed in every pass, never stored

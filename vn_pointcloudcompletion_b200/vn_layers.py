@@ -164,11 +164,14 @@ class VNMaxPool(nn.Module):
         self.last_idx = None        # selections of the most recent forward ([G, C] int64), for parity checks
         self.forced_idx = None      # teacher-forced selections; None = own arg-max
 
-    def forward_rows(self, rows, G, N):
+    def forward_rows(self, rows, G, N, tap=False):
+        """tap=True returns (pooled, alias of rows): feed the alias to the dense consumer of the same activation (ops._MaxPoolGatherTap)"""
         with torch.no_grad():
             d = ops.gemm_rows(rows.detach(), self.map_to_dir.weight.detach())
-        out, idx = ops.maxpool_rows(rows, d, G, N, self.forced_idx)
+        out, idx = ops.maxpool_rows(rows, d, G, N, self.forced_idx, tap and torch.is_grad_enabled() and rows.requires_grad)
         self.last_idx = idx
+        if tap and not isinstance(out, tuple):
+            return out, rows
         return out
 
     def forward(self, x):
