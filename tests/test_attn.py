@@ -270,7 +270,7 @@ def test_pcnnet_pointnet_attention_decoder_trains():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,N,H,ds_ws,store_p", [(1, 64, 1, True, True), (2, 130, 2, True, True), (1, 1024, 8, True, True), (2, 200, 3, True, True),
-                                                 (2, 256, 2, False, False), (2, 256, 2, True, False), (1, 1024, 8, True, False)])
+                                                 (2, 256, 2, False, False), (2, 256, 2, True, False), (1, 1024, 8, True, False), (2, 256, 2, True, True), (3, 128, 4, True, True)])
 def test_attention_core_tf32_tensor_core(B, N, H, ds_ws, store_p):
     """csrc/attention_tc.cu (tcgen05 / TMEM, TF32 operands) against the numpy oracle.  Stated TF32 tolerance: operands carry a 10-bit
     mantissa, scores are sums of 144 products of O(1) features -> |dS| <~ 3e-3, i.e. a few 1e-3 relative error on softmax weights;

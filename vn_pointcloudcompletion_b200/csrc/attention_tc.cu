@@ -41,7 +41,7 @@ constexpr int K_BYTES = (KD / 32) * BKEY * 128;      // 49152
 constexpr int VT_BYTES = (BKEY / 32) * KD * 128;     // 49152
 constexpr int P_BYTES = (BKEY / 32) * BQ * 128;      // 32768
 constexpr int TILE_BYTES = Q_BYTES + K_BYTES + VT_BYTES + P_BYTES;
-constexpr int SMEM_BYTES = TILE_BYTES + 64 + 1024;
+constexpr int SMEM_BYTES = TILE_BYTES + 128 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -159,12 +159,35 @@ __device__ __forceinline__ uint32_t sw128(int rows, int r, int kappa) {
 //           same skeleton with the operands' roles swapped, one pass, no normalisation
 constexpr int MODE_FWD = 0, MODE_DV = 1;
 
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// bulk-tensor store of one K-major SWIZZLE_128B k-block ([rows] x 128 bytes in shared memory) to a row-major global matrix
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Issue order (one thread issues TMA and MMA; tcgen05 MMAs of one thread execute in order, a commit covers everything issued before it):
+//   pass 1 (MODE_FWD)  K tiles alternate between the K and the (still unused) V buffer, S alternates between two TMEM accumulators:
+//                      Q K^T of tile i+1 runs while the lane threads reduce tile i to (max, sum); the tile after that is already in flight.
+//   pass 2             P V of tile i and Q K^T of tile i+1 are issued back to back as soon as P(i) is in shared memory; the K tile was
+//                      fetched during the softmax, the next V tile is fetched as soon as P V has read the current one (during Q K^T and
+//                      the next softmax).  The stored P goes out as bulk-tensor stores straight from the swizzled operand tile.
 template <int D, int MODE>
 __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_q,
-                                                           const __grid_constant__ CUtensorMap map_v, int N, int H, int cx, int cy, int cz,
-                                                           float scale, float* __restrict__ out, size_t ldo, float* __restrict__ lse,
+                                                           const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_p,
+                                                           int p_tma, int N, int H, int cx, int cy, int cz, float scale,
+                                                           float* __restrict__ out, size_t ldo, float* __restrict__ lse,
                                                            float* __restrict__ p_out) {
-    // p_out (MODE_FWD, may be NULL; N % 4 == 0): the normalised attention weights P [B*H*N, N], stored for the GEMM-shaped backward
+    // p_out (MODE_FWD, may be NULL; N % 4 == 0): the normalised attention weights P [B*H*N, N], stored for the GEMM-shaped backward;
+    // p_tma != 0 (needs N % 128 == 0): map_p describes p_out as a row-major matrix with boxes {32 columns, 128 rows}, SWIZZLE_128B
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
@@ -172,8 +195,8 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
     uint8_t* Vs = Ks + K_BYTES;
     uint8_t* Ps = Vs + VT_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TILE_BYTES);
-    uint64_t* qfull = bars, *kfull = bars + 1, *vfull = bars + 2, *s_done = bars + 3, *o_done = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* qfull = bars, *kfull = bars + 1 /* [2] */, *vfull = bars + 3, *s_done = bars + 4 /* [2] */, *o_done = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
@@ -181,43 +204,45 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
     const int tok0 = b * N;                       // first token of the sample in the [B*N]-token tensor maps
     const int colq = cx + h * D, colk = cy + h * D, colv = cz + h * D;      // resident rows / streamed K-major tile / streamed MN-major tile
     const int T = (N + BKEY - 1) / BKEY;
+    static_assert(K_BYTES == VT_BYTES, "pass 1 uses the V buffer as the second K buffer");
 
     if (tid == 0) {
         tma_prefetch_desc(&map_k);
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_v);
-        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        if (p_tma) tma_prefetch_desc(&map_p);
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);      // this thread's TMEM lane = its query row
-    const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64;
+    const uint32_t o_tmem = tmem_base + 2 * BKEY;                          // S accumulators at columns 0 and BKEY, O behind them
     constexpr uint32_t idesc_s = make_idesc(BQ, BKEY, 0);
     constexpr uint32_t idesc_o = make_idesc(BQ, KD, 1);
 
-    auto load_k = [&](int k0) {      // 6 boxes {32 cols, 1 component, 64 tokens} -> 6 k-blocks of 8 KB
-        mbar_expect_tx(kfull, K_BYTES);
+    auto load_k = [&](int k0, uint8_t* dst, uint64_t* bar) {      // 6 boxes {32 cols, 1 component, 64 tokens} -> 6 k-blocks of 8 KB
+        mbar_expect_tx(bar, K_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_k, kfull, Ks + kb * (BKEY * 128), colk + (kb & 1) * 32, kb >> 1, tok0 + k0);
+        for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_k, bar, dst + kb * (BKEY * 128), colk + (kb & 1) * 32, kb >> 1, tok0 + k0);
     };
     auto load_v = [&](int k0) {      // 6 slabs {32 features, 64 keys}
         mbar_expect_tx(vfull, VT_BYTES);
 #pragma unroll
         for (int sl = 0; sl < KD / 32; ++sl) tma_load_3d(&map_v, vfull, Vs + sl * (BKEY * 128), colv + (sl & 1) * 32, sl >> 1, tok0 + k0);
     };
-    auto issue_s = [&]() {
-        const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
+    auto issue_s = [&](const uint8_t* kbuf, uint32_t s_tmem, uint64_t* done) {
+        const uint32_t qa = smem_u32(Qs), ka = smem_u32(kbuf);
 #pragma unroll
         for (int ks = 0; ks < KD / 8; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
             if ((kb & 1) && kk * 8 + 32 >= D) continue;      // columns D..63 of a component belong to the next head: those k-steps are skipped
             umma_tf32(s_tmem, make_desc(qa + kb * (BQ * 128) + kk * 32), make_desc(ka + kb * (BKEY * 128) + kk * 32), idesc_s, ks != 0 ? 1u : 0u);
         }
-        umma_commit(s_done);
+        if (done) umma_commit(done);
     };
 
     // ---- resident tile: one TMA load (its padding columns are never multiplied: see issue_s)
@@ -225,65 +250,77 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
         mbar_expect_tx(qfull, Q_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_q, qfull, Qs + kb * (BQ * 128), colq + (kb & 1) * 32, kb >> 1, tok0 + q0);
-        load_k(0);
-        mbar_wait(qfull, 0);
     }
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const float sc2 = scale * LOG2E;      // scores are handled in the base-2 domain: exp(x) = 2^(x log2 e) is one MUFU.EX2
 
-    uint32_t kph = 0, vph = 0, sph = 0, oph = 0;
-
-    // ---- pass 1: row maxima and row sums of the scaled scores
+    // ---- pass 1: row maxima and row sums of the scaled scores (tile t: K buffer t & 1, S accumulator t & 1, barrier parity (t >> 1) & 1)
     float m = -INFINITY, l1 = 0.f;
-    for (int i = 0; MODE == MODE_FWD && i < T; ++i) {
-        const int k0 = i * BKEY;
+    if (MODE == MODE_FWD) {
         if (tid == 0) {
-            mbar_wait(kfull, kph);
+            load_k(0, Ks, &kfull[0]);
+            if (T > 1) load_k(BKEY, Vs, &kfull[1]);
+            mbar_wait(qfull, 0);
+            mbar_wait(&kfull[0], 0);
             tc_fence_after();
-            issue_s();
+            issue_s(Ks, tmem_base, &s_done[0]);
         }
-        kph ^= 1;
-        mbar_wait(s_done, sph);
-        sph ^= 1;
-        tc_fence_after();
-        if (tid == 0) load_k(i + 1 < T ? k0 + BKEY : 0);      // the K buffer is free; the last prefetch is tile 0 for pass 2
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float s[32];
-            tmem_ld32(t_row + half * 32, s);
-            float hm = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                s[j] = (k0 + half * 32 + j < N) ? s[j] * scale : -INFINITY;
-                hm = fmaxf(hm, s[j]);
+        for (int i = 0; i < T; ++i) {
+            const int k0 = i * BKEY, cur = i & 1;
+            if (tid == 0 && i + 1 < T) {      // accumulator cur ^ 1 was released by the __syncthreads of iteration i - 1
+                mbar_wait(&kfull[cur ^ 1], (uint32_t)(((i + 1) >> 1) & 1));
+                tc_fence_after();
+                issue_s(cur ? Ks : Vs, tmem_base + (cur ^ 1) * BKEY, &s_done[cur ^ 1]);
             }
-            if (hm > -INFINITY) {      // online (max, sum): only the scalar l is rescaled
-                const float mn = fmaxf(m, hm);
-                float acc = 0.f;
+            mbar_wait(&s_done[cur], (uint32_t)((i >> 1) & 1));
+            tc_fence_after();
+            if (tid == 0 && i + 2 < T) load_k(k0 + 2 * BKEY, cur ? Vs : Ks, &kfull[cur]);      // K buffer cur is free again
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc += expf(s[j] - mn);
-                l1 = fmaf(l1, expf(m - mn), acc);
-                m = mn;
+            for (int half = 0; half < 2; ++half) {
+                float s[32];
+                tmem_ld32(t_row + cur * BKEY + half * 32, s);
+                float hm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    s[j] = (k0 + half * 32 + j < N) ? s[j] * sc2 : -INFINITY;
+                    hm = fmaxf(hm, s[j]);
+                }
+                if (hm > -INFINITY) {      // online (max, sum): only the scalar l is rescaled
+                    const float mn = fmaxf(m, hm);
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        acc0 += ex2f(s[j] - mn);
+                        acc1 += ex2f(s[j + 1] - mn);
+                    }
+                    l1 = fmaf(l1, ex2f(m - mn), acc0 + acc1);
+                    m = mn;
+                }
             }
+            tc_fence_before();
+            __syncthreads();      // every thread has read accumulator cur before the Q K^T after next overwrites it
         }
-        tc_fence_before();
-        __syncthreads();      // every thread has read S before the next Q K^T overwrites it
     }
-    const float lse_row = m + logf(l1);      // MODE_FWD: P = exp(S - lse) is normalised, O needs no final division
+    const float lse2_row = m + log2f(l1);      // MODE_FWD: P = 2^(S - lse2) is normalised, O needs no final division
 
-    // ---- pass 2: P = exp(S - lse), O += P V
-    float l = 0.f;
-    if (tid == 0) load_v(0);
+    // ---- pass 2: P = exp(S - lse), O += P V   (K buffer = Ks, accumulator 0; their barriers continue with the parity pass 1 left)
+    const uint32_t par0 = MODE == MODE_FWD ? (uint32_t)(((T + 1) >> 1) & 1) : 0u;
+    uint32_t kph = par0, sph = par0, vph = 0, oph = 0;
+    if (tid == 0) {
+        load_k(0, Ks, &kfull[0]);
+        load_v(0);
+        if (MODE != MODE_FWD) mbar_wait(qfull, 0);
+        mbar_wait(&kfull[0], kph);
+        tc_fence_after();
+        issue_s(Ks, tmem_base, &s_done[0]);
+    }
+    kph ^= 1;
     for (int i = 0; i < T; ++i) {
         const int k0 = i * BKEY;
-        if (tid == 0) {
-            mbar_wait(kfull, kph);
-            tc_fence_after();
-            issue_s();
-        }
-        kph ^= 1;
-        mbar_wait(s_done, sph);
+        mbar_wait(&s_done[0], sph);      // S(i) complete -- and with it (in-order execution) P V of tile i - 1: P and the K buffer are free
         sph ^= 1;
         tc_fence_after();
-        if (tid == 0 && i + 1 < T) load_k(k0 + BKEY);
+        if (tid == 0 && i + 1 < T) load_k(k0 + BKEY, Ks, &kfull[0]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float s[32];
@@ -291,12 +328,11 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int col = k0 + half * 32 + j;
-                float p = 0.f;
-                if (col < N) p = expf(s[j] * scale - (MODE == MODE_FWD ? lse_row : __ldg(lse + (size_t)bh * N + col)));
-                s[j] = p;
-                l += p;
+                float pv = 0.f;
+                if (col < N) pv = ex2f(fmaf(s[j], sc2, -(MODE == MODE_FWD ? lse2_row : LOG2E * __ldg(lse + (size_t)bh * N + col))));
+                s[j] = pv;
             }
-            if (MODE == MODE_FWD && p_out != nullptr && q0 + tid < N) {
+            if (MODE == MODE_FWD && p_out != nullptr && !p_tma && q0 + tid < N) {
                 float4* dst = reinterpret_cast<float4*>(p_out + ((size_t)bh * N + q0 + tid) * N + k0 + half * 32);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4)
@@ -319,40 +355,50 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
                 umma_tf32(o_tmem, make_desc(pa + kb * (BQ * 128) + kk * 32), make_desc_mn(va + ks * 1024, BKEY * 128), idesc_o, (i | ks) != 0 ? 1u : 0u);
             }
             umma_commit(o_done);
-            // V and P may be overwritten only after these MMAs have read them.  The next Q K^T is issued behind them (tcgen05 MMAs of
-            // one thread execute in order), so the softmax threads, which wait for it before touching P, need no extra wait.
-            mbar_wait(o_done, oph);
+            if (i + 1 < T) {      // the next Q K^T queues up right behind P V
+                mbar_wait(&kfull[0], kph);
+                tc_fence_after();
+                issue_s(Ks, tmem_base, nullptr);
+            }
+            if (MODE == MODE_FWD && p_tma) {      // the stored P: two bulk-tensor stores out of the operand tile (rows q0.., columns k0..)
+                tma_store_2d(&map_p, Ps, k0, bh * N + q0);
+                tma_store_2d(&map_p, Ps + BQ * 128, k0 + 32, bh * N + q0);
+                tma_store_commit();
+                tma_store_wait_read();      // P may be overwritten once s_done fires: it must have been read by then
+            }
+            if (i + 1 < T) umma_commit(&s_done[0]);
+            mbar_wait(o_done, oph);         // P V has read V: fetch the next tile behind Q K^T and the next softmax
             if (i + 1 < T) load_v(k0 + BKEY);
         }
+        kph ^= 1;
         vph ^= 1;
         oph ^= 1;
     }
+    if (tid == 0 && MODE == MODE_FWD && p_tma) tma_store_wait_all();
     // all MMAs are complete for thread 0; make that visible to everyone before the accumulator is read
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
-    // ---- epilogue: out = O / l, lse = m + log l
+    // ---- epilogue: out = O (P is normalised in MODE_FWD and must not be in MODE_DV), lse = ln 2 (m + log2 l)
     const int n = q0 + tid;
-    const float inv = 1.0f;      // P is normalised (MODE_FWD) or must not be (MODE_DV)
-    (void)l;
 #pragma unroll 1
     for (int i = 0; i < KD / 32; ++i) {
         float o[32];
-        tmem_ld32(t_row + 64 + i * 32, o);
+        tmem_ld32(t_row + 2 * BKEY + i * 32, o);
         if (n < N) {
             const int v = i >> 1, c0 = (i & 1) * 32;
             float* dst = out + ((size_t)(b * (size_t)N + n) * 3 + v) * ldo + (size_t)h * D + c0;
             const int cnt = (c0 + 32 <= D) ? 32 : (D - c0);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+                if (j < cnt) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
     }
-    if (MODE == MODE_FWD && n < N) lse[(size_t)bh * N + n] = lse_row;
+    if (MODE == MODE_FWD && n < N) lse[(size_t)bh * N + n] = lse2_row * LN2;
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // -------------------------------------------------------------------------------------------------------------------------------
@@ -623,9 +669,10 @@ __global__ void __launch_bounds__(NT, 1) attn_acc_gemm_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // warp roles: thread 0 = TMA producer, thread 32 = MMA issuer (a single thread doing both has to wait for the MMAs of tile i before it
+    // may refill their stage, which leaves the tensor pipe idle for a commit / wake-up round trip per tile)
     if (tid == 0) {
-        constexpr uint32_t idesc = make_idesc(BQ, KD, 1, A_MN);
-        auto load = [&](int tile) {
+        for (int tile = 0; tile < T; ++tile) {
             const int st = tile % GK_NS;
             if (tile >= GK_NS) mbar_wait(&empty[st], (uint32_t)((tile / GK_NS - 1) & 1));
             uint8_t* a = smem + st * GK_STAGE_BYTES;
@@ -639,8 +686,9 @@ __global__ void __launch_bounds__(NT, 1) attn_acc_gemm_kernel(const __grid_const
 #pragma unroll
             for (int sl = 0; sl < KD / 32; ++sl)
                 tma_load_3d(&map_z, &full[st], a + GK_A_BYTES + sl * (BT * 128), colz + (sl & 1) * 32, sl >> 1, tok0 + tile * BT);
-        };
-        for (int i = 0; i < GK_NS && i < T; ++i) load(i);
+        }
+    } else if (tid == 32) {
+        constexpr uint32_t idesc = make_idesc(BQ, KD, 1, A_MN);
         for (int i = 0; i < T; ++i) {
             const int st = i % GK_NS;
             mbar_wait(&full[st], (uint32_t)((i / GK_NS) & 1));
@@ -651,13 +699,11 @@ __global__ void __launch_bounds__(NT, 1) attn_acc_gemm_kernel(const __grid_const
                 umma_tf32(tmem_base, A_MN ? make_desc_mn(aa + ks * 1024, BT * 128) : make_desc(aa + ks * 32), make_desc_mn(ba + ks * 1024, BT * 128),
                           idesc, (i | ks) != 0 ? 1u : 0u);
             umma_commit(&empty[st]);
-            if (i + GK_NS < T) load(i + GK_NS);
         }
         umma_commit(done);
-        mbar_wait(done, 0);
     }
-    tc_fence_before();
-    __syncthreads();
+    __syncwarp();
+    mbar_wait(done, 0);      // every thread: the accumulator is complete
     tc_fence_after();
     const int n_row = r0 + tid;
 #pragma unroll 1
@@ -777,6 +823,129 @@ __global__ void __launch_bounds__(NT, 1) attn_ds_kernel(const __grid_constant__ 
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
+// Same computation with the stored P moving by TMA (N % 128 == 0): the lane threads of attn_ds_kernel read and write their own 4 KB-strided
+// rows, 32 different 128-byte lines per warp instruction, which makes the load / store unit the bottleneck (6.8 us per 128 x 64 tile).
+// Here P arrives as bulk-tensor loads of {32 columns, 128 rows} boxes into a ring of two 16 KB half-tile buffers (K-major SWIZZLE_128B: a
+// thread reads its row as conflict-free 16-byte chunks), dS is written back in place and leaves as bulk-tensor stores; the load of the
+// next tile's half is issued as soon as the store has read the buffer.
+constexpr int DST_HALF_BYTES = BQ * 128;                                      // one k-block: 128 rows x 32 columns
+constexpr int DST_TILE_BYTES = Q_BYTES + 2 * K_BYTES + 2 * DST_HALF_BYTES;
+constexpr int DST_SMEM_BYTES = DST_TILE_BYTES + 128 + 1024;
+
+template <int D>
+__global__ void __launch_bounds__(NT, 1) attn_ds_tma_kernel(const __grid_constant__ CUtensorMap map_do,     // dO, K-major SW128, box 128 tokens
+                                                           const __grid_constant__ CUtensorMap map_v,      // qkv, K-major SW128, box 64 tokens
+                                                           const __grid_constant__ CUtensorMap map_p,      // P / dS [B*H*N, N], box {32, 128}, SW128
+                                                           int N, int H, int C, float scale, const float* __restrict__ delta) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* dOs = smem;
+    uint8_t* Vs = dOs + Q_BYTES;                      // two buffers of K_BYTES
+    uint8_t* Pb = Vs + 2 * K_BYTES;                   // two half-tile buffers of DST_HALF_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DST_TILE_BYTES);
+    uint64_t* xfull = bars, *vfull = bars + 1 /* [2] */, *dp_done = bars + 3 /* [2] */, *pfull = bars + 5 /* [2] */;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int q0 = blockIdx.x * BQ;
+    const int tok0 = b * N;
+    const int coldo = h * D, colv = 2 * C + h * D;
+    const int T = (N + BKEY - 1) / BKEY;
+    const int prow = bh * N + q0;                     // first row of this CTA in the P matrix
+    if (tid == 0) {
+        tma_prefetch_desc(&map_do);
+        tma_prefetch_desc(&map_v);
+        tma_prefetch_desc(&map_p);
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t idesc = make_idesc(BQ, BKEY, 0);
+    auto load_v = [&](int tile) {
+        const int bf = tile & 1;
+        mbar_expect_tx(&vfull[bf], K_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KD / 32; ++kb)
+            tma_load_3d(&map_v, &vfull[bf], Vs + bf * K_BYTES + kb * (BKEY * 128), colv + (kb & 1) * 32, kb >> 1, tok0 + tile * BKEY);
+    };
+    auto load_p = [&](int tile, int half) {
+        mbar_expect_tx(&pfull[half], DST_HALF_BYTES);
+        tma_load_2d(&map_p, &pfull[half], Pb + half * DST_HALF_BYTES, tile * BKEY + half * 32, prow);
+    };
+    auto issue_dp = [&](int tile) {
+        const int bf = tile & 1;
+        mbar_wait(&vfull[bf], (uint32_t)((tile >> 1) & 1));
+        tc_fence_after();
+        const uint32_t da = smem_u32(dOs), va = smem_u32(Vs + bf * K_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KD / 8; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            if ((kb & 1) && kk * 8 + 32 >= D) continue;
+            umma_tf32(tmem_base + bf * BKEY, make_desc(da + kb * (BQ * 128) + kk * 32), make_desc(va + kb * (BKEY * 128) + kk * 32), idesc,
+                      ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&dp_done[bf]);
+    };
+    if (tid == 0) {
+        mbar_expect_tx(xfull, Q_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KD / 32; ++kb) tma_load_3d(&map_do, xfull, dOs + kb * (BQ * 128), coldo + (kb & 1) * 32, kb >> 1, tok0 + q0);
+        load_v(0);
+        if (T > 1) load_v(1);
+        load_p(0, 0);
+        load_p(0, 1);
+        mbar_wait(xfull, 0);
+        issue_dp(0);
+    }
+    const float del = __ldg(delta + (size_t)bh * N + q0 + tid);      // N % 128 == 0: every lane is a real query
+    // this thread's row inside a half-tile buffer: 16-byte chunk c sits at chunk (c ^ (row & 7)) of the row's 128 bytes
+    const uint32_t row_off = (uint32_t)((tid >> 3) * 1024 + (tid & 7) * 128);
+    for (int i = 0; i < T; ++i) {
+        const int bf = i & 1;
+        if (tid == 0 && i + 1 < T) issue_dp(i + 1);      // its TMEM buffer was released by the last __syncthreads of iteration i - 1
+        mbar_wait(&dp_done[bf], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        if (tid == 0 && i + 2 < T) load_v(i + 2);        // V buffer bf is free: the MMAs that read it are complete
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float dp[32];
+            tmem_ld32(t_row + bf * BKEY + half * 32, dp);
+            mbar_wait(&pfull[half], (uint32_t)(i & 1));
+            uint8_t* mine = Pb + half * DST_HALF_BYTES + row_off;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                float4* q = reinterpret_cast<float4*>(mine + ((j4 ^ (tid & 7)) << 4));
+                float4 pv = *q;
+                pv.x = pv.x * (dp[j4 * 4] - del) * scale;
+                pv.y = pv.y * (dp[j4 * 4 + 1] - del) * scale;
+                pv.z = pv.z * (dp[j4 * 4 + 2] - del) * scale;
+                pv.w = pv.w * (dp[j4 * 4 + 3] - del) * scale;
+                *q = pv;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();      // the half tile is complete in shared memory (and, after the second half, accumulator bf is consumed)
+            if (tid == 0) {
+                tma_store_2d(&map_p, Pb + half * DST_HALF_BYTES, i * BKEY + half * 32, prow);
+                tma_store_commit();
+                if (i + 1 < T) {
+                    tma_store_wait_read();      // the buffer may be refilled once the store has read it
+                    load_p(i + 1, half);
+                }
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -848,8 +1017,12 @@ int vnpcc_vn_attention_fwd_tf32(const float* qkv, long long ld, int B, int N, in
         return VNPCC_ERR_DRIVER;
     dim3 grid((unsigned)((N + atc::BQ - 1) / atc::BQ), (unsigned)(B * H));
     const int C = H * D;
+    // the stored P leaves the kernel as bulk-tensor stores of the swizzled operand tile when whole 128-row tiles fit every (sample, head)
+    CUtensorMap mp = mk;
+    int p_tma = 0;
+    if (p_out != nullptr && N % atc::BQ == 0 && atc::make_map2(&mp, p_out, (long long)B * H * N, N, atc::BQ, CU_TENSOR_MAP_SWIZZLE_128B)) p_tma = 1;
     count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_FWD><<<grid, atc::NT, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
-                        mk, mq, mv, N, H, 0, C, 2 * C, scale, out, (size_t)ldo, lse, p_out);
+                        mk, mq, mv, mp, p_tma, N, H, 0, C, 2 * C, scale, out, (size_t)ldo, lse, p_out);
     return last_error();
 }
 
@@ -888,7 +1061,8 @@ int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dou
         cudaFuncSetAttribute(atc::attn_bwd_tc_kernel<48, atc::BMODE_DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::BSMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(atc::attn_acc_gemm_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::GK_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(atc::attn_acc_gemm_kernel<48, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::GK_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(atc::attn_ds_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::DSK_SMEM_BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(atc::attn_ds_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::DSK_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(atc::attn_ds_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::DST_SMEM_BYTES) != cudaSuccess) {
         fprintf(stderr, "[vnpcc] attention_bwd_tf32: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return VNPCC_ERR_DRIVER;
     }
@@ -905,7 +1079,10 @@ int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dou
         // dV = P^T dO
         count_launch(), atc::attn_acc_gemm_kernel<48, 1><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mp_mn, dom32, N, H, 0, dqkv + 2 * C, (size_t)lddq);
         // P -> dS in place
-        count_launch(), atc::attn_ds_kernel<48><<<grid, atc::NT, atc::DSK_SMEM_BYTES, st>>>(do128, q64, N, H, C, scale, delta, p_buf);
+        if (N % atc::BQ == 0)
+            count_launch(), atc::attn_ds_tma_kernel<48><<<grid, atc::NT, atc::DST_SMEM_BYTES, st>>>(do128, q64, mp_k, N, H, C, scale, delta);
+        else
+            count_launch(), atc::attn_ds_kernel<48><<<grid, atc::NT, atc::DSK_SMEM_BYTES, st>>>(do128, q64, N, H, C, scale, delta, p_buf);
         // dQ = dS K ; dK = dS^T Q
         count_launch(), atc::attn_acc_gemm_kernel<48, 0><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mp_k, qm32, N, H, C, dqkv, (size_t)lddq);
         count_launch(), atc::attn_acc_gemm_kernel<48, 1><<<grid, atc::NT, atc::GK_SMEM_BYTES, st>>>(mp_mn, qm32, N, H, 0, dqkv + C, (size_t)lddq);
@@ -913,8 +1090,9 @@ int vnpcc_vn_attention_bwd_tf32(const float* qkv, long long ld, const float* dou
     }
 
     // dV: resident K (columns C..), streamed Q (columns 0..) K-major, streamed dO MN-major; writes the v part of dqkv
-    count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_DV><<<grid, atc::NT, atc::SMEM_BYTES, st>>>(q64, q128, dom64, N, H, C, 0, 0, scale, dqkv + 2 * C,
-                                                                                                 (size_t)lddq, const_cast<float*>(lse), nullptr);
+    count_launch(), atc::attn_fwd_tc_kernel<48, atc::MODE_DV><<<grid, atc::NT, atc::SMEM_BYTES, st>>>(q64, q128, dom64, q64, 0, N, H, C, 0, 0, scale,
+                                                                                                 dqkv + 2 * C, (size_t)lddq, const_cast<float*>(lse),
+                                                                                                 nullptr);
     // dQ (and, when the caller provides B*H*N*N floats of workspace and N % 32 == 0, the dS matrix for the dK GEMM)
     const size_t ds_need = (size_t)B * H * N * N * sizeof(float);
     CUtensorMap mds;
