@@ -243,38 +243,12 @@ def main():
         p, c, R = resident[i % pool]
         return trainer.train_step(p, c, R)
 
-    # end-to-end leg: every step copies ITS inputs from pinned host memory and its loss is read back to the host.  Like a real input
-    # pipeline, the copy of step i+1 runs on a side stream while step i computes, and the host reads the loss of step i while step i+1
-    # is already enqueued (one step of lag), so neither transfer stalls the kernel queue.  All transfers lie inside the timed region.
-    loss_host = torch.zeros(2).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    e2e_state = {"next": None, "loss_ev": [None, None]}
+    loss_host = torch.zeros(1).pin_memory()
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            bufs = tuple(t.to(dev, non_blocking=True) for t in host[i % pool])
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return bufs, ev
-
-    def step_e2e(i, n):
-        if e2e_state["next"] is None:
-            e2e_state["next"] = prefetch(i)
-        (p, c, R), ev = e2e_state["next"]
-        main = torch.cuda.current_stream()
-        main.wait_event(ev)
-        for t in (p, c, R):
-            t.record_stream(main)
-        e2e_state["next"] = prefetch(i + 1) if i + 1 < n else None
+    def step_e2e(i):
+        p, c, R = (t.to(dev, non_blocking=True) for t in host[i % pool])
         loss = trainer.train_step(p, c, R)
-        slot = i & 1
-        loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)     # device -> host read of the step's result
-        lev = torch.cuda.Event()
-        lev.record(main)
-        e2e_state["loss_ev"][slot] = lev
-        prev = e2e_state["loss_ev"][slot ^ 1]
-        if prev is not None:
-            prev.synchronize()                                                 # the previous step's loss is on the host now
+        loss_host.copy_(loss.reshape(1), non_blocking=False)     # device -> host read of the step's result
         return loss
 
     timer = KernelTimer()
@@ -312,14 +286,11 @@ def main():
         barrier()
     else:
         for i in range(2):
-            step_e2e(i, 2)
+            step_e2e(i)
         barrier()
         e2.record()
         for i in range(args.steps):
-            step_e2e(i, args.steps)          # the first step's copy is issued inside the timed region (nothing is left over from warm-up)
-        for lev in e2e_state["loss_ev"]:
-            if lev is not None:
-                lev.synchronize()
+            step_e2e(i)
         e3.record()
         barrier()
     ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
