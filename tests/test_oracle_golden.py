@@ -205,3 +205,51 @@ def test_pcn_oracle_vs_reference_golden(golden, fixture, ftol):
             assert k[10:] not in G
         elif k.startswith("buf_post.") and not k.endswith("num_batches_tracked"):
             np.testing.assert_allclose(P[k[9:]], g[k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("fixture,ftol", PCN_FIXTURES)
+def test_eager_port_matches_reference_golden(golden, fixture, ftol):
+    """pins tests/eager_port.py (the plain-PyTorch restatement used as the full-size GPU reference and as the eager yardstick) against the
+    reference's own modules: same weights, same inputs, the reference's VNMaxPool selections forced; outputs, both losses (computed with
+    the C oracle's Chamfer search) and the autograd gradients of every trained parameter."""
+    from types import SimpleNamespace
+
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    import eager_port as EP          # tests/ is on sys.path (rootdir conftest)
+    g = golden(fixture)
+    cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cpu", enc_pretrained="none")
+    torch.manual_seed(0)
+    P = EP.params_from_module(V.PCNNet(cfg), requires_grad=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))      # noqa: E731
+    forced = (t(g["idx1"]).reshape(g["p"].shape[0], -1).long(), t(g["idx2"]).reshape(g["p"].shape[0], -1).long())
+    coarse, fine, _ = EP.pcn_forward(P, t(g["p"]), t(g["R"]), True, forced)
+    np.testing.assert_allclose(coarse.detach().numpy(), g["coarse"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(fine.detach().numpy(), g["fine"], rtol=ftol, atol=ftol * 0.25)
+
+    class _Chamfer(torch.autograd.Function):      # the C oracle's search (reference arithmetic) under autograd
+        @staticmethod
+        def forward(ctx, a, b):
+            d1, d2, i1, i2 = O.chamfer_forward(a.detach().numpy(), b.detach().numpy())
+            ctx.save_for_backward(a, b)
+            ctx.idx = (i1, i2)
+            return torch.from_numpy(d1), torch.from_numpy(d2)
+
+        @staticmethod
+        def backward(ctx, g1, g2):
+            a, b = ctx.saved_tensors
+            ga, gb = O.chamfer_backward(a.detach().numpy(), b.detach().numpy(), g1.contiguous().numpy(), g2.contiguous().numpy(), *ctx.idx)
+            return torch.from_numpy(ga), torch.from_numpy(gb)
+
+    c = t(g["c"])
+    l1 = EP.cd_loss_l1(_Chamfer.apply, coarse, c)
+    l2 = EP.cd_loss_l1(_Chamfer.apply, fine, c)
+    np.testing.assert_allclose(l1.item(), g["loss1"], rtol=1e-4)
+    np.testing.assert_allclose(l2.item(), g["loss2"], rtol=1e-4)
+    (l1 + l2).backward()
+    for k in g.files:
+        if k.startswith("grad."):
+            assert_grad_close(P[k[5:]].grad.numpy(), g[k], k)
+        elif k.startswith("grad_none."):
+            assert P[k[10:]].grad is None

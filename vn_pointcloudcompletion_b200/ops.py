@@ -680,11 +680,13 @@ class chamfer_3DFunction(torch.autograd.Function):
         B, N, _ = xyz1.shape
         M = xyz2.shape[1]
         dev = xyz1.device
-        # zero-initialised like the reference (outputs stay 0 when the other cloud is empty)
-        dist1 = torch.zeros((B, N), device=dev, dtype=torch.float32)
-        dist2 = torch.zeros((B, M), device=dev, dtype=torch.float32)
-        idx1 = torch.zeros((B, N), device=dev, dtype=torch.int32)
-        idx2 = torch.zeros((B, M), device=dev, dtype=torch.int32)
+        # zero-initialised like the reference only when a cloud is empty (outputs stay 0 then); otherwise the kernels overwrite every
+        # element and four fill launches per call would be most of the cost of a small search
+        alloc = torch.empty if (B > 0 and N > 0 and M > 0) else torch.zeros
+        dist1 = alloc((B, N), device=dev, dtype=torch.float32)
+        dist2 = alloc((B, M), device=dev, dtype=torch.float32)
+        idx1 = alloc((B, N), device=dev, dtype=torch.int32)
+        idx2 = alloc((B, M), device=dev, dtype=torch.int32)
         if B > 0 and N > 0 and M > 0:
             nb = _lib.raw("vnpcc_chamfer_workspace_bytes", B, N, M)
             ws = _workspace(nb, dev, "chamfer")
