@@ -55,3 +55,60 @@ def test_exchange_is_identity_for_world1():
     from vn_pointcloudcompletion_b200.trainer import exchange_gradients
     g = torch.ones(8)
     assert exchange_gradients(g, 1) == 1.0 and torch.equal(g, torch.ones(8))
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn as nn
+
+    from vn_pointcloudcompletion_b200.trainer import OverlappedExchange
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 4), nn.Tanh(), nn.Linear(4, 3))
+    unused = nn.Parameter(torch.ones(7))                      # sits in the tail bucket but never receives a gradient
+    params = list(net.parameters()) + [unused]
+    n = sum(p.numel() for p in params)
+    flat = torch.zeros(n)
+    offs, o = {}, 0
+    for p in params:
+        p.grad = flat[o:o + p.numel()].view_as(p)
+        offs[id(p)] = o
+        o += p.numel()
+    split = offs[id(net[2].weight)]                          # tail = the last two Linear layers + the unused parameter
+    ex = OverlappedExchange(flat, [(p, offs[id(p)], p.numel()) for p in params], split, world)
+    results = []
+    for step in range(3):                                    # step 0 calibrates (plain exchange), steps 1-2 overlap
+        flat.zero_()
+        x = torch.randn(8, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+        net(x).square().sum().backward()
+        local = flat.clone()
+        launched_early = ex.work is not None
+        scale = ex.finish()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        results.append((launched_early, float((flat * scale - sum(gathered) / world).abs().max()), len(ex.tail_ids), ex.tail_range, ex.head_ranges))
+    q.put((rank, results))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_exchange_world2():
+    """the early (during-backward) all-reduce of the tail bucket + the late one of the head equal the plain mean over ranks; the number of
+    gradient arrivals is calibrated on the first step (a tail parameter without gradient does not block the launch)"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, results in out:
+        assert [r[0] for r in results] == [False, True, True]
+        assert all(r[1] < 1e-6 for r in results)
+        assert results[-1][2] == 4                             # weight + bias of the two tail layers
+        assert results[-1][3] == (35, 35 + 24 + 15) and results[-1][4] == [(0, 35)]      # the unused tail parameter is not exchanged

@@ -14,8 +14,10 @@
 // of the head, i.e. 16 real channels and 16 that belong to the NEXT head.  Q's copies of those 16 columns are zeroed after its (single)
 // load, so whatever K holds there is multiplied by zero; V's extra columns only produce output columns that are never read.  V is the
 // MN-major B operand of the second MMA (feature contiguous): boxes with the 128B_ATOM_32B swizzle <-> UMMA SWIZZLE_128B_BASE32B, the
-// pairing the weight-gradient GEMM (gemm_tcgen05.cu) uses.  One thread issues TMA and MMA; the K tile of the next step is fetched while
-// the softmax threads work, the V tile while the next Q K^T runs.
+// pairing the weight-gradient GEMM (gemm_tcgen05.cu) uses.  One thread issues TMA and MMA in an order that keeps the tensor pipe fed (see
+// attn_fwd_tc_kernel): pass 1 double-buffers K and S, pass 2 queues Q K^T of the next tile right behind P V; the stored P leaves as
+// bulk-tensor stores of the swizzled operand tile.  The backward (stored-P route) is three streaming GEMMs (attn_acc_gemm_kernel, separate
+// TMA-producer and MMA-issuer threads) around attn_ds_tma_kernel, which turns P into dS in place with P / dS moving by TMA.
 // Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -13,7 +13,9 @@
 // Reference semantics: VNLinearLeakyReLU models/vn_layers.py:60-74, VNBatchNorm :116-127; backward SURVEY.md App. C.
 //
 // Thread layout: block (C/4, 256/(C/4)); threadIdx.x owns 4 consecutive channels (weights + the sample's bias rows in
-// registers), each block row walks over a chunk of points of ONE sample.  grid = (chunks per sample, B).
+// registers), each block row walks over a chunk of points of ONE sample.  grid = (chunks per sample, B), the chunk count chosen so that
+// the grid is a whole number of waves of the kernel's resident CTAs (fold_geometry).  The two backward kernels default to TWO channels per
+// thread (block (C/2, 256/(C/2)), template parameter NP = 1): half the accumulators and context fit 2 CTAs / SM without spills.
 // Row mode (many small samples, e.g. the folding MLPs of Attention_VN_FoldingNet: 32768 tokens x 16 points): every block ROW owns whole
 // samples and loops over them, so the per-block prologue, shared-memory reductions and atomics are paid once per block instead of once
 // per 16 points, and the per-sample bias gradient is a plain store from registers.
