@@ -395,13 +395,18 @@ __global__ void __launch_bounds__(256) nn_resolve2_kernel(const float* __restric
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
     };
+    static_assert(CH_CH == 32, "the winning chunk is rescanned by one warp, one candidate per lane");
+    const int lane = threadIdx.x & 31;
+    const float INF = __int_as_float(0x7f800000);
     for (size_t base = (size_t)blockIdx.x * blockDim.x; base < total; base += (size_t)gridDim.x * blockDim.x) {
         const size_t t = base + threadIdx.x;
-        if (t < total) {
-            const int b = (int)(t / N);
-            const float INF = __int_as_float(0x7f800000);
+        const bool valid = t < total;
+        int b = 0, chunk = 0;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        bool pass = false;
+        if (valid) {
+            b = (int)(t / N);
             float gb = INF, gs = INF;
-            int chunk = 0;
             for (int s = 0; s < n_splits; ++s) {
                 const float bs = best_in[t * n_splits + s], ss = second_in[t * n_splits + s];
                 if (bs < gb) {
@@ -412,29 +417,54 @@ __global__ void __launch_bounds__(256) nn_resolve2_kernel(const float* __restric
                     gs = fminf(gs, bs);
                 }
             }
-            const float qx = __ldg(xq + t * 3 + 0), qy = __ldg(xq + t * 3 + 1), qz = __ldg(xq + t * 3 + 2);
+            qx = __ldg(xq + t * 3 + 0);
+            qy = __ldg(xq + t * 3 + 1);
+            qz = __ldg(xq + t * 3 + 2);
             const float qn = sqrtf(fmaf(qz, qz, fmaf(qy, qy, qx * qx)));
             const float cm = sqrtf(__ldg(cmax2 + b));
             const float G = (qn + cm) * (qn + cm);
             const float thr = 1.5e-6f * G + 1e-37f;     // > 2 * 12 u G = 1.43e-6 G  (u = 2^-24), see the derivation above
-            if (gs - gb > thr) {
-                const int c0 = chunk * CH_CH;
-                const int c1 = min(M, c0 + CH_CH);
-                const float* src = xc + ((size_t)b * M) * 3;
-                float bestd = 0.f;
-                int best_i = c0;
-                for (int k = c0; k < c1; ++k) {
-                    const float d = sqdist_ref(__ldg(src + k * 3 + 0), __ldg(src + k * 3 + 1), __ldg(src + k * 3 + 2), qx, qy, qz);
-                    if (k == c0 || d < bestd) {
-                        bestd = d;
-                        best_i = k;
-                    }
-                }
-                dist[t] = bestd;
-                idx[t] = best_i;
-            } else {
-                s_list[atomicAdd(&s_n, 1)] = (int)t;      // (NaN comparisons land here too)
+            pass = gs - gb > thr;                        // (NaN comparisons fail and take the exact path)
+        }
+        // exact rescan of the winning chunk, one query at a time by the whole warp: lane k evaluates candidate chunk * 32 + k with the
+        // reference arithmetic (one coalesced 384-byte read instead of 32 lanes walking 32 different chunks), then a lexicographic
+        // (distance, index) minimum = the strict-< lowest-index scan of the reference
+        unsigned todo = __ballot_sync(0xffffffffu, pass);
+        float my_d = 0.f;
+        int my_i = 0;
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float x = __shfl_sync(0xffffffffu, qx, src_lane), y = __shfl_sync(0xffffffffu, qy, src_lane),
+                        z = __shfl_sync(0xffffffffu, qz, src_lane);
+            const int ch = __shfl_sync(0xffffffffu, chunk, src_lane), bb = __shfl_sync(0xffffffffu, b, src_lane);
+            const int k = ch * CH_CH + lane;
+            float d = INF;
+            int kk = 0x7fffffff;
+            if (k < M) {
+                const float* c = xc + ((size_t)bb * M + k) * 3;
+                d = sqdist_ref(__ldg(c), __ldg(c + 1), __ldg(c + 2), x, y, z);
+                kk = k;
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, d, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, kk, o);
+                if (od < d || (od == d && ok < kk)) {
+                    d = od;
+                    kk = ok;
+                }
+            }
+            if (lane == src_lane) {
+                my_d = d;
+                my_i = kk;
+            }
+        }
+        if (pass) {
+            dist[t] = my_d;
+            idx[t] = my_i;
+        } else if (valid) {
+            s_list[atomicAdd(&s_n, 1)] = (int)t;
         }
         __syncthreads();
         if (s_n > 256) flush();      // block-uniform: the next pass adds at most blockDim.x = 256 entries to the 512-entry buffer
