@@ -538,17 +538,32 @@ extern "C" {
 void vnpcc_chamfer_set_packed_math(int mode) { g_chamfer_packed = (mode == 0 || mode == 1) ? mode : 2; }
 
 // candidate-range splits for one directed pass: enough (sample, query block, split) items to fill the machine
+// Work items = (sample, block of CH_QB queries, candidate split).  The split length is a multiple of 256 candidates (whole chunks) chosen
+// by a cost model: waves of the persistent grid x (candidates per item + ~256 candidates' worth of per-item overhead: query loads, result
+// stores, tile synchronisation).  With whole 2048-candidate tiles only, 32 x 1024 queries against 16384 candidates made 256 items for 592
+// CTA slots, and 32 x 2048^2 made 64.
 static void plan_splits(int B, int N, int M, int* n_qblocks, int* n_splits, int* split_len) {
     const int nq = (N + CH_QB - 1) / CH_QB;
     const long long slots = (long long)sm_count() * 4;
-    const int max_splits = (M + CH_TC - 1) / CH_TC;
-    long long want = (slots * 8 + (long long)B * nq - 1) / ((long long)B * nq);
-    int ns = (int)(want < 1 ? 1 : (want > max_splits ? max_splits : want));
-    int sl = ((M + ns - 1) / ns + CH_TC - 1) / CH_TC * CH_TC;
-    ns = (M + sl - 1) / sl;
+    const long long groups = (long long)B * nq;
+    constexpr int GRAN = 256;
+    const int max_splits = (M + GRAN - 1) / GRAN > 64 ? 64 : (M + GRAN - 1) / GRAN;
+    int best_ns = 1, best_sl = (M + GRAN - 1) / GRAN * GRAN;
+    long long best_cost = -1;
+    for (int c = 1; c <= max_splits; ++c) {
+        const int sl = ((M + c - 1) / c + GRAN - 1) / GRAN * GRAN;
+        const int ns = (M + sl - 1) / sl;
+        const long long waves = (groups * ns + slots - 1) / slots;
+        const long long cost = waves * (sl + 256);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best_ns = ns;
+            best_sl = sl;
+        }
+    }
     *n_qblocks = nq;
-    *n_splits = ns < 1 ? 1 : ns;
-    *split_len = sl;
+    *n_splits = best_ns < 1 ? 1 : best_ns;
+    *split_len = best_sl;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
