@@ -820,12 +820,9 @@ int vnpcc_vn_maxpool_argmax(const float* x, long long ldx, const float* d, long 
     if (B <= 0 || C <= 0 || N <= 0) return 0;
     cudaMemsetAsync(ws, 0, sizeof(u64) * (size_t)B * C, st);
     const int gx = (C + 31) / 32;
-    // enough (sample, chunk) blocks to fill the machine; chunks of >= 64 points
-    int chunks = (int)(((long long)sm_count() * 8 + (long long)gx * B - 1) / ((long long)gx * B));
-    if (chunks < 1) chunks = 1;
-    int n_chunk = (N + chunks - 1) / chunks;
-    if (n_chunk < 64) n_chunk = 64;
-    chunks = (N + n_chunk - 1) / n_chunk;
+    // (sample, chunk) blocks in whole waves of the kernel's resident CTAs; chunks of >= 64 points
+    const int n_chunk = plan_chunk_len((long long)gx * B, N, (long long)sm_count() * resident_ctas(vn_maxpool_argmax_kernel, 256), 8, 64);
+    const int chunks = (N + n_chunk - 1) / n_chunk;
     count_launch(), vn_maxpool_argmax_kernel<<<dim3(gx, (unsigned)(B * chunks)), dim3(32, 8), 0, st>>>(x, (size_t)ldx, d, (size_t)ldd, B, N, C,
                                                                                      n_chunk, ws);
     const long long total = (long long)B * C;
@@ -867,11 +864,8 @@ int vnpcc_rows_sample_sum(const float* g, long long ldg, int B, int N, int C, fl
     cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)C * sizeof(float), (size_t)B * 3, st);
     if (N <= 0) return last_error();
     const int gx = (C + 31) / 32;
-    int chunks = (int)(((long long)sm_count() * 8 + (long long)gx * B - 1) / ((long long)gx * B));
-    if (chunks < 1) chunks = 1;
-    int n_chunk = (N + chunks - 1) / chunks;
-    if (n_chunk < 64) n_chunk = 64;
-    chunks = (N + n_chunk - 1) / n_chunk;
+    const int n_chunk = plan_chunk_len((long long)gx * B, N, (long long)sm_count() * resident_ctas(rows_sample_sum_kernel, 256), 8, 64);
+    const int chunks = (N + n_chunk - 1) / n_chunk;
     count_launch(), rows_sample_sum_kernel<<<dim3(gx, (unsigned)(B * chunks)), dim3(32, 8), 0, st>>>(g, (size_t)ldg, B, N, C, n_chunk, out,
                                                                                    (size_t)ldo);
     return last_error();

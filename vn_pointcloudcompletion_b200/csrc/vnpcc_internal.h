@@ -47,6 +47,30 @@ inline int resident_ctas(K* kernel, int threads, size_t smem = 0) {
 enum { TUNE_GRID_LEGACY = 0, TUNE_FOLD_MINB = 1, TUNE_N = 8 };
 int tuning(int knob);
 
+// chunk length for kernels whose grid is (groups x chunks) blocks of equal work over N points per group, each block walking its chunk with
+// `lanes` point lanes: the chunk count that minimises  waves x (steps per block + a fixed per-block cost)  for `slots` resident CTAs.
+inline int plan_chunk_len(long long groups, int N, long long slots, int lanes, int min_chunk, int fixed_steps = 4) {
+    if (groups < 1) groups = 1;
+    if (slots < 1) slots = 1;
+    int best = N > min_chunk ? N : min_chunk;
+    long long best_cost = -1;
+    const int max_chunks = N / min_chunk > 1 ? N / min_chunk : 1;
+    long long hi = (8 * slots + groups - 1) / groups;
+    if (hi > max_chunks) hi = max_chunks;
+    if (hi < 1) hi = 1;
+    for (long long c = 1; c <= hi; ++c) {
+        const int len = (int)((N + c - 1) / c);
+        const long long chunks = (N + len - 1) / len;
+        const long long waves = (groups * chunks + slots - 1) / slots;
+        const long long cost = waves * ((len + lanes - 1) / lanes + fixed_steps);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = len;
+        }
+    }
+    return best;
+}
+
 inline int grid_for(size_t total, int block, int per_sm) {
     size_t g = (total + block - 1) / block;
     size_t cap = (size_t)sm_count() * per_sm;
