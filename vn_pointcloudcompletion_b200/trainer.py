@@ -171,6 +171,8 @@ class DataParallelTrainer:
         # in the forward pass (VN_PointNet.mlp, then the decoder); parameters are laid out in module order, so the tail is contiguous
         self.exchange = None
         tail_start = getattr(getattr(model, "encoder", None), "mlp", None)
+        if tail_start is None:                 # encoders without a late mlp (VN_DGCNN_fps): the tail is the decoder
+            tail_start = getattr(model, "decoder", None)
         if overlap and world_size > 1 and tail_start is not None:
             first = next(iter(tail_start.parameters()), None)
             if first is not None and first.requires_grad:
