@@ -79,10 +79,15 @@ def _overlap_worker(rank, world, port, q):
     ex = OverlappedExchange(flat, [(p, offs[id(p)], p.numel()) for p in params], split, world)
     results = []
     for step in range(3):                                    # step 0 calibrates (plain exchange), steps 1-2 overlap
-        flat.zero_()
         x = torch.randn(8, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+        # the local gradient, taken with the hooks off (once the tail's all-reduce is in flight the buffer is being overwritten in place)
+        ex.enabled = False
+        flat.zero_()
         net(x).square().sum().backward()
         local = flat.clone()
+        ex.enabled = True
+        flat.zero_()
+        net(x).square().sum().backward()
         launched_early = ex.work is not None
         scale = ex.finish()
         gathered = [torch.zeros_like(local) for _ in range(world)]
