@@ -117,3 +117,74 @@ def test_overlapped_exchange_world2():
         assert all(r[1] < 1e-6 for r in results)
         assert results[-1][2] == 4                             # weight + bias of the two tail layers
         assert results[-1][3] == (35, 35 + 24 + 15) and results[-1][4] == [(0, 35)]      # the unused tail parameter is not exchanged
+
+
+def _overlap_fallback_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn as nn
+
+    from vn_pointcloudcompletion_b200.trainer import OverlappedExchange
+    torch.manual_seed(0)
+    a, b, c = nn.Linear(4, 4), nn.Linear(4, 4), nn.Linear(4, 4)
+    params = list(a.parameters()) + list(b.parameters()) + list(c.parameters())
+    flat = torch.zeros(sum(p.numel() for p in params))
+    offs, o = {}, 0
+    for p in params:
+        p.grad = flat[o:o + p.numel()].view_as(p)
+        offs[id(p)] = o
+        o += p.numel()
+    ex = OverlappedExchange(flat, [(p, offs[id(p)], p.numel()) for p in params], offs[id(b.weight)], world)
+    x = torch.randn(3, 4, generator=torch.Generator().manual_seed(rank))
+
+    def run(full):
+        flat.zero_()
+        h = b(a(x))
+        (c(h) if full else h).square().sum().backward()
+
+    out = {}
+    run(False)                                   # calibration on the SHORT graph: the tail is layer b only
+    ex.finish()
+    out["tail_ids"] = len(ex.tail_ids)
+    # a step with fewer arrivals than calibrated (only layer a): nothing is launched early, finish() reduces everything
+    flat.zero_()
+    a(x).square().sum().backward()
+    local = flat.clone()
+    early = ex.work is not None
+    scale = ex.finish()
+    g = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(g, local)
+    out["fewer"] = (early, float((flat * scale - sum(g) / world).abs().max()))
+    # a step with MORE arrivals (layer c joins after the tail was launched): must fail loudly, not silently mix reduced and local values
+    run(True)
+    try:
+        ex.finish()
+        out["more"] = "no error"
+    except RuntimeError as e:
+        out["more"] = "raised" if "autograd graph changed" in str(e) else str(e)
+    if ex.work is not None:
+        ex.work.wait()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_exchange_deviating_steps_world2():
+    """after calibration, a step with fewer gradient arrivals falls back to the plain exchange (correct mean), a step with more arrivals
+    than calibrated raises instead of mixing already-reduced and local gradients"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_fallback_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, o in out:
+        assert o["tail_ids"] == 2
+        assert o["fewer"][0] is False and o["fewer"][1] < 1e-6
+        assert o["more"] == "raised"
