@@ -10,41 +10,41 @@ from .dgcnn import VN_DGCNN_fps
 from .pcn import Attention_VN_FoldingNet, VN_FoldingNet, VN_PointNet
 
 
+def _make_vn_dgcnn_fps(config):
+    return VN_DGCNN_fps(config, only_coarse=config.only_coarse)
+
+
+# enc_type / dec_type strings of the reference's config.json -> builders of the sm_100a modules
+_ENCODERS = {"vn_pointnet": VN_PointNet, "vn_dgcnn_fps": _make_vn_dgcnn_fps}
+_DECODERS = {"vn_foldingnet": VN_FoldingNet, "attention_vn_foldingnet": Attention_VN_FoldingNet}
+
+
 class PCNNet(nn.Module):
+    """models/model.py:9-64: encoder -> (coarse, global feature) -> decoder -> fine, with the reference's optional frozen pretrained
+    encoder (`enc_pretrained`), `only_coarse` mode and the 448-coarse output convention."""
+
     def __init__(self, config, enc_type="vn_pointnet", dec_type="vn_foldingnet"):
         super().__init__()
+        if enc_type not in _ENCODERS:
+            raise Exception(f"encoder type {enc_type} not supported yet (B200 path covers {sorted(_ENCODERS)}, SURVEY.md 8)")
+        if not config.only_coarse and dec_type not in _DECODERS:
+            raise Exception(f"decoder type {dec_type} not supported yet (B200 hot path covers {sorted(_DECODERS)}, SURVEY.md 8)")
         self.num_coarse = config.num_coarse
         self.only_coarse = config.only_coarse
-        if enc_type == "vn_pointnet":
-            self.encoder = VN_PointNet(config).to(config.device)
-        elif enc_type == "vn_dgcnn_fps":
-            self.encoder = VN_DGCNN_fps(config, only_coarse=config.only_coarse).to(config.device)
-        else:
-            raise Exception(f"encoder type {enc_type} not supported yet (B200 path covers vn_pointnet and vn_dgcnn_fps, SURVEY.md 8)")
-        if config.enc_pretrained != "none":
-            sd = torch.load(config.enc_pretrained)
-            self.encoder.load_state_dict(sd, strict=False)
-            for param in self.encoder.parameters():
-                param.requires_grad = False
-        if not config.only_coarse:
-            if dec_type == "vn_foldingnet":
-                self.decoder = VN_FoldingNet(config).to(config.device)
-            elif dec_type == "attention_vn_foldingnet":
-                self.decoder = Attention_VN_FoldingNet(config).to(config.device)
-            else:
-                raise Exception(f"decoder type {dec_type} not supported yet (B200 hot path covers vn_foldingnet, SURVEY.md 8)")
+        self.encoder = _ENCODERS[enc_type](config).to(config.device)
+        if config.enc_pretrained != "none":      # frozen pretrained encoder (models/model.py:29-39)
+            self.encoder.load_state_dict(torch.load(config.enc_pretrained), strict=False)
+            self.encoder.requires_grad_(False)
+        if not self.only_coarse:
+            self.decoder = _DECODERS[dec_type](config).to(config.device)
 
     def forward(self, input, rot=None):
         coarse, feature_global = self.encoder(input)
-        if self.num_coarse == 448:
-            if self.only_coarse:
-                return coarse[1], None
-            fine = self.decoder(coarse[0], feature_global, rot)
-            return coarse[1], fine
+        # num_coarse == 448: the encoder returns (224 predicted, 224 predicted + 224 sampled); the decoder folds the first, the loss sees the second
+        seed_points, coarse_out = coarse if self.num_coarse == 448 else (coarse, coarse)
         if self.only_coarse:
-            return coarse, None
-        fine = self.decoder(coarse, feature_global, rot)
-        return coarse, fine
+            return coarse_out, None
+        return coarse_out, self.decoder(seed_points, feature_global, rot)
 
 
 class Rotate:
