@@ -46,6 +46,13 @@ void vnpcc_set_fast_math(int on);
  * knob 0: 1 = legacy fixed grids instead of occupancy-sized single-wave grids;  knob 1: fused small-K backward register budget */
 void vnpcc_set_tuning(int knob, int value);
 
+/* host-logic introspection: the launch planners (work-item splits, chunk lengths, grids) as pure functions of the problem size, so that
+ * tests can check them without a GPU (tests/test_planners_cpu.py).  No device work; sm counts are arguments or default to 148. */
+void vnpcc_debug_chamfer_plan(int B, int N, int M, int* out4);                       /* {query blocks, splits, split length, queries/block} */
+void vnpcc_debug_fold_geometry(int B, int N, int C, int resident, int lanes, int* out6); /* {grid.x, grid.y, block.x, block.y, chunk, row mode} */
+void vnpcc_debug_wgrad_plan(long long R, int Cout, int K, int sms, long long* out4);  /* {grid.x, grid.y, splits, rows per split} */
+int vnpcc_debug_plan_chunk_len(long long groups, int N, long long slots, int lanes, int min_chunk);
+
 /* ---------------------------------------------------------------- Chamfer ---------------------------------------- */
 size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M);
 /* xyz1 [B,N,3], xyz2 [B,M,3] contiguous fp32 -> dist1 [B,N], dist2 [B,M] (squared), idx1 [B,N], idx2 [B,M] int32.

@@ -581,6 +581,12 @@ static size_t directed_ws_bytes(int B, int N, int M) {
 
 size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M) { return directed_ws_bytes(B, N, M) + directed_ws_bytes(B, M, N); }
 
+// host-logic introspection (tests/test_planners_cpu.py): out = {query blocks per sample, candidate splits, split length, queries per block}
+void vnpcc_debug_chamfer_plan(int B, int N, int M, int* out) {
+    plan_splits(B, N, M, &out[0], &out[1], &out[2]);
+    out[3] = CH_QB;
+}
+
 // One directed pass (queries xq[B,N,3] against candidates xc[B,M,3]).
 static int nn_directed(const float* xq, const float* xc, int B, int N, int M, float* dist, int* idx, void* wsv, cudaStream_t st) {
     if (B <= 0 || N <= 0) return 0;

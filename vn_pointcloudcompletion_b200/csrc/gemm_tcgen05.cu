@@ -914,6 +914,47 @@ int vnpcc_gemm_vn_pool(const float* X, long long ldx, const float* Wcat, long lo
 
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long, int, int) { return 0; }
 
+// split of the weight-gradient reduction over CTAs: one CTA per SM is resident (192 KB of operand stages), so the grid should be a whole
+// number of waves of `slots` CTAs -- 32 output tiles x 10 splits = 320 CTAs would run 3 waves for 2.16 waves of work.  Cost model per
+// candidate split count: waves x (rows per split + ~512 rows' worth of prologue / red.add epilogue).
+static void plan_wgrad_splits(long long R, long long tiles, long long slots, long long* splits_out, long long* rows_per_split_out) {
+    const long long max_splits = (R + 1023) / 1024;
+    long long splits = 1, best_cost = -1;
+    if (tuning(TUNE_GRID_LEGACY)) {
+        splits = (slots * 2 + tiles - 1) / tiles;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    } else {
+        long long hi = (4 * slots + tiles - 1) / tiles;
+        if (hi > max_splits) hi = max_splits;
+        if (hi < 1) hi = 1;
+        for (long long c = 1; c <= hi; ++c) {
+            const long long rps = ((R + c - 1) / c + tc::BR - 1) / tc::BR * tc::BR;
+            const long long actual = (R + rps - 1) / rps;
+            const long long waves = (tiles * actual + slots - 1) / slots;
+            const long long cost = waves * (rps + 512);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                splits = actual;
+            }
+        }
+    }
+    const long long rows_per_split = ((R + splits - 1) / splits + tc::BR - 1) / tc::BR * tc::BR;
+    *rows_per_split_out = rows_per_split;
+    *splits_out = (R + rows_per_split - 1) / rows_per_split;
+}
+
+// host-logic introspection (tests/test_planners_cpu.py): out = {grid.x, grid.y, splits, rows per split}
+void vnpcc_debug_wgrad_plan(long long R, int Cout, int K, int sms, long long* out) {
+    const int gm = (Cout + tc::BM - 1) / tc::BM, gn = (K + 255) / 256;
+    long long splits, rps;
+    plan_wgrad_splits(R, (long long)gm * gn, sms, &splits, &rps);
+    out[0] = gm;
+    out[1] = gn;
+    out[2] = splits;
+    out[3] = rps;
+}
+
 int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg, long long R,
                           int Cout, int K, float* workspace, size_t workspace_bytes, void* stream) {
     (void)workspace;
@@ -936,33 +977,8 @@ int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long 
         attr_done = true;
     }
     const int gm = (Cout + tc::BM - 1) / tc::BM, gn = (K + BNW - 1) / BNW;
-    // split of the reduction over CTAs: one CTA per SM is resident (192 KB of operand stages), so the grid should be a whole number of
-    // waves of sm_count() CTAs -- 32 output tiles x 10 splits = 320 CTAs would run 3 waves for 2.16 waves of work.  Cost model per
-    // candidate split count: waves x (rows per split + ~512 rows' worth of prologue / red.add epilogue).
-    const long long tiles = (long long)gm * gn, slots = sm_count();
-    const long long max_splits = (R + 1023) / 1024;
-    long long splits = 1, best_cost = -1;
-    if (tuning(TUNE_GRID_LEGACY)) {
-        splits = (slots * 2 + tiles - 1) / tiles;
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
-    } else {
-        long long hi = (4 * slots + tiles - 1) / tiles;
-        if (hi > max_splits) hi = max_splits;
-        if (hi < 1) hi = 1;
-        for (long long c = 1; c <= hi; ++c) {
-            const long long rps = ((R + c - 1) / c + tc::BR - 1) / tc::BR * tc::BR;
-            const long long actual = (R + rps - 1) / rps;
-            const long long waves = (tiles * actual + slots - 1) / slots;
-            const long long cost = waves * (rps + 512);
-            if (best_cost < 0 || cost < best_cost) {
-                best_cost = cost;
-                splits = actual;
-            }
-        }
-    }
-    long long rows_per_split = ((R + splits - 1) / splits + tc::BR - 1) / tc::BR * tc::BR;
-    splits = (R + rows_per_split - 1) / rows_per_split;
+    long long splits, rows_per_split;
+    plan_wgrad_splits(R, (long long)gm * gn, sm_count(), &splits, &rows_per_split);
     // G is accumulated with atomics: clear it first (rows of K floats with pitch ldg)
     cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)Cout, st);
     count_launch(), kern<<<dim3(gm, gn, (unsigned)splits), tc::NUM_THREADS, L::TOTAL, st>>>(mdy, mx, G, (size_t)ldg, R, Cout, K,

@@ -138,6 +138,9 @@ void vnpcc_set_tuning(int knob, int value) {
     if (knob >= 0 && knob < TUNE_N) g_tuning[knob] = value;
 }
 unsigned long long vnpcc_launch_count(void) { return launch_counter(); }
+int vnpcc_debug_plan_chunk_len(long long groups, int N, long long slots, int lanes, int min_chunk) {
+    return plan_chunk_len(groups, N, slots, lanes, min_chunk);
+}
 
 int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M, int mode, double* scratch, float* out,
                     void* stream) {

@@ -703,6 +703,20 @@ extern "C" {
     if ((SMEM_) == 0) smem = 0;
 #define FOLD_GEOM(KERNEL, SMEM_) FOLD_GEOM_L(KERNEL, SMEM_, 4)
 
+// host-logic introspection (tests/test_planners_cpu.py): out = {grid.x, grid.y, block.x, block.y, points per chunk, row mode}
+void vnpcc_debug_fold_geometry(int B, int N, int C, int resident, int lanes, int* out) {
+    dim3 grid, block;
+    int n_chunk, row_mode;
+    size_t smem;
+    fold_geometry(B, N, C, resident, grid, block, n_chunk, smem, row_mode, lanes);
+    out[0] = (int)grid.x;
+    out[1] = (int)grid.y;
+    out[2] = (int)block.x;
+    out[3] = (int)block.y;
+    out[4] = n_chunk;
+    out[5] = row_mode;
+}
+
 // x [B*N*3, K] local rows, w [2C, K] stacked (feat | dir) weights of the local channels, bias [B*3, 2C] per-sample rows
 // (may be NULL).  sums: 2C doubles (zeroed here).
 int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ldw, const float* bias, long long ldb, int B, int N,
