@@ -11,8 +11,9 @@ L1-CD(dense, gt), backward, gradient all-reduce (N > 1), Adam -- per-GPU batch 3
 `e2e`    : samples/s through the public API with HOST inputs: every step copies partial / gt / rotation from pinned
            host memory and reads the loss back.
 `roofline`: the dominant kernel class by device time inside the timed region (CUDA events on the launching stream).
-`cpu_baseline`: the numpy/C oracle port of the reference path timed on this box's host cores on a bounded sample.
---impl reference: the same port as the reference arm (the Python reference itself cannot travel to the GPU box).
+`cpu_baseline`: the reference's own CPU path (oracle/_ref/py: the unmodified reference, byte-compiled by oracle/build_ref_py.py)
+           timed on this box's host cores on a bounded sample; the numpy/C port only if oracle/_ref/py is absent (kind says which).
+--impl reference: that same reference CPU path as the driver's reference arm, with every host thread, on this arm's config.
 """
 from __future__ import annotations
 
@@ -125,21 +126,70 @@ class KernelTimer:
         return out
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 for nproc > 1; the CPU arm must use every host core it can"""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["MKL_NUM_THREADS"] = str(n)
+    import torch
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_reference_step(batch, steps, warmup):
-    """the oracle port of the reference path (numpy + the C Chamfer restatement) timed on host cores: forward,
-    L1-CD losses and backward of one batch (no optimiser; the reference's CPU path is a reported baseline)."""
+    """The reference's own CPU path timed on this box's host cores.
+
+    kind "reference": the UNMODIFIED reference (models.model.PCNNet + metrics.loss.cd_loss_L1 over chamfer_python.distChamfer, byte-compiled
+    from /root/reference into oracle/_ref/py by oracle/build_ref_py.py, imported through oracle/ref_model.py) runs the train step of
+    train.py:127-173 -- zero_grad, forward, two L1-CD losses, backward, torch.optim.Adam.step -- on `batch` samples per step.
+    kind "port" (only when oracle/_ref/py is absent): the numpy / C oracle port, forward + losses + backward.
+    Returns (samples/s, mean s/step, info dict)."""
     import numpy as np
     import torch
 
+    from vn_pointcloudcompletion_b200.synthetic import make_batch
+    from oracle import ref_model as RM
+    cores = use_all_host_threads()
+    p, c, R = make_batch(batch, N_PARTIAL, N_GT, seed=1234)
+    if RM.available():
+        net, ref = RM.build_pcnnet("cpu", seed=0)
+        net.train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)          # train.py:70
+        pt, ct, Rt = (torch.from_numpy(a) for a in (p, c, R))
+        times, fwd_times = [], []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            coarse, dense = net(pt, RM.Rotate(Rt))                                  # train.py:142
+            loss = ref.loss.cd_loss_L1(coarse, ct) + ref.loss.cd_loss_L1(dense, ct)   # train.py:151-160 (coarse + dense L1-CD)
+            t1 = time.perf_counter()
+            loss.backward()
+            opt.step()
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+                fwd_times.append(t1 - t0)
+        sec = sum(times) / len(times)
+        info = {"kind": "reference", "cores": cores,
+                "what": "unmodified reference (models.model.PCNNet, metrics.loss.cd_loss_L1 over chamfer_python.distChamfer), torch "
+                        f"{torch.__version__} CPU, {torch.get_num_threads()} threads: zero_grad + forward + 2 L1-CD + backward + Adam",
+                "forward_loss_samples_per_s": batch * len(fwd_times) / sum(fwd_times), "final_loss": float(loss.item())}
+        return batch / sec, sec, info
+    from types import SimpleNamespace
+
     import vn_pointcloudcompletion_b200 as V
     from oracle import vn_oracle as O
-    from types import SimpleNamespace
-    from vn_pointcloudcompletion_b200.synthetic import make_batch
     cfg = SimpleNamespace(num_coarse=N_COARSE, latent_dim=2048, only_coarse=False, device="cpu", enc_pretrained="none")
     torch.manual_seed(0)
     net = V.PCNNet(cfg)   # parameter container (random init identical to the reference's under the same seed)
     P = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
-    p, c, R = make_batch(batch, N_PARTIAL, N_GT, seed=1234)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -149,7 +199,18 @@ def cpu_reference_step(batch, steps, warmup):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return batch * len(times) / sum(times), sum(times) / len(times)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, {"kind": "port", "cores": cores,
+                              "what": "oracle/_ref/py absent: numpy/OpenBLAS + C/OpenMP restatement, forward + 2 L1-CD + backward (no optimiser)"}
+
+
+def workload_config(B, world, mode, enc="vn_pointnet", dec="vn_foldingnet"):
+    headline = enc == "vn_pointnet" and dec == "vn_foldingnet"
+    return {"workload": (f"{enc}_1024+{dec} train step (fwd + L1-CD coarse/dense + bwd + Adam), so3"
+                         + ("" if headline else " [SURVEY 8f next-row network, not the BASELINE headline]")),
+            "batch_per_gpu": B, "global_batch": B * world, "n_partial": N_PARTIAL, "n_coarse": N_COARSE,
+            "n_dense": N_DENSE, "n_gt": N_GT, "parallelism": f"dp{world}", "gemm_mode": mode,
+            "l2": "per-step activations (>10 GB) exceed the 126 MB L2; inputs rotate over a pool"}
 
 
 def main():
@@ -174,20 +235,21 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
 
     if args.impl == "reference":
+        # the reference's own CPU implementation on this box's host cores, on OUR arm's config / metric / unit; each step is a bounded
+        # sample of the workload (REF_SAMPLE_BATCH of the 32 samples of a step) so that K + W steps end within a few minutes
         if rank != 0:
             return 0
-        cb = 2
-        sps, sec = cpu_reference_step(cb, max(1, min(args.steps, 3)), 1 if args.warmup > 0 else 0)
-        line = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
-                "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        cb = int(os.environ.get("VNPCC_REF_SAMPLE_BATCH", "1"))
+        sps, sec, info = cpu_reference_step(cb, max(1, args.steps), max(0, args.warmup))
+        line = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": max(1, args.steps),
+                "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": "vn_pointnet_1024+vn_foldingnet train step (fwd + L1-CD coarse/dense + bwd), CPU oracle port",
-                           "batch_per_step": cb, "n_partial": N_PARTIAL, "n_coarse": N_COARSE, "n_dense": N_DENSE, "n_gt": N_GT},
-                "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"batch {cb} (of 32), forward+loss+backward, numpy/OpenBLAS + C/OpenMP Chamfer"},
+                "config": workload_config(args.batch, max(1, args.gpus), args.mode),
+                "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": info["cores"], "kind": info["kind"],
+                                 "sample": f"{cb} sample(s) of the 32-sample step per timed step; {info['what']}",
+                                 "forward_loss_samples_per_s": info.get("forward_loss_samples_per_s")},
                 "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -383,11 +445,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if args.mode == "tf32" else "f32", "data": "synthetic",
-                "config": {"workload": (f"{args.enc}_1024+{args.dec} train step (fwd + L1-CD coarse/dense + bwd + Adam), so3"
-                                        + ("" if headline else " [SURVEY 8f next-row network, not the BASELINE headline]")),
-                           "batch_per_gpu": B, "global_batch": B * world, "n_partial": N_PARTIAL, "n_coarse": N_COARSE,
-                           "n_dense": N_DENSE, "n_gt": N_GT, "parallelism": f"dp{world}", "gemm_mode": args.mode,
-                           "l2": "per-step activations (>10 GB) exceed the 126 MB L2; inputs rotate over a pool"},
+                "config": workload_config(B, world, args.mode, args.enc, args.dec),
                 "e2e": {"value": (samples / (e2e_ms / 1e3)) if not args.no_e2e else None, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
                 "eval": {"value": (B * world * args.steps / (eval_ms / 1e3)) if not args.no_eval else None, "unit": "samples/s",
@@ -395,10 +453,11 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_classes": classes,
                 "final_loss": final_loss}
         if world == 1 and not args.no_cpu_baseline and headline:
-            cb = 2
-            sps, sec = cpu_reference_step(cb, 1, 0)
-            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": f"1 step at batch {cb} (of 32): forward+loss+backward, numpy/OpenBLAS + C/OpenMP Chamfer, {sec:.1f} s"}
+            cb = 1
+            sps, sec, info = cpu_reference_step(cb, 1, 1)
+            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": info["cores"], "kind": info["kind"],
+                                    "sample": f"1 warm-up + 1 timed step on {cb} sample(s) of the 32-sample step, {sec:.1f} s; {info['what']}",
+                                    "forward_loss_samples_per_s": info.get("forward_loss_samples_per_s")}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -12,7 +12,7 @@
  * What each entry point replaces in the reference (paths under /root/reference):
  *   vnpcc_chamfer_forward / _backward   extensions/chamfer_distance/chamfer_cuda.cpp:17-27 (pybind `forward` /
  *                                       `backward`), kernels chamfer3D.cu:12-134 and :155-174
- *   vnpcc_cd_l1_* / vnpcc_cd_l2_*       metrics/loss.py:20-43, metrics/metric.py:12-23 (sqrt / mean tails)
+ *   vnpcc_cd_reduce / _bwd              metrics/loss.py:20-43, metrics/metric.py:12-23 (sqrt / mean tails)
  *   vnpcc_gemm_*                        nn.Linear(bias=False) inside VNLinear & friends: models/vn_layers.py:21,38,65,69,162,194
  *   vnpcc_vn_norm_stats / bn_finalize / vn_bn_leaky_*   VNBatchNorm models/vn_layers.py:116-127 + the leaky projection
  *                                       models/vn_layers.py:39-42,70-73 (forward) and their autograd
@@ -42,17 +42,6 @@ unsigned long long vnpcc_launch_count(void);
 /* forward elementwise kernels: 0 (default) = IEEE sqrt / division with the reference's op-by-op rounding (parity mode),
  * 1 = MUFU reciprocal / rsqrt (throughput mode; the host layer switches it together with the TF32 GEMMs) */
 void vnpcc_set_fast_math(int on);
-/* development knobs for A/B measurements (tools/stream_bench.py); every knob defaults to 0 = the shipped behaviour.
- * knob 0: 1 = legacy fixed grids instead of occupancy-sized single-wave grids;  knob 1: fused small-K backward register budget */
-void vnpcc_set_tuning(int knob, int value);
-
-/* host-logic introspection: the launch planners (work-item splits, chunk lengths, grids) as pure functions of the problem size, so that
- * tests can check them without a GPU (tests/test_planners_cpu.py).  No device work; sm counts are arguments or default to 148. */
-void vnpcc_debug_chamfer_plan(int B, int N, int M, int* out4);                       /* {query blocks, splits, split length, queries/block} */
-void vnpcc_debug_fold_geometry(int B, int N, int C, int resident, int lanes, int* out6); /* {grid.x, grid.y, block.x, block.y, chunk, row mode} */
-void vnpcc_debug_wgrad_plan(long long R, int Cout, int K, int sms, long long* out4);  /* {grid.x, grid.y, splits, rows per split} */
-int vnpcc_debug_plan_chunk_len(long long groups, int N, long long slots, int lanes, int min_chunk);
-
 /* ---------------------------------------------------------------- Chamfer ---------------------------------------- */
 size_t vnpcc_chamfer_workspace_bytes(int B, int N, int M);
 /* xyz1 [B,N,3], xyz2 [B,M,3] contiguous fp32 -> dist1 [B,N], dist2 [B,M] (squared), idx1 [B,N], idx2 [B,M] int32.
@@ -63,7 +52,6 @@ int vnpcc_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N, in
 int vnpcc_chamfer_backward(const float* xyz1, const float* xyz2, int B, int N, int M, const float* graddist1,
                            const float* graddist2, const int* idx1, const int* idx2, float* gradxyz1, float* gradxyz2,
                            void* stream);
-void vnpcc_chamfer_set_packed_math(int on);
 /* reductions of the CD entry points.  mode 0: cd_loss_L1 (mean sqrt, /2)  1: cd_loss_L2 (mean)  2: l1_cd  3: l2_cd
  * (per-sample means summed over the batch).  out: 1 float, written (not accumulated).  scratch: 2 doubles. */
 int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M, int mode, double* scratch, float* out,
@@ -251,10 +239,6 @@ int vnpcc_voxel_iou(const unsigned* bits_a, const unsigned* bits_b, int B, int w
 /* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
 int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, float grad_scale, void* stream);
-/* FP32-pipe peak micro-benchmark used for the Chamfer roofline (mode 0: FFMA, 1: FFMA2, 2: Chamfer mix) */
-int vnpcc_measure_fp32_peak(int mode, int iters, float* scratch_dev, float* ms_out_host, double* lane_ops_out_host,
-                            void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -46,9 +46,19 @@ def _launch(fn, grid, block, args, types):
     _check(cu.cuLaunchKernel(fn, grid[0], grid[1], grid[2], block, 1, 1, 0, stream, ptrs.ctypes.data, 0))
 
 
-def forward(xyz1, xyz2):
-    """chamfer_cuda_forward (chamfer3D.cu:136-154): returns dist1, dist2, idx1, idx2"""
+def forward_into(xyz1, xyz2, d1, d2, i1, i2):
+    """chamfer_cuda_forward (chamfer3D.cu:136-154) with the pybind `forward` contract (chamfer_cuda.cpp:17-21): caller-allocated outputs,
+    raw data pointers (the reference reads .data<float>() and ignores strides)"""
     f = _load()
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    T = [np.int32, np.int32, np.uint64, np.int32, np.uint64, np.uint64, np.uint64]
+    _launch(f["fwd"], (32, 16, 1), 512, [B, N, xyz1.data_ptr(), M, xyz2.data_ptr(), d1.data_ptr(), i1.data_ptr()], T)
+    _launch(f["fwd"], (32, 16, 1), 512, [B, M, xyz2.data_ptr(), N, xyz1.data_ptr(), d2.data_ptr(), i2.data_ptr()], T)
+
+
+def forward(xyz1, xyz2):
+    """returns dist1, dist2, idx1, idx2 (zero-initialised like chamfer_distance.py:40-44)"""
     B, N, _ = xyz1.shape
     M = xyz2.shape[1]
     xyz1, xyz2 = xyz1.contiguous(), xyz2.contiguous()
@@ -56,22 +66,25 @@ def forward(xyz1, xyz2):
     d2 = torch.zeros(B, M, device="cuda")
     i1 = torch.zeros(B, N, device="cuda", dtype=torch.int32)
     i2 = torch.zeros(B, M, device="cuda", dtype=torch.int32)
-    T = [np.int32, np.int32, np.uint64, np.int32, np.uint64, np.uint64, np.uint64]
-    _launch(f["fwd"], (32, 16, 1), 512, [B, N, xyz1.data_ptr(), M, xyz2.data_ptr(), d1.data_ptr(), i1.data_ptr()], T)
-    _launch(f["fwd"], (32, 16, 1), 512, [B, M, xyz2.data_ptr(), N, xyz1.data_ptr(), d2.data_ptr(), i2.data_ptr()], T)
+    forward_into(xyz1, xyz2, d1, d2, i1, i2)
     return d1, d2, i1, i2
 
 
-def backward(xyz1, xyz2, gd1, gd2, i1, i2):
-    """chamfer_cuda_backward (chamfer3D.cu:176-195): returns gradxyz1, gradxyz2 (accumulated into zeros)"""
+def backward_into(xyz1, xyz2, gd1, gd2, i1, i2, g1, g2):
+    """chamfer_cuda_backward (chamfer3D.cu:176-195): accumulates into the caller-zeroed g1, g2"""
     f = _load()
     B, N, _ = xyz1.shape
     M = xyz2.shape[1]
+    T = [np.int32, np.int32, np.uint64, np.int32, np.uint64, np.uint64, np.uint64, np.uint64, np.uint64]
+    _launch(f["bwd"], (1, 16, 1), 256, [B, N, xyz1.data_ptr(), M, xyz2.data_ptr(), gd1.data_ptr(), i1.data_ptr(),
+                                       g1.data_ptr(), g2.data_ptr()], T)
+    _launch(f["bwd"], (1, 16, 1), 256, [B, M, xyz2.data_ptr(), N, xyz1.data_ptr(), gd2.data_ptr(), i2.data_ptr(),
+                                       g2.data_ptr(), g1.data_ptr()], T)
+
+
+def backward(xyz1, xyz2, gd1, gd2, i1, i2):
+    """returns gradxyz1, gradxyz2 (accumulated into zeros)"""
     g1 = torch.zeros_like(xyz1)
     g2 = torch.zeros_like(xyz2)
-    T = [np.int32, np.int32, np.uint64, np.int32, np.uint64, np.uint64, np.uint64, np.uint64, np.uint64]
-    _launch(f["bwd"], (1, 16, 1), 256, [B, N, xyz1.data_ptr(), M, xyz2.data_ptr(), gd1.contiguous().data_ptr(), i1.data_ptr(),
-                                       g1.data_ptr(), g2.data_ptr()], T)
-    _launch(f["bwd"], (1, 16, 1), 256, [B, M, xyz2.data_ptr(), N, xyz1.data_ptr(), gd2.contiguous().data_ptr(), i2.data_ptr(),
-                                       g2.data_ptr(), g1.data_ptr()], T)
+    backward_into(xyz1, xyz2, gd1.contiguous(), gd2.contiguous(), i1, i2, g1, g2)
     return g1, g2

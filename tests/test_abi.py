@@ -9,10 +9,19 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols():
-    src = open(os.path.join(REPO, "include", "vnpcc.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(vnpcc_[a-z0-9_]+)\s*\(", src)))
+def _header_symbols(names=("vnpcc.h", "vnpcc_debug.h")):
+    syms = set()
+    for n in names:
+        src = open(os.path.join(REPO, "include", n)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b(vnpcc_[a-z0-9_]+)\s*\(", src))
+    return sorted(syms)
+
+
+def test_product_header_has_no_debug_symbols():
+    """development knobs / planner introspection live in include/vnpcc_debug.h, not in the drop-in boundary"""
+    prod = _header_symbols(("vnpcc.h",))
+    assert not [s for s in prod if "debug" in s or s in ("vnpcc_set_tuning", "vnpcc_measure_fp32_peak", "vnpcc_chamfer_set_packed_math")]
 
 
 def test_header_declares_symbols():

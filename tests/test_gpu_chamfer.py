@@ -9,18 +9,27 @@ pytestmark = pytest.mark.gpu
 
 CH_CASES = ["unit", "ragged", "tiny", "one2one", "big"]
 
+# vnpcc_chamfer_set_packed_math: 2 = pre-filtered search (the library default and what bench.py times), 1 = exact packed-fp32 search,
+# 0 = exact scalar search.  EVERY test of this module runs under all three, the default first; the default is restored afterwards.
+SEARCH_MODES = {"prefilter": 2, "packed": 1, "scalar": 0}
+
+
+@pytest.fixture(autouse=True, params=list(SEARCH_MODES))
+def search_mode(request):
+    from vn_pointcloudcompletion_b200 import _lib
+    _lib.load().vnpcc_chamfer_set_packed_math(SEARCH_MODES[request.param])
+    yield request.param
+    _lib.load().vnpcc_chamfer_set_packed_math(2)
+
 
 def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
 @pytest.mark.parametrize("case", CH_CASES)
-@pytest.mark.parametrize("packed", [1, 0])
-def test_forward_backward_vs_golden_and_oracle(golden, case, packed):
+def test_forward_backward_vs_golden_and_oracle(golden, case):
     import vn_pointcloudcompletion_b200 as V
-    from vn_pointcloudcompletion_b200 import _lib
     from oracle import vn_oracle as O
-    _lib.load().vnpcc_chamfer_set_packed_math(packed)
     g = golden("chamfer_unit")
     p1, p2 = g[f"ch_{case}_p1"], g[f"ch_{case}_p2"]
     a = _dev(p1).requires_grad_(True)
@@ -38,7 +47,6 @@ def test_forward_backward_vs_golden_and_oracle(golden, case, packed):
     ((d1 * w1).sum() + (d2 * w2).sum()).backward()
     np.testing.assert_allclose(a.grad.cpu().numpy(), g[f"ch_{case}_g1"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(b.grad.cpu().numpy(), g[f"ch_{case}_g2"], rtol=1e-4, atol=1e-6)
-    _lib.load().vnpcc_chamfer_set_packed_math(1)
 
 
 @pytest.mark.parametrize("case", CH_CASES)
@@ -96,6 +104,86 @@ def test_ties_and_duplicates():
     c = np.concatenate([q, q], axis=1)
     d1, _, i1, _ = V.chamfer_3DFunction.apply(_dev(q), _dev(c))
     assert (d1.cpu().numpy() == 0).all() and np.array_equal(i1.cpu().numpy()[0], np.arange(300))
+
+
+def _adversary(name, rng):
+    """clouds built to stress the pre-filter's error bound (|fl(e) + |q|^2 - d_ref| <= 11 u G, csrc/chamfer.cu) and its bookkeeping"""
+    f = np.float32
+    if name == "far_offset":            # |c| ~ 100, spread 1e-3: G ~ 4e4, every margin test fails -> all queries take the exact path
+        c = np.array([57.0, -63.0, 49.0])
+        return (c + 1e-3 * rng.randn(2, 700, 3)).astype(f), (c + 1e-3 * rng.randn(2, 1500, 3)).astype(f)
+    if name == "far_offset_wide":       # |c| ~ 100, spread 1: most margins pass with a threshold 1e4 x the usual one
+        c = np.array([60.0, 60.0, -50.0])
+        return (c + rng.randn(2, 1100, 3)).astype(f), (c + rng.randn(2, 4099, 3)).astype(f)
+    if name == "mixed_magnitudes":      # half of each cloud at scale 1e-3, half at scale 1e2: max|c| dwarfs the small half's distances
+        a = np.concatenate([1e-3 * rng.randn(2, 600, 3), 1e2 * rng.randn(2, 600, 3)], 1)
+        b = np.concatenate([1e-3 * rng.randn(2, 2500, 3), 1e2 * rng.randn(2, 2500, 3)], 1)
+        return a.astype(f), b.astype(f)
+    if name == "duplicates_across_splits":   # 7 distinct candidates repeated over 12288 slots: every chunk / tile / split ties exactly
+        base = rng.uniform(-0.5, 0.5, (1, 7, 3))
+        b = np.tile(base, (2, 12288 // 7 + 1, 1))[:, :12288]
+        return rng.uniform(-0.5, 0.5, (2, 1024, 3)).astype(f), b.astype(f)
+    if name == "clustered":             # 40 tight clusters (sigma 1e-4): near-equidistant neighbours, > 10 % of queries on the slow path
+        cen = rng.uniform(-0.5, 0.5, (2, 40, 3))
+        a = cen[:, rng.randint(0, 40, 3000)] + 1e-4 * rng.randn(2, 3000, 3)
+        b = cen[:, rng.randint(0, 40, 5000)] + 1e-4 * rng.randn(2, 5000, 3)
+        return a.astype(f), b.astype(f)
+    if name == "ragged_sizes":          # N, M not multiples of 32 (chunk), 256 (split granule), 1024 (query block), 2048 (tile)
+        return rng.uniform(-0.5, 0.5, (3, 1031, 3)).astype(f), rng.uniform(-0.5, 0.5, (3, 4127, 3)).astype(f)
+    if name == "lattice":               # integer lattice / 64: exactly representable coordinates, masses of exact distance ties
+        return (rng.randint(-16, 17, (2, 2000, 3)) / 64.0).astype(f), (rng.randint(-16, 17, (2, 6000, 3)) / 64.0).astype(f)
+    if name == "collinear_tiny":        # denormal-scale spread around the origin: thresholds underflow to the 1e-37 floor
+        return (1e-20 * rng.randn(1, 300, 3)).astype(f), (1e-20 * rng.randn(1, 900, 3)).astype(f)
+    raise KeyError(name)
+
+
+ADVERSARIES = ["far_offset", "far_offset_wide", "mixed_magnitudes", "duplicates_across_splits", "clustered", "ragged_sizes", "lattice",
+               "collinear_tiny"]
+
+
+@pytest.mark.parametrize("name", ADVERSARIES)
+def test_prefilter_adversaries(name, search_mode):
+    """dist / idx bit-exact against the CPU oracle (chamfer3D.cu:23-129 restated) AND the reference's own kernel on inputs that attack the
+    pre-filtered search: far-from-origin clouds, mixed magnitudes, duplicated candidates across all splits, clustered clouds that push a
+    large share of the queries onto the exact re-search, ragged sizes, exact-tie lattices"""
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import _lib, ops
+    from oracle import ref_chamfer as RC
+    from oracle import vn_oracle as O
+    import ctypes
+    p1, p2 = _adversary(name, np.random.RandomState(len(name)))
+    a, b = _dev(p1), _dev(p2)
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(a, b)
+    od1, od2, oi1, oi2 = O.chamfer_forward(p1, p2)
+    assert np.array_equal(i1.cpu().numpy(), oi1) and np.array_equal(i2.cpu().numpy(), oi2)
+    assert np.array_equal(d1.cpu().numpy(), od1) and np.array_equal(d2.cpu().numpy(), od2)
+    if RC.available():
+        r1, r2, j1, j2 = RC.forward(a, b)
+        assert torch.equal(i1, j1) and torch.equal(i2, j2) and torch.equal(d1, r1) and torch.equal(d2, r2)
+    if search_mode == "prefilter":
+        B, N, M = p1.shape[0], p1.shape[1], p2.shape[1]
+        cnt = (ctypes.c_int * 2)()
+        ws = ops._workspace(0, a.device, "chamfer")
+        _lib.call("vnpcc_debug_chamfer_slow_counts", ws.data_ptr(), B, N, M, cnt, _lib.stream())
+        frac = (cnt[0] + cnt[1]) / float(B * (N + M))
+        print(f"{name}: {cnt[0]} + {cnt[1]} of {B * (N + M)} queries re-searched exactly ({100 * frac:.1f} %)")
+        if name in ("far_offset", "clustered", "duplicates_across_splits"):
+            assert frac > 0.10, frac       # these cases are meant to exercise nn_exact_list_kernel heavily
+
+
+def test_prefilter_slow_path_at_training_shape(search_mode):
+    """B=32, 16384 x 16384 with clustered predictions (what a random-init decoder emits): bit-exact vs the reference's own kernel"""
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import ref_chamfer as RC
+    if not RC.available():
+        pytest.skip("oracle/_ref/ref_chamfer3D.cubin not built")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cen = torch.rand(32, 1024, 1, 3, device="cuda", generator=g) - 0.5
+    a = (cen + 2e-3 * torch.randn(32, 1024, 16, 3, device="cuda", generator=g)).reshape(32, 16384, 3).contiguous()
+    b = torch.rand(32, 16384, 3, device="cuda", generator=g) - 0.5
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(a, b)
+    r1, r2, j1, j2 = RC.forward(a, b)
+    assert torch.equal(i1, j1) and torch.equal(i2, j2) and torch.equal(d1, r1) and torch.equal(d2, r2)
 
 
 def test_empty_clouds_leave_zero_outputs():

@@ -1,9 +1,21 @@
-"""GPU parity at the FULL BASELINE shapes (2048-point partial input -> 1024 coarse / 16384 dense points against a 16384-point ground truth),
-where the numpy oracle takes minutes: the CUDA path (parity mode, fp32) against tests/eager_port.py, the plain-PyTorch restatement of the
-reference's operator chain that tests/test_oracle_golden.py pins to the reference's own outputs and gradients.  Same weights
-(torch.manual_seed(0) default init = the reference's), same synthetic SO(3)-rotated batch, VNMaxPool selections of the CUDA path forced
-into the port (near-ties flip between any two fp32 evaluations) after checking that the port's own selections agree except at
-near-ties.  Tolerances: values 1e-4 relative (BASELINE north star), gradients rel-L2 5e-3 (conftest.assert_grad_close)."""
+"""GPU parity at the FULL BASELINE shapes (2048-point partial input -> 1024 coarse / 16384 dense points against a 16384-point ground
+truth), where the numpy oracle takes minutes.  Two oracles, both in BOTH GEMM modes of the product ("fp32" = parity mode, "tf32" = the
+tensor-core mode bench.py times):
+
+  * the UNMODIFIED reference itself run eagerly on the same GPU in fp32 (tests/ref_harness.py: models.model.PCNNet +
+    metrics.loss.cd_loss_L1 + the reference's own Chamfer kernels, from oracle/_ref) -- skipped only when oracle/_ref was not built;
+  * tests/eager_port.py, the plain-PyTorch restatement that tests/test_oracle_golden.py pins to the reference's goldens.
+
+Same weights (torch.manual_seed(0) default init = the reference's), same synthetic SO(3)-rotated batch.  VNMaxPool selections are
+teacher-forced from the oracle into the CUDA path (near-ties flip between any two fp32 evaluations) after checking that the
+CUDA path's own selections agree except at near-ties.
+
+Tolerances.  fp32 mode: values 1e-4 relative (BASELINE north star), gradients rel-L2 5e-3 (conftest.assert_grad_close: the network has
+discontinuities).  tf32 mode: operands are rounded to 11 significant bits (unit round-off 2^-11 = 4.9e-4) before every tensor-core
+product; a K-term dot product of such operands carries a relative error of about 4.9e-4 x sqrt(2) against its own norm, and the
+7-GEMM-deep network compounds that to a few 1e-3 of the output scale -- the same size as what the reference itself shows between
+torch.backends.cuda.matmul.allow_tf32 = True / False (measured in test_reference_tf32_flag_spread below and used as the yardstick):
+values rel-L2 5e-3 and max 2e-2 of the output scale, loss 5e-3, gradients rel-L2 5e-2."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -11,38 +23,147 @@ import pytest
 import torch
 
 import eager_port as EP
+import ref_harness as RH
 from conftest import assert_grad_close
 
 pytestmark = pytest.mark.gpu
 
+TOL = {  # mode: (value rel-L2, value max / scale, loss rel, grad rel-L2, grad max / max|ref|)
+    "fp32": (1e-4, 1e-4, 1e-4, 5e-3, 2e-2),
+    "tf32": (5e-3, 2e-2, 5e-3, 5e-2, 2e-1),
+}
 
-@pytest.mark.parametrize("B", [6])
-def test_full_size_train_step_vs_eager_port(B):
-    import vn_pointcloudcompletion_b200 as V
+
+def _errs(a, r):
+    a, r = a.double(), r.double()
+    return float((a - r).norm() / r.norm()), float((a - r).abs().max() / r.abs().max())
+
+
+def _batch(B):
     from vn_pointcloudcompletion_b200.synthetic import make_batch
-    V.set_gemm_mode("fp32")
+    return tuple(torch.from_numpy(a).cuda() for a in make_batch(B, 2048, 16384, seed=4321))
+
+
+def _our_net(mode):
+    import vn_pointcloudcompletion_b200 as V
+    V.set_gemm_mode(mode)
     cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cuda", enc_pretrained="none")
     torch.manual_seed(0)
-    net = V.PCNNet(cfg).train()
+    return V.PCNNet(cfg).train()
+
+
+@pytest.fixture(autouse=True)
+def _restore_mode():
+    import vn_pointcloudcompletion_b200 as V
+    yield
+    V.set_gemm_mode("fp32")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("B", [6])
+def test_full_size_train_step_vs_unmodified_reference(B, mode):
+    import vn_pointcloudcompletion_b200 as V
+    if not RH.available():
+        pytest.skip("oracle/_ref (byte-compiled reference + its Chamfer cubin) not built: needs /root/reference in the build container")
+    net = _our_net(mode)
+    p, c, R = _batch(B)
+    ref = RH.reference_train_step({k: v.clone() for k, v in net.state_dict().items()}, p, c, R, tf32=False)
+
+    # own selections first (what a user gets), then the reference's selections teacher-forced for the value comparison
+    with torch.no_grad():
+        net(p, V.Rotate(R))
+    own1, own2 = net.encoder.maxpool1.last_idx.reshape(B, -1), net.encoder.maxpool2.last_idx.reshape(B, -1)
+    flips1 = (own1 != ref["idx1"]).float().mean().item()
+    flips2 = (own2 != ref["idx2"]).float().mean().item()
+    print(f"[{mode}] own VNMaxPool selections differing from the reference's: maxpool1 {100 * flips1:.2f} %, maxpool2 {100 * flips2:.2f} %")
+    assert flips1 < (0.02 if mode == "fp32" else 0.10), flips1       # near-ties only (TF32 direction GEMM: 49/1024 measured there)
+    # the forward above was a training-mode forward: rewind the BatchNorm buffers it updated
+    net.load_state_dict({k: v for k, v in _our_net(mode).state_dict().items()})
+    net.encoder.maxpool1.forced_idx, net.encoder.maxpool2.forced_idx = ref["idx1"], ref["idx2"]
+
+    coarse, fine = net(p, V.Rotate(R))
+    loss = V.cd_loss_L1(coarse, c) + V.cd_loss_L1(fine, c)
+    loss.backward()
+    vl2, vmax, lrel, gl2, gmax = TOL[mode]
+    for name, a, r in (("coarse", coarse.detach(), ref["coarse"]), ("fine", fine.detach(), ref["fine"])):
+        e2, em = _errs(a, r)
+        print(f"[{mode}] {name}: rel-L2 {e2:.3e}, max/scale {em:.3e}")
+        assert e2 <= vl2 and em <= max(vmax, 1e-4), (name, e2, em)
+    if mode == "fp32":
+        np.testing.assert_allclose(coarse.detach().cpu().numpy(), ref["coarse"].cpu().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(fine.detach().cpu().numpy(), ref["fine"].cpu().numpy(), rtol=1e-4, atol=1e-5)
+    print(f"[{mode}] loss {loss.item():.7f} vs reference {ref['loss']:.7f}")
+    assert abs(loss.item() - ref["loss"]) <= lrel * abs(ref["loss"])
+    checked, worst = 0, (0.0, "")
+    for name, prm in net.named_parameters():
+        rg = ref["grads"][name]
+        if rg is None:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        e2, _ = _errs(prm.grad, rg)
+        worst = max(worst, (e2, name))
+        assert_grad_close(prm.grad.cpu().numpy(), rg.cpu().numpy(), f"[{mode}] {name}", l2=gl2, mx=gmax)
+        checked += 1
+    print(f"[{mode}] {checked} parameter gradients checked, worst rel-L2 {worst[0]:.3e} ({worst[1]})")
+    assert checked >= 20
+    # BatchNorm running statistics after the step (train.py checkpoints them)
+    for name, buf in net.named_buffers():
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            e2, _ = _errs(buf, ref["buffers"][name])
+            assert e2 <= (1e-4 if mode == "fp32" else 5e-3), (name, e2)
+
+
+def test_reference_tf32_flag_spread():
+    """the yardstick for the TF32 tolerance: the unmodified reference against ITSELF with torch.backends.cuda.matmul.allow_tf32 on / off
+    (its pinned torch 1.11 defaults to on), selections compared, values and gradients rel-L2.  Reported, and asserted only to be of the
+    size the tolerance table above assumes."""
+    if not RH.available():
+        pytest.skip("oracle/_ref not built")
+    net = _our_net("fp32")
+    p, c, R = _batch(6)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    del net
+    a = RH.reference_train_step(sd, p, c, R, tf32=False)
+    b = RH.reference_train_step(sd, p, c, R, tf32=True)
+    f1 = (a["idx1"] != b["idx1"]).float().mean().item()
+    f2 = (a["idx2"] != b["idx2"]).float().mean().item()
+    e_c, e_f = _errs(b["coarse"], a["coarse"])[0], _errs(b["fine"], a["fine"])[0]
+    print(f"reference tf32-flag vs fp32: selections flipped {100 * f1:.2f} % / {100 * f2:.2f} %, coarse rel-L2 {e_c:.3e}, fine rel-L2 {e_f:.3e}, "
+          f"loss {b['loss']:.6f} vs {a['loss']:.6f}")
+    # with its OWN (flipped) selections the reference moves by far more than our teacher-forced TF32 tolerance
+    assert e_c > 1e-4 and e_f > 1e-4
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("B", [6])
+def test_full_size_train_step_vs_eager_port(B, mode):
+    import vn_pointcloudcompletion_b200 as V
+    net = _our_net(mode)
     P = EP.params_from_module(net, requires_grad=True)
-    p, c, R = (torch.from_numpy(a).cuda() for a in make_batch(B, 2048, 16384, seed=4321))
+    p, c, R = _batch(B)
 
     coarse, fine = net(p, V.Rotate(R))
     idx = (net.encoder.maxpool1.last_idx.reshape(B, -1), net.encoder.maxpool2.last_idx.reshape(B, -1))
-    # the port's own selections: equal except where its top-2 score gap is within fp32 noise
+    # the port's own selections: equal except where its top-2 score gap is within fp32 (TF32) noise
     with torch.no_grad():
         _, _, own = EP.encoder(P, p, True)
-    assert (own[0] != idx[0]).float().mean().item() < 0.02, "maxpool1 selections differ on more than 2 % of the channels"
+    assert (own[0] != idx[0]).float().mean().item() < (0.02 if mode == "fp32" else 0.10), "maxpool1 selections differ on too many channels"
 
     rc, rf, _ = EP.pcn_forward(P, p, R, True, idx)
     assert coarse.shape == (B, 1024, 3) and fine.shape == (B, 16384, 3)
-    np.testing.assert_allclose(coarse.detach().cpu().numpy(), rc.detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(fine.detach().cpu().numpy(), rf.detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+    vl2, vmax, lrel, gl2, gmax = TOL[mode]
+    if mode == "fp32":
+        np.testing.assert_allclose(coarse.detach().cpu().numpy(), rc.detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(fine.detach().cpu().numpy(), rf.detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+    else:
+        for a, r in ((coarse.detach(), rc.detach()), (fine.detach(), rf.detach())):
+            e2, em = _errs(a, r)
+            assert e2 <= vl2 and em <= vmax, (e2, em)
 
     chamfer = V.chamfer_3DFunction.apply          # bit-identical to the reference kernel (tests/test_gpu_chamfer.py)
     loss = V.cd_loss_L1(coarse, c) + V.cd_loss_L1(fine, c)
     rloss = EP.cd_loss_l1(chamfer, rc, c) + EP.cd_loss_l1(chamfer, rf, c)
-    np.testing.assert_allclose(loss.item(), rloss.item(), rtol=1e-4)
+    np.testing.assert_allclose(loss.item(), rloss.item(), rtol=lrel)
     loss.backward()
     rloss.backward()
     checked = 0
@@ -51,6 +172,6 @@ def test_full_size_train_step_vs_eager_port(B):
         if ref is None:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
             continue
-        assert_grad_close(prm.grad.cpu().numpy(), ref.cpu().numpy(), name)
+        assert_grad_close(prm.grad.cpu().numpy(), ref.cpu().numpy(), f"[{mode}] {name}", l2=gl2, mx=gmax)
         checked += 1
     assert checked >= 20

@@ -1,0 +1,169 @@
+"""The arithmetic modes of the product against the float64 oracle (oracle/vn_oracle.py, pinned to the reference's goldens by
+tests/test_oracle_golden.py), network by network, at channel widths that select the vectorised / packed / fused kernels the timed path
+runs (C = 128 ... 2048; the golden fixtures of tests/golden/vn_layers.npz are too narrow for them):
+
+  "fp32"       exact fp32 GEMMs (SIMT) + IEEE sqrt / division kernels                                   -- parity mode
+  "fp32+fast"  exact fp32 GEMMs + the MUFU-reciprocal / rsqrt kernels that the tensor-core mode uses    -- isolates bn_leaky_fwd_p2,
+               bn_leaky_bwd1_p2, fold_fwd_p2, fold_bwd_*, bn_leaky_dot_fwd_v4<fast>, ... from TF32 rounding: they must meet the SAME
+               tolerance as parity mode
+  "tf32"       tcgen05 TF32 GEMMs + the fast kernels (what bench.py times), incl. the no-grad fused epilogues gemm_vn_apply / gemm_vn_pool
+
+Reference semantics: models/vn_layers.py:60-74,116-127 (VNLinearLeakyReLU / VNBatchNorm), models/pcn.py:163-184 (VN_PointNet.forward),
+:364-389 (VN_FoldingNet.forward).  VNMaxPool selections are teacher-forced from the oracle."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp32", "fp32+fast", "tf32"]
+# (values rel-L2, values max / scale, gradients rel-L2)
+TOL = {"fp32": (2e-5, 1e-4, 5e-3), "fp32+fast": (2e-5, 1e-4, 5e-3), "tf32": (5e-3, 2e-2, 5e-2)}
+
+
+@pytest.fixture(params=MODES)
+def mode(request):
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import _lib
+    m = request.param
+    V.set_gemm_mode("tf32" if m == "tf32" else "fp32")
+    if m == "fp32+fast":
+        _lib.load().vnpcc_set_fast_math(1)
+    yield m
+    V.set_gemm_mode("fp32")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def _errs(a, r):
+    a = np.asarray(a, np.float64)
+    r = np.asarray(r, np.float64)
+    return np.linalg.norm(a - r) / (np.linalg.norm(r) + 1e-300), np.abs(a - r).max() / (np.abs(r).max() + 1e-300)
+
+
+def _check_values(name, mode, a, r):
+    e2, em = _errs(a, r)
+    print(f"[{mode}] {name}: rel-L2 {e2:.2e}, max/scale {em:.2e}")
+    assert e2 <= TOL[mode][0] and em <= TOL[mode][1], (name, mode, e2, em)
+
+
+def _check_grads(mode, named_params, G, min_checked):
+    checked, worst = 0, (0.0, "")
+    for name, prm in named_params:
+        if name not in G:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        e2, _ = _errs(prm.grad.cpu().numpy(), G[name])
+        worst = max(worst, (e2, name))
+        assert e2 <= TOL[mode][2], (name, mode, e2)
+        checked += 1
+    print(f"[{mode}] {checked} parameter gradients, worst rel-L2 {worst[0]:.2e} ({worst[1]})")
+    assert checked >= min_checked
+
+
+def _cfg(num_coarse, latent_dim):
+    return SimpleNamespace(num_coarse=num_coarse, latent_dim=latent_dim, only_coarse=False, device="cuda", enc_pretrained="none")
+
+
+def test_encoder_vs_float64_oracle(mode):
+    """VN_PointNet: first_conv[0] (K=1 streaming kernel), VNLinear 128->512, maxpool1 + tap, second_conv[0] with the per-sample bias
+    epilogue + bn_leaky on the stacked (p|d) rows at C=1024, fused VNLinear->VNMaxPool with the sparse backward, the R=18 mlp GEMMs"""
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import vn_oracle as O
+    B, N = 6, 160
+    torch.manual_seed(0)
+    enc = V.VN_PointNet(_cfg(1024, 2048), latent_dim=1024).cuda().train()
+    P = {"encoder." + k: v.detach().cpu().numpy().astype(np.float64) for k, v in enc.state_dict().items()}
+    rng = np.random.RandomState(7)
+    xyz = rng.uniform(-0.5, 0.5, (B, N, 3))
+    wc, wg = rng.standard_normal((B, 1024, 3)), rng.standard_normal((B, 2048, 3, 1))
+    orc = O.VNPointNetOracle(P, "encoder.", 1024)
+    oc, ofg = orc.forward(xyz, training=True)
+    G, _ = orc.backward(wc, wg)
+    enc.maxpool1.forced_idx = torch.from_numpy(orc.idx[0]).cuda().reshape(B, -1)
+    enc.maxpool2.forced_idx = torch.from_numpy(orc.idx[1]).cuda().reshape(B, -1)
+    coarse, fg = enc(_dev(xyz))
+    ((coarse * _dev(wc)).sum() + (fg * _dev(wg)).sum()).backward()
+    _check_values("coarse", mode, coarse.detach().cpu().numpy(), oc)
+    _check_values("feature_global", mode, fg.detach().cpu().numpy(), ofg)
+    _check_grads(mode, (("encoder." + n, p) for n, p in enc.named_parameters()), G, 14)
+    for k in ("first_conv.0.batchnorm.bn.running_mean", "second_conv.0.batchnorm.bn.running_var"):
+        _check_values(k, mode, enc.state_dict()[k].cpu().numpy(), P["encoder." + k])
+
+
+def test_decoder_vs_float64_oracle(mode):
+    """VN_FoldingNet: final_conv[0] as the fused small-K layer (fold_stats / fold_fwd(_p2) / fold_bwd_*: p, d recomputed, never stored),
+    final_conv[1] GEMM on stacked weights, and the fused BN + leaky + VNLinear(256,1) + residual tail (bn_leaky_dot_*)"""
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import vn_oracle as O
+    B, nc, latent = 6, 96, 126           # 126 + 2 = 128 input channels; num_dense = 96 * 16 = 1536 points per sample
+    torch.manual_seed(1)
+    dec = V.VN_FoldingNet(_cfg(nc, latent)).cuda().train()
+    P = {"decoder." + k: v.detach().cpu().numpy().astype(np.float64) for k, v in dec.state_dict().items()}
+    rng = np.random.RandomState(8)
+    coarse = rng.uniform(-0.5, 0.5, (B, nc, 3))
+    fg = rng.standard_normal((B, latent, 3, 1)) * 0.3
+    Rm = np.linalg.qr(rng.standard_normal((B, 3, 3)))[0]
+    wf = rng.standard_normal((B, nc * 16, 3))
+    orc = O.VNFoldingNetOracle(P, "decoder.", nc)
+    of = orc.forward(coarse, fg, Rm, training=True)
+    G, g_coarse, g_fg = orc.backward(wf)
+    ct = _dev(coarse).requires_grad_(True)
+    ft = _dev(fg).requires_grad_(True)
+    fine = dec(ct, ft, V.Rotate(_dev(Rm)))
+    (fine * _dev(wf)).sum().backward()
+    _check_values("fine", mode, fine.detach().cpu().numpy(), of)
+    _check_grads(mode, (("decoder." + n, p) for n, p in dec.named_parameters()), G, 9)
+    e2, _ = _errs(ct.grad.cpu().numpy(), g_coarse)
+    assert e2 <= TOL[mode][2], ("g_coarse", e2)
+    e2, _ = _errs(ft.grad.cpu().numpy(), g_fg)
+    assert e2 <= TOL[mode][2], ("g_feature_global", e2)
+    for k in ("final_conv.0.batchnorm.bn.running_mean", "final_conv.1.batchnorm.bn.running_var"):
+        _check_values(k, mode, dec.state_dict()[k].cpu().numpy(), P["decoder." + k])
+
+
+@pytest.mark.parametrize("train_stats", [False, True])
+def test_nograd_fused_epilogues_vs_float64_oracle(mode, train_stats):
+    """no-grad forward (validation loop, train.py:199-226): in TF32 mode VNLinearLeakyReLU runs as ONE tcgen05 kernel with BatchNorm-on-norm
+    + leaky in the epilogue (gemm_vn_apply; gemm_vn_stats when the module is in training mode) and VNLinear -> VNMaxPool as gemm_vn_pool.
+    Selections: a mismatch is accepted only where the oracle's score at our index is within the TF32 error of the oracle's maximum."""
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import vn_oracle as O
+    B, N, nc = 6, 224, 128         # B = 6: well-conditioned BatchNorm-on-norm statistics in the decoder; dense = 128 * 16 points
+
+    def build():
+        torch.manual_seed(2)
+        net = V.PCNNet(_cfg(nc, 2048)).train(train_stats)
+        with torch.no_grad():          # non-trivial running statistics for the eval-mode case
+            for m in net.modules():
+                if isinstance(m, torch.nn.BatchNorm1d):
+                    m.running_mean.uniform_(0.2, 0.8)
+                    m.running_var.uniform_(0.5, 1.5)
+        return net
+
+    net = build()
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in net.state_dict().items()}
+    rng = np.random.RandomState(9)
+    xyz = rng.uniform(-0.5, 0.5, (B, N, 3))
+    Rm = np.linalg.qr(rng.standard_normal((B, 3, 3)))[0]
+    orc = O.PCNNetOracle(P, num_coarse=nc)
+    oc, of = orc.forward(xyz, Rm, training=train_stats)
+    with torch.no_grad():
+        net(_dev(xyz), V.Rotate(_dev(Rm)))
+    own = (net.encoder.maxpool1.last_idx.cpu().numpy().reshape(B, -1), net.encoder.maxpool2.last_idx.cpu().numpy().reshape(B, -1))
+    flips = [(own[i] != orc.enc.idx[i].reshape(B, -1)).mean() for i in range(2)]
+    print(f"[{mode}] own selections differing from the float64 oracle's: {100 * flips[0]:.2f} % / {100 * flips[1]:.2f} %")
+    lim = 0.12 if mode == "tf32" else 0.03        # 31/1024 flips under an fp32 re-ordering, 49/1024 under TF32 operands
+    assert flips[0] < lim, flips
+    # values with the oracle's selections teacher-forced, on a fresh copy (the forward above moved the BatchNorm buffers in training mode)
+    net = build()
+    net.encoder.maxpool1.forced_idx = torch.from_numpy(orc.enc.idx[0]).cuda().reshape(B, -1)
+    net.encoder.maxpool2.forced_idx = torch.from_numpy(orc.enc.idx[1]).cuda().reshape(B, -1)
+    with torch.no_grad():
+        coarse, fine = net(_dev(xyz), V.Rotate(_dev(Rm)))
+    _check_values("coarse", mode, coarse.cpu().numpy(), oc)
+    _check_values("fine", mode, fine.cpu().numpy(), of)

@@ -169,3 +169,35 @@ def test_gemm_fp32_vs_float64(R, K, Cout):
     np.testing.assert_allclose(gx, gy.astype(np.float64) @ w.astype(np.float64), rtol=1e-4, atol=1e-4)
     gw = ops.gemm_wgrad(_dev(gy), _dev(x)).cpu().numpy()
     np.testing.assert_allclose(gw, gy.astype(np.float64).T @ x.astype(np.float64), rtol=1e-4, atol=2e-3)
+
+
+def test_layer_runs_on_the_tensors_device_not_the_current_one():
+    """the reference lets a model live on config.device without torch.cuda.set_device (models/model.py:14-20): every launch must go to
+    the device (and that device's current stream) its tensors live on"""
+    import vn_pointcloudcompletion_b200 as V
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    torch.manual_seed(0)
+    lin = V.VNLinearLeakyReLU(8, 16, dim=4)
+    x = torch.randn(2, 8, 3, 33)
+    y0 = lin.cuda(0)(x.cuda(0)).cpu()
+    lin1 = lin.to("cuda:1")
+    lin1.batchnorm.bn.reset_running_stats()
+    assert torch.cuda.current_device() == 0
+    x1 = x.to("cuda:1").requires_grad_(True)
+    y1 = lin1(x1)
+    y1.sum().backward()
+    torch.cuda.synchronize(1)
+    assert y1.device.index == 1 and x1.grad.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.allclose(y1.cpu(), y0, rtol=1e-6, atol=1e-6)
+    d1, d2, i1, i2 = V.chamfer_3DFunction.apply(torch.rand(2, 50, 3, device="cuda:1"), torch.rand(2, 70, 3, device="cuda:1"))
+    assert d1.device.index == 1 and i2.device.index == 1
+
+
+def test_mixed_device_operands_are_rejected():
+    from vn_pointcloudcompletion_b200 import _lib, ops
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with pytest.raises(_lib.VnpccError):
+        ops.gemm_rows(torch.randn(64, 8, device="cuda:0"), torch.randn(16, 8, device="cuda:1"))

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libvnpcc.so")
 
 _p, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
 
-# name -> (restype, argtypes); must list every symbol include/vnpcc.h declares (tests check this)
+# name -> (restype, argtypes); must list every symbol include/vnpcc.h and include/vnpcc_debug.h declare (tests check this)
 SIGNATURES = {
     "vnpcc_abi_version": (_i, []),
     "vnpcc_launch_count": (C.c_ulonglong, []),
@@ -27,6 +27,7 @@ SIGNATURES = {
     "vnpcc_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "vnpcc_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "vnpcc_chamfer_set_packed_math": (None, [_i]),
+    "vnpcc_debug_chamfer_slow_counts": (_i, [_p, _i, _i, _i, _p, _p]),
     "vnpcc_cd_reduce": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "vnpcc_cd_reduce_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "vnpcc_gemm_rows_fp32": (_i, [_p, _ll, _p, _ll, _i, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _i, _p]),
@@ -113,25 +114,67 @@ def load():
     return lib
 
 
+class _StreamArg:
+    """placeholder for the `void* stream` argument: resolved inside call()/raw() to the CURRENT stream OF THE DEVICE THE TENSOR
+    ARGUMENTS LIVE ON (not of the current device)"""
+    __slots__ = ()
+
+
+_STREAM = _StreamArg()
+
+
 def ptr(t):
-    """device pointer of a tensor (None -> NULL)"""
-    return None if t is None else t.data_ptr()
+    """device-pointer argument of a tensor (None -> NULL).  The tensor itself is handed on: call()/raw() take its data_ptr() and use its
+    device to pick the stream and the device guard, and reject operands that live on different devices."""
+    return t
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    return _STREAM
+
+
+def _invoke(name, args):
+    fn = getattr(load(), name)
+    dev = None
+    n = len(args)
+    out = [None] * n
+    spos = -1
+    for i in range(n):
+        a = args[i]
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise VnpccError(f"{name}: CPU tensor passed to a B200 kernel (there is no CPU fallback)")
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise VnpccError(f"{name}: operands on different devices ({dev} and {a.device})")
+            out[i] = a.data_ptr()
+        elif a is _STREAM:
+            spos = i
+        else:
+            out[i] = a
+    if dev is None or dev.index == torch.cuda.current_device():
+        if spos >= 0:
+            out[spos] = torch.cuda.current_stream().cuda_stream
+        return fn(*out)
+    # the reference lets a model live on config.device without torch.cuda.set_device (models/model.py:14-20): launch on the
+    # tensors' device and on ITS current stream
+    with torch.cuda.device(dev):
+        if spos >= 0:
+            out[spos] = torch.cuda.current_stream(dev).cuda_stream
+        return fn(*out)
 
 
 def call(name, *args):
     """call an int-returning entry point and raise on a non-zero return"""
-    rc = getattr(load(), name)(*args)
+    rc = _invoke(name, args)
     if rc != 0:
         raise VnpccError(f"{name} failed with code {rc}")
     return rc
 
 
 def raw(name, *args):
-    return getattr(load(), name)(*args)
+    return _invoke(name, args)
 
 
 def launch_count():

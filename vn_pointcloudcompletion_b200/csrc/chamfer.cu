@@ -587,6 +587,25 @@ void vnpcc_debug_chamfer_plan(int B, int N, int M, int* out) {
     out[3] = CH_QB;
 }
 
+// offset of the slow-path counter inside one directed pass's workspace (layout of nn_directed below)
+static size_t count_offset(int B, int N, int M) {
+    int nq, ns, sl;
+    plan_splits(B, N, M, &nq, &ns, &sl);
+    const size_t total = (size_t)B * N;
+    return 3 * align256(total * ns * 4) + align256(total * 4) + align256((size_t)B * 4);
+}
+
+// include/vnpcc_debug.h: slow-path query counts of the most recent pre-filtered forward on this workspace
+int vnpcc_debug_chamfer_slow_counts(const void* workspace, int B, int N, int M, int* out2_host, void* stream) {
+    out2_host[0] = out2_host[1] = 0;
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* ws = (const char*)workspace;
+    cudaMemcpyAsync(&out2_host[0], ws + count_offset(B, N, M), sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&out2_host[1], ws + directed_ws_bytes(B, N, M) + count_offset(B, M, N), sizeof(int), cudaMemcpyDeviceToHost, st);
+    return (int)cudaStreamSynchronize(st);
+}
+
 // One directed pass (queries xq[B,N,3] against candidates xc[B,M,3]).
 static int nn_directed(const float* xq, const float* xc, int B, int N, int M, float* dist, int* idx, void* wsv, cudaStream_t st) {
     if (B <= 0 || N <= 0) return 0;

@@ -805,7 +805,8 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     CUtensorMap mw, mx;
     if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
     if (!make_map(&mx, X, R, K, ldx, BK, BN)) return VNPCC_ERR_DRIVER;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};      // the attribute is per device
+    bool& attr_done = attr_done_dev[current_device_slot()];
     auto kern = bias ? gemm_rows_tf32_kernel<BN, STAGES, true> : gemm_rows_tf32_kernel<BN, STAGES, false>;
     if (!attr_done) {
         if (cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
@@ -837,7 +838,8 @@ static int launch_fused(const float* X, long long ldx, const float* Wcat, long l
     if (!make_map(&mw, Wcat, MODE == MODE_STATS ? C : 2 * C, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
     if (!make_map(&mx, X, R, K, ldx, BK, FBN)) return VNPCC_ERR_DRIVER;
     auto kern = gemm_vn_fused_kernel<STAGES, MODE, FAST, FBN, NACC>;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};      // the attribute is per device
+    bool& attr_done = attr_done_dev[current_device_slot()];
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
         attr_done = true;
@@ -971,7 +973,8 @@ int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long 
     if (!tc::make_map(&mdy, dY, R, Cout, lddy, 32, tc::BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
     if (!tc::make_map(&mx, X, R, K, ldx, 32, tc::BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
     auto kern = tc::gemm_wgrad_tf32_kernel<BNW, STAGES>;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};      // the attribute is per device
+    bool& attr_done = attr_done_dev[current_device_slot()];
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
         attr_done = true;

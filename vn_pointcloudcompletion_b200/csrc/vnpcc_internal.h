@@ -25,6 +25,13 @@ inline int sm_count() {
     return cached[dev];
 }
 
+// index of the current device into per-device caches (function attributes are per device)
+inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
 // launch-time errors only (no synchronisation); 0 on success, the cudaError_t value otherwise
 inline int last_error() { return (int)cudaGetLastError(); }
 

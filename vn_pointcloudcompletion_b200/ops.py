@@ -150,7 +150,9 @@ _WS = {}
 
 
 def _workspace(nbytes, device, key="ws"):
-    k = (key, device)
+    """scratch buffer cached per (purpose, device, stream): two streams running the same op concurrently (validation on a side stream
+    during training) must not share scratch, and a buffer is only ever reused in the order of the stream it was handed to"""
+    k = (key, device, torch.cuda.current_stream(device).cuda_stream)
     buf = _WS.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
