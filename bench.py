@@ -11,8 +11,8 @@ L1-CD(dense, gt), backward, gradient all-reduce (N > 1), Adam -- per-GPU batch 3
 `e2e`    : samples/s through the public API with HOST inputs: every step copies partial / gt / rotation from pinned
            host memory and reads the loss back.
 `roofline`: the dominant kernel class by device time inside the timed region (CUDA events on the launching stream).
-`cpu_baseline`: the reference's own CPU path (oracle/_ref/py: the unmodified reference, byte-compiled by oracle/build_ref_py.py)
-           timed on this box's host cores on a bounded sample; the numpy/C port only if oracle/_ref/py is absent (kind says which).
+`cpu_baseline`: the reference's own CPU path (oracle/_ref/refpy.zip: the unmodified reference, byte-compiled by oracle/build_ref_py.py)
+           timed on this box's host cores on a bounded sample; the numpy/C port only if oracle/_ref/refpy.zip is absent (kind says which).
 --impl reference: that same reference CPU path as the driver's reference arm, with every host thread, on this arm's config.
 """
 from __future__ import annotations
@@ -147,9 +147,9 @@ def cpu_reference_step(batch, steps, warmup):
     """The reference's own CPU path timed on this box's host cores.
 
     kind "reference": the UNMODIFIED reference (models.model.PCNNet + metrics.loss.cd_loss_L1 over chamfer_python.distChamfer, byte-compiled
-    from /root/reference into oracle/_ref/py by oracle/build_ref_py.py, imported through oracle/ref_model.py) runs the train step of
+    from /root/reference into oracle/_ref/refpy.zip by oracle/build_ref_py.py, imported through oracle/ref_model.py) runs the train step of
     train.py:127-173 -- zero_grad, forward, two L1-CD losses, backward, torch.optim.Adam.step -- on `batch` samples per step.
-    kind "port" (only when oracle/_ref/py is absent): the numpy / C oracle port, forward + losses + backward.
+    kind "port" (only when oracle/_ref/refpy.zip is absent): the numpy / C oracle port, forward + losses + backward.
     Returns (samples/s, mean s/step, info dict)."""
     import numpy as np
     import torch
@@ -201,7 +201,7 @@ def cpu_reference_step(batch, steps, warmup):
             times.append(dt)
     sec = sum(times) / len(times)
     return batch / sec, sec, {"kind": "port", "cores": cores,
-                              "what": "oracle/_ref/py absent: numpy/OpenBLAS + C/OpenMP restatement, forward + 2 L1-CD + backward (no optimiser)"}
+                              "what": "oracle/_ref/refpy.zip absent: numpy/OpenBLAS + C/OpenMP restatement, forward + 2 L1-CD + backward (no optimiser)"}
 
 
 def workload_config(B, world, mode, enc="vn_pointnet", dec="vn_foldingnet"):

@@ -1,5 +1,5 @@
 """oracle/ref_model.py -- TEST / BASELINE INFRASTRUCTURE.  Imports the reference's OWN Python implementation (byte-compiled, unmodified,
-by oracle/build_ref_py.py into oracle/_ref/py) through the import shim of SURVEY.md Appendix F, so that
+by oracle/build_ref_py.py into oracle/_ref/refpy.zip) through the import shim of SURVEY.md Appendix F, so that
 
   * bench.py --impl reference and bench.py's cpu_baseline leg time models.model.PCNNet + metrics.loss.cd_loss_L1 on the box's host
     cores with the reference's CPU-capable Chamfer (chamfer_python.distChamfer) -- BASELINE.md 3;
@@ -24,12 +24,12 @@ from types import SimpleNamespace
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-PY = os.path.join(HERE, "_ref", "py")
+PY = os.path.join(HERE, "_ref", "refpy.zip")      # sourceless byte code, imported through zipimport
 _loaded = None
 
 
 def available():
-    return os.path.exists(os.path.join(PY, "models", "model.pyc"))
+    return os.path.exists(PY)
 
 
 def _stub(name, **attrs):
@@ -48,7 +48,7 @@ def load(backend="cpu"):
             raise RuntimeError(f"reference already loaded with backend {_loaded.backend}")
         return _loaded
     if not available():
-        raise RuntimeError("oracle/_ref/py is missing: run `python oracle/build_ref_py.py` in the build container")
+        raise RuntimeError("oracle/_ref/refpy.zip is missing: run `python oracle/build_ref_py.py` in the build container")
     for shadow in ("models", "metrics", "utils", "extensions"):
         if shadow in sys.modules:
             raise RuntimeError(f"a module named {shadow!r} is already imported; the reference's package of that name cannot be loaded")

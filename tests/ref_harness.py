@@ -1,5 +1,5 @@
 """tests/ref_harness.py -- runs the UNMODIFIED reference (oracle/ref_model.py: models.model.PCNNet + metrics.loss.cd_loss_L1, byte-compiled
-from /root/reference into oracle/_ref/py) eagerly on the GPU as the full-size oracle of the -m gpu parity tests: its ATen operator chain
+from /root/reference into oracle/_ref/refpy.zip) eagerly on the GPU as the full-size oracle of the -m gpu parity tests: its ATen operator chain
 and its own Chamfer kernels (oracle/_ref/ref_chamfer3D.cubin).  Test infrastructure only."""
 import torch
 

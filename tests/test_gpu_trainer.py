@@ -40,11 +40,13 @@ def test_train_steps_reduce_loss_and_state_dict_roundtrip(tmp_path):
         cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cuda", enc_pretrained="none")
         torch.manual_seed(0)
         net = V.PCNNet(cfg).train()
-        tr = DataParallelTrainer(net, lr=1e-3, world_size=1)
+        # lr 1e-4 = the reference's shipped configuration (experiments/.../config.json).  At random init the trajectory is noisy (VNMaxPool
+        # selections flip between steps, SURVEY B.2, and the Chamfer scatter uses atomics), so the check is on the mean of the last steps
+        tr = DataParallelTrainer(net, lr=1e-4, world_size=1)
         p, c, R = (torch.from_numpy(a).cuda() for a in make_batch(4, 256, 2048, seed=21))
-        losses = [tr.train_step(p, c, R).item() for _ in range(12)]
+        losses = [tr.train_step(p, c, R).item() for _ in range(16)]
         assert np.isfinite(losses).all()
-        assert min(losses[-3:]) < losses[0], losses           # same batch: the loss must go down
+        assert np.mean(losses[-4:]) < 0.9 * losses[0], losses           # same batch: the loss must go down
         # the two VNMaxPool direction weights never receive a gradient: unchanged by training
         torch.manual_seed(0)
         fresh = V.PCNNet(cfg)

@@ -1,6 +1,6 @@
-"""The byte-compiled reference under oracle/_ref/py (oracle/build_ref_py.py) -- what bench.py --impl reference times and what the -m gpu
+"""The byte-compiled reference under oracle/_ref/refpy.zip (oracle/build_ref_py.py) -- what bench.py --impl reference times and what the -m gpu
 full-size tests use as their oracle -- IS the reference: on CPU it reproduces the committed goldens that tests/golden/make_golden.py made
-from /root/reference directly (same seeded weights, inputs, outputs, losses).  Skipped when oracle/_ref/py was not built."""
+from /root/reference directly (same seeded weights, inputs, outputs, losses).  Skipped when oracle/_ref/refpy.zip was not built."""
 import numpy as np
 import pytest
 import torch
@@ -9,7 +9,7 @@ import torch
 def test_staged_reference_reproduces_pcn_small_golden(golden):
     from oracle import ref_model as RM
     if not RM.available():
-        pytest.skip("oracle/_ref/py not built (needs /root/reference in the build container)")
+        pytest.skip("oracle/_ref/refpy.zip not built (needs /root/reference in the build container)")
     try:
         net, ref = RM.build_pcnnet("cpu", seed=0)
     except RuntimeError as e:      # the other backend was loaded earlier in this process (a combined CPU + GPU pytest run)
@@ -33,7 +33,7 @@ def test_staged_reference_reproduces_pcn_small_golden(golden):
 
 
 def test_bench_reference_arm_uses_the_staged_reference():
-    """bench.py's CPU arm reports kind 'reference' exactly when oracle/_ref/py exists (the port is a fallback only)"""
+    """bench.py's CPU arm reports kind 'reference' exactly when oracle/_ref/refpy.zip exists (the port is a fallback only)"""
     import inspect
 
     import bench
