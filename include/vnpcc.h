@@ -75,6 +75,13 @@ int vnpcc_transpose(const float* in, long long ldi, float* out, long long ldo, i
 int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy,
                          long long R, int K, int Cout, const float* bias, long long ldbias, long long rows_per_sample,
                          void* stream);
+/* vnpcc_gemm_rows_tf32 for a training-mode VNLinearLeakyReLU (models/vn_layers.py:60-74,116-127): the epilogue also accumulates the
+ * BatchNorm-on-norm batch statistics of the first Cstat output channels -- sums[c] = sum over points of (||Y[point, c]|| + 1e-6),
+ * sums[Cstat + c] = the same squared, fp64, zeroed here -- so no separate pass re-reads Y.  R % 3 == 0, Cstat % 32 == 0,
+ * Cstat <= min(Cout, 1024); VNPCC_ERR_UNSUPPORTED otherwise (callers then use vnpcc_gemm_rows_* + vnpcc_vn_norm_stats). */
+int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy,
+                               long long R, int K, int Cout, const float* bias, long long ldbias, long long rows_per_sample,
+                               double* sums, int Cstat, void* stream);
 int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg,
                           long long R, int Cout, int K, float* workspace, size_t workspace_bytes, void* stream);
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long R, int Cout, int K);

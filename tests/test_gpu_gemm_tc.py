@@ -198,3 +198,36 @@ def test_fused_pool_gemm_selects_like_unfused(tf32_mode):
     o2, _ = ops.linear_maxpool_rows(x, w, wdir, G, N)
     o2.sum().backward()
     assert x.grad.abs().sum() > 0 and w.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("R,K,Cout,Cs,with_bias", [(3 * 1000, 64, 256, 128, False), (3 * 4321, 256, 512, 256, False), (3 * 2048 * 3, 512, 2048, 1024, True),
+                                                   (3 * 80, 32, 64, 32, False), (3 * 1110, 128, 256, 256, True)])
+def test_gemm_rows_stats_epilogue(tf32_mode, R, K, Cout, Cs, with_bias):
+    """vnpcc_gemm_rows_tf32_stats: the output equals the plain tcgen05 GEMM's bit for bit (same MMA sequence per element; only the row tile
+    differs: 240 = 80 whole points instead of 256), and the BatchNorm-on-norm statistics accumulated in its epilogue equal a separate
+    fp64 pass over that output (vnpcc_vn_norm_stats) to fp64 summation-order noise"""
+    from vn_pointcloudcompletion_b200 import _lib, ops
+    torch.manual_seed(R + K)
+    x = torch.randn(R, K, device="cuda")
+    w = torch.randn(Cout, K, device="cuda") / K ** 0.5
+    nsamp = 3
+    bias = torch.randn(nsamp * 3, Cout, device="cuda") if with_bias else None
+    rps = R // nsamp if with_bias else 0
+    if with_bias:
+        assert rps % 3 == 0
+    y0 = ops.gemm_rows(x, w, False, bias, rps)
+    assert ops._LAST_KERNEL[0] == "gemm_rows_tf32"
+    sums = torch.full((2 * Cs,), 7.0, device="cuda", dtype=torch.float64)      # garbage: the entry point zeroes it
+    y1 = torch.empty_like(y0)
+    rc = _lib.raw("vnpcc_gemm_rows_tf32_stats", x, K, w, K, y1, Cout, R, K, Cout, bias, Cout if with_bias else 0, rps, sums, Cs, _lib.stream())
+    assert rc == 0, rc
+    assert torch.equal(y0, y1)
+    ref = torch.empty(2 * Cs, device="cuda", dtype=torch.float64)
+    _lib.call("vnpcc_vn_norm_stats", y0, Cout, R // 3, Cs, ref, _lib.stream())
+    n = (y0.view(R // 3, 3, Cout)[:, :, :Cs].double().pow(2).sum(1).sqrt().float() + 1e-6).double()
+    assert torch.allclose(ref[:Cs], n.sum(0), rtol=1e-6) and torch.allclose(ref[Cs:], (n * n).sum(0), rtol=1e-6)
+    assert torch.allclose(sums, ref, rtol=1e-9, atol=0), (sums - ref).abs().max()
+    # and through the operator: ops.gemm_rows(stats=...) routes to the same kernel
+    s2 = torch.empty(2 * Cs, device="cuda", dtype=torch.float64)
+    y2 = ops.gemm_rows(x, w, False, bias, rps, stats=(s2, Cs))
+    assert torch.equal(y2, y0) and torch.allclose(s2, ref, rtol=1e-9, atol=0)

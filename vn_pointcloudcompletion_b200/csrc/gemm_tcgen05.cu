@@ -119,6 +119,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B)
 // layout: 2 = SWIZZLE_128B (16-byte chunks XOR row%8, K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR
@@ -160,15 +175,25 @@ struct RowsSmem {
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int STATS_OFFSET = BAR_OFFSET + 256;   // STATS kernels: 2 * MAX_STAT_C doubles (per-CTA partial sums)
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+    static constexpr int TOTAL_STATS = TOTAL + 2 * 1024 * 8;
 };
+constexpr int MAX_STAT_C = 1024;
+constexpr int ACC_STRIDE = 256;    // TMEM columns between the two accumulator stages (BN <= 256)
 
-template <int BN, int STAGES, bool HAS_BIAS>
+// STATS = true (training-mode VNLinearLeakyReLU, models/vn_layers.py:60-74 + :116-127): the tile is BN = 240 rows = 80 whole points, and
+// while an epilogue thread stores its channel's rows it also accumulates  sum ||p||, sum ||p||^2  (p = 3 consecutive TMEM columns, norm +
+// 1e-6 as VNBatchNorm adds it) for the first Cstat output channels (the W_feat half of the stacked weight) in fp64: per-CTA partials in
+// shared memory (a channel has exactly one owner thread per CTA, so plain read-modify-write), one fp64 atomicAdd per (CTA, channel) at
+// the end.  The separate statistics pass over the freshly written activation (one full HBM read) disappears.
+template <int BN, int STAGES, bool HAS_BIAS, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ Y,
                       size_t ldy, long long R, int K, int Cout, const float* __restrict__ bias, size_t ldbias,
-                      long long rows_per_sample, int num_m, long long num_tiles) {
+                      long long rows_per_sample, int num_m, long long num_tiles, double* __restrict__ sums, int Cstat) {
     using L = RowsSmem<BN, STAGES>;
+    static_assert(!STATS || BN % 48 == 0, "the statistics epilogue walks whole points, 16 at a time");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -176,6 +201,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    double* s_stats = reinterpret_cast<double*>(smem + L::STATS_OFFSET);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (K + BK - 1) / BK;
@@ -195,6 +221,8 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         }
         fence_barrier_init();
     }
+    if (STATS)
+        for (int i = threadIdx.x; i < 2 * Cstat; i += NUM_THREADS) s_stats[i] = 0.0;
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -227,7 +255,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[ps.stage], ps.phase);
                     tc_fence_after();
@@ -278,7 +306,85 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+            if (STATS) {
+                // 48 columns = 16 whole points per pass (n0 and the pass offsets are multiples of 3: column j holds component j % 3)
+                const bool do_stat = o < Cstat;      // warp-uniform (Cstat % 32 == 0)
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 48) {
+                    const long long r0 = n0 + c0;
+                    if (r0 >= R) break;      // warp-uniform
+                    float v[48];
+                    tmem_ld16(t_base + c0, v);
+                    tmem_ld16(t_base + c0 + 16, v + 16);
+                    tmem_ld16(t_base + c0 + 32, v + 32);
+                    tmem_ld_wait();
+                    if (!o_ok) continue;
+                    if (HAS_BIAS) {
+                        const long long remc = tile_rem + c0;
+                        const bool in_a = remc + 48 <= rows_per_sample;
+                        const bool in_b = remc >= rows_per_sample && remc + 48 <= 2 * rows_per_sample;
+                        if (in_a || in_b) {
+                            const float t0 = in_a ? za[0] : zb[0], t1 = in_a ? za[1] : zb[1], t2 = in_a ? za[2] : zb[2];
+#pragma unroll
+                            for (int j = 0; j < 48; ++j) v[j] += (j % 3 == 0) ? t0 : ((j % 3 == 1) ? t1 : t2);
+                        } else {        // the pass straddles a sample boundary, or rows_per_sample < BN: walk point by point
+                            long long bc = r0 / rows_per_sample;
+                            long long rc = r0 - bc * rows_per_sample;
+#pragma unroll
+                            for (int jp = 0; jp < 16; ++jp) {
+                                if (r0 + 3 * jp < R) {
+                                    const float* bp = bias + (size_t)(bc * 3) * ldbias + o;
+                                    v[3 * jp] += __ldg(bp);
+                                    v[3 * jp + 1] += __ldg(bp + ldbias);
+                                    v[3 * jp + 2] += __ldg(bp + 2 * ldbias);
+                                }
+                                rc += 3;
+                                if (rc >= rows_per_sample) {
+                                    rc = 0;
+                                    ++bc;
+                                }
+                            }
+                        }
+                    }
+                    float* dst = Y + (size_t)r0 * ldy + o;
+                    if (r0 + 48 <= R) {
+#pragma unroll
+                        for (int j = 0; j < 48; ++j) dst[(size_t)j * ldy] = v[j];
+                        if (do_stat) {
+#pragma unroll
+                            for (int jp = 0; jp < 16; ++jp) {
+                                const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(v[3 * jp], v[3 * jp]), __fmul_rn(v[3 * jp + 1], v[3 * jp + 1])),
+                                                           __fmul_rn(v[3 * jp + 2], v[3 * jp + 2]));
+                                const double n = (double)(sqrtf(n2) + 1e-6f);
+                                s1 += n;
+                                s2 = fma(n, n, s2);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int jp = 0; jp < 16; ++jp) {
+                            if (r0 + 3 * jp < R) {      // R is a multiple of 3: whole points only
+                                dst[(size_t)(3 * jp) * ldy] = v[3 * jp];
+                                dst[(size_t)(3 * jp + 1) * ldy] = v[3 * jp + 1];
+                                dst[(size_t)(3 * jp + 2) * ldy] = v[3 * jp + 2];
+                                if (do_stat) {
+                                    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(v[3 * jp], v[3 * jp]), __fmul_rn(v[3 * jp + 1], v[3 * jp + 1])),
+                                                               __fmul_rn(v[3 * jp + 2], v[3 * jp + 2]));
+                                    const double n = (double)(sqrtf(n2) + 1e-6f);
+                                    s1 += n;
+                                    s2 = fma(n, n, s2);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (do_stat && o_ok) {      // this thread is the only one in the CTA that ever touches channel o
+                    s_stats[o] += s1;
+                    s_stats[Cstat + o] += s2;
+                }
+            } else
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const long long r0 = n0 + c0;
@@ -336,6 +442,11 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (STATS)
+        for (int i = threadIdx.x; i < 2 * Cstat; i += NUM_THREADS) {
+            const double v = s_stats[i];
+            if (v != 0.0) atomicAdd(sums + i, v);
+        }
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -369,20 +480,6 @@ struct FusedSmem {
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-// 32 lanes x 16 consecutive columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int STAGES, int MODE, bool FAST, int FBN, int NACC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -798,20 +895,21 @@ static bool make_map(CUtensorMap* m, const float* base, long long rows, long lon
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STATS>
 static int launch_rows(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K,
-                       int Cout, const float* bias, long long ldbias, long long rps, cudaStream_t st) {
+                       int Cout, const float* bias, long long ldbias, long long rps, double* sums, int Cstat, cudaStream_t st) {
     using L = RowsSmem<BN, STAGES>;
+    constexpr int SMEM = STATS ? L::TOTAL_STATS : L::TOTAL;
     CUtensorMap mw, mx;
     if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
     if (!make_map(&mx, X, R, K, ldx, BK, BN)) return VNPCC_ERR_DRIVER;
     static bool attr_done_dev[64] = {false};      // the attribute is per device
     bool& attr_done = attr_done_dev[current_device_slot()];
-    auto kern = bias ? gemm_rows_tf32_kernel<BN, STAGES, true> : gemm_rows_tf32_kernel<BN, STAGES, false>;
+    auto kern = bias ? gemm_rows_tf32_kernel<BN, STAGES, true, STATS> : gemm_rows_tf32_kernel<BN, STAGES, false, STATS>;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+        if (cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, true, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+            cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, false, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
                 cudaSuccess)
             return last_error();
         attr_done = true;
@@ -820,8 +918,8 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     const long long num_n = (R + BN - 1) / BN;
     const long long num_tiles = num_m * num_n;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-    count_launch(), kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(mw, mx, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
-                                                             rps > 0 ? rps : 1, num_m, num_tiles);
+    count_launch(), kern<<<grid, NUM_THREADS, SMEM, st>>>(mw, mx, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
+                                                         rps > 0 ? rps : 1, num_m, num_tiles, sums, Cstat);
     return last_error();
 }
 
@@ -869,8 +967,26 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
     if (Cout < 64 || R < 64) return VNPCC_ERR_UNSUPPORTED;
     if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;   // a sample is whole points (3 rows each)
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 128) return tc::launch_rows<128, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
-    return tc::launch_rows<256, 4>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, st);
+    if (R <= 128) return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+    return tc::launch_rows<256, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+}
+
+// the same GEMM for a training-mode VNLinearLeakyReLU (models/vn_layers.py:60-74): additionally returns the BatchNorm-on-norm batch
+// statistics of the first Cstat output channels, sums[c] = sum_points (||y[.,c]|| + 1e-6), sums[Cstat + c] = the same squared (fp64;
+// zeroed here), accumulated in the epilogue while the rows are stored -- no separate pass over Y (vnpcc_vn_norm_stats) is needed.
+// R must be whole points (R % 3 == 0), Cstat % 32 == 0, Cstat <= min(Cout, 1024).
+int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R,
+                               int K, int Cout, const float* bias, long long ldbias, long long rows_per_sample, double* sums,
+                               int Cstat, void* stream) {
+    if (R <= 0 || Cout <= 0) return 0;
+    if (K < 32 || (K & 3) || (ldx & 3) || (ldw & 3) || !tc::aligned16(X) || !tc::aligned16(W) || R >= (1ll << 31))
+        return VNPCC_ERR_UNSUPPORTED;
+    if (Cout < 64 || R < 240 || R % 3 != 0 || !sums || Cstat <= 0 || (Cstat & 31) || Cstat > Cout || Cstat > tc::MAX_STAT_C)
+        return VNPCC_ERR_UNSUPPORTED;
+    if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cstat, st);
+    return tc::launch_rows<240, 4, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, Cstat, st);
 }
 
 static bool fused_ok(const float* X, long long ldx, const float* W, long long ldw, long long R, int K, int C, const float* bias,

@@ -97,18 +97,37 @@ def _ld(t):
 # ---------------------------------------------------------------------------------------------------------------
 # raw launch helpers (no autograd)
 # ---------------------------------------------------------------------------------------------------------------
-def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accumulate=False, exact=False):
+def gemm_rows(x, w, trans_w=False, bias=None, rows_per_sample=0, out=None, accumulate=False, exact=False, stats=None):
     """y[r,o] = sum_k x[r,k] * (w[o,k] | w[k,o] if trans_w) (+ bias[(r // rows_per_sample)*3 + r%3, o]); exact=True forces the
-    fp32 SIMT kernel even in TF32 mode (operands whose differences matter, e.g. the edge-convolution point GEMM)"""
+    fp32 SIMT kernel even in TF32 mode (operands whose differences matter, e.g. the edge-convolution point GEMM).
+    stats = (sums [2*Cs] float64, Cs): also produce the BatchNorm-on-norm batch statistics of the first Cs output channels
+    (sum ||y|| + 1e-6, and squared) -- in the tcgen05 kernel's epilogue when it takes the shape, else by a pass over y."""
     R, K = x.shape
     Cout = w.shape[1] if trans_w else w.shape[0]
     assert (w.shape[0] if trans_w else w.shape[1]) == K, (x.shape, w.shape, trans_w)
     if out is None:
         out = torch.empty((R, Cout), device=x.device, dtype=torch.float32)
     if R == 0 or Cout == 0:
+        if stats is not None:
+            stats[0].zero_()
         return out
+    if stats is not None:
+        sums, Cs = stats
+        if _GEMM_MODE == "tf32" and not accumulate and not exact and not trans_w:
+            with _Timed("gemm", 2.0 * R * K * Cout, 4.0 * (R * K + R * Cout + K * Cout)):
+                rc = _lib.raw("vnpcc_gemm_rows_tf32_stats", ptr(x), _ld(x), ptr(w), _ld(w), ptr(out), _ld(out), R, K, Cout, ptr(bias),
+                              _ld(bias) if bias is not None else 0, rows_per_sample, ptr(sums), Cs, stream())
+                if rc == 0:
+                    _LAST_KERNEL[0] = "gemm_rows_tf32"
+            if rc == 0:
+                return out
+            if rc != 10003:
+                raise _lib.VnpccError(f"vnpcc_gemm_rows_tf32_stats failed with code {rc}")
     with _Timed("gemm", 2.0 * R * K * Cout, 4.0 * (R * K + R * Cout + K * Cout)):
-        return _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout, exact)
+        _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout, exact)
+    if stats is not None:
+        call("vnpcc_vn_norm_stats", ptr(out), _ld(out), R // 3, stats[1], ptr(stats[0]), stream())
+    return out
 
 
 def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, K, Cout, exact=False):
@@ -218,14 +237,14 @@ def rows_sample_sum(g, B, N):
 # ---------------------------------------------------------------------------------------------------------------
 class _LinearRows(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, rows_per_sample, exact=False):
+    def forward(ctx, x, w, bias, rows_per_sample, exact=False, stats=None):
         x = _rows2d(x, "x")
         _check(w, "weight")
         if w.stride(1) != 1:
             w = w.contiguous()
         if bias is not None:
             bias = _rows2d(bias, "bias")
-        y = gemm_rows(x, w, False, bias, rows_per_sample, exact=exact)
+        y = gemm_rows(x, w, False, bias, rows_per_sample, exact=exact, stats=stats)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.rps = rows_per_sample
@@ -242,33 +261,53 @@ class _LinearRows(torch.autograd.Function):
                 and gy.shape[1] % 4 == 0 and _ld(gy) % 4 == 0):
             R = gy.shape[0]
             gw, gb = smallk_wgrad(gy, x, R // ctx.rps, ctx.rps // 3, True)
-            return gx, gw, gb, None, None
+            return gx, gw, gb, None, None, None
         if ctx.needs_input_grad[1]:
             gw = gemm_wgrad(gy, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             R = gy.shape[0]
             B = R // ctx.rps
             gb = rows_sample_sum(gy, B, ctx.rps // 3)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def linear_rows(x, w, bias=None, rows_per_sample=0, exact=False):
+def linear_rows(x, w, bias=None, rows_per_sample=0, exact=False, stats=None):
     """x [R,K], w [Cout,K] -> [R,Cout]; optional per-sample bias rows [B*3, Cout] (row (b,v)) added to every point of
-    sample b (the broadcast half of torch.cat([global.expand(N), local]) folded out of the GEMM, models/pcn.py:172,385)"""
-    return _LinearRows.apply(x, w, bias, rows_per_sample, exact)
+    sample b (the broadcast half of torch.cat([global.expand(N), local]) folded out of the GEMM, models/pcn.py:172,385).
+    stats: see gemm_rows (BatchNorm-on-norm batch statistics from the GEMM epilogue)."""
+    return _LinearRows.apply(x, w, bias, rows_per_sample, exact, stats)
+
+
+def bn_needs_batch_stats(bn, training):
+    return bn is not None and (training or bn.running_mean is None)
+
+
+def linear_bn_leaky_rows(x, wcat, bias, rows_per_sample, bn, training, ns):
+    """training-capable VNLinearLeakyReLU on rows with stacked weights wcat [2C, K] = (W_feat ; W_dir) (models/vn_layers.py:60-74):
+    ONE GEMM writes (p | d) and, in its epilogue, accumulates the BatchNorm-on-norm batch statistics of p; one streaming pass applies
+    BatchNorm + the leaky projection."""
+    C = wcat.shape[0] // 2
+    sums = None
+    if bn_needs_batch_stats(bn, training):
+        sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+    pd = linear_rows(x, wcat, bias, rows_per_sample, stats=(sums, C) if sums is not None else None)
+    return bn_leaky(pd, None, bn, training, ns, stacked=True, sums=sums)
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # VNBatchNorm (+ leaky projection) on rows
 # ---------------------------------------------------------------------------------------------------------------
-def _bn_prepare(p, C, bn, training, count, stats_fn=None):
+def _bn_prepare(p, C, bn, training, count, stats_fn=None, sums=None):
     """returns stat [2C] (mean | invstd) and updates the running buffers in training mode.  stats_fn(sums) may supply
-    the per-channel sums (sum n | sum n^2, fp64) itself; by default they are reduced from the rows p."""
+    the per-channel sums (sum n | sum n^2, fp64) itself, or `sums` may already hold them (GEMM epilogue); by default they are
+    reduced from the rows p."""
     dev = bn.weight.device if p is None else p.device
     stat = torch.empty(2 * C, device=dev, dtype=torch.float32)
-    sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
     use_batch = training or bn.running_mean is None
-    if use_batch:
+    have = sums is not None
+    if not have:
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+    if use_batch and not have:
         if stats_fn is not None:
             stats_fn(sums)
         else:
@@ -340,13 +379,14 @@ class _BNLeaky(torch.autograd.Function):
         return gp, gd, ggamma, gbeta, None, None, None, None
 
 
-def bn_leaky(p, d, bn, training, ns, stacked=False):
-    """p (and d) rows; bn: an nn.BatchNorm1d/2d module or None; returns leaky(BN(p), d) rows [R, C]"""
+def bn_leaky(p, d, bn, training, ns, stacked=False, sums=None):
+    """p (and d) rows; bn: an nn.BatchNorm1d/2d module or None; returns leaky(BN(p), d) rows [R, C].  sums: batch statistics of p
+    already accumulated by the producing GEMM (gemm_rows(stats=...))."""
     p = _rows2d(p, "p")
     C = p.shape[1] // 2 if stacked else p.shape[1]
     stat, use_batch, gamma, beta = None, False, None, None
     if bn is not None:
-        stat, use_batch = _bn_prepare(p[:, :C] if stacked else p, C, bn, training, p.shape[0] // 3)
+        stat, use_batch = _bn_prepare(p[:, :C] if stacked else p, C, bn, training, p.shape[0] // 3, sums=sums)
         gamma = bn.weight if bn.weight is not None else torch.ones(C, device=p.device)
         beta = bn.bias if bn.bias is not None else torch.zeros(C, device=p.device)
     return _BNLeaky.apply(p, d, gamma, beta, stat, use_batch, ns, stacked)
@@ -483,13 +523,13 @@ def bn_leaky_dot_supported(C):
     return C % 128 == 0 and C <= 1024
 
 
-def bn_leaky_dot(pd, bn, training, ns, w2, res=None):
+def bn_leaky_dot(pd, bn, training, ns, w2, res=None, sums=None):
     """fused  leaky(BN(p), d) . w2 (+ res)  on the stacked (p | d) rows; w2 is the [1, C] weight of VNLinear(C, 1)"""
     pd = _rows2d(pd, "pd")
     C = pd.shape[1] // 2
     stat, use_batch, gamma, beta = None, False, None, None
     if bn is not None:
-        stat, use_batch = _bn_prepare(pd[:, :C], C, bn, training, pd.shape[0] // 3)
+        stat, use_batch = _bn_prepare(pd[:, :C], C, bn, training, pd.shape[0] // 3, sums=sums)
         gamma = bn.weight if bn.weight is not None else torch.ones(C, device=pd.device)
         beta = bn.bias if bn.bias is not None else torch.zeros(C, device=pd.device)
     return _BNLeakyDot.apply(pd, gamma, beta, stat, use_batch, ns, w2, res)

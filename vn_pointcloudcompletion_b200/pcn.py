@@ -52,9 +52,8 @@ class VN_PointNet(nn.Module):
         wcat = torch.cat([l0.map_to_feat.weight, l0.map_to_dir.weight], dim=0)            # [2048,1024]
         bias = ops.linear_rows(g1, wcat[:, :Cg])                                          # [B*3,2048]
         f2 = ops.linear_bn_leaky_fused_nograd(f1, wcat[:, Cg:], bias, 3 * N, l0.batchnorm.bn, l0.training, l0.negative_slope)
-        if f2 is None:
-            pd = ops.linear_rows(f1, wcat[:, Cg:], bias, 3 * N)                           # [R,2048]
-            f2 = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)   # [R,1024]
+        if f2 is None:      # GEMM -> (p | d) [R,2048] with the BatchNorm statistics from its epilogue, then one BN + leaky pass -> [R,1024]
+            f2 = ops.linear_bn_leaky_rows(f1, wcat[:, Cg:], bias, 3 * N, l0.batchnorm.bn, l0.training, l0.negative_slope)
         # second_conv[1] feeds only maxpool2: fused, its [R,2048] output is transient and its backward is sparse
         fg, idx2 = ops.linear_maxpool_rows(f2, self.second_conv[1].map_to_feat.weight, self.maxpool2.map_to_dir.weight, B, N,
                                            self.maxpool2.forced_idx)                       # [B*3,2048]
@@ -132,14 +131,16 @@ class VN_FoldingNet(nn.Module):
             seed_const = 0 if seed_pts.requires_grad else 1
             h = ops.smallk_bn_leaky(local, wcat[:, Cg:], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, B, nd, seed_const)
         else:
-            pd = ops.linear_rows(local, wcat[:, Cg:], bias, 3 * nd)                        # [R,512]
-            h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
+            h = ops.linear_bn_leaky_rows(local, wcat[:, Cg:], bias, 3 * nd, l0.batchnorm.bn, l0.training, l0.negative_slope)
         C1 = l1.map_to_feat.weight.shape[0]
         if torch.is_grad_enabled() and l1.map_to_dir.weight.shape[0] == C1 and ops.bn_leaky_dot_supported(C1):
             # final_conv[1] (BN + leaky) fused with final_conv[2] = VNLinear(256,1) and the residual: its [R,256] output
             # and gradient never touch HBM
-            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0))
-            fine = ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, local[:, 1])
+            sums = (torch.empty(2 * C1, device=dev, dtype=torch.float64)
+                    if ops.bn_needs_batch_stats(l1.batchnorm.bn, l1.training) else None)
+            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0),
+                                  stats=(sums, C1) if sums is not None else None)      # BatchNorm statistics from the GEMM epilogue
+            fine = ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, local[:, 1], sums=sums)
         else:
             h = l1.forward_rows(h)      # no-grad: BN + leaky fused into the tcgen05 GEMM epilogue (vn_layers.VNLinearLeakyReLU)
             fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                     # final VNLinear(256,1) + point_feat
@@ -200,12 +201,14 @@ class Attention_VN_FoldingNet(nn.Module):
         if ops.smallk_bn_leaky_supported(1, C0, bias) and l0.batchnorm.bn.affine:
             h = ops.smallk_bn_leaky(local, wcat[:, :1], bias, l0.batchnorm.bn, l0.training, l0.negative_slope, T, S, 1 if const_local else 0)
         else:
-            pd = ops.linear_rows(local, wcat[:, :1], bias, 3 * S)
-            h = ops.bn_leaky(pd, None, l0.batchnorm.bn, l0.training, l0.negative_slope, stacked=True)
+            h = ops.linear_bn_leaky_rows(local, wcat[:, :1], bias, 3 * S, l0.batchnorm.bn, l0.training, l0.negative_slope)
         C1 = l1.map_to_feat.weight.shape[0]
         if torch.is_grad_enabled() and ops.bn_leaky_dot_supported(C1):
-            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0))
-            return ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, res)
+            sums = (torch.empty(2 * C1, device=h.device, dtype=torch.float64)
+                    if ops.bn_needs_batch_stats(l1.batchnorm.bn, l1.training) else None)
+            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0),
+                                  stats=(sums, C1) if sums is not None else None)
+            return ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, res, sums=sums)
         h = l1.forward_rows(h)
         return ops.rows_dot(h, l2.map_to_feat.weight, res)
 

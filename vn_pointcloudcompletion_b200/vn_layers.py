@@ -126,8 +126,7 @@ class VNLinearLeakyReLU(nn.Module):
                                                      self.negative_slope)
             if fused is not None:               # inference: BN + leaky in the GEMM epilogue, p / d never stored
                 return fused
-        pd = ops.linear_rows(rows, w, bias_rows, rows_per_sample)
-        return ops.bn_leaky(pd, None, self.batchnorm.bn, self.training, self.negative_slope, stacked=True)
+        return ops.linear_bn_leaky_rows(rows, w, bias_rows, rows_per_sample, self.batchnorm.bn, self.training, self.negative_slope)
 
     def forward(self, x):
         rows, B, sp = to_rows(x)
