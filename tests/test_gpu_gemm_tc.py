@@ -205,7 +205,7 @@ def test_fused_pool_gemm_selects_like_unfused(tf32_mode):
 def test_gemm_rows_stats_epilogue(tf32_mode, R, K, Cout, Cs, with_bias):
     """vnpcc_gemm_rows_tf32_stats: the output equals the plain tcgen05 GEMM's bit for bit (same MMA sequence per element; only the row tile
     differs: 240 = 80 whole points instead of 256), and the BatchNorm-on-norm statistics accumulated in its epilogue equal a separate
-    fp64 pass over that output (vnpcc_vn_norm_stats) to fp64 summation-order noise"""
+    fp64 pass over that output (vnpcc_vn_norm_stats) to 2e-6 relative (fp32 partial sums over 16 points, MUFU rsqrt)"""
     from vn_pointcloudcompletion_b200 import _lib, ops
     torch.manual_seed(R + K)
     x = torch.randn(R, K, device="cuda")
@@ -226,8 +226,9 @@ def test_gemm_rows_stats_epilogue(tf32_mode, R, K, Cout, Cs, with_bias):
     _lib.call("vnpcc_vn_norm_stats", y0, Cout, R // 3, Cs, ref, _lib.stream())
     n = (y0.view(R // 3, 3, Cout)[:, :, :Cs].double().pow(2).sum(1).sqrt().float() + 1e-6).double()
     assert torch.allclose(ref[:Cs], n.sum(0), rtol=1e-6) and torch.allclose(ref[Cs:], (n * n).sum(0), rtol=1e-6)
-    assert torch.allclose(sums, ref, rtol=1e-9, atol=0), (sums - ref).abs().max()
+    # epilogue: MUFU rsqrt norms (2 ulp) and fp32 pairwise partial sums of 16 points, fp64 across passes
+    assert torch.allclose(sums, ref, rtol=2e-6, atol=0), ((sums - ref).abs() / ref.abs()).max()
     # and through the operator: ops.gemm_rows(stats=...) routes to the same kernel
     s2 = torch.empty(2 * Cs, device="cuda", dtype=torch.float64)
     y2 = ops.gemm_rows(x, w, False, bias, rps, stats=(s2, Cs))
-    assert torch.equal(y2, y0) and torch.allclose(s2, ref, rtol=1e-9, atol=0)
+    assert torch.equal(y2, y0) and torch.allclose(s2, ref, rtol=2e-6, atol=0)

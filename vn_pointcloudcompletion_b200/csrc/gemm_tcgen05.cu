@@ -78,6 +78,18 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// bulk tensor STORE shared -> global (clipped at the tensor bounds), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {      // at most N groups still READING their shared-memory source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -177,7 +189,10 @@ struct RowsSmem {
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int STATS_OFFSET = BAR_OFFSET + 256;   // STATS kernels: 2 * MAX_STAT_C doubles (per-CTA partial sums)
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
-    static constexpr int TOTAL_STATS = TOTAL + 2 * 1024 * 8;
+    // STATS kernels: + output staging for the TMA-store epilogue, per epilogue warp 2 buffers of 48 rows x 32 channels
+    static constexpr int OUT_OFFSET = STATS_OFFSET + 2 * 1024 * 8;
+    static constexpr int OUT_BUF_BYTES = 48 * 32 * 4;
+    static constexpr int TOTAL_STATS = OUT_OFFSET + 4 * 2 * OUT_BUF_BYTES + 1024;
 };
 constexpr int MAX_STAT_C = 1024;
 constexpr int ACC_STRIDE = 256;    // TMEM columns between the two accumulator stages (BN <= 256)
@@ -187,9 +202,13 @@ constexpr int ACC_STRIDE = 256;    // TMEM columns between the two accumulator s
 // 1e-6 as VNBatchNorm adds it) for the first Cstat output channels (the W_feat half of the stacked weight) in fp64: per-CTA partials in
 // shared memory (a channel has exactly one owner thread per CTA, so plain read-modify-write), one fp64 atomicAdd per (CTA, channel) at
 // the end.  The separate statistics pass over the freshly written activation (one full HBM read) disappears.
-template <int BN, int STAGES, bool HAS_BIAS, bool STATS>
+// In this variant the output leaves through shared memory and BULK TENSOR STORES (cp.async.bulk.tensor ... global.shared::cta, two
+// 48-row x 32-channel staging buffers per epilogue warp): when HBM back-pressures the stores the warp does not stall on them, so the
+// statistics arithmetic overlaps the draining stores instead of queueing behind them.
+template <int BN, int STAGES, bool HAS_BIAS, bool STATS, bool TMA_OUT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ Y,
+gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                      const __grid_constant__ CUtensorMap map_y, float* __restrict__ Y,
                       size_t ldy, long long R, int K, int Cout, const float* __restrict__ bias, size_t ldbias,
                       long long rows_per_sample, int num_m, long long num_tiles, double* __restrict__ sums, int Cstat) {
     using L = RowsSmem<BN, STAGES>;
@@ -209,6 +228,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_x);
+        if (STATS && TMA_OUT) tma_prefetch_desc(&map_y);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -281,6 +301,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         const int quad = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int out_buf = 0;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (int)(tile % num_m) * BM;
             const long long n0 = (tile / num_m) * BN;
@@ -310,6 +331,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             if (STATS) {
                 // 48 columns = 16 whole points per pass (n0 and the pass offsets are multiples of 3: column j holds component j % 3)
                 const bool do_stat = o < Cstat;      // warp-uniform (Cstat % 32 == 0)
+                float* s_out = reinterpret_cast<float*>(smem + L::OUT_OFFSET) + (size_t)quad * 2 * (L::OUT_BUF_BYTES / 4);
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 48) {
@@ -320,8 +342,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     tmem_ld16(t_base + c0 + 16, v + 16);
                     tmem_ld16(t_base + c0 + 32, v + 32);
                     tmem_ld_wait();
-                    if (!o_ok) continue;
-                    if (HAS_BIAS) {
+                    if (HAS_BIAS && o_ok) {
                         const long long remc = tile_rem + c0;
                         const bool in_a = remc + 48 <= rows_per_sample;
                         const bool in_b = remc >= rows_per_sample && remc + 48 <= 2 * rows_per_sample;
@@ -348,36 +369,55 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                             }
                         }
                     }
-                    float* dst = Y + (size_t)r0 * ldy + o;
-                    if (r0 + 48 <= R) {
+                    // stage the pass (row-major 48 x 32: a warp writes one 128-byte row per instruction, conflict-free) and hand it to
+                    // the TMA engine; rows >= R and channels >= Cout are clipped by the tensor map
+                    if (TMA_OUT) {
+                        if (lane == 0) tma_store_wait_read<1>();      // the buffer used two passes ago has been read
+                        __syncwarp();
+                        float* sb = s_out + (size_t)out_buf * (L::OUT_BUF_BYTES / 4);
 #pragma unroll
-                        for (int j = 0; j < 48; ++j) dst[(size_t)j * ldy] = v[j];
-                        if (do_stat) {
-#pragma unroll
-                            for (int jp = 0; jp < 16; ++jp) {
-                                const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(v[3 * jp], v[3 * jp]), __fmul_rn(v[3 * jp + 1], v[3 * jp + 1])),
-                                                           __fmul_rn(v[3 * jp + 2], v[3 * jp + 2]));
-                                const double n = (double)(sqrtf(n2) + 1e-6f);
-                                s1 += n;
-                                s2 = fma(n, n, s2);
-                            }
+                        for (int j = 0; j < 48; ++j) sb[j * 32 + lane] = v[j];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_y, sb, m0 + quad * 32, (int)r0);
+                            tma_store_commit();
                         }
-                    } else {
+                        out_buf ^= 1;
+                    } else if (o_ok) {
+                        float* dst = Y + (size_t)r0 * ldy + o;
+                        if (r0 + 48 <= R) {
+#pragma unroll
+                            for (int j = 0; j < 48; ++j) dst[(size_t)j * ldy] = v[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 48; ++j)
+                                if (r0 + j < R) dst[(size_t)j * ldy] = v[j];
+                        }
+                    }
+                    if (do_stat) {
+                        // 16 norms per pass: MUFU rsqrt (this kernel only runs in the throughput mode), fp32 pairwise trees for the
+                        // pass's two partial sums (16 terms: relative error ~1e-7, unbiased, averaged over >= 1e4 passes per channel),
+                        // ONE fp64 add per sum per pass -- a per-point fp64 chain (cvt + DADD + DFMA, one warp per scheduler, no other
+                        // warp to hide its latency) cost 0.77 ms on the decoder GEMM, more than the pass it replaces
+                        float nn[16], qq[16];
 #pragma unroll
                         for (int jp = 0; jp < 16; ++jp) {
-                            if (r0 + 3 * jp < R) {      // R is a multiple of 3: whole points only
-                                dst[(size_t)(3 * jp) * ldy] = v[3 * jp];
-                                dst[(size_t)(3 * jp + 1) * ldy] = v[3 * jp + 1];
-                                dst[(size_t)(3 * jp + 2) * ldy] = v[3 * jp + 2];
-                                if (do_stat) {
-                                    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(v[3 * jp], v[3 * jp]), __fmul_rn(v[3 * jp + 1], v[3 * jp + 1])),
-                                                               __fmul_rn(v[3 * jp + 2], v[3 * jp + 2]));
-                                    const double n = (double)(sqrtf(n2) + 1e-6f);
-                                    s1 += n;
-                                    s2 = fma(n, n, s2);
-                                }
-                            }
+                            const float n2 = fmaf(v[3 * jp + 2], v[3 * jp + 2], fmaf(v[3 * jp + 1], v[3 * jp + 1], v[3 * jp] * v[3 * jp]));
+                            float n = (n2 > 0.f ? n2 * rsqrtf(n2) : 0.f) + 1e-6f;
+                            n = (r0 + 3 * jp < R) ? n : 0.f;      // R is a multiple of 3: whole points only
+                            nn[jp] = n;
+                            qq[jp] = n * n;
                         }
+#pragma unroll
+                        for (int w_ = 8; w_ > 0; w_ >>= 1)
+#pragma unroll
+                            for (int jp = 0; jp < w_; ++jp) {
+                                nn[jp] += nn[jp + w_];
+                                qq[jp] += qq[jp + w_];
+                            }
+                        s1 += (double)nn[0];
+                        s2 += (double)qq[0];
                     }
                 }
                 if (do_stat && o_ok) {      // this thread is the only one in the CTA that ever touches channel o
@@ -440,6 +480,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             }
         }
     }
+    if (STATS && TMA_OUT && warp >= 4 && lane == 0) tma_store_wait_read<0>();      // staging buffers must outlive their bulk stores
     tc_fence_before();
     __syncthreads();
     if (STATS)
@@ -895,21 +936,26 @@ static bool make_map(CUtensorMap* m, const float* base, long long rows, long lon
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, int STAGES, bool STATS>
+template <int BN, int STAGES, bool STATS, bool TMA_OUT = false>
 static int launch_rows(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K,
                        int Cout, const float* bias, long long ldbias, long long rps, double* sums, int Cstat, cudaStream_t st) {
     using L = RowsSmem<BN, STAGES>;
-    constexpr int SMEM = STATS ? L::TOTAL_STATS : L::TOTAL;
-    CUtensorMap mw, mx;
+    constexpr int SMEM = STATS ? (TMA_OUT ? L::TOTAL_STATS : L::OUT_OFFSET + 1024) : L::TOTAL;
+    CUtensorMap mw, mx, my;
     if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
     if (!make_map(&mx, X, R, K, ldx, BK, BN)) return VNPCC_ERR_DRIVER;
+    if (STATS && TMA_OUT) {      // output boxes of 32 channels x 48 rows, plain row-major staging (no swizzle)
+        if (!make_map(&my, Y, R, Cout, ldy, 32, 48, CU_TENSOR_MAP_SWIZZLE_NONE)) return VNPCC_ERR_DRIVER;
+    } else {
+        my = mx;
+    }
     static bool attr_done_dev[64] = {false};      // the attribute is per device
     bool& attr_done = attr_done_dev[current_device_slot()];
-    auto kern = bias ? gemm_rows_tf32_kernel<BN, STAGES, true, STATS> : gemm_rows_tf32_kernel<BN, STAGES, false, STATS>;
+    auto kern = bias ? gemm_rows_tf32_kernel<BN, STAGES, true, STATS, TMA_OUT> : gemm_rows_tf32_kernel<BN, STAGES, false, STATS, TMA_OUT>;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, true, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+        if (cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, true, STATS, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, false, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+            cudaFuncSetAttribute(gemm_rows_tf32_kernel<BN, STAGES, false, STATS, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
                 cudaSuccess)
             return last_error();
         attr_done = true;
@@ -918,7 +964,7 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     const long long num_n = (R + BN - 1) / BN;
     const long long num_tiles = num_m * num_n;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-    count_launch(), kern<<<grid, NUM_THREADS, SMEM, st>>>(mw, mx, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
+    count_launch(), kern<<<grid, NUM_THREADS, SMEM, st>>>(mw, mx, my, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
                                                          rps > 0 ? rps : 1, num_m, num_tiles, sums, Cstat);
     return last_error();
 }
@@ -981,12 +1027,18 @@ int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, lo
     if (R <= 0 || Cout <= 0) return 0;
     if (K < 32 || (K & 3) || (ldx & 3) || (ldw & 3) || !tc::aligned16(X) || !tc::aligned16(W) || R >= (1ll << 31))
         return VNPCC_ERR_UNSUPPORTED;
-    if (Cout < 64 || R < 240 || R % 3 != 0 || !sums || Cstat <= 0 || (Cstat & 31) || Cstat > Cout || Cstat > tc::MAX_STAT_C)
+    if (Cout < 64 || R < 240 || R % 3 != 0 || !sums || Cstat <= 0 || (Cstat & 31) || Cstat > Cout || Cstat > tc::MAX_STAT_C ||
+        (ldy & 3) || !tc::aligned16(Y))
         return VNPCC_ERR_UNSUPPORTED;
     if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cstat, st);
-    return tc::launch_rows<240, 4, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, Cstat, st);
+    const int kc = tuning(TUNE_STATS_NOMATH) ? 0 : Cstat;
+    switch (tuning(TUNE_STATS_GEMM)) {
+        case 2: return tc::launch_rows<240, 3, true, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
+        case 3: return tc::launch_rows<240, 3, true, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
+        default: return tc::launch_rows<240, 4, true, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
+    }
 }
 
 static bool fused_ok(const float* X, long long ldx, const float* W, long long ldw, long long R, int K, int C, const float* bias,
