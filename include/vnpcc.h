@@ -60,6 +60,25 @@ int vnpcc_cd_reduce(const float* dist1, const float* dist2, int B, int N, int M,
 int vnpcc_cd_reduce_bwd(const float* dist1, const float* dist2, int B, int N, int M, int mode, const float* gout,
                         float* graddist1, float* graddist2, void* stream);
 
+/* Chamfer-based loss variants (utils/loss.py:14-74, extensions/ChamferDistancePytorch/fscore.py:3-16) on the search's outputs.
+ * _cd_persample: out [B,6] = per sample (cd_p = (mean sqrt d1 + mean sqrt d2)/2, cd_t = mean d1 + mean d2, mean sqrt d1, mean sqrt d2,
+ * mean d1, mean d2); part: workspace of 4*B floats; _bwd: gradient of any function of those six w.r.t. dist1 / dist2.
+ * _fscore_sq: out [B,3] = (f, precision_1, precision_2), precision_k = mean(dist_k < threshold) on SQUARED distances.
+ * _nn_counts: counts [B,K] (zeroed here) = histogram of idx [B,N] (the bincount of calc_dcd).
+ * _dcd: density-aware CD, loss [B]; dist1/idx1 [B,N] index the M points of the other cloud (count1 [B,M]), dist2/idx2 [B,M] the N
+ * points (count2 [B,N]); part: workspace of 2*B floats; counts carry no gradient. */
+int vnpcc_cd_persample_fwd(const float* dist1, const float* dist2, int B, int N, int M, float* part, float* out, void* stream);
+int vnpcc_cd_persample_bwd(const float* dist1, const float* dist2, int B, int N, int M, const float* gout, float* gdist1,
+                           float* gdist2, void* stream);
+int vnpcc_fscore_sq(const float* dist1, const float* dist2, int B, int N, int M, float threshold, float* out, void* stream);
+int vnpcc_nn_counts(const int* idx, int B, int N, int K, int* counts, void* stream);
+int vnpcc_dcd_fwd(const float* dist1, const float* dist2, const int* idx1, const int* idx2, const int* count1, const int* count2,
+                  int B, int N, int M, float alpha, float n_lambda, float frac_21, float frac_12, float* part, float* loss,
+                  void* stream);
+int vnpcc_dcd_bwd(const float* dist1, const float* dist2, const int* idx1, const int* idx2, const int* count1, const int* count2,
+                  int B, int N, int M, float alpha, float n_lambda, float frac_21, float frac_12, const float* gloss,
+                  float* gdist1, float* gdist2, void* stream);
+
 /* ---------------------------------------------------------------- GEMMs ------------------------------------------ */
 /* Y[r,o] (+)= sum_k X[r,k] * Wop[o,k] (+ bias[(r / rows_per_sample)*3 + r%3, o]);  trans_w: 0 -> W [Cout,K], 1 -> W [K,Cout] */
 int vnpcc_gemm_rows_fp32(const float* X, long long ldx, const float* W, long long ldw, int trans_w, float* Y,
@@ -121,6 +140,14 @@ int vnpcc_rows_dot(const float* x, long long ldx, const float* w, long long R, i
                    void* stream);
 int vnpcc_rows_dot_bwd(const float* gy, const float* x, long long ldx, const float* w, long long R, int C, float* gx,
                        long long ldgx, float* gw, void* stream);
+
+/* VNStdFeature's invariant-feature step (models/vn_layers.py:197-219): z rows (point, v) x J are the J = 3 (or 2: normalize_frame, Gram-
+ * Schmidt + cross product, eps 1e-6) frame vectors from vn_lin; out rows (point, k) x C = <x[point, c, :], f_k>; zout [P*3, 3] = the frame,
+ * rows (point, k) x component.  _bwd: gx rows (point, v) x C and gz rows (point, v) x J from gout and (optionally) gzout. */
+int vnpcc_vn_frame_fwd(const float* x, long long ldx, const float* z, long long ldz, long long P, int C, int J, float* out,
+                       long long ldo, float* zout, void* stream);
+int vnpcc_vn_frame_bwd(const float* gout, long long ldgo, const float* gzout, const float* x, long long ldx, const float* z,
+                       long long ldz, long long P, int C, int J, float* gx, long long ldgx, float* gz, long long ldgz, void* stream);
 
 /* fused tail VNLinearLeakyReLU -> VNLinear(C,1) (+ residual), models/pcn.py:340-345,387: no [R,C] activation / gradient in HBM */
 int vnpcc_bn_leaky_dot_fwd(const float* p, long long ldp, const float* d, long long ldd, long long P, int C, const float* stat,

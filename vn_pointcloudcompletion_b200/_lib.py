@@ -30,6 +30,12 @@ SIGNATURES = {
     "vnpcc_debug_chamfer_slow_counts": (_i, [_p, _i, _i, _i, _p, _p]),
     "vnpcc_cd_reduce": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "vnpcc_cd_reduce_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vnpcc_cd_persample_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "vnpcc_cd_persample_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "vnpcc_fscore_sq": (_i, [_p, _p, _i, _i, _i, _f, _p, _p]),
+    "vnpcc_nn_counts": (_i, [_p, _i, _i, _i, _p, _p]),
+    "vnpcc_dcd_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p]),
+    "vnpcc_dcd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p, _p]),
     "vnpcc_gemm_rows_fp32": (_i, [_p, _ll, _p, _ll, _i, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _i, _p]),
     "vnpcc_gemm_wgrad_fp32": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
     "vnpcc_transpose": (_i, [_p, _ll, _p, _ll, _i, _i, _p]),
@@ -50,6 +56,8 @@ SIGNATURES = {
     "vnpcc_vn_maxpool_argmax": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _p, _p, _p]),
     "vnpcc_vn_maxpool_gather": (_i, [_p, _ll, _p, _i, _i, _i, _p, _ll, _p]),
     "vnpcc_vn_maxpool_scatter_add": (_i, [_p, _ll, _p, _i, _i, _i, _p, _ll, _p]),
+    "vnpcc_vn_frame_fwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _p, _p]),
+    "vnpcc_vn_frame_bwd": (_i, [_p, _ll, _p, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _p, _ll, _p]),
     "vnpcc_rows_add_sample_bias": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _p]),
     "vnpcc_rows_sample_sum": (_i, [_p, _ll, _i, _i, _i, _p, _ll, _p]),
     "vnpcc_rows_dot": (_i, [_p, _ll, _p, _ll, _i, _p, _p, _p]),

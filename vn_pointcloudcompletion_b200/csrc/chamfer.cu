@@ -554,7 +554,7 @@ static void plan_splits(int B, int N, int M, int* n_qblocks, int* n_splits, int*
         const int sl = ((M + c - 1) / c + GRAN - 1) / GRAN * GRAN;
         const int ns = (M + sl - 1) / sl;
         const long long waves = (groups * ns + slots - 1) / slots;
-        const long long cost = waves * (sl + 256);
+        const long long cost = waves * (sl + (tuning(TUNE_CHAMFER_OVERHEAD) > 0 ? tuning(TUNE_CHAMFER_OVERHEAD) : 256));
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best_ns = ns;

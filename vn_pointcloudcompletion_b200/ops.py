@@ -672,6 +672,43 @@ def linear_maxpool_rows(x, w, wdir, G, N, forced_idx=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# VNStdFeature: frame construction + projection of every channel onto the frame (csrc/vn_frame.cu)
+# ---------------------------------------------------------------------------------------------------------------
+class _VNFrame(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, z):
+        x = _rows2d(x, "x")
+        z = _rows2d(z, "z")
+        R, C = x.shape
+        P = R // 3
+        J = z.shape[1]
+        out = torch.empty((R, C), device=x.device, dtype=torch.float32)
+        zout = torch.empty((R, 3), device=x.device, dtype=torch.float32)
+        call("vnpcc_vn_frame_fwd", ptr(x), _ld(x), ptr(z), _ld(z), P, C, J, ptr(out), C, ptr(zout), stream())
+        ctx.save_for_backward(x, z)
+        return out, zout
+
+    @staticmethod
+    def backward(ctx, gout, gzout):
+        x, z = ctx.saved_tensors
+        R, C = x.shape
+        J = z.shape[1]
+        gout = _rows2d(gout, "grad") if gout is not None else torch.zeros((R, C), device=x.device, dtype=torch.float32)
+        if gzout is not None:
+            gzout = gzout.contiguous()
+        gx = torch.empty((R, C), device=x.device, dtype=torch.float32)
+        gz = torch.empty((R, J), device=x.device, dtype=torch.float32)
+        call("vnpcc_vn_frame_bwd", ptr(gout), _ld(gout), ptr(gzout), ptr(x), _ld(x), ptr(z), _ld(z), R // 3, C, J, ptr(gx), C, ptr(gz), J,
+             stream())
+        return gx, gz
+
+
+def vn_frame(x, z):
+    """x rows (point, v) x C, z rows (point, v) x J (J = 3, or 2 = normalised frame) -> (x_std rows (point, k) x C, frame rows (point, k) x 3)"""
+    return _VNFrame.apply(x, z)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # VNLinear(C -> 1) (+ residual)
 # ---------------------------------------------------------------------------------------------------------------
 class _RowsDot(torch.autograd.Function):

@@ -117,15 +117,32 @@ def rank_seed(base_seed, rank, step=0):
     return base_seed + rank + 1000 * step
 
 
-class FlatAdam:
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (train.py:70: Adam(model.parameters(), lr, betas=(0.9, 0.999))) as ONE fused kernel over flat buffers.
+
+    It IS a torch.optim.Optimizer: `param_groups[0]["lr"]` is what the kernel reads, so torch.optim.lr_scheduler.StepLR (train.py:93)
+    drives it unchanged, and state_dict() / load_state_dict() speak torch.optim.Adam's format ({"state": {index: {"step", "exp_avg",
+    "exp_avg_sq"}}, "param_groups": [...]}), so the reference's optimizer/optim_last.pth (train.py:72-80, 262-277) can be resumed from and
+    is what a checkpoint written here looks like.  Like torch's Adam, parameters that never received a gradient (the two VNMaxPool
+    direction weights) have no state entry.
+
+    Every parameter is rebound as a view of `flat_p` and its .grad as a view of `flat_g`.  Moving the model afterwards (model.to(),
+    .cuda()) or zero_grad(set_to_none=True) through another optimizer would silently detach them: step() checks the bindings and raises."""
+
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        self.params = [p for p in params if p.requires_grad]
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                                      capturable=False, differentiable=False, fused=None))
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam takes one parameter group (the reference uses one)")
+        self.params = self.param_groups[0]["params"]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self._spans = []
         o = 0
         with torch.no_grad():
             for p in self.params:
@@ -133,30 +150,78 @@ class FlatAdam:
                 self.flat_p[o:o + k].copy_(p.reshape(-1))
                 p.data = self.flat_p[o:o + k].view_as(p)
                 p.grad = self.flat_g[o:o + k].view_as(p)
+                self._spans.append((o, k))
                 o += k
-        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self._bound = [(p, p.data_ptr(), p.grad.data_ptr()) for p in self.params]
         self.step_count = 0
+
+    # the hyper-parameters live in the param group (what LR schedulers edit)
+    lr = property(lambda self: self.param_groups[0]["lr"])
+    betas = property(lambda self: self.param_groups[0]["betas"])
+    eps = property(lambda self: self.param_groups[0]["eps"])
+    wd = property(lambda self: self.param_groups[0]["weight_decay"])
 
     def offset_of(self, param):
         """offset of a parameter's view inside the flat buffers"""
         return (param.data_ptr() - self.flat_p.data_ptr()) // 4
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=False):
+        # never set_to_none: the .grad views ARE the flat gradient buffer the exchange and the fused kernel read
         self.flat_g.zero_()
 
-    def step(self, grad_scale=1.0):
+    def _check_bindings(self):
+        for p, dp, gp in self._bound:
+            if p.data_ptr() != dp or p.grad is None or p.grad.data_ptr() != gp:
+                raise RuntimeError("a parameter (or its .grad) no longer aliases FlatAdam's flat buffers: the model was moved / re-created "
+                                   "or its gradients were set to None after the optimizer was built; rebuild the optimizer")
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        loss = closure() if closure is not None else None
+        self._check_bindings()
         self.step_count += 1
         ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                       self.step_count, grad_scale)
+        return loss
 
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v, "lr": self.lr}
+        """torch.optim.Adam's format; exp_avg / exp_avg_sq are copies shaped like their parameters"""
+        self.state.clear()
+        if self.step_count > 0:
+            touched = [bool(self.v[o:o + k].any()) or bool(self.m[o:o + k].any()) for o, k in self._spans]
+            for p, (o, k), t in zip(self.params, self._spans, touched):
+                if t:
+                    self.state[p] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[o:o + k].view_as(p).clone(),
+                                     "exp_avg_sq": self.v[o:o + k].view_as(p).clone()}
+        sd = super().state_dict()
+        self.state.clear()
+        return sd
 
-    def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.m.copy_(sd["exp_avg"])
-        self.v.copy_(sd["exp_avg_sq"])
-        self.lr = sd.get("lr", self.lr)
+    def load_state_dict(self, state_dict):
+        """accepts torch.optim.Adam's format (any torch version: `step` an int or a tensor) and this class's round-1 flat format"""
+        if "exp_avg" in state_dict and "state" not in state_dict:      # round-1 flat format
+            self.step_count = int(state_dict["step"])
+            self.m.copy_(state_dict["exp_avg"])
+            self.v.copy_(state_dict["exp_avg_sq"])
+            if "lr" in state_dict:
+                self.param_groups[0]["lr"] = state_dict["lr"]
+            return
+        super().load_state_dict(state_dict)
+        self.m.zero_()
+        self.v.zero_()
+        steps = []
+        for p, (o, k) in zip(self.params, self._spans):
+            st = self.state.get(p)
+            if st:
+                self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.append(int(float(st["step"])))
+        if steps and min(steps) != max(steps):
+            raise ValueError("parameters with different Adam step counts: FlatAdam keeps one step counter (the reference steps all "
+                             "parameters together)")
+        self.step_count = steps[0] if steps else 0
+        self.state.clear()
+        self.params = self.param_groups[0]["params"]
 
 
 class DataParallelTrainer:
@@ -179,6 +244,42 @@ class DataParallelTrainer:
                 split = self.opt.offset_of(first)
                 plist = [(p, self.opt.offset_of(p), p.numel()) for p in self.opt.params]
                 self.exchange = OverlappedExchange(self.opt.flat_g, plist, split, world_size, process_group)
+
+    def make_scheduler(self, step_size=50, gamma=0.8):
+        """train.py:93: StepLR(optimizer, step_size=50, gamma=0.8); call .step() once per epoch like the reference (train.py:186)"""
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.opt, step_size=step_size, gamma=gamma)
+        return self.scheduler
+
+    def optimizer_checkpoint(self, epoch, best_metrics, best_epoch):
+        """the dict train.py:262-277 saves as optimizer/optim_last.pth (and optim_best.pth)"""
+        return {"epoch": epoch, "optim_state_dict": self.opt.state_dict(), "best_metrics": best_metrics, "best_epoch": best_epoch}
+
+    def load_optimizer_checkpoint(self, ckpt):
+        """resume like train.py:72-82; returns (start_epoch, best_metrics, best_epoch)"""
+        self.opt.load_state_dict(ckpt["optim_state_dict"])
+        return ckpt["epoch"] + 1, ckpt["best_metrics"], ckpt["best_epoch"]
+
+    @torch.no_grad()
+    def evaluate(self, batches):
+        """The validation loop of train.py:199-242 sharded by batch: every rank runs eval-mode forwards over ITS batches
+        (p, c, R-or-None), sums l1_cd(coarse, c) and l1_cd(dense, c) (sum-over-batch metrics, metrics/metric.py:19-23) and the sample
+        count on the device, and ONE all-reduce of three scalars yields the dataset means on every rank: (coarse, dense, total)."""
+        from .loss import l1_cd
+        was_training = self.model.training
+        self.model.eval()
+        dev = self.opt.flat_p.device
+        acc = torch.zeros(3, device=dev, dtype=torch.float64)
+        for p, c, R in batches:
+            coarse, dense = self.model(p, Rotate(R) if R is not None else None)
+            acc[0] += l1_cd(coarse, c)
+            if dense is not None:
+                acc[1] += l1_cd(dense, c)
+            acc[2] += p.shape[0]
+        if self.world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.pg)
+        self.model.train(was_training)
+        coarse_m, dense_m = (acc[0] / acc[2]).item(), (acc[1] / acc[2]).item()
+        return coarse_m, dense_m, coarse_m + dense_m
 
     def train_step(self, p, c, R=None):
         """p [B,2048,3] partial, c [B,16384,3] complete, R [B,3,3] rotation already applied to both (train.py:133-138).

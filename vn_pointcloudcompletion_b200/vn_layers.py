@@ -205,28 +205,11 @@ class VNStdFeature(nn.Module):
         rows, B, sp = to_rows(x)
         z = self.vn1.forward_rows(rows)
         z = self.vn2.forward_rows(z)
-        z0 = from_rows(ops.linear_rows(z, self.vn_lin.weight), B, sp)       # [B, 3|2, 3, *spatial]
-        # The frame algebra below is O(9) per point on a [B,3,3,N] tensor (not defined on the timed path):
-        # it stays in plain tensor ops exactly as the reference writes it (vn_layers.py:197-219).
-        if self.normalize_frame:
-            v1 = z0[:, 0, :]
-            v1_norm = torch.sqrt((v1 * v1).sum(1, keepdims=True))
-            u1 = v1 / (v1_norm + EPS)
-            v2 = z0[:, 1, :]
-            v2 = v2 - (v2 * u1).sum(1, keepdims=True) * u1
-            v2_norm = torch.sqrt((v2 * v2).sum(1, keepdims=True))
-            u2 = v2 / (v2_norm + EPS)
-            u3 = torch.cross(u1, u2, dim=1)
-            z0 = torch.stack([u1, u2, u3], dim=1).transpose(1, 2)
-        else:
-            z0 = z0.transpose(1, 2)
-        if self.dim == 4:
-            x_std = torch.einsum('bijm,bjkm->bikm', x, z0)
-        elif self.dim == 3:
-            x_std = torch.einsum('bij,bjk->bik', x, z0)
-        elif self.dim == 5:
-            x_std = torch.einsum('bijmn,bjkmn->bikmn', x, z0)
-        return x_std, z0
+        zj = ops.linear_rows(z, self.vn_lin.weight)                  # rows (point, v) x J: the J = 3 (2) frame vectors of every point
+        # frame (Gram-Schmidt + cross product when normalize_frame) and the projection of every channel onto it: one kernel each way
+        # (csrc/vn_frame.cu); x_std [B, C, 3 (frame axis k), *spatial], frame [B, 3 (component), 3 (k), *spatial] as the reference returns it
+        x_std, frame = ops.vn_frame(rows, zj)
+        return from_rows(x_std, B, sp), from_rows(frame, B, sp)
 
 
 class VNLayerNorm(nn.Module):
