@@ -204,6 +204,72 @@ def cpu_reference_step(batch, steps, warmup):
                               "what": "oracle/_ref/refpy.zip absent: numpy/OpenBLAS + C/OpenMP restatement, forward + 2 L1-CD + backward (no optimiser)"}
 
 
+def chamfer_leg(dev, sm_mhz, shapes=((16384, 16384), (1024, 16384)), B=32, iters=10, with_cpu=True):
+    """BASELINE.json's second metric, "Chamfer Gpairs/s (% FP32 peak)" (configs[3]): forward and forward+backward (L1) of the Chamfer
+    entry points at the training shapes, next to the reference's OWN kernel recompiled for sm_100a (oracle/_ref cubin, the checker --
+    timed here as the comparator, exactly as SURVEY 8d asks) and the reference's CPU distChamfer on the host cores (bounded: one sample).
+    Gpairs/s = directed pairs of the forward (2 B N M) / forward time.  Two roofline readings, both against 148 SMs x 128 FP32 lanes x the
+    SM clock sampled under load: `pct_fp32_peak_6instr` counts the reference arithmetic's 6 FP32 instructions per pair (SURVEY 8d's
+    definition: > 100 % is possible because the pre-filtered search ranks with 3 FMAs per pair and recomputes the reference arithmetic
+    for the winners only), `pct_fp32_peak_issued` counts the 3 FMA lane-operations per pair the search kernel actually issues."""
+    import torch
+
+    import vn_pointcloudcompletion_b200 as V
+    from oracle import ref_chamfer as RC
+
+    def timeit(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    lanes = 148 * 128 * sm_mhz * 1e6
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = []
+    for N, M in shapes:
+        a = (torch.rand(B, N, 3, device=dev, generator=g) - 0.5).requires_grad_(True)
+        b = torch.rand(B, M, 3, device=dev, generator=g) - 0.5
+        pairs = 2.0 * B * N * M
+        t_f = timeit(lambda: V.chamfer_3DFunction.apply(a.detach(), b), iters)
+
+        def fb():
+            a.grad = None
+            V.cd_loss_L1(a, b).backward()
+        t_fb = timeit(fb, iters)
+        ent = {"shape": f"B={B} N={N} M={M}", "fwd_ms": t_f, "fwd_bwd_l1_ms": t_fb, "gpairs_per_s": pairs / t_f / 1e6,
+               "pct_fp32_peak_6instr": 100 * 6 * pairs / (t_f * 1e-3) / lanes, "pct_fp32_peak_issued": 100 * 3 * pairs / (t_f * 1e-3) / lanes}
+        if RC.available():
+            t_r = timeit(lambda: RC.forward(a.detach(), b), max(2, iters // 3))
+            r, o = RC.forward(a.detach(), b), V.chamfer_3DFunction.apply(a.detach(), b)
+            ent.update({"reference_kernel_fwd_ms": t_r, "reference_kernel_gpairs_per_s": pairs / t_r / 1e6, "speedup_vs_reference_kernel": t_r / t_f,
+                        "bit_identical_to_reference_kernel": bool(all(torch.equal(x, y) for x, y in zip(o, r)))})
+        out.append(ent)
+    cpu = None
+    if with_cpu:
+        try:
+            from oracle import ref_model as RM
+            if RM.available():
+                use_all_host_threads()
+                ref = RM.load("cpu")
+                N, M = shapes[0]
+                ah, bh = torch.rand(1, N, 3) - 0.5, torch.rand(1, M, 3) - 0.5
+                ref.chamfer_python.distChamfer(ah, bh)
+                t0 = time.perf_counter()
+                ref.chamfer_python.distChamfer(ah, bh)
+                dt = time.perf_counter() - t0
+                cpu = {"what": "reference chamfer_python.distChamfer (float64 expansion form), 1 sample", "shape": f"B=1 N={N} M={M}",
+                       "seconds": dt, "gpairs_per_s": 2.0 * N * M / dt / 1e9, "cores": torch.get_num_threads()}
+        except Exception as e:      # a reported side figure must never break the headline line
+            cpu = {"error": repr(e)[:200]}
+    return {"shapes": out, "cpu_distChamfer": cpu, "sm_mhz": sm_mhz}
+
+
 def workload_config(B, world, mode, enc="vn_pointnet", dec="vn_foldingnet"):
     headline = enc == "vn_pointnet" and dec == "vn_foldingnet"
     return {"workload": (f"{enc}_1024+{dec} train step (fwd + L1-CD coarse/dense + bwd + Adam), so3"
@@ -211,6 +277,143 @@ def workload_config(B, world, mode, enc="vn_pointnet", dec="vn_foldingnet"):
             "batch_per_gpu": B, "global_batch": B * world, "n_partial": N_PARTIAL, "n_coarse": N_COARSE,
             "n_dense": N_DENSE, "n_gt": N_GT, "parallelism": f"dp{world}", "gemm_mode": mode,
             "l2": "per-step activations (>10 GB) exceed the 126 MB L2; inputs rotate over a pool"}
+
+
+CHAMFER_METRIC = "chamfer_fwd_gpairs_per_s"
+CHAMFER_SWEEP = [(n, n) for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536)] + [(1024, 16384)]
+
+
+def chamfer_config(world):
+    return {"workload": "Chamfer L1 forward (+ backward reported) at B=32, N=M=16384 (BASELINE configs[3]; the sweep 1k..64k and 1024x16384 "
+                        "rides in `chamfer.shapes`)", "batch_per_gpu": 32, "global_batch": 32 * world, "n": 16384, "m": 16384,
+            "parallelism": f"dp{world} (independent clouds per rank, no collective)",
+            "l2": "xyz inputs are 12.6 MB (L2-resident by design: the search is FP32-issue-bound, not HBM-bound); a 256 MB buffer is "
+                  "written between timed iterations"}
+
+
+def main_chamfer(args, rank, local_rank, world):
+    """--workload chamfer: BASELINE configs[3].  A step = one forward search of B=32 clouds of 16384 x 16384 points."""
+    import torch
+    import torch.distributed as dist
+    N = M = 16384
+    B = 32
+    pairs = 2.0 * B * N * M
+    if args.impl == "reference":
+        # the reference's CPU-capable Chamfer (chamfer_python.distChamfer) on the host cores; bounded sample: one cloud pair per step
+        if rank != 0:
+            return 0
+        from oracle import ref_model as RM
+        cores = use_all_host_threads()
+        ref = RM.load("cpu")
+        a, b = torch.rand(1, N, 3) - 0.5, torch.rand(1, M, 3) - 0.5
+        times = []
+        for it in range(max(0, args.warmup) + max(1, args.steps)):
+            t0 = time.perf_counter()
+            ref.chamfer_python.distChamfer(a, b)
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        sec = sum(times) / len(times)
+        v = 2.0 * N * M / sec / 1e9
+        print(json.dumps({"metric": CHAMFER_METRIC, "value": v, "unit": "Gpairs/s", "n_gpus": args.gpus, "steps": max(1, args.steps),
+                          "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "impl": "reference", "config": chamfer_config(max(1, args.gpus)),
+                          "cpu_baseline": {"value": v, "unit": "Gpairs/s", "cores": cores, "kind": "reference",
+                                           "sample": "1 of the 32 cloud pairs per step; reference chamfer_python.distChamfer (float64 expansion form)"},
+                          "e2e": {"value": v, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    a = torch.rand(B, N, 3, device=dev, generator=g) - 0.5
+    b = torch.rand(B, M, 3, device=dev, generator=g) - 0.5
+    ah, bh = a.cpu().pin_memory(), b.cpu().pin_memory()
+    flush = torch.empty(64 << 20, device=dev, dtype=torch.float32)
+    d1h = torch.empty(B, N).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        flush.zero_()
+        return V.chamfer_3DFunction.apply(a, b)
+
+    def step_e2e():
+        flush.zero_()
+        d1, d2, i1, i2 = V.chamfer_3DFunction.apply(ah.to(dev, non_blocking=True), bh.to(dev, non_blocking=True))
+        d1h.copy_(d1, non_blocking=False)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # the search alone, without the L2 flush writes, for the roofline: CUDA events around each call
+    evs = []
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        V.chamfer_3DFunction.apply(a, b)
+        s1.record()
+        evs.append((s0, s1))
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    kern_ms = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
+    ms = torch.tensor([e0.elapsed_time(e1), kern_ms], device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e3.record()
+    barrier()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        step_ms = float(ms[0].item()) / args.steps
+        kern = float(ms[1].item())
+        sm_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
+        lanes = 148 * 128 * sm_mhz * 1e6
+        line = {"metric": CHAMFER_METRIC, "value": world * pairs / (step_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": chamfer_config(world),
+                "e2e": {"value": world * pairs / (float(ms2.item()) / args.steps * 1e-3) / 1e9, "unit": "Gpairs/s",
+                        "h2d_bytes_per_step": int(ah.numel() + bh.numel()) * 4, "d2h_bytes_per_step": int(d1h.numel()) * 4},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "fp32", "kernel": "nn_prefilter_kernel (+ resolve / exact re-search)", "achieved": pairs / (kern * 1e-3) / 1e9,
+                             "peak": lanes / 6 / 1e9, "unit": "Gpairs/s", "frac": 6 * pairs / (kern * 1e-3) / lanes,
+                             "frac_issued_fma": 3 * pairs / (kern * 1e-3) / lanes, "traffic": None,
+                             "peak_note": "148 SMs x 128 FP32 lanes x SM clock under load / 6 FP32 instructions per directed pair (the reference "
+                                          "arithmetic, SURVEY 8d); frac > 1 is possible because the pre-filtered search ranks with 3 FMAs per pair "
+                                          "(frac_issued_fma = those 3 / the same peak) and recomputes the reference arithmetic for winners only"}}
+        if world == 1:
+            line["chamfer"] = chamfer_leg(dev, sm_mhz, shapes=CHAMFER_SWEEP, iters=5, with_cpu=not args.no_cpu_baseline)
+            cpu = line["chamfer"].get("cpu_distChamfer")
+            if cpu and "gpairs_per_s" in cpu:
+                line["cpu_baseline"] = {"value": cpu["gpairs_per_s"], "unit": "Gpairs/s", "cores": cpu["cores"], "kind": "reference",
+                                        "sample": cpu["what"] + ", " + cpu["shape"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 def main():
@@ -225,7 +428,10 @@ def main():
                     help="encoder (default = BASELINE configs[1]; vn_dgcnn_fps is the SURVEY 8f row f1 network, paired with latent_dim 512)")
     ap.add_argument("--dec", default="vn_foldingnet", choices=["vn_foldingnet", "attention_vn_foldingnet"],
                     help="decoder (attention_vn_foldingnet is the SURVEY 8f row f2 network; needs the vn_pointnet encoder)")
+    ap.add_argument("--workload", default="train", choices=["train", "chamfer"],
+                    help="train = BASELINE configs[1] (default, the headline); chamfer = configs[3], the Chamfer sweep alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chamfer-leg", action="store_true", help="skip the Chamfer Gpairs/s leg of the default run (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
     ap.add_argument("--no-eval", action="store_true", help="skip the inference leg (profiling runs)")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
@@ -235,6 +441,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "chamfer":
+        return main_chamfer(args, rank, local_rank, world)
 
     if args.impl == "reference":
         # the reference's own CPU implementation on this box's host cores, on OUR arm's config / metric / unit; each step is a bounded
@@ -388,6 +596,26 @@ def main():
     eval_ms = float(ms3.item())
     net.train()
 
+    # N > 1: how much of the step the one exchange (gradient all-reduce over NVLink) costs that is NOT hidden behind the backward pass:
+    # the same K steps with the exchange switched off (ranks diverge afterwards -- this is the last leg), max over ranks
+    comm_exposed_ms = None
+    if world > 1:
+        trainer.exchange_off = True
+        if trainer.exchange is not None:
+            trainer.exchange.enabled = False
+        for i in range(2):
+            step_resident(i)
+        barrier()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        for i in range(args.steps):
+            step_resident(i)
+        e7.record()
+        barrier()
+        ms4 = torch.tensor([e6.elapsed_time(e7)], device=dev)
+        dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        comm_exposed_ms = (ms_total - float(ms4.item())) / args.steps
+
     if rank == 0:
         pk = peaks()
         samples = B * world * args.steps
@@ -452,6 +680,10 @@ def main():
                          "what": "eval-mode forward + l1_cd under no_grad (fused VN GEMM epilogue)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_classes": classes,
                 "final_loss": final_loss}
+        if comm_exposed_ms is not None:
+            line["comm_exposed_ms"] = comm_exposed_ms      # ms per step: timed region minus the same steps without the gradient exchange
+        if world == 1 and headline and not args.no_chamfer_leg:
+            line["chamfer"] = chamfer_leg(dev, (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"], with_cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline and headline:
             cb = 1
             sps, sec, info = cpu_reference_step(cb, 1, 1)

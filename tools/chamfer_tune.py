@@ -26,11 +26,11 @@ for (N, M) in [(16384, 16384), (1024, 16384), (2048, 2048), (4096, 4096), (8192,
     a = torch.rand(32, N, 3, device="cuda", generator=g) - 0.5
     b = torch.rand(32, M, 3, device="cuda", generator=g) - 0.5
     res = []
-    for ov in (4, 5, 6, 8):
-        _lib.raw("vnpcc_set_tuning", 5, ov)
+    for ov in (0, 1):
+        _lib.raw("vnpcc_set_tuning", 6, ov)
         plan = (ctypes.c_int * 4)()
         _lib.load().vnpcc_debug_chamfer_plan(32, N, M, plan)
         t = timeit(lambda: V.chamfer_3DFunction.apply(a, b))
-        res.append(f"ctas/SM={ov}: {t:.3f} ms (splits {plan[1]} x {plan[2]}, {2 * 32 * N * M / t / 1e9:.0f} Gpairs/s)")
+        res.append(f"variant={ov}: {t:.3f} ms (splits {plan[1]} x {plan[2]}, {2 * 32 * N * M / t / 1e9:.0f} Gpairs/s)")
     print(f"N={N} M={M}: " + "; ".join(res), flush=True)
-_lib.raw("vnpcc_set_tuning", 5, 0)
+_lib.raw("vnpcc_set_tuning", 6, 0)

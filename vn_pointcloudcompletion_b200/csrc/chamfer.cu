@@ -269,6 +269,7 @@ __global__ void cand_prepare_kernel(const float* __restrict__ xc, int B, int M, 
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *count = 0;
 }
 
+template <int VARIANT>      // 0: packed FFMA2 ranking (two candidates per instruction), 1: scalar FFMA ranking (same roundings, same results)
 __global__ void __launch_bounds__(CH_T) nn_prefilter_kernel(const float* __restrict__ xq, const float* __restrict__ xc, int B,
                                                              int N, int M, float* __restrict__ best_out,
                                                              float* __restrict__ second_out, int* __restrict__ chunk_out,
@@ -327,6 +328,38 @@ __global__ void __launch_bounds__(CH_T) nn_prefilter_kernel(const float* __restr
                 const uint32_t gaddr = tile_addr + (uint32_t)(ch * (CH_CH / 4) * 64);
 #pragma unroll
                 for (int gi = 0; gi < CH_CH / 4; ++gi) {
+                    if (VARIANT == 1) {
+                        const float4 X = tile[ch * (CH_CH / 4) * 4 + gi * 4 + 0], Y = tile[ch * (CH_CH / 4) * 4 + gi * 4 + 1],
+                                     Z = tile[ch * (CH_CH / 4) * 4 + gi * 4 + 2], W = tile[ch * (CH_CH / 4) * 4 + gi * 4 + 3];
+                        float f0[CH_Q], f1[CH_Q], f2[CH_Q], f3[CH_Q];
+#pragma unroll
+                        for (int i = 0; i < CH_Q; ++i) {
+                            const float qz = lo32(az[i]);
+                            f0[i] = __fmaf_rn(qz, Z.x, W.x);
+                            f1[i] = __fmaf_rn(qz, Z.y, W.y);
+                            f2[i] = __fmaf_rn(qz, Z.z, W.z);
+                            f3[i] = __fmaf_rn(qz, Z.w, W.w);
+                        }
+#pragma unroll
+                        for (int i = 0; i < CH_Q; ++i) {
+                            const float qy = lo32(ay[i]);
+                            f0[i] = __fmaf_rn(qy, Y.x, f0[i]);
+                            f1[i] = __fmaf_rn(qy, Y.y, f1[i]);
+                            f2[i] = __fmaf_rn(qy, Y.z, f2[i]);
+                            f3[i] = __fmaf_rn(qy, Y.w, f3[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < CH_Q; ++i) {
+                            const float qx = lo32(ax[i]);
+                            f0[i] = __fmaf_rn(qx, X.x, f0[i]);
+                            f1[i] = __fmaf_rn(qx, X.y, f1[i]);
+                            f2[i] = __fmaf_rn(qx, X.z, f2[i]);
+                            f3[i] = __fmaf_rn(qx, X.w, f3[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < CH_Q; ++i) cmin[i] = fmin3(fmin3(cmin[i], f0[i], f1[i]), f2[i], f3[i]);
+                        continue;
+                    }
                     u64 x01, x23, y01, y23, z01, z23, w01, w23;
                     lds_2x64(gaddr + gi * 64 + 0, x01, x23);
                     lds_2x64(gaddr + gi * 64 + 16, y01, y23);
@@ -642,7 +675,10 @@ static int nn_directed(const float* xq, const float* xc, int B, int N, int M, fl
         int pg = (M + 255) / 256;
         if (pg > 32) pg = 32;
         count_launch(), cand_prepare_kernel<<<dim3(pg, B), 256, 0, st>>>(xc, B, M, cmax2, count);
-        count_launch(), nn_prefilter_kernel<<<grid, CH_T, 0, st>>>(xq, xc, B, N, M, best, second, chunk, n_qblocks, n_splits, split_len);
+        if (tuning(TUNE_CHAMFER_VARIANT) == 1)
+            count_launch(), nn_prefilter_kernel<1><<<grid, CH_T, 0, st>>>(xq, xc, B, N, M, best, second, chunk, n_qblocks, n_splits, split_len);
+        else
+            count_launch(), nn_prefilter_kernel<0><<<grid, CH_T, 0, st>>>(xq, xc, B, N, M, best, second, chunk, n_qblocks, n_splits, split_len);
         count_launch(), nn_resolve2_kernel<<<rgrid, 256, 0, st>>>(xq, xc, B, N, M, best, second, chunk, n_splits, cmax2, dist, idx, count,
                                                                  list);
         count_launch(), nn_exact_list_kernel<<<sms * 4, 256, 0, st>>>(xq, xc, N, M, count, list, dist, idx);

@@ -235,6 +235,7 @@ class DataParallelTrainer:
         # overlap the gradient exchange with the backward pass: the tail bucket starts at the first parameter of the layers that run last
         # in the forward pass (VN_PointNet.mlp, then the decoder); parameters are laid out in module order, so the tail is contiguous
         self.exchange = None
+        self.exchange_off = False
         tail_start = getattr(getattr(model, "encoder", None), "mlp", None)
         if tail_start is None:                 # encoders without a late mlp (VN_DGCNN_fps): the tail is the decoder
             tail_start = getattr(model, "decoder", None)
@@ -290,7 +291,9 @@ class DataParallelTrainer:
         if dense is not None:
             loss = loss + cd_loss_L1(dense, c)
         loss.backward()
-        if self.exchange is not None:
+        if self.exchange_off:          # measurement only (bench.py comm_exposed_ms): the step without its one exchange
+            scale = 1.0
+        elif self.exchange is not None:
             scale = self.exchange.finish()
         else:
             scale = exchange_gradients(self.opt.flat_g, self.world, self.pg)
