@@ -126,6 +126,13 @@ int vnpcc_vn_bn_leaky_bwd1(const float* g, long long ldg, const float* p, long l
 int vnpcc_vn_bn_bwd2(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat,
                      const float* gamma, const float* beta, const double* sums, double count, int training,
                      float* gweight, float* gbias, void* stream);
+/* vnpcc_vn_bn_bwd2 fused with the per-sample bias gradient of the producing GEMM (models/pcn.py:172: the broadcast half of the
+ * concatenation): gbias [B*3, 2C] (zeroed here) = per-sample column sums of the final gp | of gd ([P*3, C], pitch ldgd).
+ * VNPCC_ERR_UNSUPPORTED for shapes the vectorised kernel does not take. */
+int vnpcc_vn_bn_bwd2_sbias(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat,
+                           const float* gamma, const float* beta, const double* sums, double count, int training, float* gweight,
+                           float* gbn_bias, const float* gd, long long ldgd, float* gbias, long long ldgb, long long pts_per_sample,
+                           void* stream);
 /* VNMaxPool over groups of N consecutive points: ws = B*C u64, idx int64 [B,C] */
 int vnpcc_vn_maxpool_argmax(const float* x, long long ldx, const float* d, long long ldd, int B, int N, int C,
                             unsigned long long* ws, long long* idx, void* stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vnpcc_vn_bn_leaky_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p]),
     "vnpcc_vn_bn_leaky_bwd1": (_i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p, _p]),
     "vnpcc_vn_bn_bwd2": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _d, _i, _p, _p, _p]),
+    "vnpcc_vn_bn_bwd2_sbias": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _d, _i, _p, _p, _p, _ll, _p, _ll, _ll, _p]),
     "vnpcc_vn_maxpool_argmax": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _p, _p, _p]),
     "vnpcc_vn_maxpool_gather": (_i, [_p, _ll, _p, _i, _i, _i, _p, _ll, _p]),
     "vnpcc_vn_maxpool_scatter_add": (_i, [_p, _ll, _p, _i, _i, _i, _p, _ll, _p]),

@@ -813,6 +813,25 @@ int vnpcc_vn_bn_bwd2(float* gp, long long ldgp, const float* p, long long ldp, l
     return last_error();
 }
 
+// vnpcc_vn_bn_bwd2 that additionally returns the gradient of the per-sample bias rows of the producing GEMM (the broadcast half of
+// cat([global.expand(N), local]), models/pcn.py:172): gbias [B*3, 2C] (leading dimension ldgb, zeroed here) = per-sample column sums of the
+// final gp (p half) and of gd (d half, [P*3, C] with pitch ldgd, final since bwd1).  VNPCC_ERR_UNSUPPORTED when the vectorised kernel does
+// not take the shape (callers then run vnpcc_vn_bn_bwd2 + vnpcc_rows_sample_sum).
+int vnpcc_vn_bn_bwd2_sbias(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat,
+                           const float* gamma, const float* beta, const double* sums, double count, int training, float* gweight,
+                           float* gbn_bias, const float* gd, long long ldgd, float* gbias, long long ldgb, long long pts_per_sample,
+                           void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 0 || P <= 0 || pts_per_sample <= 0 || P % pts_per_sample != 0) return VNPCC_ERR_UNSUPPORTED;
+    const long long B = P / pts_per_sample;
+    cudaMemset2DAsync(gbias, (size_t)ldgb * sizeof(float), 0, (size_t)2 * C * sizeof(float), (size_t)B * 3, st);
+    if (!try_bn_bwd2_v4_sbias(gp, ldgp, p, ldp, P, C, stat, gamma, beta, sums, count, training, gd, ldgd, gbias, ldgb, pts_per_sample, st))
+        return VNPCC_ERR_UNSUPPORTED;
+    if (gbn_bias) count_launch(), double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gbn_bias, C);
+    if (gweight) count_launch(), double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums + C, gweight, C);
+    return last_error();
+}
+
 // ws: B*C u64.  idx (int64 [B,C]) receives the selections.
 int vnpcc_vn_maxpool_argmax(const float* x, long long ldx, const float* d, long long ldd, int B, int N, int C,
                             unsigned long long* ws, long long* idx, void* stream) {

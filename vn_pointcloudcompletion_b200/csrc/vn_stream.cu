@@ -356,6 +356,37 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_p2_kernel(const float* _
     }
 }
 
+// per-sample column sums for the per-sample-bias gradient (the broadcast half of cat([global.expand(N), local]), models/pcn.py:172):
+// a thread that walks a CONTIGUOUS range of points keeps the running sums of its channels for the current sample in registers and
+// flushes them with fp32 atomics when the sample changes / at the end (1-2 flushes per thread).
+template <int NCH>
+struct SampleAcc {
+    float a[3][NCH];
+    long long cur;
+    __device__ __forceinline__ SampleAcc() : cur(-1) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int l = 0; l < NCH; ++l) a[v][l] = 0.f;
+    }
+    __device__ __forceinline__ void flush(float* __restrict__ gb, size_t ldgb, int c0) {
+        if (cur < 0) return;
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int l = 0; l < NCH; ++l) {
+                atomicAdd(gb + (size_t)(cur * 3 + v) * ldgb + c0 + l, a[v][l]);
+                a[v][l] = 0.f;
+            }
+    }
+    __device__ __forceinline__ void at(long long sample, float* __restrict__ gb, size_t ldgb, int c0) {
+        if (sample != cur) {
+            flush(gb, ldgb, c0);
+            cur = sample;
+        }
+    }
+};
+
 // fused forward tail: y[r] = sum_c leaky(BN(p), d)[r, c] * w2[c] (+ res[r]); block (C/4, 256/(C/4)): one point per block row
 template <bool HAS_BN, bool FAST>
 __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* __restrict__ p, size_t ldp, const float* __restrict__ d,
@@ -427,10 +458,16 @@ __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* _
     }
 }
 
+// SBIAS: each block row walks a contiguous range of points and the thread also accumulates the per-sample column sums of the final gp
+// (its own write) and of the matching channels of gd (final since bwd1; one extra read) = the gradient of the per-sample bias rows
+// [B*3, 2C] = (p half | d half).  Replaces the rows_sample_sum pass that re-read the whole stacked gradient.
+template <bool SBIAS>
 __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp, size_t ldgp, const float* __restrict__ p, size_t ldp,
                                                           long long P, int C, const float* __restrict__ stat,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          const double* __restrict__ sums, double count, int training) {
+                                                          const double* __restrict__ sums, double count, int training,
+                                                          const float* __restrict__ gd, size_t ldgd, float* __restrict__ gbias,
+                                                          size_t ldgb, long long pts_per_sample) {
     const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     if (c0 >= C) return;
     const ChanParams cp = load_params(stat, gamma, beta, C, c0);
@@ -440,12 +477,26 @@ __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp,
         m1[l] = training ? (float)(sums[c0 + l] / count) * cp.gamma[l] : 0.f;
         m2[l] = training ? (float)(sums[C + c0 + l] / count) * cp.gamma[l] : 0.f;
     }
-    const long long stride = (long long)gridDim.y * 8;
-#pragma unroll 2
-    for (long long pt = (long long)blockIdx.y * 8 + threadIdx.y; pt < P; pt += stride) {
+    SampleAcc<4> acc, accd;
+    const long long per = SBIAS ? (P + gridDim.y - 1) / gridDim.y : 0;
+    const long long pt_begin = SBIAS ? (long long)blockIdx.y * per + threadIdx.y : (long long)blockIdx.y * 8 + threadIdx.y;
+    const long long pt_end = SBIAS ? (((long long)blockIdx.y + 1) * per < P ? ((long long)blockIdx.y + 1) * per : P) : P;
+    const long long stride = SBIAS ? 8 : (long long)gridDim.y * 8;
+#pragma unroll 1
+    for (long long pt = pt_begin; pt < pt_end; pt += stride) {
         const V4x3 pr = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
         float* gptr = gp + (size_t)pt * 3 * ldgp + c0;
         V4x3 gv = ld43_rw(gptr, ldgp);
+        if (SBIAS) {
+            const long long smp = pt / pts_per_sample;
+            acc.at(smp, gbias, ldgb, c0);
+            accd.at(smp, gbias, ldgb, C + c0);
+            const V4x3 dv = ld43(gd + (size_t)pt * 3 * ldgd + c0, ldgd);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int l = 0; l < 4; ++l) accd.a[c][l] += dv.v[c][l];
+        }
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const float r = fsqrt_fast(dot3l(pr, pr, l));
@@ -461,9 +512,16 @@ __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp,
             const float sc = nb * rn;
             const float ur = r > 0.f ? dn * frcp(r) : 0.f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gv.v[c][l] = gv.v[c][l] * sc + ur * pr.v[c][l];
+            for (int c = 0; c < 3; ++c) {
+                gv.v[c][l] = gv.v[c][l] * sc + ur * pr.v[c][l];
+                if (SBIAS) acc.a[c][l] += gv.v[c][l];
+            }
         }
         st43(gptr, ldgp, gv);
+    }
+    if (SBIAS) {
+        acc.flush(gbias, ldgb, c0);
+        accd.flush(gbias, ldgb, C + c0);
     }
 }
 
@@ -545,8 +603,20 @@ bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long lo
 bool try_bn_bwd2_v4(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
                     const float* beta, const double* sums, double count, int training, cudaStream_t st) {
     if ((C & 3) || !ok4(gp, ldgp) || !ok4(p, ldp)) return false;
-    count_launch(), bn_bwd2_v4_kernel<<<STREAM_GRID(bn_bwd2_v4_kernel), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
-                                                                             sums, count, training);
+    count_launch(), bn_bwd2_v4_kernel<false><<<STREAM_GRID(bn_bwd2_v4_kernel<false>), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
+                                                                             sums, count, training, nullptr, 0, nullptr, 0, 1);
+    return true;
+}
+
+// bwd2 that also produces the per-sample bias gradient gbias rows (sample, v) x 2C = (sums of gp | sums of gd), zeroed by the caller.
+// Returns false when the shape is not taken.
+bool try_bn_bwd2_v4_sbias(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
+                          const float* beta, const double* sums, double count, int training, const float* gd, long long ldgd, float* gbias,
+                          long long ldgb, long long pts_per_sample, cudaStream_t st) {
+    if ((C & 3) || !ok4(gp, ldgp) || !ok4(p, ldp) || !gd || !ok4(gd, ldgd) || !gbias || pts_per_sample <= 0) return false;
+    count_launch(), bn_bwd2_v4_kernel<true><<<STREAM_GRID(bn_bwd2_v4_kernel<true>), dim3(32, 8), 0, st>>>(gp, (size_t)ldgp, p, (size_t)ldp, P, C, stat, gamma, beta,
+                                                                           sums, count, training, gd, (size_t)ldgd, gbias, (size_t)ldgb,
+                                                                           pts_per_sample);
     return true;
 }
 

@@ -96,6 +96,10 @@ bool try_bn_leaky_bwd1_v4(const float* g, long long ldg, const float* p, long lo
 bool try_bn_bwd2_v4(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
                     const float* beta, const double* sums, double count, int training, cudaStream_t st);
 
+bool try_bn_bwd2_v4_sbias(float* gp, long long ldgp, const float* p, long long ldp, long long P, int C, const float* stat, const float* gamma,
+                          const float* beta, const double* sums, double count, int training, const float* gd, long long ldgd, float* gbias,
+                          long long ldgb, long long pts_per_sample, cudaStream_t st);
+
 bool try_bn_leaky_dot_fwd_v4(const float* p, long long ldp, const float* d, long long ldd, long long P, int C, const float* stat,
                              const float* gamma, const float* beta, float ns, const float* w2, const float* res, float* y,
                              cudaStream_t st);

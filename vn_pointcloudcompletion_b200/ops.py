@@ -282,11 +282,76 @@ def bn_needs_batch_stats(bn, training):
     return bn is not None and (training or bn.running_mean is None)
 
 
+class _LinearBNLeaky(torch.autograd.Function):
+    """out = leaky(BN(x Wf^T + b_p), x Wd^T + b_d) for stacked weights wcat = (Wf ; Wd) as ONE autograd node: the forward is GEMM (+ batch
+    statistics in its epilogue) -> BN + leaky pass; the backward is bwd1 -> bwd2 -> dgrad -> wgrad, and because the node owns all four it
+    can take the per-sample bias gradient out of bwd2 (vnpcc_vn_bn_bwd2_sbias) instead of re-reading the stacked gradient."""
+
+    @staticmethod
+    def forward(ctx, x, wcat, bias, gamma, beta, rows_per_sample, ns, bn, training):
+        x = _rows2d(x, "x")
+        _check(wcat, "weight")
+        if wcat.stride(1) != 1:
+            wcat = wcat.contiguous()
+        if bias is not None:
+            bias = _rows2d(bias, "bias")
+        R = x.shape[0]
+        C = wcat.shape[0] // 2
+        sums = torch.empty(2 * C, device=x.device, dtype=torch.float64) if bn_needs_batch_stats(bn, training) else None
+        pd = gemm_rows(x, wcat, False, bias, rows_per_sample, stats=(sums, C) if sums is not None else None)
+        stat, use_batch = _bn_prepare(pd[:, :C], C, bn, training, R // 3, sums=sums)
+        out = torch.empty((R, C), device=x.device, dtype=torch.float32)
+        if R > 0:
+            call("vnpcc_vn_bn_leaky_fwd", ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), ptr(out), C, R // 3, C, ptr(stat), ptr(gamma), ptr(beta),
+                 float(ns), stream())
+        ctx.save_for_backward(x, wcat, pd, gamma, beta, stat)
+        ctx.cfg = (C, float(ns), bool(use_batch), int(rows_per_sample), bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wcat, pd, gamma, beta, stat = ctx.saved_tensors
+        C, ns, use_batch, rps, has_bias = ctx.cfg
+        g = _rows2d(g, "grad")
+        R = pd.shape[0]
+        P = R // 3
+        dev = pd.device
+        gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        ggamma = torch.empty(C, device=dev, dtype=torch.float32)
+        gbeta = torch.empty(C, device=dev, dtype=torch.float32)
+        gb = None
+        if R > 0:
+            call("vnpcc_vn_bn_leaky_bwd1", ptr(g), _ld(g), ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), ptr(gpd), 2 * C, ptr(gpd[:, C:]), 2 * C, P, C,
+                 ptr(stat), ptr(gamma), ptr(beta), ns, ptr(sums), stream())
+            want_gb = has_bias and ctx.needs_input_grad[2]
+            if want_gb:
+                B = R // rps
+                gb = torch.empty((B * 3, 2 * C), device=dev, dtype=torch.float32)
+                rc = _lib.raw("vnpcc_vn_bn_bwd2_sbias", ptr(gpd), 2 * C, ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ptr(sums),
+                              float(P), 1 if use_batch else 0, ptr(ggamma), ptr(gbeta), ptr(gpd[:, C:]), 2 * C, ptr(gb), 2 * C, rps // 3,
+                              stream())
+                if rc == 10003:
+                    gb = None
+                elif rc != 0:
+                    raise _lib.VnpccError(f"vnpcc_vn_bn_bwd2_sbias failed with code {rc}")
+            if gb is None:
+                call("vnpcc_vn_bn_bwd2", ptr(gpd), 2 * C, ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ptr(sums), float(P),
+                     1 if use_batch else 0, ptr(ggamma), ptr(gbeta), stream())
+                if want_gb:
+                    gb = rows_sample_sum(gpd, R // rps, rps // 3)
+        gx = gemm_rows(gpd, wcat, True) if ctx.needs_input_grad[0] else None
+        gw = gemm_wgrad(gpd, x) if ctx.needs_input_grad[1] else None
+        return gx, gw, gb, ggamma, gbeta, None, None, None, None
+
+
 def linear_bn_leaky_rows(x, wcat, bias, rows_per_sample, bn, training, ns):
     """training-capable VNLinearLeakyReLU on rows with stacked weights wcat [2C, K] = (W_feat ; W_dir) (models/vn_layers.py:60-74):
     ONE GEMM writes (p | d) and, in its epilogue, accumulates the BatchNorm-on-norm batch statistics of p; one streaming pass applies
     BatchNorm + the leaky projection."""
     C = wcat.shape[0] // 2
+    if bn is not None and bn.affine and x.shape[1] > 4 and x.shape[0] > 0:
+        return _LinearBNLeaky.apply(x, wcat, bias, bn.weight, bn.bias, rows_per_sample, ns, bn, training)
     sums = None
     if bn_needs_batch_stats(bn, training):
         sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
@@ -294,9 +359,6 @@ def linear_bn_leaky_rows(x, wcat, bias, rows_per_sample, bn, training, ns):
     return bn_leaky(pd, None, bn, training, ns, stacked=True, sums=sums)
 
 
-# ---------------------------------------------------------------------------------------------------------------
-# VNBatchNorm (+ leaky projection) on rows
-# ---------------------------------------------------------------------------------------------------------------
 def _bn_prepare(p, C, bn, training, count, stats_fn=None, sums=None):
     """returns stat [2C] (mean | invstd) and updates the running buffers in training mode.  stats_fn(sums) may supply
     the per-channel sums (sum n | sum n^2, fp64) itself, or `sums` may already hold them (GEMM epilogue); by default they are
