@@ -104,6 +104,11 @@ int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, lo
 int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long long ldx, float* G, long long ldg,
                           long long R, int Cout, int K, float* workspace, size_t workspace_bytes, void* stream);
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long R, int Cout, int K);
+/* fp32-accurate GEMMs on the TF32 tensor cores ("3xTF32"): x = hi + lo, hi = tf32(x), lo = tf32(x - hi); the three products hi.hi +
+ * lo.hi + hi.lo are ONE vnpcc_gemm_rows_tf32 / vnpcc_gemm_wgrad_tf32 over operands whose contraction axis is tripled.  This writes the
+ * tripled operand: layout 0 = columns [hi | lo | hi] (out [R, 3K]), 1 = columns [hi | hi | lo], 2 = rows [hi ; lo ; hi] (out [3R, K]),
+ * 3 = rows [hi ; hi ; lo].  Pair an activation split 0 (2) with a weight split 1 (3).  Relative error of a product ~2^-21. */
+int vnpcc_split_tf32(const float* x, long long ldx, long long R, int K, float* out, long long ldo, int layout, void* stream);
 /* VNLinearLeakyReLU (models/vn_layers.py:60-74) with BatchNorm-on-norm + leaky projection fused into the tcgen05 GEMM epilogue
  * (no-grad / inference forward: the linear outputs p, d never reach HBM).  Wcat [2C, K] = (W_feat ; W_dir); C % 128 == 0.
  * _stats: per-channel (sum ||p||, sum ||p||^2) in fp64 for training-mode statistics; _apply: out [R, C]. */

@@ -8,7 +8,7 @@ from .eval_metrics import RotateAxisAngle, evaluate_iou, f_score, points_to_voxe
 from .graph_ops import KNN, furthest_point_sample, gather_operation  # noqa: F401
 from .loss import cd_loss_L1, cd_loss_L2, l1_cd, l2_cd  # noqa: F401
 from .model import PCNNet, Rotate, random_rotations  # noqa: F401
-from .ops import get_gemm_mode, set_gemm_mode  # noqa: F401
+from .ops import get_fp32_impl, get_gemm_mode, set_fp32_impl, set_gemm_mode  # noqa: F401
 from .pcn import Attention_VN_FoldingNet, VN_FoldingNet, VN_PointNet  # noqa: F401
 from .vn_layers import (VNBatchNorm, VNLeakyReLU, VNLinear, VNLinearAndLeakyReLU, VNLinearLeakyReLU,  # noqa: F401
                         VNLayerNorm, VNMaxPool, VNStdFeature, mean_pool)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "vnpcc_transpose": (_i, [_p, _ll, _p, _ll, _i, _i, _p]),
     "vnpcc_gemm_rows_tf32": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _p]),
     "vnpcc_gemm_rows_tf32_stats": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _p, _i, _p]),
+    "vnpcc_split_tf32": (_i, [_p, _ll, _ll, _i, _p, _ll, _i, _p]),
     "vnpcc_gemm_wgrad_tf32": (_i, [_p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _p, _sz, _p]),
     "vnpcc_gemm_wgrad_tf32_workspace_bytes": (_sz, [_ll, _i, _i]),
     "vnpcc_gemm_vn_stats": (_i, [_p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _ll, _p, _p]),

@@ -126,11 +126,54 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// ---- 3xTF32 operand split --------------------------------------------------------------------------------------
+// fp32-accurate GEMMs on the TF32 tensor cores: x = hi + lo with hi = tf32(x) (round to nearest, 11 significant bits) and lo = tf32(x - hi)
+// (x - hi is exact in fp32).  x . w = hi_x hi_w + lo_x hi_w + hi_x lo_w + O(2^-22 |x||w|): three TF32 products accumulated in fp32.  The
+// three products are ONE ordinary TF32 GEMM over operands whose contraction axis is tripled -- [hi | lo | hi] against [hi | hi | lo] -- so
+// the tcgen05 kernels run unchanged; this kernel writes the tripled operand.
+//   layout 0: columns  out[r, 0:K] = hi, [K:2K] = lo, [2K:3K] = hi        layout 1: columns  hi | hi | lo
+//   layout 2: rows     out[0:R] = hi, [R:2R] = lo, [2R:3R] = hi           layout 3: rows     hi ; hi ; lo      (reduction over rows: wgrad)
+__device__ __forceinline__ float to_tf32(float x) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, size_t ldx, long long R, int K, float* __restrict__ out,
+                                                          size_t ldo, int layout) {
+    const long long total = R * (long long)K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        const int k = (int)(i - r * K);
+        const float v = __ldg(x + (size_t)r * ldx + k);
+        const float hi = to_tf32(v);
+        const float lo = to_tf32(v - hi);
+        const float a = hi, b = (layout & 1) ? hi : lo, c = (layout & 1) ? lo : hi;
+        if (layout < 2) {
+            float* o = out + (size_t)r * ldo + k;
+            o[0] = a;
+            o[K] = b;
+            o[2 * K] = c;
+        } else {
+            out[(size_t)r * ldo + k] = a;
+            out[(size_t)(r + R) * ldo + k] = b;
+            out[(size_t)(r + 2 * R) * ldo + k] = c;
+        }
+    }
+}
+
 }  // namespace vnpcc
 
 using namespace vnpcc;
 
 extern "C" {
+
+int vnpcc_split_tf32(const float* x, long long ldx, long long R, int K, float* out, long long ldo, int layout, void* stream) {
+    if (R <= 0 || K <= 0) return 0;
+    if (layout < 0 || layout > 3) return VNPCC_ERR_BAD_ARG;
+    count_launch(), split_tf32_kernel<<<grid_for((size_t)R * K, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, (size_t)ldx, R, K, out,
+                                                                                                        (size_t)ldo, layout);
+    return last_error();
+}
 
 int vnpcc_abi_version(void) { return 1; }
 void vnpcc_set_fast_math(int on) { g_fast_math = on != 0; }

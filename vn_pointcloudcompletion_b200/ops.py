@@ -37,6 +37,31 @@ def get_gemm_mode():
     return _GEMM_MODE
 
 
+# how the parity mode ("fp32") contracts: "tf32x3" = fp32-accurate on the tensor cores (operands split into TF32 hi + lo parts, three
+# products accumulated in fp32: relative error ~2^-21 per product; csrc/misc.cu split_tf32_kernel + the ordinary tcgen05 GEMM kernels over
+# a tripled contraction axis) wherever the tensor-core kernels take the shape, else "simt" = fp32 FMAs (csrc/gemm_simt.cu)
+_FP32_IMPL = "tf32x3"
+
+
+def set_fp32_impl(impl):
+    global _FP32_IMPL
+    if impl not in ("tf32x3", "simt"):
+        raise ValueError(impl)
+    _FP32_IMPL = impl
+
+
+def get_fp32_impl():
+    return _FP32_IMPL
+
+
+def _split3(t, layout):
+    """tripled TF32 operand of a [R, K] matrix (see vnpcc_split_tf32)"""
+    R, K = t.shape
+    out = torch.empty((R, 3 * K) if layout < 2 else (3 * R, K), device=t.device, dtype=torch.float32)
+    call("vnpcc_split_tf32", ptr(t), _ld(t), R, K, ptr(out), _ld(out), layout, stream())
+    return out
+
+
 # optional kernel-class timer (bench.py): an object with .start(cls, work) -> token and .stop(token); CUDA events on
 # the launching stream, so it adds no synchronisation
 _TIMER = None
@@ -159,6 +184,20 @@ def _gemm_rows_launch(x, w, trans_w, bias, rows_per_sample, out, accumulate, R, 
             return out
         if rc != 10003:   # VNPCC_ERR_UNSUPPORTED -> shape not taken by the tensor-core kernel
             raise _lib.VnpccError(f"vnpcc_gemm_rows_tf32 failed with code {rc}")
+    if _GEMM_MODE == "fp32" and _FP32_IMPL == "tf32x3" and not accumulate and K >= 32 and K % 4 == 0 and Cout >= 64 and R >= 64:
+        wt = w
+        if trans_w:
+            wt = torch.empty((Cout, K), device=w.device, dtype=torch.float32)
+            call("vnpcc_transpose", ptr(w), _ld(w), ptr(wt), K, K, Cout, stream())
+        if _ld(x) % 4 == 0 and x.data_ptr() % 16 == 0:
+            x3, w3 = _split3(x, 0), _split3(wt, 1)
+            rc = _lib.raw("vnpcc_gemm_rows_tf32", ptr(x3), 3 * K, ptr(w3), 3 * K, ptr(out), _ld(out), R, 3 * K, Cout, ptr(bias),
+                          _ld(bias) if bias is not None else 0, rows_per_sample, stream())
+            if rc == 0:
+                _LAST_KERNEL[0] = "gemm_rows_tf32x3"
+                return out
+            if rc != 10003:
+                raise _lib.VnpccError(f"vnpcc_gemm_rows_tf32 (3xTF32) failed with code {rc}")
     _LAST_KERNEL[0] = "sgemm_fp32"
     call("vnpcc_gemm_rows_fp32", ptr(x), _ld(x), ptr(w), _ld(w), 1 if trans_w else 0, ptr(out), _ld(out), R, K, Cout,
          ptr(bias), _ld(bias) if bias is not None else 0, rows_per_sample, 1 if accumulate else 0, stream())
@@ -218,6 +257,15 @@ def _gemm_wgrad_launch(dy, x, out, accumulate, R, Cout, K):
             return out
         if rc != 10003:
             raise _lib.VnpccError(f"vnpcc_gemm_wgrad_tf32 failed with code {rc}")
+    if (_GEMM_MODE == "fp32" and _FP32_IMPL == "tf32x3" and not accumulate and R >= 256 and Cout >= 32 and K >= 32 and Cout % 4 == 0
+            and K % 4 == 0 and 3 * R < (1 << 31)):
+        dy3, x3 = _split3(dy, 2), _split3(x, 3)
+        rc = _lib.raw("vnpcc_gemm_wgrad_tf32", ptr(dy3), Cout, ptr(x3), K, ptr(out), _ld(out), 3 * R, Cout, K, None, 0, stream())
+        if rc == 0:
+            _LAST_KERNEL[0] = "gemm_wgrad_tf32x3"
+            return out
+        if rc != 10003:
+            raise _lib.VnpccError(f"vnpcc_gemm_wgrad_tf32 (3xTF32) failed with code {rc}")
     _LAST_KERNEL[0] = "sgemm_fp32"
     call("vnpcc_gemm_wgrad_fp32", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(out), _ld(out), R, Cout, K, 1 if accumulate else 0,
          stream())
