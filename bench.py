@@ -422,7 +422,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
-    ap.add_argument("--mode", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "fp32", "fp32x3"],
+                    help="tf32 = BASELINE configs[1] (fp32/TF32); fp32x3 = fp32-accurate 3xTF32 tensor-core GEMMs; fp32 = SIMT parity mode")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--enc", default="vn_pointnet", choices=["vn_pointnet", "vn_dgcnn_fps"],
                     help="encoder (default = BASELINE configs[1]; vn_dgcnn_fps is the SURVEY 8f row f1 network, paired with latent_dim 512)")
@@ -672,7 +673,7 @@ def main():
             roof["kernel"] = top
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if args.mode == "tf32" else "f32", "data": "synthetic",
+                "dtype": "tf32" if args.mode == "tf32" else ("f32 (3xTF32 GEMMs)" if args.mode == "fp32x3" else "f32"), "data": "synthetic",
                 "config": workload_config(B, world, args.mode, args.enc, args.dec),
                 "e2e": {"value": (samples / (e2e_ms / 1e3)) if not args.no_e2e else None, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},

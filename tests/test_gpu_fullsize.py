@@ -35,6 +35,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {  # mode: (value rel-L2, value max / scale, loss rel, grad rel-L2, grad max / max|ref|)
     "fp32": (1e-4, 1e-4, 1e-4, 5e-3, 2e-2),
+    "fp32x3": (1e-4, 1e-4, 1e-4, 5e-3, 2e-2),      # 3xTF32 tensor-core GEMMs: the north star's fp32 tolerance (1e-4 relative)
     "tf32": (1.5e-2, 3e-2, 1e-2, 1.5e-1, 1.0),
 }
 
@@ -64,7 +65,7 @@ def _restore_mode():
     V.set_gemm_mode("fp32")
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "tf32"])
 @pytest.mark.parametrize("B", [6])
 def test_full_size_train_step_vs_unmodified_reference(B, mode):
     import vn_pointcloudcompletion_b200 as V
@@ -81,7 +82,7 @@ def test_full_size_train_step_vs_unmodified_reference(B, mode):
     flips1 = (own1 != ref["idx1"]).float().mean().item()
     flips2 = (own2 != ref["idx2"]).float().mean().item()
     print(f"[{mode}] own VNMaxPool selections differing from the reference's: maxpool1 {100 * flips1:.2f} %, maxpool2 {100 * flips2:.2f} %")
-    assert flips1 < (0.02 if mode == "fp32" else 0.10), flips1       # near-ties only (TF32 direction GEMM: 49/1024 measured there)
+    assert flips1 < (0.10 if mode == "tf32" else 0.02), flips1       # near-ties only (TF32 direction GEMM: 49/1024 measured there)
     # the forward above was a training-mode forward: rewind the BatchNorm buffers it updated
     net.load_state_dict({k: v for k, v in _our_net(mode).state_dict().items()})
     net.encoder.maxpool1.forced_idx, net.encoder.maxpool2.forced_idx = ref["idx1"], ref["idx2"]
@@ -94,9 +95,10 @@ def test_full_size_train_step_vs_unmodified_reference(B, mode):
         e2, em = _errs(a, r)
         print(f"[{mode}] {name}: rel-L2 {e2:.3e}, max/scale {em:.3e}")
         assert e2 <= vl2 and em <= max(vmax, 1e-4), (name, e2, em)
-    if mode == "fp32":
-        np.testing.assert_allclose(coarse.detach().cpu().numpy(), ref["coarse"].cpu().numpy(), rtol=1e-4, atol=1e-5)
-        np.testing.assert_allclose(fine.detach().cpu().numpy(), ref["fine"].cpu().numpy(), rtol=1e-4, atol=1e-5)
+    if mode != "tf32":      # element-wise, the north star's "within 1e-4 relative in fp32" (atol for the entries that cross zero)
+        atol = 1e-5 if mode == "fp32" else 5e-5
+        np.testing.assert_allclose(coarse.detach().cpu().numpy(), ref["coarse"].cpu().numpy(), rtol=1e-4, atol=atol)
+        np.testing.assert_allclose(fine.detach().cpu().numpy(), ref["fine"].cpu().numpy(), rtol=1e-4, atol=atol)
     print(f"[{mode}] loss {loss.item():.7f} vs reference {ref['loss']:.7f}")
     assert abs(loss.item() - ref["loss"]) <= lrel * abs(ref["loss"])
     checked, worst = 0, (0.0, "")
@@ -115,7 +117,7 @@ def test_full_size_train_step_vs_unmodified_reference(B, mode):
     for name, buf in net.named_buffers():
         if name.endswith("running_mean") or name.endswith("running_var"):
             e2, _ = _errs(buf, ref["buffers"][name])
-            assert e2 <= (1e-4 if mode == "fp32" else 5e-3), (name, e2)
+            assert e2 <= (5e-3 if mode == "tf32" else 1e-4), (name, e2)
 
 
 def test_reference_tf32_flag_spread():

@@ -232,3 +232,37 @@ def test_gemm_rows_stats_epilogue(tf32_mode, R, K, Cout, Cs, with_bias):
     s2 = torch.empty(2 * Cs, device="cuda", dtype=torch.float64)
     y2 = ops.gemm_rows(x, w, False, bias, rps, stats=(s2, Cs))
     assert torch.equal(y2, y0) and torch.allclose(s2, ref, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("R,K,Cout", [(4096, 256, 256), (96 * 8, 2048, 1024), (30000, 512, 2048), (3000, 128, 512)])
+def test_3xtf32_is_fp32_accurate(R, K, Cout):
+    """'fp32x3' mode: operands split into TF32 hi + lo (vnpcc_split_tf32), three products in one tcgen05 GEMM.  Against float64 the error
+    must be ~1e-5 of the result scale (the tensor core's fp32 accumulator truncates once per K=8 instruction, so it is a little coarser than
+    sequential fp32 FMAs), two orders below plain TF32, for forward, dgrad and wgrad"""
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import ops
+    rng = np.random.RandomState(R + K)
+    x = rng.standard_normal((R, K)).astype(np.float32)
+    w = (rng.standard_normal((Cout, K)) / np.sqrt(K)).astype(np.float32)
+    gy = rng.standard_normal((R, Cout)).astype(np.float32)
+    xd, wd, gd = _dev(x), _dev(w), _dev(gy)
+    ref_y = x.astype(np.float64) @ w.astype(np.float64).T
+    ref_gx = gy.astype(np.float64) @ w.astype(np.float64)
+    ref_gw = gy.astype(np.float64).T @ x.astype(np.float64)
+    errs = {}
+    try:
+        for mode in ("fp32x3", "fp32", "tf32"):
+            V.set_gemm_mode(mode)
+            y = ops.gemm_rows(xd, wd).cpu().numpy()
+            kern = ops._LAST_KERNEL[0]
+            gx = ops.gemm_rows(gd, wd, True).cpu().numpy()
+            gw = ops.gemm_wgrad(gd, xd).cpu().numpy()
+            errs[mode] = (kern, np.abs(y - ref_y).max() / np.abs(ref_y).max(), np.abs(gx - ref_gx).max() / np.abs(ref_gx).max(),
+                          np.abs(gw - ref_gw).max() / np.abs(ref_gw).max())
+    finally:
+        V.set_gemm_mode("fp32")
+    print(errs)
+    k3, e3y, e3x, e3w = errs["fp32x3"]
+    assert k3 == "gemm_rows_tf32x3" and errs["fp32"][0] == "sgemm_fp32" and errs["tf32"][0] == "gemm_rows_tf32"
+    assert e3y < 3e-5 and e3x < 3e-5 and e3w < 3e-5, errs
+    assert errs["tf32"][1] > 20 * e3y          # plain TF32 is far coarser

@@ -25,22 +25,27 @@ _GEMM_MODE = "fp32"      # "fp32": SIMT fp32-exact ; "tf32": tcgen05 tensor core
 
 
 def set_gemm_mode(mode):
-    """'fp32' (parity mode, exact fp32 FMAs) or 'tf32' (tcgen05 tensor cores; SURVEY 8d tolerance applies)."""
-    global _GEMM_MODE
-    if mode not in ("fp32", "tf32"):
+    """'fp32'   parity mode: exact fp32 FMAs (SIMT GEMMs), IEEE sqrt / division -- the mode the 1e-6-level parity tests run in;
+    'fp32x3' parity mode on the tensor cores: every GEMM the tcgen05 kernels take runs as 3xTF32 (operands split into TF32 hi + lo parts,
+             three products accumulated in fp32: ~1e-5 of the result scale, inside the north star's 1e-4), 2.4x the SIMT mode's step rate;
+    'tf32'   throughput mode: tcgen05 TF32 GEMMs + MUFU elementwise kernels (what bench.py times; SURVEY 8d tolerance applies)."""
+    global _GEMM_MODE, _FP32_IMPL
+    if mode not in ("fp32", "fp32x3", "tf32"):
         raise ValueError(mode)
-    _GEMM_MODE = mode
+    _GEMM_MODE = "tf32" if mode == "tf32" else "fp32"
+    _FP32_IMPL = "tf32x3" if mode != "fp32" else "simt"
     _lib.load().vnpcc_set_fast_math(1 if mode == "tf32" else 0)
 
 
 def get_gemm_mode():
-    return _GEMM_MODE
+    return "fp32x3" if (_GEMM_MODE == "fp32" and _FP32_IMPL == "tf32x3") else _GEMM_MODE
 
 
-# how the parity mode ("fp32") contracts: "tf32x3" = fp32-accurate on the tensor cores (operands split into TF32 hi + lo parts, three
-# products accumulated in fp32: relative error ~2^-21 per product; csrc/misc.cu split_tf32_kernel + the ordinary tcgen05 GEMM kernels over
-# a tripled contraction axis) wherever the tensor-core kernels take the shape, else "simt" = fp32 FMAs (csrc/gemm_simt.cu)
-_FP32_IMPL = "tf32x3"
+# how fp32-accurate contractions run: "tf32x3" = on the tensor cores (operands split into TF32 hi + lo parts, three products accumulated
+# in fp32; csrc/misc.cu split_tf32_kernel + the ordinary tcgen05 GEMM kernels over a tripled contraction axis) wherever the tensor-core
+# kernels take the shape, "simt" = fp32 FMAs (csrc/gemm_simt.cu).  Set by set_gemm_mode; `exact=True` GEMMs of the throughput mode (the
+# edge-convolution point GEMM) use tf32x3.
+_FP32_IMPL = "simt"
 
 
 def set_fp32_impl(impl):
