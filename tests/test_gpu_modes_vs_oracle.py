@@ -6,6 +6,8 @@ runs (C = 128 ... 2048; the golden fixtures of tests/golden/vn_layers.npz are to
   "fp32+fast"  exact fp32 GEMMs + the MUFU-reciprocal / rsqrt kernels that the tensor-core mode uses    -- isolates bn_leaky_fwd_p2,
                bn_leaky_bwd1_p2, fold_fwd_p2, fold_bwd_*, bn_leaky_dot_fwd_v4<fast>, ... from TF32 rounding: they must meet the SAME
                tolerance as parity mode
+  "fp32x3"     3xTF32 tensor-core GEMMs (TF32 hi/lo operand split, fp32 accumulation) + IEEE elementwise kernels: the north star's fp32
+               tolerance, 1e-4 relative
   "tf32"       tcgen05 TF32 GEMMs + the fast kernels (what bench.py times), incl. the no-grad fused epilogues gemm_vn_apply / gemm_vn_pool
 
 Reference semantics: models/vn_layers.py:60-74,116-127 (VNLinearLeakyReLU / VNBatchNorm), models/pcn.py:163-184 (VN_PointNet.forward),
@@ -18,9 +20,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["fp32", "fp32+fast", "tf32"]
+MODES = ["fp32", "fp32+fast", "fp32x3", "tf32"]
 # (values rel-L2, values max / scale, gradients rel-L2)
-TOL = {"fp32": (2e-5, 1e-4, 5e-3), "fp32+fast": (2e-5, 1e-4, 5e-3), "tf32": (1.5e-2, 3e-2, 1.5e-1)}       # TF32 tolerance: see tests/test_gpu_fullsize.py
+TOL = {"fp32": (2e-5, 1e-4, 5e-3), "fp32+fast": (2e-5, 1e-4, 5e-3), "fp32x3": (1e-4, 1e-4, 5e-3), "tf32": (1.5e-2, 3e-2, 1.5e-1)}       # TF32 tolerance: see tests/test_gpu_fullsize.py
 
 
 @pytest.fixture(params=MODES)
@@ -28,7 +30,7 @@ def mode(request):
     import vn_pointcloudcompletion_b200 as V
     from vn_pointcloudcompletion_b200 import _lib
     m = request.param
-    V.set_gemm_mode("tf32" if m == "tf32" else "fp32")
+    V.set_gemm_mode(m if m in ("tf32", "fp32x3") else "fp32")
     if m == "fp32+fast":
         _lib.load().vnpcc_set_fast_math(1)
     yield m
