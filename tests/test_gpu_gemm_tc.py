@@ -266,3 +266,45 @@ def test_3xtf32_is_fp32_accurate(R, K, Cout):
     assert k3 == "gemm_rows_tf32x3" and errs["fp32"][0] == "sgemm_fp32" and errs["tf32"][0] == "gemm_rows_tf32"
     assert e3y < 3e-5 and e3x < 3e-5 and e3w < 3e-5, errs
     assert errs["tf32"][1] > 20 * e3y          # plain TF32 is far coarser
+
+
+@pytest.mark.parametrize("P,Cin,C,with_res", [(32 * 40 + 13, 256, 256, True), (5000, 128, 128, False), (7, 256, 128, True), (96 * 33, 256, 256, False)])
+def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
+    """the decoder tail VNLinearLeakyReLU(Cin -> C) -> VNLinear(C, 1) (+ residual), models/pcn.py:340-345,387, as one autograd node: the fused
+    TF32 backward (sums pre-pass + tail_dgrad_tf32_kernel, which forms the final gradient of (p | d) inside the dgrad GEMM) against the
+    unfused kernel sequence (bwd1 -> bwd2 -> dgrad GEMM) on the same saved tensors; ragged point counts included"""
+    import torch.nn as nn
+    from vn_pointcloudcompletion_b200 import ops
+    torch.manual_seed(P + C)
+    R = 3 * P
+    h = torch.randn(R, Cin, device="cuda")
+    wcat = torch.randn(2 * C, Cin, device="cuda") / Cin ** 0.5
+    w2 = torch.randn(1, C, device="cuda") / C ** 0.5
+    res = torch.randn(R, device="cuda") if with_res else None
+    gy = torch.randn(R, device="cuda")
+    out = {}
+    for fused in (True, False):
+        ops._TAIL_FUSED_BWD = fused
+        try:
+            bn = nn.BatchNorm1d(C).cuda().train()
+            with torch.no_grad():
+                bn.weight.copy_(torch.rand(C) + 0.5)
+                bn.bias.copy_(torch.randn(C) * 0.3)
+            hh, ww, w22 = h.clone().requires_grad_(True), wcat.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+            rr = res.clone().requires_grad_(True) if with_res else None
+            y = ops.linear_bn_leaky_dot(hh, ww, bn, True, 0.2, w22, rr)
+            y.backward(gy)
+            kern = ops._LAST_KERNEL[0]
+            out[fused] = (y.detach(), hh.grad, ww.grad, w22.grad, bn.weight.grad, bn.bias.grad, rr.grad if with_res else None, kern)
+        finally:
+            ops._TAIL_FUSED_BWD = True
+    a, b = out[True], out[False]
+    assert torch.equal(a[0], b[0])
+    names = ["y", "gh", "gw", "gw2", "ggamma", "gbeta", "gres"]
+    for i in range(1, 7):
+        if a[i] is None:
+            assert b[i] is None
+            continue
+        rel = float((a[i] - b[i]).norm() / (b[i].norm() + 1e-30))
+        print(names[i], rel)
+        assert rel < 2e-4, (names[i], rel)

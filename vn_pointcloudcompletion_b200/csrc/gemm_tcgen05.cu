@@ -773,6 +773,266 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Fused backward of the decoder tail  VNLinearLeakyReLU(Cin -> C) -> VNLinear(C, 1) (+ residual)  (models/pcn.py:340-345,387), dgrad half:
+//     gh[r, k] = sum_c gpd[r, c] Wcat[c, k],   gpd = (gp | gd) = gradient of the stacked linear output (p | d)
+// Unfused, gpd makes three HBM trips between four kernels (bwd1 writes it, bwd2 rewrites its gp half, the dgrad GEMM and the
+// weight-gradient GEMM read it).  Here the gradient of the layer output is rank one (g[r, c] = gy[r] w2[c]), the BatchNorm-backward sums
+// come from a sums-only pre-pass (vn_stream.cu, bn_leaky_bwd1_p2_kernel<.., STORE = false>), so FINAL gp and gd of a (point, channel)
+// are a function of that point's p, d, gy alone: eight producer warps compute them for 32 points x 32 channels at a time (lane = channel:
+// every global access is a full 128-byte row segment), write them ONCE to HBM (for the weight-gradient GEMM) and, in the K-major
+// SWIZZLE_128B operand layout, to shared memory, from where tcgen05.mma contracts them against Wcat^T (TMA, from L2) into TMEM:
+//     D[k (Cin lanes, MT = Cin / 128 tiles), rows (96 = 32 points)] += Wt[k, c-block] . gpd[rows, c-block]^T     (p half, then d half)
+// HBM traffic of the tail backward: (pd read) + (pd read, gpd written, gh written) instead of 2 pd + 5 gpd-sized transfers + gh.
+// Warp roles: 0 TMA producer (weights), 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue (gh), 8-15 gradient producers.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TB_BN = 96;           // rows per tile = 32 points
+constexpr int TB_PW = 8;            // producer warps (4 points each)
+constexpr int TB_THREADS = 32 * (8 + TB_PW);
+constexpr int TB_SA = 2, TB_SB = 3;
+constexpr int TB_A_HALF = 256 * BK * 4;          // one half (p or d) of a weight stage: up to 256 output rows x 32 channels
+constexpr int TB_B_HALF = TB_BN * BK * 4;        // 96 rows x 32 channels
+struct TailSmem {
+    static constexpr int A_STAGE = 2 * TB_A_HALF;
+    static constexpr int B_STAGE = 2 * TB_B_HALF;
+    static constexpr int B_OFFSET = TB_SA * A_STAGE;
+    static constexpr int BAR_OFFSET = B_OFFSET + TB_SB * B_STAGE;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t sw128_off(int r, int kappa) {      // element (row r, k index kappa < 32) of a K-major SWIZZLE_128B k-block
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kappa >> 2) ^ (r & 7))) << 4) + (kappa & 3) * 4);
+}
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* __restrict__ gy, const float* __restrict__ pd, size_t ldpd,
+                       long long P, int C, int Cin, const float* __restrict__ stat, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float ns, const float* __restrict__ w2, const double* __restrict__ sums, double count,
+                       int training, float* __restrict__ gpd, size_t ldg, float* __restrict__ gh, size_t ldgh, long long num_tiles) {
+    using L = TailSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* a_empty = a_full + TB_SA;
+    uint64_t* b_full = a_empty + TB_SA;
+    uint64_t* b_empty = b_full + TB_SB;
+    uint64_t* t_full = b_empty + TB_SB;
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncb = C / 32;            // channel blocks of the p (and of the d) half
+    const int MT = Cin / 128;          // output-row tiles of 128 TMEM lanes
+    const long long R = P * 3;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&map_wt);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TB_SA; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < TB_SB; ++s) {
+            mbar_init(&b_full[s], TB_PW);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&t_full[a], 1);
+            mbar_init(&t_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            PipeState ps;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int cb = 0; cb < ncb; ++cb) {
+                    mbar_wait(&a_empty[ps.stage], ps.phase ^ 1);
+                    uint8_t* sa = smem + ps.stage * L::A_STAGE;
+                    mbar_expect_tx(&a_full[ps.stage], (uint32_t)(2 * MT * BM * BK * 4));
+                    for (int m = 0; m < MT; ++m) {
+                        tma_load_2d(&map_wt, &a_full[ps.stage], sa + m * (BM * BK * 4), cb * 32, m * BM);                      // p-half columns
+                        tma_load_2d(&map_wt, &a_full[ps.stage], sa + TB_A_HALF + m * (BM * BK * 4), C + cb * 32, m * BM);      // d-half columns
+                    }
+                    ps.advance<TB_SA>();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, TB_BN, 0, 0);
+            PipeState pa, pb;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&t_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                for (int cb = 0; cb < ncb; ++cb) {
+                    mbar_wait(&a_full[pa.stage], pa.phase);
+                    mbar_wait(&b_full[pb.stage], pb.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + pa.stage * L::A_STAGE);
+                    const uint32_t sb = smem_u32(smem + L::B_OFFSET + pb.stage * L::B_STAGE);
+                    for (int m = 0; m < MT; ++m) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256 + m * 128);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                const uint64_t ad = make_desc(sa + half * TB_A_HALF + m * (BM * BK * 4) + k * UMMA_K * 4, 16, 1024);
+                                const uint64_t bd = make_desc(sb + half * TB_B_HALF + k * UMMA_K * 4, 16, 1024);
+                                umma_tf32(d_tmem, ad, bd, idesc, (cb | half | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(&a_empty[pa.stage]);
+                    umma_commit(&b_empty[pb.stage]);
+                    pa.advance<TB_SA>();
+                    pb.advance<TB_SB>();
+                }
+                umma_commit(&t_full[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // epilogue: thread = output channel k of gh (TMEM lane), 32 rows per tcgen05.ld
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long long n0 = tile * TB_BN;
+            mbar_wait(&t_full[acc], acc_phase);
+            tc_fence_after();
+            for (int m = 0; m < MT; ++m) {
+                const int kch = m * BM + quad * 32 + lane;
+                const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + m * 128);
+#pragma unroll 1
+                for (int c0 = 0; c0 < TB_BN; c0 += 32) {
+                    const long long r0 = n0 + c0;
+                    if (r0 >= R) break;
+                    float v[32];
+                    tmem_ld32(t_base + c0, v);
+                    float* dst = gh + (size_t)r0 * ldgh + kch;
+                    if (r0 + 32 <= R) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[(size_t)j * ldgh] = v[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (r0 + j < R) dst[(size_t)j * ldgh] = v[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 8) {
+        // gradient producers: warp pw owns points 4 pw .. 4 pw + 3 of the tile, lane = channel inside the 32-channel block
+        const int pw = warp - 8;
+        const float k1 = 1.f - ns;
+        PipeState pb;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long long pt0 = tile * 32 + pw * 4;
+            float gyv[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int v = 0; v < 3; ++v) gyv[i][v] = (pt0 + i < P) ? __ldg(gy + (size_t)(pt0 + i) * 3 + v) : 0.f;
+            for (int cb = 0; cb < ncb; ++cb) {
+                const int c = cb * 32 + lane;
+                const float mean = __ldg(stat + c), invstd = __ldg(stat + C + c), ga = __ldg(gamma + c), be = __ldg(beta + c), w2c = __ldg(w2 + c);
+                const float m1 = training ? (float)(sums[c] / count) * ga : 0.f;
+                const float m2 = training ? (float)(sums[C + c] / count) * ga : 0.f;
+                // loads of the block first (12 rows in flight per thread), then the arithmetic
+                float pv[4][3], dv[4][3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        const bool ok = pt0 + i < P;
+                        const float* row = pd + (size_t)((pt0 + i) * 3 + v) * ldpd + c;
+                        pv[i][v] = ok ? __ldg(row) : 0.f;
+                        dv[i][v] = ok ? __ldg(row + C) : 0.f;
+                    }
+                mbar_wait(&b_empty[pb.stage], pb.phase ^ 1);      // the MMAs that read this stage have completed
+                uint8_t* sbp = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float p0 = pv[i][0], p1 = pv[i][1], p2 = pv[i][2], d0 = dv[i][0], d1 = dv[i][1], d2 = dv[i][2];
+                    const float pp = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
+                    const float r = pp > 0.f ? pp * rsqrtf(pp) : 0.f;
+                    const float n = r + 1e-6f;
+                    const float rn = __fdividef(1.f, n);
+                    const float nhat = (n - mean) * invstd;
+                    const float nb = fmaf(nhat, ga, be);
+                    const float t = nb * rn;
+                    const float s = t * fmaf(p2, d2, fmaf(p1, d1, p0 * d0));            // <BN(p), d>
+                    const float g0 = gyv[i][0] * w2c, g1 = gyv[i][1] * w2c, g2 = gyv[i][2] * w2c;      // rank-one gradient of the layer output
+                    float e0 = g0, e1 = g1, e2 = g2;      // dL/d BN(p)
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f;   // dL/d d
+                    if (s < 0.f) {
+                        const float rq = __fdividef(1.f, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)) + 1e-6f);
+                        const float a = s * rq;
+                        const float gdq = fmaf(g2, d2, fmaf(g1, d1, g0 * d0)) * rq;
+                        const float c1 = k1 * gdq;
+                        e0 = fmaf(-c1, d0, g0);
+                        e1 = fmaf(-c1, d1, g1);
+                        e2 = fmaf(-c1, d2, g2);
+                        const float ca = -k1 * a, cb2 = -c1 * t, cc = 2.f * a * c1;
+                        q0 = fmaf(cc, d0, fmaf(cb2, p0, ca * g0));
+                        q1 = fmaf(cc, d1, fmaf(cb2, p1, ca * g1));
+                        q2 = fmaf(cc, d2, fmaf(cb2, p2, ca * g2));
+                    }
+                    // BatchNorm-on-norm backward with the batch sums of the pre-pass: final gradient w.r.t. the linear output p
+                    const float gx = fmaf(e2, p2, fmaf(e1, p1, e0 * p0));
+                    const float dnb = gx * rn;
+                    float dn = ga * dnb;
+                    if (training) dn = dn - m1 - nhat * m2;
+                    dn = dn * invstd - gx * nb * rn * rn;
+                    const float ur = r > 0.f ? dn * __fdividef(1.f, r) : 0.f;
+                    const float o0 = fmaf(e0, t, ur * p0), o1 = fmaf(e1, t, ur * p1), o2 = fmaf(e2, t, ur * p2);
+                    const int rr = (pw * 4 + i) * 3;
+                    *reinterpret_cast<float*>(sbp + sw128_off(rr + 0, lane)) = o0;
+                    *reinterpret_cast<float*>(sbp + sw128_off(rr + 1, lane)) = o1;
+                    *reinterpret_cast<float*>(sbp + sw128_off(rr + 2, lane)) = o2;
+                    *reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 0, lane)) = q0;
+                    *reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 1, lane)) = q1;
+                    *reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 2, lane)) = q2;
+                    if (pt0 + i < P) {
+                        float* grow = gpd + (size_t)((pt0 + i) * 3) * ldg + c;
+                        grow[0] = o0;
+                        grow[ldg] = o1;
+                        grow[2 * ldg] = o2;
+                        grow[C] = q0;
+                        grow[ldg + C] = q1;
+                        grow[2 * ldg + C] = q2;
+                    }
+                }
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[pb.stage]);
+                pb.advance<TB_SB>();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // weight gradient:  G[o, k] += sum_{r in chunk} dY[r, o] X[r, k]      (both operands MN-major, split over r)
 //   A = dY^T : MN-major, 4 slabs of {32 o} x BR rows ; B = X : MN-major, BNW/32 slabs of {32 k} x BR rows
 //   (TMA swizzle mode 128B_ATOM_32B <-> UMMA layout SWIZZLE_128B_BASE32B, the pairing tf32 MN-major requires)
@@ -1080,6 +1340,39 @@ int vnpcc_gemm_vn_pool(const float* X, long long ldx, const float* Wcat, long lo
     cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)(R / (3 * N)) * C, st);
     return tc::launch_fused<tc::MODE_POOL, false>(X, ldx, Wcat, ldw, nullptr, 0, R, K, C, nullptr, 0, 3 * N, nullptr, nullptr, nullptr, 0.f,
                                                   reinterpret_cast<double*>(best), st);
+}
+
+// Backward of the fused tail VNLinearLeakyReLU(Cin -> C) -> VNLinear(C, 1) (+ residual) up to the layer input:
+//   sums [2C] / gw2 [C] (fp64, zeroed here): BatchNorm backward sums (-> dgamma = sums[C:], dbeta = sums[:C]) and the tail weight gradient
+//   gpd [P*3, 2C]: final gradient of the stacked linear output (p | d)   (input of the weight-gradient GEMM)
+//   gh  [P*3, Cin]: gradient of the layer input = gpd Wcat, with Wt [Cin, 2C] = Wcat^T
+// pd [P*3, 2C] is the stacked linear output saved by the forward.  C % 32 == 0, Cin in {128, 256}; VNPCC_ERR_UNSUPPORTED otherwise.
+int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long long P, int C, const float* stat, const float* gamma,
+                        const float* beta, float ns, const float* w2, const float* Wt, long long ldwt, int Cin, int training,
+                        double* sums, double* gw2, float* gpd, long long ldgpd, float* gh, long long ldgh, void* stream) {
+    if (P <= 0) return 0;
+    if (C <= 0 || (C & 31) || (Cin != 128 && Cin != 256) || !stat || !gamma || !beta || !w2 || (ldpd & 3) || (ldwt & 3) || !tc::aligned16(pd) ||
+        !tc::aligned16(Wt) || P * 3 >= (1ll << 31))
+        return VNPCC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    cudaMemsetAsync(gw2, 0, sizeof(double) * C, st);
+    if (!try_bn_leaky_dot_sums_v4(gy, pd, ldpd, pd + C, ldpd, P, C, stat, gamma, beta, ns, sums, w2, gw2, st)) return VNPCC_ERR_UNSUPPORTED;
+    CUtensorMap mwt;
+    if (!tc::make_map(&mwt, Wt, Cin, 2 * C, ldwt, tc::BK, tc::BM)) return VNPCC_ERR_DRIVER;
+    static bool attr_done_dev[64] = {false};
+    bool& attr_done = attr_done_dev[current_device_slot()];
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(tc::tail_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmem::TOTAL) != cudaSuccess)
+            return last_error();
+        attr_done = true;
+    }
+    const long long num_tiles = (P + 31) / 32;
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    count_launch(), tc::tail_dgrad_tf32_kernel<<<grid, tc::TB_THREADS, tc::TailSmem::TOTAL, st>>>(
+        mwt, gy, pd, (size_t)ldpd, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gpd, (size_t)ldgpd, gh, (size_t)ldgh,
+        num_tiles);
+    return last_error();
 }
 
 size_t vnpcc_gemm_wgrad_tf32_workspace_bytes(long long, int, int) { return 0; }

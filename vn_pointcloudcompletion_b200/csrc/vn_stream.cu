@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_v4_kernel(const float* _
 // Packed (fp32x2) version of the pass above for the case with a direction (HAS_D): the four channel lanes are two pairs
 // and the backward is expressed through the dot products p.p, p.d, d.d, g.p, g.d (see vn_fused.cu for the formulas), so
 // the `s < 0` branch only selects two scalar coefficients and every vector update is a packed FMA.
-template <bool HAS_BN, bool TAIL>
+// STORE = false: only the per-channel reductions (BatchNorm backward sums, tail weight gradient) are produced -- the sums pre-pass of
+// the fused tail backward (gemm_tcgen05.cu, tail_dgrad_tf32_kernel), which forms gp / gd itself, final, inside the dgrad GEMM.
+template <bool HAS_BN, bool TAIL, bool STORE = true>
 __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_p2_kernel(const float* __restrict__ g, size_t ldg, const float* __restrict__ p,
                                                                    size_t ldp, const float* __restrict__ d, size_t ldd,
                                                                    float* __restrict__ gp, size_t ldgp, float* __restrict__ gd,
@@ -318,10 +320,12 @@ __global__ void __launch_bounds__(256, 2) bn_leaky_bwd1_p2_kernel(const float* _
                     s3[2 * h + 1] += q.v.y;
                 }
             }
+            if (STORE) {
 #pragma unroll
-            for (int v = 0; v < 3; ++v) {
-                *reinterpret_cast<float4*>(gp + ((size_t)pt * 3 + v) * ldgp + c0) = ogp[v];
-                *reinterpret_cast<float4*>(gd + ((size_t)pt * 3 + v) * ldgd + c0) = ogd[v];
+                for (int v = 0; v < 3; ++v) {
+                    *reinterpret_cast<float4*>(gp + ((size_t)pt * 3 + v) * ldgp + c0) = ogp[v];
+                    *reinterpret_cast<float4*>(gd + ((size_t)pt * 3 + v) * ldgd + c0) = ogd[v];
+                }
             }
             if (HAS_BN && ++since_flush == 32) {
 #pragma unroll
@@ -660,6 +664,16 @@ bool try_bn_leaky_dot_bwd1_v4(const float* gy, const float* p, long long ldp, co
     else
         count_launch(), bn_leaky_bwd1_p2_kernel<false, true><<<STREAM_GRID((bn_leaky_bwd1_p2_kernel<false, true>)), block, 0, st>>>(gy, 0, p, (size_t)ldp, d, (size_t)ldd, gp, (size_t)ldgp, gd,
                                                                                  (size_t)ldgd, P, C, stat, gamma, beta, ns, sums, w2, gw2);
+    return true;
+}
+
+// sums pre-pass of the fused tail backward: sums [2C] (sum dnb | sum dnb * nhat) and gw2 [C] accumulated (zeroed by the caller)
+bool try_bn_leaky_dot_sums_v4(const float* gy, const float* p, long long ldp, const float* d, long long ldd, long long P, int C,
+                              const float* stat, const float* gamma, const float* beta, float ns, double* sums, const float* w2, double* gw2,
+                              cudaStream_t st) {
+    if ((C & 3) || !ok4(p, ldp) || !ok4(d, ldd) || d == nullptr || stat == nullptr) return false;
+    count_launch(), bn_leaky_bwd1_p2_kernel<true, true, false><<<STREAM_GRID((bn_leaky_bwd1_p2_kernel<true, true, false>)), dim3(32, 8), 0, st>>>(
+        gy, 0, p, (size_t)ldp, d, (size_t)ldd, nullptr, 0, nullptr, 0, P, C, stat, gamma, beta, ns, sums, w2, gw2);
     return true;
 }
 

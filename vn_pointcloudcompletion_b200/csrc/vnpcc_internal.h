@@ -107,4 +107,8 @@ bool try_bn_leaky_dot_bwd1_v4(const float* gy, const float* p, long long ldp, co
                               float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
                               float ns, double* sums, const float* w2, double* gw2, cudaStream_t st);
 
+bool try_bn_leaky_dot_sums_v4(const float* gy, const float* p, long long ldp, const float* d, long long ldd, long long P, int C,
+                              const float* stat, const float* gamma, const float* beta, float ns, double* sums, const float* w2, double* gw2,
+                              cudaStream_t st);
+
 }  // namespace vnpcc

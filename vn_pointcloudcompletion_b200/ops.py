@@ -550,6 +550,84 @@ class _BNLeakyDot(torch.autograd.Function):
         return gpd, ggamma, gbeta, None, None, None, gw2.view(1, C), (gy if has_res else None)
 
 
+_TAIL_FUSED_BWD = True      # tests switch it off to compare the fused tail backward with the unfused kernel sequence
+
+
+class _LinearBNLeakyDot(torch.autograd.Function):
+    """y[r] = sum_c leaky(BN(h Wf^T), h Wd^T)[r, c] w2[c] (+ res[r]): VNLinearLeakyReLU(Cin -> C) fused with VNLinear(C, 1) and the residual
+    (the decoder tail, models/pcn.py:340-345,387) as ONE autograd node: GEMM (+ batch statistics in its epilogue) -> fused BN + leaky + dot
+    forward; the backward, in TF32 mode, is the sums pre-pass + the fused tcgen05 dgrad kernel (vnpcc_tail_bwd_tf32: the final gradient of
+    (p | d) is formed inside the GEMM and written once) + the weight-gradient GEMM."""
+
+    @staticmethod
+    def forward(ctx, h, wcat, gamma, beta, w2, res, ns, bn, training):
+        h = _rows2d(h, "h")
+        if wcat.stride(1) != 1:
+            wcat = wcat.contiguous()
+        R = h.shape[0]
+        C = wcat.shape[0] // 2
+        sums = torch.empty(2 * C, device=h.device, dtype=torch.float64) if bn_needs_batch_stats(bn, training) else None
+        pd = gemm_rows(h, wcat, stats=(sums, C) if sums is not None else None)
+        stat, use_batch = _bn_prepare(pd[:, :C], C, bn, training, R // 3, sums=sums)
+        w2 = w2.reshape(-1).contiguous()
+        if res is not None:
+            res = res.reshape(-1).contiguous()
+        y = torch.empty(R, device=h.device, dtype=torch.float32)
+        call("vnpcc_bn_leaky_dot_fwd", ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), R // 3, C, ptr(stat), ptr(gamma), ptr(beta), float(ns),
+             ptr(w2), ptr(res), ptr(y), stream())
+        ctx.save_for_backward(h, wcat, pd, gamma, beta, stat, w2)
+        ctx.cfg = (C, float(ns), bool(use_batch), res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        h, wcat, pd, gamma, beta, stat, w2 = ctx.saved_tensors
+        C, ns, use_batch, has_res = ctx.cfg
+        gy = gy.contiguous()
+        R = pd.shape[0]
+        P = R // 3
+        Cin = h.shape[1]
+        dev = pd.device
+        gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        gw2d = torch.empty(C, device=dev, dtype=torch.float64)
+        ggamma = torch.empty(C, device=dev, dtype=torch.float32)
+        gbeta = torch.empty(C, device=dev, dtype=torch.float32)
+        gh = None
+        if _GEMM_MODE == "tf32" and _TAIL_FUSED_BWD and ctx.needs_input_grad[0] and P > 0:
+            wt = torch.empty((Cin, 2 * C), device=dev, dtype=torch.float32)
+            call("vnpcc_transpose", ptr(wcat), _ld(wcat), ptr(wt), 2 * C, 2 * C, Cin, stream())
+            gh = torch.empty((R, Cin), device=dev, dtype=torch.float32)
+            with _Timed("gemm", 2.0 * R * 2 * C * Cin, 4.0 * (2.0 * R * 2 * C + R * Cin)):
+                rc = _lib.raw("vnpcc_tail_bwd_tf32", ptr(gy), ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ns, ptr(w2), ptr(wt),
+                              2 * C, Cin, 1 if use_batch else 0, ptr(sums), ptr(gw2d), ptr(gpd), 2 * C, ptr(gh), Cin, stream())
+                if rc == 0:
+                    _LAST_KERNEL[0] = "tail_dgrad_tf32"
+            if rc == 10003:
+                gh = None
+            elif rc != 0:
+                raise _lib.VnpccError(f"vnpcc_tail_bwd_tf32 failed with code {rc}")
+            else:
+                call("vnpcc_double_to_float", ptr(sums), ptr(gbeta), C, stream())
+                call("vnpcc_double_to_float", ptr(sums[C:]), ptr(ggamma), C, stream())
+        if gh is None:
+            call("vnpcc_bn_leaky_dot_bwd1", ptr(gy), ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), ptr(gpd), 2 * C, ptr(gpd[:, C:]), 2 * C, P, C,
+                 ptr(stat), ptr(gamma), ptr(beta), ns, ptr(sums), ptr(w2), ptr(gw2d), stream())
+            call("vnpcc_vn_bn_bwd2", ptr(gpd), 2 * C, ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ptr(sums), float(P),
+                 1 if use_batch else 0, ptr(ggamma), ptr(gbeta), stream())
+            if ctx.needs_input_grad[0]:
+                gh = gemm_rows(gpd, wcat, True)
+        gw = gemm_wgrad(gpd, h) if ctx.needs_input_grad[1] else None
+        gw2 = torch.empty(C, device=dev, dtype=torch.float32)
+        call("vnpcc_double_to_float", ptr(gw2d), ptr(gw2), C, stream())
+        return gh, gw, ggamma, gbeta, gw2.view(1, C), (gy if has_res else None), None, None, None
+
+
+def linear_bn_leaky_dot(h, wcat, bn, training, ns, w2, res=None):
+    """the decoder tail on rows h [R, Cin] with stacked weights wcat [2C, Cin]; w2 is the [1, C] weight of VNLinear(C, 1)"""
+    return _LinearBNLeakyDot.apply(h, wcat, bn.weight, bn.bias, w2, res, ns, bn, training)
+
+
 def linear_bn_leaky_fused_nograd(x, wcat, bias, rows_per_sample, bn, training, ns):
     """No-grad forward of VNLinearLeakyReLU with BatchNorm-on-norm + leaky projection fused into the tcgen05 GEMM epilogue
     (csrc/gemm_tcgen05.cu, gemm_vn_fused_kernel): p and d never reach HBM.  Returns None when the shape is not taken (the

@@ -136,11 +136,8 @@ class VN_FoldingNet(nn.Module):
         if torch.is_grad_enabled() and l1.map_to_dir.weight.shape[0] == C1 and ops.bn_leaky_dot_supported(C1):
             # final_conv[1] (BN + leaky) fused with final_conv[2] = VNLinear(256,1) and the residual: its [R,256] output
             # and gradient never touch HBM
-            sums = (torch.empty(2 * C1, device=dev, dtype=torch.float64)
-                    if ops.bn_needs_batch_stats(l1.batchnorm.bn, l1.training) else None)
-            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0),
-                                  stats=(sums, C1) if sums is not None else None)      # BatchNorm statistics from the GEMM epilogue
-            fine = ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, local[:, 1], sums=sums)
+            fine = ops.linear_bn_leaky_dot(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0), l1.batchnorm.bn, l1.training,
+                                           l1.negative_slope, l2.map_to_feat.weight, local[:, 1])
         else:
             h = l1.forward_rows(h)      # no-grad: BN + leaky fused into the tcgen05 GEMM epilogue (vn_layers.VNLinearLeakyReLU)
             fine = ops.rows_dot(h, l2.map_to_feat.weight, local[:, 1])                     # final VNLinear(256,1) + point_feat
@@ -204,11 +201,8 @@ class Attention_VN_FoldingNet(nn.Module):
             h = ops.linear_bn_leaky_rows(local, wcat[:, :1], bias, 3 * S, l0.batchnorm.bn, l0.training, l0.negative_slope)
         C1 = l1.map_to_feat.weight.shape[0]
         if torch.is_grad_enabled() and ops.bn_leaky_dot_supported(C1):
-            sums = (torch.empty(2 * C1, device=h.device, dtype=torch.float64)
-                    if ops.bn_needs_batch_stats(l1.batchnorm.bn, l1.training) else None)
-            pd1 = ops.linear_rows(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0),
-                                  stats=(sums, C1) if sums is not None else None)
-            return ops.bn_leaky_dot(pd1, l1.batchnorm.bn, l1.training, l1.negative_slope, l2.map_to_feat.weight, res, sums=sums)
+            return ops.linear_bn_leaky_dot(h, torch.cat([l1.map_to_feat.weight, l1.map_to_dir.weight], dim=0), l1.batchnorm.bn, l1.training,
+                                           l1.negative_slope, l2.map_to_feat.weight, res)
         h = l1.forward_rows(h)
         return ops.rows_dot(h, l2.map_to_feat.weight, res)
 
