@@ -282,14 +282,15 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
     w2 = torch.randn(1, C, device="cuda") / C ** 0.5
     res = torch.randn(R, device="cuda") if with_res else None
     gy = torch.randn(R, device="cuda")
+    bw, bb = torch.rand(C) + 0.5, torch.randn(C) * 0.3
     out = {}
     for fused in (True, False):
         ops._TAIL_FUSED_BWD = fused
         try:
             bn = nn.BatchNorm1d(C).cuda().train()
             with torch.no_grad():
-                bn.weight.copy_(torch.rand(C) + 0.5)
-                bn.bias.copy_(torch.randn(C) * 0.3)
+                bn.weight.copy_(bw)
+                bn.bias.copy_(bb)
             hh, ww, w22 = h.clone().requires_grad_(True), wcat.clone().requires_grad_(True), w2.clone().requires_grad_(True)
             rr = res.clone().requires_grad_(True) if with_res else None
             y = ops.linear_bn_leaky_dot(hh, ww, bn, True, 0.2, w22, rr)
