@@ -308,4 +308,5 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
             continue
         rel = float((a[i] - b[i]).norm() / (b[i].norm() + 1e-30))
         print(names[i], rel)
-        assert rel < 2e-4, (names[i], rel)
+        # (R < 64: the unfused dgrad falls back to the exact SIMT kernel, so the difference is TF32 operand rounding itself)
+        assert rel < (2e-4 if R >= 64 else 3e-3), (names[i], rel)

@@ -791,11 +791,13 @@ constexpr int TB_THREADS = 32 * (8 + TB_PW);
 constexpr int TB_SA = 2, TB_SB = 3;
 constexpr int TB_A_HALF = 256 * BK * 4;          // one half (p or d) of a weight stage: up to 256 output rows x 32 channels
 constexpr int TB_B_HALF = TB_BN * BK * 4;        // 96 rows x 32 channels
+constexpr int TB_MAX_C = 256;
 struct TailSmem {
     static constexpr int A_STAGE = 2 * TB_A_HALF;
     static constexpr int B_STAGE = 2 * TB_B_HALF;
     static constexpr int B_OFFSET = TB_SA * A_STAGE;
-    static constexpr int BAR_OFFSET = B_OFFSET + TB_SB * B_STAGE;
+    static constexpr int PAR_OFFSET = B_OFFSET + TB_SB * B_STAGE;      // 7 per-channel parameter rows of TB_MAX_C floats
+    static constexpr int BAR_OFFSET = PAR_OFFSET + 7 * TB_MAX_C * 4;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
@@ -803,19 +805,27 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int kappa) {      // elemen
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kappa >> 2) ^ (r & 7))) << 4) + (kappa & 3) * 4);
 }
 
+// Data path of one (tile, channel block): TMA brings the (p | d) blocks [96 rows x 32 channels] of pd into a B stage (SWIZZLE_128B, the
+// MMA operand layout) -- asynchronously, TB_SB stages deep, so HBM latency is covered by the ring and not by registers --, the producer warps
+// turn them IN PLACE into (gp | gd), the MMA contracts them and a store warp sends the same shared-memory blocks to gpd by bulk tensor stores.
+// Warp roles: 0 TMA loads (weights + pd), 1 MMA issuer, 2 TMEM allocator, 3 TMA stores (gpd), 4-7 epilogue (gh), 8-15 gradient producers.
 __global__ void __launch_bounds__(TB_THREADS, 1)
-tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* __restrict__ gy, const float* __restrict__ pd, size_t ldpd,
-                       long long P, int C, int Cin, const float* __restrict__ stat, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float ns, const float* __restrict__ w2, const double* __restrict__ sums, double count,
-                       int training, float* __restrict__ gpd, size_t ldg, float* __restrict__ gh, size_t ldgh, long long num_tiles) {
+tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_pd,
+                       const __grid_constant__ CUtensorMap map_gpd, const float* __restrict__ gy, long long P, int C, int Cin,
+                       const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
+                       const float* __restrict__ w2, const double* __restrict__ sums, double count, int training, float* __restrict__ gh,
+                       size_t ldgh, long long num_tiles) {
     using L = TailSmem;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_par = reinterpret_cast<float*>(smem + L::PAR_OFFSET);      // [7][TB_MAX_C]: mean, invstd, gamma, beta, w2, m1, m2
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* a_empty = a_full + TB_SA;
-    uint64_t* b_full = a_empty + TB_SA;
-    uint64_t* b_empty = b_full + TB_SB;
-    uint64_t* t_full = b_empty + TB_SB;
+    uint64_t* b_loaded = a_empty + TB_SA;      // TMA: the pd blocks of the stage have landed
+    uint64_t* b_full = b_loaded + TB_SB;       // producers: (gp | gd) written (count TB_PW); waited on by the MMA warp AND the store warp
+    uint64_t* b_empty = b_full + TB_SB;        // MMA: the stage has been read by the tensor core
+    uint64_t* b_stored = b_empty + TB_SB;      // store warp: the stage has been read by its bulk stores
+    uint64_t* t_full = b_stored + TB_SB;
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
@@ -824,21 +834,37 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* 
     const int MT = Cin / 128;          // output-row tiles of 128 TMEM lanes
     const long long R = P * 3;
 
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&map_wt);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_wt);
+        tma_prefetch_desc(&map_pd);
+        tma_prefetch_desc(&map_gpd);
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TB_SA; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < TB_SB; ++s) {
+            mbar_init(&b_loaded[s], 1);
             mbar_init(&b_full[s], TB_PW);
             mbar_init(&b_empty[s], 1);
+            mbar_init(&b_stored[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&t_full[a], 1);
             mbar_init(&t_empty[a], 4);
         }
         fence_barrier_init();
+    }
+    for (int c = threadIdx.x; c < C; c += TB_THREADS) {
+        const float ga = __ldg(gamma + c);
+        s_par[0 * TB_MAX_C + c] = __ldg(stat + c);
+        s_par[1 * TB_MAX_C + c] = __ldg(stat + C + c);
+        s_par[2 * TB_MAX_C + c] = ga;
+        s_par[3 * TB_MAX_C + c] = __ldg(beta + c);
+        s_par[4 * TB_MAX_C + c] = __ldg(w2 + c);
+        s_par[5 * TB_MAX_C + c] = training ? (float)(sums[c] / count) * ga : 0.f;
+        s_par[6 * TB_MAX_C + c] = training ? (float)(sums[C + c] / count) * ga : 0.f;
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -848,17 +874,26 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* 
 
     if (warp == 0) {
         if (lane == 0) {
-            PipeState ps;
+            PipeState pa, pb;
             for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row0 = (int)(tile * TB_BN);
                 for (int cb = 0; cb < ncb; ++cb) {
-                    mbar_wait(&a_empty[ps.stage], ps.phase ^ 1);
-                    uint8_t* sa = smem + ps.stage * L::A_STAGE;
-                    mbar_expect_tx(&a_full[ps.stage], (uint32_t)(2 * MT * BM * BK * 4));
+                    // pd blocks first (HBM latency), then this step's weights (L2)
+                    mbar_wait(&b_empty[pb.stage], pb.phase ^ 1);
+                    mbar_wait(&b_stored[pb.stage], pb.phase ^ 1);
+                    uint8_t* sb = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
+                    mbar_expect_tx(&b_loaded[pb.stage], (uint32_t)L::B_STAGE);
+                    tma_load_2d(&map_pd, &b_loaded[pb.stage], sb, cb * 32, row0);
+                    tma_load_2d(&map_pd, &b_loaded[pb.stage], sb + TB_B_HALF, C + cb * 32, row0);
+                    pb.advance<TB_SB>();
+                    mbar_wait(&a_empty[pa.stage], pa.phase ^ 1);
+                    uint8_t* sa = smem + pa.stage * L::A_STAGE;
+                    mbar_expect_tx(&a_full[pa.stage], (uint32_t)(2 * MT * BM * BK * 4));
                     for (int m = 0; m < MT; ++m) {
-                        tma_load_2d(&map_wt, &a_full[ps.stage], sa + m * (BM * BK * 4), cb * 32, m * BM);                      // p-half columns
-                        tma_load_2d(&map_wt, &a_full[ps.stage], sa + TB_A_HALF + m * (BM * BK * 4), C + cb * 32, m * BM);      // d-half columns
+                        tma_load_2d(&map_wt, &a_full[pa.stage], sa + m * (BM * BK * 4), cb * 32, m * BM);                      // p-half columns
+                        tma_load_2d(&map_wt, &a_full[pa.stage], sa + TB_A_HALF + m * (BM * BK * 4), C + cb * 32, m * BM);      // d-half columns
                     }
-                    ps.advance<TB_SA>();
+                    pa.advance<TB_SA>();
                 }
             }
         }
@@ -898,6 +933,24 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* 
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // gpd leaves from the same shared-memory blocks the MMA reads: two bulk tensor stores per stage (clipped at the tensor bounds)
+        if (lane == 0) {
+            PipeState pb;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row0 = (int)(tile * TB_BN);
+                for (int cb = 0; cb < ncb; ++cb) {
+                    mbar_wait(&b_full[pb.stage], pb.phase);
+                    const uint8_t* sb = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
+                    tma_store_2d(&map_gpd, sb, cb * 32, row0);
+                    tma_store_2d(&map_gpd, sb + TB_B_HALF, C + cb * 32, row0);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                    mbar_arrive(&b_stored[pb.stage]);
+                    pb.advance<TB_SB>();
                 }
             }
         }
@@ -952,25 +1005,20 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* 
                 for (int v = 0; v < 3; ++v) gyv[i][v] = (pt0 + i < P) ? __ldg(gy + (size_t)(pt0 + i) * 3 + v) : 0.f;
             for (int cb = 0; cb < ncb; ++cb) {
                 const int c = cb * 32 + lane;
-                const float mean = __ldg(stat + c), invstd = __ldg(stat + C + c), ga = __ldg(gamma + c), be = __ldg(beta + c), w2c = __ldg(w2 + c);
-                const float m1 = training ? (float)(sums[c] / count) * ga : 0.f;
-                const float m2 = training ? (float)(sums[C + c] / count) * ga : 0.f;
-                // loads of the block first (12 rows in flight per thread), then the arithmetic
-                float pv[4][3], dv[4][3];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) {
-                        const bool ok = pt0 + i < P;
-                        const float* row = pd + (size_t)((pt0 + i) * 3 + v) * ldpd + c;
-                        pv[i][v] = ok ? __ldg(row) : 0.f;
-                        dv[i][v] = ok ? __ldg(row + C) : 0.f;
-                    }
-                mbar_wait(&b_empty[pb.stage], pb.phase ^ 1);      // the MMAs that read this stage have completed
+                const float mean = s_par[c], invstd = s_par[TB_MAX_C + c], ga = s_par[2 * TB_MAX_C + c], be = s_par[3 * TB_MAX_C + c],
+                            w2c = s_par[4 * TB_MAX_C + c], m1 = s_par[5 * TB_MAX_C + c], m2 = s_par[6 * TB_MAX_C + c];
+                mbar_wait(&b_loaded[pb.stage], pb.phase);      // the (p | d) blocks of this stage are in shared memory
                 uint8_t* sbp = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
-#pragma unroll
+#pragma unroll 2
                 for (int i = 0; i < 4; ++i) {
-                    const float p0 = pv[i][0], p1 = pv[i][1], p2 = pv[i][2], d0 = dv[i][0], d1 = dv[i][1], d2 = dv[i][2];
+                    const int rr = (pw * 4 + i) * 3;
+                    float* ap0 = reinterpret_cast<float*>(sbp + sw128_off(rr + 0, lane));
+                    float* ap1 = reinterpret_cast<float*>(sbp + sw128_off(rr + 1, lane));
+                    float* ap2 = reinterpret_cast<float*>(sbp + sw128_off(rr + 2, lane));
+                    float* ad0 = reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 0, lane));
+                    float* ad1 = reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 1, lane));
+                    float* ad2 = reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 2, lane));
+                    const float p0 = *ap0, p1 = *ap1, p2 = *ap2, d0 = *ad0, d1 = *ad1, d2 = *ad2;
                     const float pp = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
                     const float r = pp > 0.f ? pp * rsqrtf(pp) : 0.f;
                     const float n = r + 1e-6f;
@@ -1002,25 +1050,14 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const float* 
                     if (training) dn = dn - m1 - nhat * m2;
                     dn = dn * invstd - gx * nb * rn * rn;
                     const float ur = r > 0.f ? dn * __fdividef(1.f, r) : 0.f;
-                    const float o0 = fmaf(e0, t, ur * p0), o1 = fmaf(e1, t, ur * p1), o2 = fmaf(e2, t, ur * p2);
-                    const int rr = (pw * 4 + i) * 3;
-                    *reinterpret_cast<float*>(sbp + sw128_off(rr + 0, lane)) = o0;
-                    *reinterpret_cast<float*>(sbp + sw128_off(rr + 1, lane)) = o1;
-                    *reinterpret_cast<float*>(sbp + sw128_off(rr + 2, lane)) = o2;
-                    *reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 0, lane)) = q0;
-                    *reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 1, lane)) = q1;
-                    *reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 2, lane)) = q2;
-                    if (pt0 + i < P) {
-                        float* grow = gpd + (size_t)((pt0 + i) * 3) * ldg + c;
-                        grow[0] = o0;
-                        grow[ldg] = o1;
-                        grow[2 * ldg] = o2;
-                        grow[C] = q0;
-                        grow[ldg + C] = q1;
-                        grow[2 * ldg + C] = q2;
-                    }
+                    *ap0 = fmaf(e0, t, ur * p0);
+                    *ap1 = fmaf(e1, t, ur * p1);
+                    *ap2 = fmaf(e2, t, ur * p2);
+                    *ad0 = q0;
+                    *ad1 = q1;
+                    *ad2 = q2;
                 }
-                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the async proxy (tensor core, bulk stores)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b_full[pb.stage]);
                 pb.advance<TB_SB>();
@@ -1351,15 +1388,17 @@ int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long l
                         const float* beta, float ns, const float* w2, const float* Wt, long long ldwt, int Cin, int training,
                         double* sums, double* gw2, float* gpd, long long ldgpd, float* gh, long long ldgh, void* stream) {
     if (P <= 0) return 0;
-    if (C <= 0 || (C & 31) || (Cin != 128 && Cin != 256) || !stat || !gamma || !beta || !w2 || (ldpd & 3) || (ldwt & 3) || !tc::aligned16(pd) ||
-        !tc::aligned16(Wt) || P * 3 >= (1ll << 31))
+    if (C <= 0 || (C & 31) || C > tc::TB_MAX_C || (Cin != 128 && Cin != 256) || !stat || !gamma || !beta || !w2 || (ldpd & 3) || (ldwt & 3) ||
+        (ldgpd & 3) || !tc::aligned16(pd) || !tc::aligned16(Wt) || !tc::aligned16(gpd) || P * 3 >= (1ll << 31))
         return VNPCC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     cudaMemsetAsync(gw2, 0, sizeof(double) * C, st);
     if (!try_bn_leaky_dot_sums_v4(gy, pd, ldpd, pd + C, ldpd, P, C, stat, gamma, beta, ns, sums, w2, gw2, st)) return VNPCC_ERR_UNSUPPORTED;
-    CUtensorMap mwt;
+    CUtensorMap mwt, mpd, mgpd;
     if (!tc::make_map(&mwt, Wt, Cin, 2 * C, ldwt, tc::BK, tc::BM)) return VNPCC_ERR_DRIVER;
+    if (!tc::make_map(&mpd, pd, P * 3, 2 * C, ldpd, tc::BK, tc::TB_BN)) return VNPCC_ERR_DRIVER;
+    if (!tc::make_map(&mgpd, gpd, P * 3, 2 * C, ldgpd, tc::BK, tc::TB_BN)) return VNPCC_ERR_DRIVER;
     static bool attr_done_dev[64] = {false};
     bool& attr_done = attr_done_dev[current_device_slot()];
     if (!attr_done) {
@@ -1370,8 +1409,7 @@ int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long l
     const long long num_tiles = (P + 31) / 32;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
     count_launch(), tc::tail_dgrad_tf32_kernel<<<grid, tc::TB_THREADS, tc::TailSmem::TOTAL, st>>>(
-        mwt, gy, pd, (size_t)ldpd, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gpd, (size_t)ldgpd, gh, (size_t)ldgh,
-        num_tiles);
+        mwt, mpd, mgpd, gy, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gh, (size_t)ldgh, num_tiles);
     return last_error();
 }
 
