@@ -119,6 +119,65 @@ def test_overlapped_exchange_world2():
         assert results[-1][3] == (35, 35 + 24 + 15) and results[-1][4] == [(0, 35)]      # the unused tail parameter is not exchanged
 
 
+def _overlap_mid_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn as nn
+
+    from vn_pointcloudcompletion_b200.trainer import OverlappedExchange
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 4), nn.Tanh(), nn.Linear(4, 3))
+    params = list(net.parameters())
+    flat = torch.zeros(sum(p.numel() for p in params))
+    offs, o = {}, 0
+    for p in params:
+        p.grad = flat[o:o + p.numel()].view_as(p)
+        offs[id(p)] = o
+        o += p.numel()
+    # three buckets: layer 0 (after backward), layer 2 (middle, early), layer 4 (tail, earliest)
+    ex = OverlappedExchange(flat, [(p, offs[id(p)], p.numel()) for p in params], offs[id(net[4].weight)], world,
+                            extra_splits=[offs[id(net[2].weight)]])
+    results = []
+    for step in range(3):
+        x = torch.randn(8, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+        ex.enabled = False
+        flat.zero_()
+        net(x).square().sum().backward()
+        local = flat.clone()
+        ex.enabled = True
+        flat.zero_()
+        net(x).square().sum().backward()
+        early = (ex.work is not None, [m["work"] is not None for m in ex.mid])
+        scale = ex.finish()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        results.append((early, float((flat * scale - sum(gathered) / world).abs().max()), [m["range"] for m in ex.mid], ex.head_ranges))
+    q.put((rank, results))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_exchange_three_buckets_world2():
+    """tail + one middle bucket are reduced during backward, only the bucket of the first-executed layer after it; result = plain mean"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_mid_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, results in out:
+        assert results[0][0] == (False, [])                            # calibration step: nothing early
+        assert results[1][0] == (True, [True]) and results[2][0] == (True, [True])
+        assert all(r[1] < 1e-6 for r in results)
+        assert results[-1][2] == [(35, 35 + 24)] and results[-1][3] == [(0, 35)]
+
+
 def _overlap_fallback_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -38,9 +38,14 @@ class OverlappedExchange:
     the plain exchange: afterwards only the ranges that are written are exchanged.  The graph is static; a step that deviates falls back
     to the plain exchange or fails loudly."""
 
-    def __init__(self, flat_grad, params, split, world_size, process_group=None):
+    def __init__(self, flat_grad, params, split, world_size, process_group=None, extra_splits=()):
+        """extra_splits: offsets below `split` that cut the head into further buckets [s_i, s_{i+1}); each is reduced asynchronously as
+        soon as all of its parameters have received their gradient (backward reaches them in reverse buffer order), so that only the
+        bucket of the FIRST-executed layers -- complete only when backward ends -- is reduced after backward."""
         self.flat = flat_grad
         self.split = int(split)
+        self.extra = sorted(int(x) for x in extra_splits if 0 < int(x) < int(split))
+        self.mid = []                 # after calibration: [{"range": (a, b), "ids": frozenset, "seen": 0, "work": None}], one per extra bucket
         self.world = world_size
         self.pg = process_group
         self.info = {id(p): (int(o), int(n)) for p, o, n in params}
@@ -75,11 +80,22 @@ class OverlappedExchange:
                 # NCCL: the collective is enqueued on the communication stream behind everything the compute stream has done so far
                 a, b = self.tail_range
                 self.work = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            return
+        for m in self.mid:
+            if pid in m["ids"]:
+                m["seen"] += 1
+                if m["seen"] == len(m["ids"]):
+                    a, b = m["range"]
+                    m["work"] = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                return
 
     def finish(self):
         """call after backward(): reduces the head, joins the tail; returns the 1/world scale for the optimiser"""
         fired, work = self.fired, self.work
         self.fired, self.work, self.tail_seen = set(), None, 0
+        mid_works = [m["work"] for m in self.mid]
+        for m in self.mid:
+            m["seen"], m["work"] = 0, None
         if self.world > 1:
             if self.expected is None:          # calibration step: plain exchange, remember who received a gradient
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.pg)
@@ -89,17 +105,31 @@ class OverlappedExchange:
                     spans = [(self.info[i][0], self.info[i][0] + self.info[i][1]) for i in fired]
                     tail = [s for s in spans if s[0] >= self.split]
                     self.tail_range = (min(s[0] for s in tail), max(s[1] for s in tail)) if tail else None
-                    self.head_ranges = self._merge([s for s in spans if s[0] < self.split])
+                    # head buckets: [0, e_0) is reduced after backward, [e_i, e_{i+1}) ... [e_last, split) asynchronously when complete
+                    edges = self.extra + [self.split]
+                    first_edge = edges[0]
+                    self.head_ranges = self._merge([s for s in spans if s[0] < first_edge])
+                    self.mid = []
+                    for lo, hi in zip(edges[:-1], edges[1:]):
+                        ids = frozenset(i for i in fired if lo <= self.info[i][0] < hi)
+                        if ids:
+                            sp = [(self.info[i][0], self.info[i][0] + self.info[i][1]) for i in ids]
+                            self.mid.append({"range": (min(x[0] for x in sp), max(x[1] for x in sp)), "ids": ids, "seen": 0, "work": None})
                     if not tail:
                         self.tail_ids = None
             elif fired != self.expected:
-                if work is not None:
+                if work is not None or any(w is not None for w in mid_works):
                     raise RuntimeError("the set of parameters receiving a gradient changed after the tail bucket was reduced: the "
                                        "autograd graph changed; rebuild the trainer")
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.pg)
             else:
                 for a, b in self.head_ranges:
                     dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.pg)
+                for m, w in zip(self.mid, mid_works):
+                    if w is not None:
+                        w.wait()
+                    else:
+                        dist.all_reduce(self.flat[m["range"][0]:m["range"][1]], op=dist.ReduceOp.SUM, group=self.pg)
                 if work is not None:
                     work.wait()
                 elif self.tail_range is not None:      # no tail hook fired (cannot happen when fired == expected), be safe
@@ -244,7 +274,15 @@ class DataParallelTrainer:
             if first is not None and first.requires_grad:
                 split = self.opt.offset_of(first)
                 plist = [(p, self.opt.offset_of(p), p.numel()) for p in self.opt.params]
-                self.exchange = OverlappedExchange(self.opt.flat_g, plist, split, world_size, process_group)
+                # a second early bucket: VN_PointNet.second_conv[1] (8.4 MB) is complete ~1.5 ms before backward ends; what is left for
+                # after backward is second_conv[0] + first_conv
+                extra = []
+                sc = getattr(getattr(model, "encoder", None), "second_conv", None)
+                if sc is not None and len(sc) > 1:
+                    q = next(iter(sc[1].parameters()), None)
+                    if q is not None and q.requires_grad:
+                        extra.append(self.opt.offset_of(q))
+                self.exchange = OverlappedExchange(self.opt.flat_g, plist, split, world_size, process_group, extra_splits=extra)
 
     def make_scheduler(self, step_size=50, gamma=0.8):
         """train.py:93: StepLR(optimizer, step_size=50, gamma=0.8); call .step() once per epoch like the reference (train.py:186)"""
