@@ -169,14 +169,17 @@ int vnpcc_bn_leaky_dot_bwd1(const float* gy, const float* p, long long ldp, cons
                             float* gd, long long ldgd, long long P, int C, const float* stat, const float* gamma, const float* beta,
                             float ns, double* sums, const float* w2, double* gw2, void* stream);
 int vnpcc_double_to_float(const double* in, float* out, int n, void* stream);
-/* the whole backward of that tail up to the layer input, TF32 mode (csrc/gemm_tcgen05.cu, tail_dgrad_tf32_kernel): a sums-only pre-pass
- * (BatchNorm backward sums -> sums [2C], tail weight gradient -> gw2 [C]; fp64, zeroed here), then ONE tcgen05 kernel whose producer warps
- * form the FINAL gradient gpd [P*3, 2C] of the stacked linear output (p | d) from (pd, gy), write it once (for the weight-gradient GEMM)
- * and feed it from shared memory to the dgrad MMA: gh [P*3, Cin] = gpd Wcat.  Wt [Cin, 2C] = Wcat^T.  C % 32 == 0, Cin in {128, 256};
- * VNPCC_ERR_UNSUPPORTED otherwise (callers then run vnpcc_bn_leaky_dot_bwd1 + vnpcc_vn_bn_bwd2 + vnpcc_gemm_rows_*). */
+/* the whole backward of that tail, TF32 mode (csrc/gemm_tcgen05.cu): a sums-only pre-pass (BatchNorm backward sums -> sums [2C], tail
+ * weight gradient -> gw2 [C]; fp64, zeroed here), then tail_dgrad_tf32_kernel: producer warps form the FINAL gradient gpd of the stacked
+ * linear output (p | d) from (pd, gy) in shared memory and feed it to the dgrad MMA: gh [P*3, Cin] = gpd Wcat (Wt [Cin, 2C] = Wcat^T).
+ * The weight gradient of the stacked weight: either gW != NULL (needs h [P*3, Cin] and C % 128 == 0): tail_wgrad_tf32_kernel forms gpd
+ * on the fly again and accumulates gW [2C, Cin] (zeroed here) -- gpd never exists in HBM, pass gpd = NULL; or gW == NULL: gpd [P*3, 2C]
+ * is written once for vnpcc_gemm_wgrad_tf32.  C % 32 == 0, C <= 256, Cin in {128, 256}; VNPCC_ERR_UNSUPPORTED otherwise (callers then
+ * run vnpcc_bn_leaky_dot_bwd1 + vnpcc_vn_bn_bwd2 + vnpcc_gemm_rows_* + vnpcc_gemm_wgrad_*). */
 int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long long P, int C, const float* stat, const float* gamma,
                         const float* beta, float ns, const float* w2, const float* Wt, long long ldwt, int Cin, int training,
-                        double* sums, double* gw2, float* gpd, long long ldgpd, float* gh, long long ldgh, void* stream);
+                        double* sums, double* gw2, float* gpd, long long ldgpd, float* gh, long long ldgh, const float* h,
+                        long long ldh, float* gW, long long ldgw, void* stream);
 /* VNLinearLeakyReLU with <= 4 local input channels + per-sample bias, never materialising p / d (decoder final_conv[0]):
  * x [B*N*3, K], w [2C, K] (feat | dir), bias [B*3, 2C] or NULL.  See csrc/vn_fused.cu. */
 int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ldw, const float* bias, long long ldb, int B, int N,

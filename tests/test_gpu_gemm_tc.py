@@ -284,8 +284,9 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
     gy = torch.randn(R, device="cuda")
     bw, bb = torch.rand(C) + 0.5, torch.randn(C) * 0.3
     out = {}
-    for fused in (True, False):
-        ops._TAIL_FUSED_BWD = fused
+    for fused in (True, "no-wgrad", False):
+        ops._TAIL_FUSED_BWD = bool(fused)
+        ops._TAIL_FUSED_WGRAD = fused is True
         try:
             bn = nn.BatchNorm1d(C).cuda().train()
             with torch.no_grad():
@@ -299,14 +300,17 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
             out[fused] = (y.detach(), hh.grad, ww.grad, w22.grad, bn.weight.grad, bn.bias.grad, rr.grad if with_res else None, kern)
         finally:
             ops._TAIL_FUSED_BWD = True
-    a, b = out[True], out[False]
-    assert torch.equal(a[0], b[0])
+            ops._TAIL_FUSED_WGRAD = True
+    b = out[False]
     names = ["y", "gh", "gw", "gw2", "ggamma", "gbeta", "gres"]
-    for i in range(1, 7):
+    for key in (True, "no-wgrad"):
+      a = out[key]
+      assert torch.equal(a[0], b[0])
+      for i in range(1, 7):
         if a[i] is None:
             assert b[i] is None
             continue
         rel = float((a[i] - b[i]).norm() / (b[i].norm() + 1e-30))
-        print(names[i], rel)
+        print(key, names[i], rel)
         # (R < 64: the unfused dgrad falls back to the exact SIMT kernel, so the difference is TF32 operand rounding itself)
         assert rel < (2e-4 if R >= 64 else 3e-3), (names[i], rel)

@@ -66,7 +66,7 @@ SIGNATURES = {
     "vnpcc_rows_dot_bwd": (_i, [_p, _p, _ll, _p, _ll, _i, _p, _ll, _p, _p]),
     "vnpcc_bn_leaky_dot_fwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p, _p, _p, _p]),
     "vnpcc_bn_leaky_dot_bwd1": (_i, [_p, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _f, _p, _p, _p, _p]),
-    "vnpcc_tail_bwd_tf32": (_i, [_p, _p, _ll, _ll, _i, _p, _p, _p, _f, _p, _p, _ll, _i, _i, _p, _p, _p, _ll, _p, _ll, _p]),
+    "vnpcc_tail_bwd_tf32": (_i, [_p, _p, _ll, _ll, _i, _p, _p, _p, _f, _p, _p, _ll, _i, _i, _p, _p, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p]),
     "vnpcc_double_to_float": (_i, [_p, _p, _i, _p]),
     "vnpcc_fold_stats": (_i, [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p]),
     "vnpcc_fold_fwd": (_i, [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _p, _p, _f, _p, _ll, _p]),

@@ -809,6 +809,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int kappa) {      // elemen
 // MMA operand layout) -- asynchronously, TB_SB stages deep, so HBM latency is covered by the ring and not by registers --, the producer warps
 // turn them IN PLACE into (gp | gd), the MMA contracts them and a store warp sends the same shared-memory blocks to gpd by bulk tensor stores.
 // Warp roles: 0 TMA loads (weights + pd), 1 MMA issuer, 2 TMEM allocator, 3 TMA stores (gpd), 4-7 epilogue (gh), 8-15 gradient producers.
+template <bool STORE_GPD>      // false: gpd is not written (the weight gradient comes from tail_wgrad_tf32_kernel, which forms it itself)
 __global__ void __launch_bounds__(TB_THREADS, 1)
 tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_pd,
                        const __grid_constant__ CUtensorMap map_gpd, const float* __restrict__ gy, long long P, int C, int Cin,
@@ -880,7 +881,7 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                 for (int cb = 0; cb < ncb; ++cb) {
                     // pd blocks first (HBM latency), then this step's weights (L2)
                     mbar_wait(&b_empty[pb.stage], pb.phase ^ 1);
-                    mbar_wait(&b_stored[pb.stage], pb.phase ^ 1);
+                    if (STORE_GPD) mbar_wait(&b_stored[pb.stage], pb.phase ^ 1);
                     uint8_t* sb = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
                     mbar_expect_tx(&b_loaded[pb.stage], (uint32_t)L::B_STAGE);
                     tma_load_2d(&map_pd, &b_loaded[pb.stage], sb, cb * 32, row0);
@@ -938,7 +939,7 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
         }
     } else if (warp == 3) {
         // gpd leaves from the same shared-memory blocks the MMA reads: two bulk tensor stores per stage (clipped at the tensor bounds)
-        if (lane == 0) {
+        if (lane == 0 && STORE_GPD) {
             PipeState pb;
             for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int row0 = (int)(tile * TB_BN);
@@ -1062,6 +1063,223 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                 if (lane == 0) mbar_arrive(&b_full[pb.stage]);
                 pb.advance<TB_SB>();
             }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused backward of the decoder tail, weight-gradient half:  gW[c, k] = sum_r gpd[r, c] h[r, k]  with gpd formed on the fly, so that the
+// stacked gradient (p | d) never exists in HBM.  Same producers as tail_dgrad_tf32_kernel, MN-major operands as gemm_wgrad_tf32_kernel:
+// a stage is 24 rows (8 whole points); TMA (swizzle 128B_ATOM_32B) brings the (p | d) slabs [24 rows x 32 channels] x 4 of this CTA's 128
+// channels and the eight 32-channel slabs of h; the producer warps turn (p | d) into (gp | gd) IN PLACE (UMMA layout SWIZZLE_128B_BASE32B:
+// 32-byte chunk index XOR (row mod 4)); tcgen05.mma accumulates gp^T h and gd^T h (M = 128 channels each, N = Cin, K = 24 rows) in the 512
+// TMEM columns over the CTA's whole row range; the epilogue adds the two tiles into gW with fp32 red.add.
+// Grid: (C / 128 channel groups, row splits).  Warp roles: 0 TMA, 1 MMA, 2 TMEM allocator, 4-7 epilogue, 8-15 producers (warp = point).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TW_BR = 24;                        // rows per stage = 8 points
+constexpr int TW_SLAB = TW_BR * 128;             // one 32-channel slab of a stage
+constexpr int TW_STAGES = 4;
+struct TailWSmem {
+    static constexpr int A_HALF = 4 * TW_SLAB;             // 128 channels of p (or d)
+    static constexpr int B_BYTES = 8 * TW_SLAB;            // up to 256 channels of h
+    static constexpr int STAGE = 2 * A_HALF + B_BYTES;     // 48 KB
+    static constexpr int PAR_OFFSET = TW_STAGES * STAGE;
+    static constexpr int BAR_OFFSET = PAR_OFFSET + 7 * 128 * 4;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t sw32_off(int r, int c) {      // element (row r, channel c < 32) of an MN-major SWIZZLE_128B_BASE32B slab
+    return (uint32_t)(r * 128 + ((((c >> 3) ^ (r & 3))) << 5) + (c & 7) * 4);
+}
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+tail_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_pd, const __grid_constant__ CUtensorMap map_h, const float* __restrict__ gy,
+                       long long P, int C, int Cin, const float* __restrict__ stat, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float ns, const float* __restrict__ w2, const double* __restrict__ sums, double count,
+                       int training, float* __restrict__ gW, size_t ldgw, long long pts_per_split) {
+    using L = TailWSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_par = reinterpret_cast<float*>(smem + L::PAR_OFFSET);      // [7][128]
+    uint64_t* loaded = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* full = loaded + TW_STAGES;
+    uint64_t* empty = full + TW_STAGES;
+    uint64_t* t_full = empty + TW_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = blockIdx.x;                    // channels [cg * 128, cg * 128 + 128) of both halves
+    const long long pt_begin = (long long)blockIdx.y * pts_per_split;
+    const long long pt_end = pt_begin + pts_per_split < P ? pt_begin + pts_per_split : P;
+    const int num_st = pt_end > pt_begin ? (int)((pt_end - pt_begin + 7) / 8) : 0;
+    const int nslab_h = Cin / 32;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_pd);
+        tma_prefetch_desc(&map_h);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TW_STAGES; ++s) {
+            mbar_init(&loaded[s], 1);
+            mbar_init(&full[s], TB_PW);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&t_full[0], 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 128; i += TB_THREADS) {
+        const int c = cg * 128 + i;
+        const float ga = __ldg(gamma + c);
+        s_par[0 * 128 + i] = __ldg(stat + c);
+        s_par[1 * 128 + i] = __ldg(stat + C + c);
+        s_par[2 * 128 + i] = ga;
+        s_par[3 * 128 + i] = __ldg(beta + c);
+        s_par[4 * 128 + i] = __ldg(w2 + c);
+        s_par[5 * 128 + i] = training ? (float)(sums[c] / count) * ga : 0.f;
+        s_par[6 * 128 + i] = training ? (float)(sums[C + c] / count) * ga : 0.f;
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            PipeState ps;
+            for (int st = 0; st < num_st; ++st) {
+                mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+                uint8_t* sa = smem + ps.stage * L::STAGE;
+                const int row0 = (int)((pt_begin + (long long)st * 8) * 3);
+                // rows past pt_end * 3 (but < R) inside the last box of a split belong to the next split: the producers zero them;
+                // rows >= R are zero-filled by TMA
+                mbar_expect_tx(&loaded[ps.stage], (uint32_t)(2 * L::A_HALF + nslab_h * TW_SLAB));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tma_load_2d(&map_pd, &loaded[ps.stage], sa + j * TW_SLAB, cg * 128 + j * 32, row0);
+                    tma_load_2d(&map_pd, &loaded[ps.stage], sa + L::A_HALF + j * TW_SLAB, C + cg * 128 + j * 32, row0);
+                }
+                for (int j = 0; j < nslab_h; ++j) tma_load_2d(&map_h, &loaded[ps.stage], sa + 2 * L::A_HALF + j * TW_SLAB, j * 32, row0);
+                ps.advance<TW_STAGES>();
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BM, Cin, 1, 1);
+            PipeState ps;
+            for (int st = 0; st < num_st; ++st) {
+                mbar_wait(&full[ps.stage], ps.phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + ps.stage * L::STAGE);
+                const uint32_t sb = sa + 2 * L::A_HALF;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < TW_BR / UMMA_K; ++k) {
+                        const uint64_t ad = make_desc(sa + half * L::A_HALF + k * 1024, TW_SLAB, 512, 1);
+                        const uint64_t bd = make_desc(sb + k * 1024, TW_SLAB, 512, 1);
+                        umma_tf32(tmem_base + (uint32_t)(half * 256), ad, bd, idesc, (st | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[ps.stage]);
+                ps.advance<TW_STAGES>();
+            }
+            umma_commit(&t_full[0]);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        const int quad = warp & 3;
+        if (num_st > 0) {
+            mbar_wait(&t_full[0], 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int o = half * C + cg * 128 + quad * 32 + lane;      // row of gW = channel of the stacked weight
+                const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 256);
+#pragma unroll 1
+                for (int c0 = 0; c0 < Cin; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(t_base + c0, v);
+                    float* dst = gW + (size_t)o * ldgw + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        const int pw = warp - 8;                  // point of the stage
+        const float k1 = 1.f - ns;
+        PipeState ps;
+        for (int st = 0; st < num_st; ++st) {
+            const long long pt = pt_begin + (long long)st * 8 + pw;
+            const bool live = pt < pt_end;
+            float gyv[3];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) gyv[v] = live ? __ldg(gy + (size_t)pt * 3 + v) : 0.f;
+            mbar_wait(&loaded[ps.stage], ps.phase);
+            uint8_t* sa = smem + ps.stage * L::STAGE;
+#pragma unroll 2
+            for (int j = 0; j < 4; ++j) {
+                const int ci = j * 32 + lane;
+                const float mean = s_par[ci], invstd = s_par[128 + ci], ga = s_par[256 + ci], be = s_par[384 + ci], w2c = s_par[512 + ci],
+                            m1 = s_par[640 + ci], m2 = s_par[768 + ci];
+                uint8_t* sp = sa + j * TW_SLAB;
+                uint8_t* sd = sa + L::A_HALF + j * TW_SLAB;
+                float* ap0 = reinterpret_cast<float*>(sp + sw32_off(pw * 3 + 0, lane));
+                float* ap1 = reinterpret_cast<float*>(sp + sw32_off(pw * 3 + 1, lane));
+                float* ap2 = reinterpret_cast<float*>(sp + sw32_off(pw * 3 + 2, lane));
+                float* ad0 = reinterpret_cast<float*>(sd + sw32_off(pw * 3 + 0, lane));
+                float* ad1 = reinterpret_cast<float*>(sd + sw32_off(pw * 3 + 1, lane));
+                float* ad2 = reinterpret_cast<float*>(sd + sw32_off(pw * 3 + 2, lane));
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+                if (live) {
+                    const float p0 = *ap0, p1 = *ap1, p2 = *ap2, d0 = *ad0, d1 = *ad1, d2 = *ad2;
+                    const float pp = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
+                    const float r = pp > 0.f ? pp * rsqrtf(pp) : 0.f;
+                    const float n = r + 1e-6f;
+                    const float rn = __fdividef(1.f, n);
+                    const float nhat = (n - mean) * invstd;
+                    const float nb = fmaf(nhat, ga, be);
+                    const float t = nb * rn;
+                    const float s = t * fmaf(p2, d2, fmaf(p1, d1, p0 * d0));
+                    const float g0 = gyv[0] * w2c, g1 = gyv[1] * w2c, g2 = gyv[2] * w2c;
+                    float e0 = g0, e1 = g1, e2 = g2;
+                    if (s < 0.f) {
+                        const float rq = __fdividef(1.f, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)) + 1e-6f);
+                        const float a = s * rq;
+                        const float gdq = fmaf(g2, d2, fmaf(g1, d1, g0 * d0)) * rq;
+                        const float c1 = k1 * gdq;
+                        e0 = fmaf(-c1, d0, g0);
+                        e1 = fmaf(-c1, d1, g1);
+                        e2 = fmaf(-c1, d2, g2);
+                        const float ca = -k1 * a, cb2 = -c1 * t, cc = 2.f * a * c1;
+                        q0 = fmaf(cc, d0, fmaf(cb2, p0, ca * g0));
+                        q1 = fmaf(cc, d1, fmaf(cb2, p1, ca * g1));
+                        q2 = fmaf(cc, d2, fmaf(cb2, p2, ca * g2));
+                    }
+                    const float gx = fmaf(e2, p2, fmaf(e1, p1, e0 * p0));
+                    const float dnb = gx * rn;
+                    float dn = ga * dnb;
+                    if (training) dn = dn - m1 - nhat * m2;
+                    dn = dn * invstd - gx * nb * rn * rn;
+                    const float ur = r > 0.f ? dn * __fdividef(1.f, r) : 0.f;
+                    o0 = fmaf(e0, t, ur * p0);
+                    o1 = fmaf(e1, t, ur * p1);
+                    o2 = fmaf(e2, t, ur * p2);
+                }
+                *ap0 = o0;
+                *ap1 = o1;
+                *ap2 = o2;
+                *ad0 = q0;
+                *ad1 = q1;
+                *ad2 = q2;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[ps.stage]);
+            ps.advance<TW_STAGES>();
         }
     }
     tc_fence_before();
@@ -1386,11 +1604,15 @@ int vnpcc_gemm_vn_pool(const float* X, long long ldx, const float* Wcat, long lo
 // pd [P*3, 2C] is the stacked linear output saved by the forward.  C % 32 == 0, Cin in {128, 256}; VNPCC_ERR_UNSUPPORTED otherwise.
 int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long long P, int C, const float* stat, const float* gamma,
                         const float* beta, float ns, const float* w2, const float* Wt, long long ldwt, int Cin, int training,
-                        double* sums, double* gw2, float* gpd, long long ldgpd, float* gh, long long ldgh, void* stream) {
+                        double* sums, double* gw2, float* gpd, long long ldgpd, float* gh, long long ldgh, const float* h, long long ldh,
+                        float* gW, long long ldgw, void* stream) {
     if (P <= 0) return 0;
     if (C <= 0 || (C & 31) || C > tc::TB_MAX_C || (Cin != 128 && Cin != 256) || !stat || !gamma || !beta || !w2 || (ldpd & 3) || (ldwt & 3) ||
-        (ldgpd & 3) || !tc::aligned16(pd) || !tc::aligned16(Wt) || !tc::aligned16(gpd) || P * 3 >= (1ll << 31))
+        !tc::aligned16(pd) || !tc::aligned16(Wt) || P * 3 >= (1ll << 31))
         return VNPCC_ERR_UNSUPPORTED;
+    const bool fused_w = gW != nullptr && tuning(TUNE_TAIL_WGRAD) != 1;
+    if (fused_w && ((C & 127) || !h || (ldh & 3) || !tc::aligned16(h))) return VNPCC_ERR_UNSUPPORTED;
+    if (!fused_w && (!gpd || (ldgpd & 3) || !tc::aligned16(gpd))) return VNPCC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     cudaMemsetAsync(gw2, 0, sizeof(double) * C, st);
@@ -1398,18 +1620,39 @@ int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long l
     CUtensorMap mwt, mpd, mgpd;
     if (!tc::make_map(&mwt, Wt, Cin, 2 * C, ldwt, tc::BK, tc::BM)) return VNPCC_ERR_DRIVER;
     if (!tc::make_map(&mpd, pd, P * 3, 2 * C, ldpd, tc::BK, tc::TB_BN)) return VNPCC_ERR_DRIVER;
-    if (!tc::make_map(&mgpd, gpd, P * 3, 2 * C, ldgpd, tc::BK, tc::TB_BN)) return VNPCC_ERR_DRIVER;
+    if (fused_w) mgpd = mpd;
+    else if (!tc::make_map(&mgpd, gpd, P * 3, 2 * C, ldgpd, tc::BK, tc::TB_BN)) return VNPCC_ERR_DRIVER;
     static bool attr_done_dev[64] = {false};
     bool& attr_done = attr_done_dev[current_device_slot()];
     if (!attr_done) {
-        if (cudaFuncSetAttribute(tc::tail_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmem::TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::tail_dgrad_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmem::TOTAL) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::tail_dgrad_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmem::TOTAL) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::tail_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailWSmem::TOTAL) != cudaSuccess)
             return last_error();
         attr_done = true;
     }
     const long long num_tiles = (P + 31) / 32;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-    count_launch(), tc::tail_dgrad_tf32_kernel<<<grid, tc::TB_THREADS, tc::TailSmem::TOTAL, st>>>(
-        mwt, mpd, mgpd, gy, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gh, (size_t)ldgh, num_tiles);
+    if (fused_w)
+        count_launch(), tc::tail_dgrad_tf32_kernel<false><<<grid, tc::TB_THREADS, tc::TailSmem::TOTAL, st>>>(
+            mwt, mpd, mgpd, gy, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gh, (size_t)ldgh, num_tiles);
+    else
+        count_launch(), tc::tail_dgrad_tf32_kernel<true><<<grid, tc::TB_THREADS, tc::TailSmem::TOTAL, st>>>(
+            mwt, mpd, mgpd, gy, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gh, (size_t)ldgh, num_tiles);
+    if (fused_w) {
+        // weight gradient of the stacked weight [2C, Cin] with the gradient formed on the fly: (C / 128) channel groups x row splits = one wave
+        CUtensorMap mpd2, mh;
+        if (!tc::make_map(&mpd2, pd, P * 3, 2 * C, ldpd, 32, tc::TW_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
+        if (!tc::make_map(&mh, h, P * 3, Cin, ldh, 32, tc::TW_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
+        const int groups = C / 128;
+        long long splits = sm_count() / groups;
+        if (splits < 1) splits = 1;
+        long long pps = ((P + splits - 1) / splits + 7) / 8 * 8;      // whole stages of 8 points
+        splits = (P + pps - 1) / pps;
+        cudaMemset2DAsync(gW, (size_t)ldgw * sizeof(float), 0, (size_t)Cin * sizeof(float), (size_t)2 * C, st);
+        count_launch(), tc::tail_wgrad_tf32_kernel<<<dim3(groups, (unsigned)splits), tc::TB_THREADS, tc::TailWSmem::TOTAL, st>>>(
+            mpd2, mh, gy, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gW, (size_t)ldgw, pps);
+    }
     return last_error();
 }
 

@@ -550,7 +550,8 @@ class _BNLeakyDot(torch.autograd.Function):
         return gpd, ggamma, gbeta, None, None, None, gw2.view(1, C), (gy if has_res else None)
 
 
-_TAIL_FUSED_BWD = True      # tests switch it off to compare the fused tail backward with the unfused kernel sequence
+_TAIL_FUSED_BWD = True      # tests switch these off to compare the fused tail backward with the unfused kernel sequence
+_TAIL_FUSED_WGRAD = True    # weight gradient with the gradient formed on the fly (gpd never stored) when C % 128 == 0
 
 
 class _LinearBNLeakyDot(torch.autograd.Function):
@@ -588,36 +589,45 @@ class _LinearBNLeakyDot(torch.autograd.Function):
         P = R // 3
         Cin = h.shape[1]
         dev = pd.device
-        gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
+        gpd = None
         sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
         gw2d = torch.empty(C, device=dev, dtype=torch.float64)
         ggamma = torch.empty(C, device=dev, dtype=torch.float32)
         gbeta = torch.empty(C, device=dev, dtype=torch.float32)
-        gh = None
+        gh = gw = None
         if _GEMM_MODE == "tf32" and _TAIL_FUSED_BWD and ctx.needs_input_grad[0] and P > 0:
             wt = torch.empty((Cin, 2 * C), device=dev, dtype=torch.float32)
             call("vnpcc_transpose", ptr(wcat), _ld(wcat), ptr(wt), 2 * C, 2 * C, Cin, stream())
             gh = torch.empty((R, Cin), device=dev, dtype=torch.float32)
-            with _Timed("gemm", 2.0 * R * 2 * C * Cin, 4.0 * (2.0 * R * 2 * C + R * Cin)):
+            fused_w = _TAIL_FUSED_WGRAD and ctx.needs_input_grad[1] and C % 128 == 0 and _ld(h) % 4 == 0 and h.data_ptr() % 16 == 0
+            if fused_w:
+                gw = torch.empty((2 * C, Cin), device=dev, dtype=torch.float32)
+            else:
+                gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
+            flops = 2.0 * R * 2 * C * Cin * (2 if fused_w else 1)
+            with _Timed("gemm", flops, 4.0 * (2.0 * R * 2 * C + R * Cin)):
                 rc = _lib.raw("vnpcc_tail_bwd_tf32", ptr(gy), ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ns, ptr(w2), ptr(wt),
-                              2 * C, Cin, 1 if use_batch else 0, ptr(sums), ptr(gw2d), ptr(gpd), 2 * C, ptr(gh), Cin, stream())
+                              2 * C, Cin, 1 if use_batch else 0, ptr(sums), ptr(gw2d), ptr(gpd), 2 * C if gpd is not None else 0, ptr(gh), Cin,
+                              ptr(h) if fused_w else None, _ld(h) if fused_w else 0, ptr(gw), Cin if fused_w else 0, stream())
                 if rc == 0:
-                    _LAST_KERNEL[0] = "tail_dgrad_tf32"
+                    _LAST_KERNEL[0] = "tail_bwd_tf32"
             if rc == 10003:
-                gh = None
+                gh = gw = gpd = None
             elif rc != 0:
                 raise _lib.VnpccError(f"vnpcc_tail_bwd_tf32 failed with code {rc}")
             else:
                 call("vnpcc_double_to_float", ptr(sums), ptr(gbeta), C, stream())
                 call("vnpcc_double_to_float", ptr(sums[C:]), ptr(ggamma), C, stream())
         if gh is None:
+            gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
             call("vnpcc_bn_leaky_dot_bwd1", ptr(gy), ptr(pd), _ld(pd), ptr(pd[:, C:]), _ld(pd), ptr(gpd), 2 * C, ptr(gpd[:, C:]), 2 * C, P, C,
                  ptr(stat), ptr(gamma), ptr(beta), ns, ptr(sums), ptr(w2), ptr(gw2d), stream())
             call("vnpcc_vn_bn_bwd2", ptr(gpd), 2 * C, ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ptr(sums), float(P),
                  1 if use_batch else 0, ptr(ggamma), ptr(gbeta), stream())
             if ctx.needs_input_grad[0]:
                 gh = gemm_rows(gpd, wcat, True)
-        gw = gemm_wgrad(gpd, h) if ctx.needs_input_grad[1] else None
+        if gw is None and ctx.needs_input_grad[1]:
+            gw = gemm_wgrad(gpd, h)
         gw2 = torch.empty(C, device=dev, dtype=torch.float32)
         call("vnpcc_double_to_float", ptr(gw2d), ptr(gw2), C, stream())
         return gh, gw, ggamma, gbeta, gw2.view(1, C), (gy if has_res else None), None, None, None
