@@ -300,7 +300,7 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
             out[fused] = (y.detach(), hh.grad, ww.grad, w22.grad, bn.weight.grad, bn.bias.grad, rr.grad if with_res else None, kern)
         finally:
             ops._TAIL_FUSED_BWD = True
-            ops._TAIL_FUSED_WGRAD = True
+            ops._TAIL_FUSED_WGRAD = False
     b = out[False]
     names = ["y", "gh", "gw", "gw2", "ggamma", "gbeta", "gres"]
     for key in (True, "no-wgrad"):

@@ -36,9 +36,15 @@ gpd = torch.empty(R, 2 * C, device="cuda")
 gh = torch.empty(R, Cin, device="cuda")
 gg, gb = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
 st = _lib.stream()
-t_fused = timeit(lambda: _lib.call("vnpcc_tail_bwd_tf32", gy, pd, 2 * C, P, C, stat, gamma, beta, 0.2, w2, wt, 2 * C, Cin, 1, sums, gw2, gpd, 2 * C, gh, Cin, st))
+h = torch.randn(R, Cin, device="cuda")
+gW = torch.empty(2 * C, Cin, device="cuda")
+t_fused = timeit(lambda: _lib.call("vnpcc_tail_bwd_tf32", gy, pd, 2 * C, P, C, stat, gamma, beta, 0.2, w2, wt, 2 * C, Cin, 1, sums, gw2, gpd, 2 * C, gh, Cin, None, 0, None, 0, st))
+t_fused_w = timeit(lambda: _lib.call("vnpcc_tail_bwd_tf32", gy, pd, 2 * C, P, C, stat, gamma, beta, 0.2, w2, wt, 2 * C, Cin, 1, sums, gw2, None, 0, gh, Cin, h, Cin, gW, Cin, st))
+t_wg = timeit(lambda: ops.gemm_wgrad(gpd, h, out=gW))
 t_b1 = timeit(lambda: _lib.call("vnpcc_bn_leaky_dot_bwd1", gy, pd, 2 * C, pd[:, C:], 2 * C, gpd, 2 * C, gpd[:, C:], 2 * C, P, C, stat, gamma, beta, 0.2, sums, w2, gw2, st))
 t_b2 = timeit(lambda: _lib.call("vnpcc_vn_bn_bwd2", gpd, 2 * C, pd, 2 * C, P, C, stat, gamma, beta, sums, float(P), 1, gg, gb, st))
 gpd.normal_()
 t_dg = timeit(lambda: ops.gemm_rows(gpd, wcat, True, out=gh))
-print(f"fused (pre-pass + tail_dgrad) {t_fused:.3f} ms   vs   bwd1 {t_b1:.3f} + bwd2 {t_b2:.3f} + dgrad {t_dg:.3f} = {t_b1 + t_b2 + t_dg:.3f} ms")
+print(f"fused (pre-pass + tail_dgrad writing gpd) {t_fused:.3f} ms + wgrad GEMM {t_wg:.3f} = {t_fused + t_wg:.3f} ms")
+print(f"fused (pre-pass + tail_dgrad + tail_wgrad, gpd never stored) {t_fused_w:.3f} ms")
+print(f"unfused: bwd1 {t_b1:.3f} + bwd2 {t_b2:.3f} + dgrad {t_dg:.3f} + wgrad {t_wg:.3f} = {t_b1 + t_b2 + t_dg + t_wg:.3f} ms")

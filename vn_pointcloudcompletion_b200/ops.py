@@ -551,7 +551,11 @@ class _BNLeakyDot(torch.autograd.Function):
 
 
 _TAIL_FUSED_BWD = True      # tests switch these off to compare the fused tail backward with the unfused kernel sequence
-_TAIL_FUSED_WGRAD = True    # weight gradient with the gradient formed on the fly (gpd never stored) when C % 128 == 0
+# weight gradient with the gradient formed on the fly as well (tail_wgrad_tf32_kernel: gpd never stored).  Correct (tests) but MEASURED
+# SLOWER at the decoder shape -- 3.74 ms against 3.08 ms for "fused dgrad writes gpd once + ordinary weight-gradient GEMM": without the gpd
+# store the dgrad kernel only drops from 1.76 to 1.55 ms (it re-streams the 512 KB of weights from L2 for every 96-row tile: bound by the
+# per-SM L2 bandwidth, not by HBM) while the fused weight gradient takes 1.38 ms against 0.80 ms (profiles/r2_tail_bench.md).  Off.
+_TAIL_FUSED_WGRAD = False
 
 
 class _LinearBNLeakyDot(torch.autograd.Function):
