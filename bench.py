@@ -625,20 +625,24 @@ def main():
         roof = None
         classes = {}
         traffic = {}
-        tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+        tpath = os.path.join(REPO, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):
             traffic = {k: v for k, v in json.load(open(tpath)).items() if not k.startswith("_")}
         for cls, d in ksum.items():
             sec = d["ms"] / 1e3
             if cls in ("gemm_rows_tf32", "gemm_wgrad_tf32", "gemm_vn_fused", "sgemm_fp32", "gemm"):
                 tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
-                # TF32 dense peak is half the bf16 one; the driver measures bf16 only
-                peak = (pk["bf16_sustained"] / 2.0) if (cls.endswith("tf32") or cls == "gemm_vn_fused") else None
+                # TF32 dense peak is half the bf16 one; the driver measures bf16 only.  The step runs at 1.9-1.97 GHz (see `clocks`), where
+                # the BURST figure was taken (the sustained one was measured at 1.3 GHz under a seconds-long cuBLAS loop): burst / 2 is the
+                # denominator, the fraction against sustained / 2 is reported beside it
+                peak = (pk["bf16"] / 2.0) if (cls.endswith("tf32") or cls == "gemm_vn_fused") else None
                 ent = {"bound": "tensor" if peak else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
-                       "frac": (tf / peak) if peak else None, "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
+                       "frac": (tf / peak) if peak else None,
+                       "frac_vs_sustained_peak": (tf / (pk["bf16_sustained"] / 2.0)) if peak else None,
+                       "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
                        "launches_per_step": d["launches"] / args.steps,
                        "flop_per_launch": d["work"] / max(d["launches"], 1),
-                       "peak_note": f"bf16 sustained ({pk['source']}) / 2 for TF32 operands; achieved = sum of 2*R*K*Cout "
+                       "peak_note": f"bf16 burst ({pk['source']}) / 2 for TF32 operands; achieved = sum of 2*R*K*Cout "
                                     "over the class's launches / their CUDA-event time" if peak else
                                     "fp32 SIMT kernel: no tensor-core peak applies"}
                 if peak:
@@ -650,6 +654,14 @@ def main():
                                              "bytes_per_launch": d["bytes"] / max(d["launches"], 1), "hbm_peak_gbs": pk["hbm"],
                                              "note": "sum over launches of max(flops/peak_tensor, algorithmic bytes/peak_hbm) / measured time"}
                 classes[cls] = ent
+            elif cls == "tail_bwd_tf32":
+                # the fused decoder-tail backward (sums pre-pass + tail_dgrad_tf32_kernel): HBM-bound by construction
+                gbs = d["bytes"] / sec / 1e9 if sec > 0 else 0.0
+                classes[cls] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] / args.steps,
+                                "tflops": d["work"] / sec / 1e12 if sec > 0 else 0.0,
+                                "peak_note": f"algorithmic bytes (pd read twice, gpd and gh written once) / CUDA-event time vs the measured copy "
+                                             f"bandwidth ({pk['source']}); the write-heavy mix (3.2 GB in, 4.8 GB out) tops out near 4.7 TB/s"}
             elif cls.startswith("attention"):
                 tf = d["work"] / sec / 1e12 if sec > 0 else 0.0
                 tc_cls = cls.endswith("tf32")

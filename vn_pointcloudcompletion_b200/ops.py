@@ -609,7 +609,8 @@ class _LinearBNLeakyDot(torch.autograd.Function):
             else:
                 gpd = torch.empty((R, 2 * C), device=dev, dtype=torch.float32)
             flops = 2.0 * R * 2 * C * Cin * (2 if fused_w else 1)
-            with _Timed("gemm", flops, 4.0 * (2.0 * R * 2 * C + R * Cin)):
+            nbytes = 4.0 * (2.0 * R * 2 * C + R * Cin + (0 if fused_w else R * 2 * C) + (2 * R * Cin if fused_w else 0))
+            with _Timed("gemm", flops, nbytes):
                 rc = _lib.raw("vnpcc_tail_bwd_tf32", ptr(gy), ptr(pd), _ld(pd), P, C, ptr(stat), ptr(gamma), ptr(beta), ns, ptr(w2), ptr(wt),
                               2 * C, Cin, 1 if use_batch else 0, ptr(sums), ptr(gw2d), ptr(gpd), 2 * C if gpd is not None else 0, ptr(gh), Cin,
                               ptr(h) if fused_w else None, _ld(h) if fused_w else 0, ptr(gw), Cin if fused_w else 0, stream())
