@@ -25,7 +25,7 @@ def test_chamfer_plan(B, N, M):
     assert ns >= 1 and sl % 256 == 0 and sl >= 256            # whole 32-candidate chunks, the kernel's tile granularity
     assert ns * sl >= M and (ns - 1) * sl < M                  # the splits cover every candidate, none is empty
     assert ns <= 64
-    slots = SMS * 4
+    slots = SMS * 8          # the planner sizes the grid for 8 CTAs per SM (chamfer_ctas_per_sm): late CTAs back-fill the tail wave
     items = B * nq * ns
     waves = math.ceil(items / slots)
     # never worse than the unsplit plan by the planner's own cost model

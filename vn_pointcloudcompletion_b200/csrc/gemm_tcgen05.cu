@@ -90,6 +90,12 @@ __device__ __forceinline__ void tma_store_wait_read() {      // at most N groups
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -1157,12 +1163,10 @@ tail_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_pd, const __grid_
                 // rows past pt_end * 3 (but < R) inside the last box of a split belong to the next split: the producers zero them;
                 // rows >= R are zero-filled by TMA
                 mbar_expect_tx(&loaded[ps.stage], (uint32_t)(2 * L::A_HALF + nslab_h * TW_SLAB));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    tma_load_2d(&map_pd, &loaded[ps.stage], sa + j * TW_SLAB, cg * 128 + j * 32, row0);
-                    tma_load_2d(&map_pd, &loaded[ps.stage], sa + L::A_HALF + j * TW_SLAB, C + cg * 128 + j * 32, row0);
-                }
-                for (int j = 0; j < nslab_h; ++j) tma_load_2d(&map_h, &loaded[ps.stage], sa + 2 * L::A_HALF + j * TW_SLAB, j * 32, row0);
+                // three bulk copies per stage (slab maps): 4 slabs of p, 4 of d, all of h
+                tma_load_3d(&map_pd, &loaded[ps.stage], sa, 0, row0, cg * 4);
+                tma_load_3d(&map_pd, &loaded[ps.stage], sa + L::A_HALF, 0, row0, (C >> 5) + cg * 4);
+                tma_load_3d(&map_h, &loaded[ps.stage], sa + 2 * L::A_HALF, 0, row0, 0);
                 ps.advance<TW_STAGES>();
             }
         }
@@ -1449,6 +1453,21 @@ static bool make_map(CUtensorMap* m, const float* base, long long rows, long lon
     return r == CUDA_SUCCESS;
 }
 
+// The same matrix seen as [rows][cols / 32 slabs][32]: ONE bulk copy of box {32, box_rows, nslabs} lands as `nslabs` consecutive MN-major
+// slabs [box_rows x 128 bytes] in shared memory (slab outermost), instead of one TMA instruction per slab -- a stage of the weight-gradient
+// kernels is 12-16 slabs of 3-4 KB, and at ~50 ns per TMA instruction their issue alone was most of a stage's time.
+static bool make_map_slabs(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int box_rows, int nslabs,
+                           CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || (cols & 31)) return false;
+    cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)nslabs};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN, int STAGES, bool STATS, bool TMA_OUT = false>
@@ -1642,8 +1661,8 @@ int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long l
     if (fused_w) {
         // weight gradient of the stacked weight [2C, Cin] with the gradient formed on the fly: (C / 128) channel groups x row splits = one wave
         CUtensorMap mpd2, mh;
-        if (!tc::make_map(&mpd2, pd, P * 3, 2 * C, ldpd, 32, tc::TW_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
-        if (!tc::make_map(&mh, h, P * 3, Cin, ldh, 32, tc::TW_BR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
+        if (!tc::make_map_slabs(&mpd2, pd, P * 3, 2 * C, ldpd, tc::TW_BR, 4, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
+        if (!tc::make_map_slabs(&mh, h, P * 3, Cin, ldh, tc::TW_BR, Cin / 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return VNPCC_ERR_DRIVER;
         const int groups = C / 128;
         long long splits = sm_count() / groups;
         if (splits < 1) splits = 1;
