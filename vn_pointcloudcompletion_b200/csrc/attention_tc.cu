@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_tc_kernel(const __grid_constan
     // p_out (MODE_FWD, may be NULL; N % 4 == 0): the normalised attention weights P [B*H*N, N], stored for the GEMM-shaped backward;
     // p_tma != 0 (needs N % 128 == 0): map_p describes p_out as a row-major matrix with boxes {32 columns, 128 rows}, SWIZZLE_128B
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint8_t* Qs = smem;
     uint8_t* Ks = Qs + Q_BYTES;
     uint8_t* Vs = Ks + K_BYTES;
@@ -437,7 +437,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x,      // qkv, K-maj
     // ds_out (BMODE_DQ only, may be NULL): dS [B*H*N, N] row-major, written tile by tile so that dK = dS^T Q can run as a plain streaming
     // GEMM (attn_acc_gemm_kernel) instead of recomputing S and dP in the other orientation
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint8_t* Xs = smem;
     uint8_t* Ys = Xs + BX_BYTES;
     uint8_t* Ym = Ys + BY_BYTES;
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(NT, 1) attn_acc_gemm_kernel(const __grid_const
                                                              const __grid_constant__ CUtensorMap map_z,      // Z rows, MN-major ATOM_32B, box 32 tokens
                                                              int N, int H, int colz0, float* __restrict__ outp, size_t ldo) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GK_NS * GK_STAGE_BYTES);
     uint64_t* full = bars, *empty = bars + GK_NS, *done = bars + 2 * GK_NS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GK_NS + 1);
@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(NT, 1) attn_ds_kernel(const __grid_constant__ 
                                                        const __grid_constant__ CUtensorMap map_v,       // qkv, K-major SW128, box 64 tokens
                                                        int N, int H, int C, float scale, const float* __restrict__ delta, float* __restrict__ pds) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint8_t* dOs = smem;
     uint8_t* Vs = dOs + Q_BYTES;      // two buffers of K_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + 2 * K_BYTES);
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(NT, 1) attn_ds_tma_kernel(const __grid_constan
                                                            const __grid_constant__ CUtensorMap map_p,      // P / dS [B*H*N, N], box {32, 128}, SW128
                                                            int N, int H, int C, float scale, const float* __restrict__ delta) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint8_t* dOs = smem;
     uint8_t* Vs = dOs + Q_BYTES;                      // two buffers of K_BYTES
     uint8_t* Pb = Vs + 2 * K_BYTES;                   // two half-tile buffers of DST_HALF_BYTES

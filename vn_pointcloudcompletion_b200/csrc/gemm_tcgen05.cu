@@ -220,7 +220,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     using L = RowsSmem<BN, STAGES>;
     static_assert(!STATS || BN % 48 == 0, "the statistics epilogue walks whole points, 16 at a time");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
@@ -536,7 +536,7 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                      double* __restrict__ sums, int num_m, long long num_tiles) {
     using L = FusedSmem<STAGES, MODE, FBN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
@@ -811,6 +811,61 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int kappa) {      // elemen
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kappa >> 2) ^ (r & 7))) << 4) + (kappa & 3) * 4);
 }
 
+// approximate reciprocal / reciprocal square root as ONE MUFU instruction each (the plain intrinsics add denormal range-scaling code;
+// every operand here is either >= 1e-6 or guarded by the caller)
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Backward of  y = w2 . leaky(BN(p), d)  for ONE (point, channel):  (p, d) -> (dL/dp, dL/dd) in place, given the point's output gradient
+// gy (3 components), the channel's BatchNorm parameters / statistics and the batch means m1, m2 of the pre-pass (zero in eval mode).
+// Branch-free (the negative-side terms are selected, not jumped over) so that the unrolled callers interleave several points.
+// Reference: models/vn_layers.py:60-74 (VNLinearLeakyReLU.forward), :116-127 (VNBatchNorm.forward), differentiated.
+struct TailChan {
+    float mean, invstd, ga, be, w2c, m1, m2;
+};
+__device__ __forceinline__ void tail_grad_point(const TailChan& ch, float k1, bool live, float gy0, float gy1, float gy2, float& p0, float& p1,
+                                                float& p2, float& d0, float& d1, float& d2) {
+    const float pp = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
+    const bool nz = live && pp >= 1.17549435e-38f;
+    const float rs = rsqrt_fast(nz ? pp : 1.f);       // 1 / |p|
+    const float r = nz ? pp * rs : 0.f;
+    const float n = r + 1e-6f;
+    const float rn = rcp_fast(n);
+    const float nhat = (n - ch.mean) * ch.invstd;
+    const float nb = fmaf(nhat, ch.ga, ch.be);
+    const float t = nb * rn;
+    const float s = t * fmaf(p2, d2, fmaf(p1, d1, p0 * d0));            // <BN(p), d>
+    const float g0 = gy0 * ch.w2c, g1 = gy1 * ch.w2c, g2 = gy2 * ch.w2c;      // rank-one gradient of the layer output
+    const float rq = rcp_fast(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)) + 1e-6f);
+    const bool neg = s < 0.f;
+    const float a = s * rq;
+    const float c1 = neg ? k1 * (fmaf(g2, d2, fmaf(g1, d1, g0 * d0)) * rq) : 0.f;
+    const float e0 = fmaf(-c1, d0, g0), e1 = fmaf(-c1, d1, g1), e2 = fmaf(-c1, d2, g2);      // dL/d BN(p)
+    const float ca = neg ? -k1 * a : 0.f, cb2 = -c1 * t, cc = 2.f * a * c1;
+    const float q0 = fmaf(cc, d0, fmaf(cb2, p0, ca * g0));                                    // dL/d d
+    const float q1 = fmaf(cc, d1, fmaf(cb2, p1, ca * g1));
+    const float q2 = fmaf(cc, d2, fmaf(cb2, p2, ca * g2));
+    // BatchNorm-on-norm backward with the batch sums of the pre-pass: final gradient w.r.t. the linear output p
+    const float gx = fmaf(e2, p2, fmaf(e1, p1, e0 * p0));
+    float dn = fmaf(-nhat, ch.m2, ch.ga * (gx * rn) - ch.m1);
+    dn = dn * ch.invstd - gx * nb * rn * rn;
+    const float ur = nz ? dn * rs : 0.f;
+    p0 = fmaf(e0, t, ur * p0);
+    p1 = fmaf(e1, t, ur * p1);
+    p2 = fmaf(e2, t, ur * p2);
+    d0 = live ? q0 : 0.f;
+    d1 = live ? q1 : 0.f;
+    d2 = live ? q2 : 0.f;
+}
+
 // Data path of one (tile, channel block): TMA brings the (p | d) blocks [96 rows x 32 channels] of pd into a B stage (SWIZZLE_128B, the
 // MMA operand layout) -- asynchronously, TB_SB stages deep, so HBM latency is covered by the ring and not by registers --, the producer warps
 // turn them IN PLACE into (gp | gd), the MMA contracts them and a store warp sends the same shared-memory blocks to gpd by bulk tensor stores.
@@ -824,7 +879,7 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                        size_t ldgh, long long num_tiles) {
     using L = TailSmem;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     float* s_par = reinterpret_cast<float*>(smem + L::PAR_OFFSET);      // [7][TB_MAX_C]: mean, invstd, gamma, beta, w2, m1, m2
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* a_empty = a_full + TB_SA;
@@ -1012,57 +1067,25 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                 for (int v = 0; v < 3; ++v) gyv[i][v] = (pt0 + i < P) ? __ldg(gy + (size_t)(pt0 + i) * 3 + v) : 0.f;
             for (int cb = 0; cb < ncb; ++cb) {
                 const int c = cb * 32 + lane;
-                const float mean = s_par[c], invstd = s_par[TB_MAX_C + c], ga = s_par[2 * TB_MAX_C + c], be = s_par[3 * TB_MAX_C + c],
-                            w2c = s_par[4 * TB_MAX_C + c], m1 = s_par[5 * TB_MAX_C + c], m2 = s_par[6 * TB_MAX_C + c];
+                const TailChan ch = {s_par[c], s_par[TB_MAX_C + c], s_par[2 * TB_MAX_C + c], s_par[3 * TB_MAX_C + c], s_par[4 * TB_MAX_C + c],
+                                     s_par[5 * TB_MAX_C + c], s_par[6 * TB_MAX_C + c]};
                 mbar_wait(&b_loaded[pb.stage], pb.phase);      // the (p | d) blocks of this stage are in shared memory
                 uint8_t* sbp = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
-#pragma unroll 2
+#pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int rr = (pw * 4 + i) * 3;
                     float* ap0 = reinterpret_cast<float*>(sbp + sw128_off(rr + 0, lane));
                     float* ap1 = reinterpret_cast<float*>(sbp + sw128_off(rr + 1, lane));
                     float* ap2 = reinterpret_cast<float*>(sbp + sw128_off(rr + 2, lane));
-                    float* ad0 = reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 0, lane));
-                    float* ad1 = reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 1, lane));
-                    float* ad2 = reinterpret_cast<float*>(sbp + TB_B_HALF + sw128_off(rr + 2, lane));
-                    const float p0 = *ap0, p1 = *ap1, p2 = *ap2, d0 = *ad0, d1 = *ad1, d2 = *ad2;
-                    const float pp = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
-                    const float r = pp > 0.f ? pp * rsqrtf(pp) : 0.f;
-                    const float n = r + 1e-6f;
-                    const float rn = __fdividef(1.f, n);
-                    const float nhat = (n - mean) * invstd;
-                    const float nb = fmaf(nhat, ga, be);
-                    const float t = nb * rn;
-                    const float s = t * fmaf(p2, d2, fmaf(p1, d1, p0 * d0));            // <BN(p), d>
-                    const float g0 = gyv[i][0] * w2c, g1 = gyv[i][1] * w2c, g2 = gyv[i][2] * w2c;      // rank-one gradient of the layer output
-                    float e0 = g0, e1 = g1, e2 = g2;      // dL/d BN(p)
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f;   // dL/d d
-                    if (s < 0.f) {
-                        const float rq = __fdividef(1.f, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)) + 1e-6f);
-                        const float a = s * rq;
-                        const float gdq = fmaf(g2, d2, fmaf(g1, d1, g0 * d0)) * rq;
-                        const float c1 = k1 * gdq;
-                        e0 = fmaf(-c1, d0, g0);
-                        e1 = fmaf(-c1, d1, g1);
-                        e2 = fmaf(-c1, d2, g2);
-                        const float ca = -k1 * a, cb2 = -c1 * t, cc = 2.f * a * c1;
-                        q0 = fmaf(cc, d0, fmaf(cb2, p0, ca * g0));
-                        q1 = fmaf(cc, d1, fmaf(cb2, p1, ca * g1));
-                        q2 = fmaf(cc, d2, fmaf(cb2, p2, ca * g2));
-                    }
-                    // BatchNorm-on-norm backward with the batch sums of the pre-pass: final gradient w.r.t. the linear output p
-                    const float gx = fmaf(e2, p2, fmaf(e1, p1, e0 * p0));
-                    const float dnb = gx * rn;
-                    float dn = ga * dnb;
-                    if (training) dn = dn - m1 - nhat * m2;
-                    dn = dn * invstd - gx * nb * rn * rn;
-                    const float ur = r > 0.f ? dn * __fdividef(1.f, r) : 0.f;
-                    *ap0 = fmaf(e0, t, ur * p0);
-                    *ap1 = fmaf(e1, t, ur * p1);
-                    *ap2 = fmaf(e2, t, ur * p2);
-                    *ad0 = q0;
-                    *ad1 = q1;
-                    *ad2 = q2;
+                    float p0 = *ap0, p1 = *ap1, p2 = *ap2;
+                    float d0 = ap0[TB_B_HALF / 4], d1 = ap1[TB_B_HALF / 4], d2 = ap2[TB_B_HALF / 4];
+                    tail_grad_point(ch, k1, true, gyv[i][0], gyv[i][1], gyv[i][2], p0, p1, p2, d0, d1, d2);
+                    *ap0 = p0;
+                    *ap1 = p1;
+                    *ap2 = p2;
+                    ap0[TB_B_HALF / 4] = d0;
+                    ap1[TB_B_HALF / 4] = d1;
+                    ap2[TB_B_HALF / 4] = d2;
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the async proxy (tensor core, bulk stores)
                 __syncwarp();
@@ -1108,7 +1131,7 @@ tail_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_pd, const __grid_
                        int training, float* __restrict__ gW, size_t ldgw, long long pts_per_split) {
     using L = TailWSmem;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     float* s_par = reinterpret_cast<float*>(smem + L::PAR_OFFSET);      // [7][128]
     uint64_t* loaded = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* full = loaded + TW_STAGES;
@@ -1224,61 +1247,23 @@ tail_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_pd, const __grid_
             for (int v = 0; v < 3; ++v) gyv[v] = live ? __ldg(gy + (size_t)pt * 3 + v) : 0.f;
             mbar_wait(&loaded[ps.stage], ps.phase);
             uint8_t* sa = smem + ps.stage * L::STAGE;
-#pragma unroll 2
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int ci = j * 32 + lane;
-                const float mean = s_par[ci], invstd = s_par[128 + ci], ga = s_par[256 + ci], be = s_par[384 + ci], w2c = s_par[512 + ci],
-                            m1 = s_par[640 + ci], m2 = s_par[768 + ci];
+                const TailChan ch = {s_par[ci], s_par[128 + ci], s_par[256 + ci], s_par[384 + ci], s_par[512 + ci], s_par[640 + ci], s_par[768 + ci]};
                 uint8_t* sp = sa + j * TW_SLAB;
-                uint8_t* sd = sa + L::A_HALF + j * TW_SLAB;
                 float* ap0 = reinterpret_cast<float*>(sp + sw32_off(pw * 3 + 0, lane));
                 float* ap1 = reinterpret_cast<float*>(sp + sw32_off(pw * 3 + 1, lane));
                 float* ap2 = reinterpret_cast<float*>(sp + sw32_off(pw * 3 + 2, lane));
-                float* ad0 = reinterpret_cast<float*>(sd + sw32_off(pw * 3 + 0, lane));
-                float* ad1 = reinterpret_cast<float*>(sd + sw32_off(pw * 3 + 1, lane));
-                float* ad2 = reinterpret_cast<float*>(sd + sw32_off(pw * 3 + 2, lane));
-                float o0 = 0.f, o1 = 0.f, o2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
-                if (live) {
-                    const float p0 = *ap0, p1 = *ap1, p2 = *ap2, d0 = *ad0, d1 = *ad1, d2 = *ad2;
-                    const float pp = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
-                    const float r = pp > 0.f ? pp * rsqrtf(pp) : 0.f;
-                    const float n = r + 1e-6f;
-                    const float rn = __fdividef(1.f, n);
-                    const float nhat = (n - mean) * invstd;
-                    const float nb = fmaf(nhat, ga, be);
-                    const float t = nb * rn;
-                    const float s = t * fmaf(p2, d2, fmaf(p1, d1, p0 * d0));
-                    const float g0 = gyv[0] * w2c, g1 = gyv[1] * w2c, g2 = gyv[2] * w2c;
-                    float e0 = g0, e1 = g1, e2 = g2;
-                    if (s < 0.f) {
-                        const float rq = __fdividef(1.f, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)) + 1e-6f);
-                        const float a = s * rq;
-                        const float gdq = fmaf(g2, d2, fmaf(g1, d1, g0 * d0)) * rq;
-                        const float c1 = k1 * gdq;
-                        e0 = fmaf(-c1, d0, g0);
-                        e1 = fmaf(-c1, d1, g1);
-                        e2 = fmaf(-c1, d2, g2);
-                        const float ca = -k1 * a, cb2 = -c1 * t, cc = 2.f * a * c1;
-                        q0 = fmaf(cc, d0, fmaf(cb2, p0, ca * g0));
-                        q1 = fmaf(cc, d1, fmaf(cb2, p1, ca * g1));
-                        q2 = fmaf(cc, d2, fmaf(cb2, p2, ca * g2));
-                    }
-                    const float gx = fmaf(e2, p2, fmaf(e1, p1, e0 * p0));
-                    const float dnb = gx * rn;
-                    float dn = ga * dnb;
-                    if (training) dn = dn - m1 - nhat * m2;
-                    dn = dn * invstd - gx * nb * rn * rn;
-                    const float ur = r > 0.f ? dn * __fdividef(1.f, r) : 0.f;
-                    o0 = fmaf(e0, t, ur * p0);
-                    o1 = fmaf(e1, t, ur * p1);
-                    o2 = fmaf(e2, t, ur * p2);
-                }
-                *ap0 = o0;
-                *ap1 = o1;
-                *ap2 = o2;
-                *ad0 = q0;
-                *ad1 = q1;
-                *ad2 = q2;
+                float p0 = *ap0, p1 = *ap1, p2 = *ap2;
+                float d0 = ap0[L::A_HALF / 4], d1 = ap1[L::A_HALF / 4], d2 = ap2[L::A_HALF / 4];
+                tail_grad_point(ch, k1, live, gyv[0], gyv[1], gyv[2], p0, p1, p2, d0, d1, d2);
+                *ap0 = p0;
+                *ap1 = p1;
+                *ap2 = p2;
+                ap0[L::A_HALF / 4] = d0;
+                ap1[L::A_HALF / 4] = d1;
+                ap2[L::A_HALF / 4] = d2;
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -1313,7 +1298,7 @@ gemm_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
                        size_t ldg, long long R, int Cout, int K, long long rows_per_split) {
     using L = WgradSmem<BNW, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;

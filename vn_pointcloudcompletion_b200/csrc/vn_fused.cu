@@ -111,7 +111,7 @@ __device__ __forceinline__ void fold_reduce_channels(double (&acc)[NRED][NL], do
     }
 }
 
-template <int KS>
+template <int KS, bool FAST = false>
 __global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
                                                           const float* __restrict__ bias, size_t ldb, int B, int N, int C, int n_chunk,
                                                           int row_mode, double* __restrict__ sums) {
@@ -121,16 +121,50 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict
     FOLD_SAMPLES_BEGIN
     FoldCtx<KS> cx;
     fold_load_ctx<KS>(cx, w, ldw, bias, ldb, b, C, c0);
-    for (int n = nbeg; n < n1; n += nstep) {
-        float xv[3][KS];
-        fold_load_x<KS>(x, ldx, ((size_t)b * N + n) * 3, xv);
-        V4x3 p, d;
-        fold_pd<KS, false>(cx, xv, p, d);
+    if (FAST) {
+        // throughput mode: fp32 partial sums over 16 points, flushed to the fp64 totals (the totals feed a mean / variance)
+        float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+        int since_flush = 0;
+#pragma unroll 2
+        for (int n = nbeg; n < n1; n += nstep) {
+            float xv[3][KS];
+            fold_load_x<KS>(x, ldx, ((size_t)b * N + n) * 3, xv);
+            V4x3 p, d;
+            fold_pd<KS, false>(cx, xv, p, d);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float pp = dot3l(p, p, l);
+                const float nn = (pp > 0.f ? pp * rsqrtf(pp) : 0.f) + VS_EPS;
+                f1[l] += nn;
+                f2[l] = fmaf(nn, nn, f2[l]);
+            }
+            if (++since_flush == 16) {
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    acc[0][l] += (double)f1[l];
+                    acc[1][l] += (double)f2[l];
+                    f1[l] = f2[l] = 0.f;
+                }
+                since_flush = 0;
+            }
+        }
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-            const double nn = (double)(sqrtf(dot3l(p, p, l)) + VS_EPS);
-            acc[0][l] += nn;
-            acc[1][l] = fma(nn, nn, acc[1][l]);
+            acc[0][l] += (double)f1[l];
+            acc[1][l] += (double)f2[l];
+        }
+    } else {
+        for (int n = nbeg; n < n1; n += nstep) {
+            float xv[3][KS];
+            fold_load_x<KS>(x, ldx, ((size_t)b * N + n) * 3, xv);
+            V4x3 p, d;
+            fold_pd<KS, false>(cx, xv, p, d);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const double nn = (double)(sqrtf(dot3l(p, p, l)) + VS_EPS);
+                acc[0][l] += nn;
+                acc[1][l] = fma(nn, nn, acc[1][l]);
+            }
         }
     }
     FOLD_SAMPLES_END
@@ -581,8 +615,8 @@ __global__ void __launch_bounds__(256, MINB) fold_bwd_main_kernel(const float* _
 }
 
 // throughput-mode forward of the fused small-K layer, packed fp32x2
-template <int KS>
-__global__ void __launch_bounds__(256) fold_fwd_p2_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
+template <int KS, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) fold_fwd_p2_kernel(const float* __restrict__ x, size_t ldx, const float* __restrict__ w, size_t ldw,
                                                            const float* __restrict__ bias, size_t ldb, int B, int N, int C, int n_chunk,
                                                            int row_mode, const float* __restrict__ stat, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float ns, float* __restrict__ out, size_t ldo) {
@@ -682,7 +716,7 @@ static void fold_geometry(int B, int N, int C, int resident, dim3& grid, dim3& b
 using namespace vnpcc;
 
 static constexpr size_t FOLD_SMEM = sizeof(double) * 256 * 4;
-static constexpr int FOLD_BWD_DEFAULT_VARIANT = 3;   // two channels per thread, 2 CTAs / SM (tools/stream_bench.py: 2.39 -> 2.27 ms forward + backward)
+static constexpr int FOLD_BWD_DEFAULT_VARIANT = 4;   // two channels per thread; sums pass at 3 CTAs / SM (80 registers), main pass at 2 (tools/fold_bench.py: backward 1.65 -> 1.47 ms)
 
 #define FOLD_KS_DISPATCH(KS, ...)                                \
     switch (KS) {                                                \
@@ -726,8 +760,15 @@ int vnpcc_fold_stats(const float* x, long long ldx, const float* w, long long ld
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (B <= 0 || N <= 0) return last_error();
     FOLD_KS_DISPATCH(K, {
-        FOLD_GEOM(fold_stats_kernel<K_>, FOLD_SMEM);
-        count_launch(), fold_stats_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, sums);
+        if (fast_math_enabled() && tuning(TUNE_FOLD_FWD) != 1) {
+            auto kern = fold_stats_kernel<K_, true>;
+            FOLD_GEOM(kern, FOLD_SMEM);
+            count_launch(), kern<<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, sums);
+        } else {
+            auto kern = fold_stats_kernel<K_, false>;
+            FOLD_GEOM(kern, FOLD_SMEM);
+            count_launch(), kern<<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, sums);
+        }
     });
     return last_error();
 }
@@ -739,11 +780,20 @@ int vnpcc_fold_fwd(const float* x, long long ldx, const float* w, long long ldw,
     if (B <= 0 || N <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (fast_math_enabled()) {
+        const int fv = tuning(TUNE_FOLD_FWD);
+#define FOLD_FWD_LAUNCH(MINB_)                                                                                                                  \
+    {                                                                                                                                           \
+        auto kern = fold_fwd_p2_kernel<K_, MINB_>;                                                                                              \
+        FOLD_GEOM(kern, 0);                                                                                                                     \
+        count_launch(), kern<<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode, stat,  \
+                                                       gamma, beta, ns, out, (size_t)ldo);                                                     \
+    }
         FOLD_KS_DISPATCH(K, {
-            FOLD_GEOM(fold_fwd_p2_kernel<K_>, 0);
-            count_launch(), fold_fwd_p2_kernel<K_><<<grid, block, smem, st>>>(x, (size_t)ldx, w, (size_t)ldw, bias, (size_t)ldb, B, N, C, n_chunk, row_mode,
-                                                                             stat, gamma, beta, ns, out, (size_t)ldo);
+            if (fv == 3) FOLD_FWD_LAUNCH(3)
+            else if (fv == 4) FOLD_FWD_LAUNCH(4)
+            else FOLD_FWD_LAUNCH(1)
         });
+#undef FOLD_FWD_LAUNCH
     } else {
         FOLD_KS_DISPATCH(K, {
             auto kern = fold_fwd_kernel<K_, false>;
@@ -775,7 +825,7 @@ int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx,
     //   3 = two channels per thread, 2 CTAs / SM                   0 = default
     int variant = tuning(TUNE_FOLD_MINB);
     if (variant == 0) variant = FOLD_BWD_DEFAULT_VARIANT;
-    if (variant == 3 && C > 512) variant = 1;
+    if (variant >= 3 && C > 512) variant = 1;
 #define FOLD_SUMS_LAUNCH(NP_, MINB_)                                                                                                             \
     {                                                                                                                                            \
         auto kern = fold_bwd_sums_kernel<K_, NP_, MINB_>;                                                                                       \
@@ -794,12 +844,15 @@ int vnpcc_fold_bwd(const float* g, long long ldg, const float* x, long long ldx,
     if (stat) {
         FOLD_KS_DISPATCH(K, {
             if (variant == 3) FOLD_SUMS_LAUNCH(1, 2)
+            else if (variant == 4 || variant == 5) FOLD_SUMS_LAUNCH(1, 3)
+            else if (variant == 6 || variant == 7) FOLD_SUMS_LAUNCH(1, 4)
             else if (variant == 2) FOLD_SUMS_LAUNCH(2, 2)
             else FOLD_SUMS_LAUNCH(2, 1)
         });
     }
     FOLD_KS_DISPATCH(K, {
-        if (variant == 3) FOLD_MAIN_LAUNCH(1, 2)
+        if (variant == 3 || variant == 4 || variant == 6) FOLD_MAIN_LAUNCH(1, 2)
+        else if (variant == 5 || variant == 7) FOLD_MAIN_LAUNCH(1, 3)
         else if (variant == 2) FOLD_MAIN_LAUNCH(2, 2)
         else FOLD_MAIN_LAUNCH(2, 1)
     });

@@ -51,7 +51,7 @@ inline int resident_ctas(K* kernel, int threads, size_t smem = 0) {
     return resident_ctas_impl(reinterpret_cast<const void*>(kernel), threads, smem);
 }
 // development knobs (vnpcc_set_tuning): 0 = default behaviour
-enum { TUNE_GRID_LEGACY = 0, TUNE_FOLD_MINB = 1, TUNE_STATS_GEMM = 2, TUNE_STATS_NOMATH = 3, TUNE_CHAMFER_OVERHEAD = 4, TUNE_CHAMFER_CTAS = 5, TUNE_CHAMFER_VARIANT = 6, TUNE_TAIL_WGRAD = 7, TUNE_N = 8 };
+enum { TUNE_GRID_LEGACY = 0, TUNE_FOLD_MINB = 1, TUNE_STATS_GEMM = 2, TUNE_STATS_NOMATH = 3, TUNE_CHAMFER_OVERHEAD = 4, TUNE_CHAMFER_CTAS = 5, TUNE_CHAMFER_VARIANT = 6, TUNE_TAIL_WGRAD = 7, TUNE_FOLD_FWD = 8, TUNE_N = 9 };
 int tuning(int knob);
 
 // chunk length for kernels whose grid is (groups x chunks) blocks of equal work over N points per group, each block walking its chunk with
