@@ -42,6 +42,20 @@ constexpr uint32_t SPIN_LIMIT = 1u << 22;   // x (try_wait latency ~0.1-1 us): a
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// approximate reciprocal / reciprocal square root as ONE MUFU instruction each (the plain intrinsics add denormal range-scaling code;
+// every operand here is either >= 1e-6 or guarded by the caller)
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -410,7 +424,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #pragma unroll
                         for (int jp = 0; jp < 16; ++jp) {
                             const float n2 = fmaf(v[3 * jp + 2], v[3 * jp + 2], fmaf(v[3 * jp + 1], v[3 * jp + 1], v[3 * jp] * v[3 * jp]));
-                            float n = (n2 > 0.f ? n2 * rsqrtf(n2) : 0.f) + 1e-6f;
+                            float n = (n2 > 0.f ? n2 * rsqrt_fast(fmaxf(n2, 1.17549435e-38f)) : 0.f) + 1e-6f;
                             n = (r0 + 3 * jp < R) ? n : 0.f;      // R is a multiple of 3: whole points only
                             nn[jp] = n;
                             qq[jp] = n * n;
@@ -726,10 +740,10 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         s2 = fma(n, n, s2);
                     } else {
                         if (stat) {
-                            const float n = (FAST ? (nrm2 > 0.f ? nrm2 * rsqrtf(nrm2) : 0.f) : sqrtf(nrm2)) + 1e-6f;
+                            const float n = (FAST ? (nrm2 > 0.f ? nrm2 * rsqrt_fast(fmaxf(nrm2, 1.17549435e-38f)) : 0.f) : sqrtf(nrm2)) + 1e-6f;
                             const float nb = ((n - mean) * invstd) * ga + be;
                             if (FAST) {
-                                const float t = __fdividef(nb, n);
+                                const float t = nb * rcp_fast(n);
                                 p0 *= t;
                                 p1 *= t;
                                 p2 *= t;
@@ -744,7 +758,7 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         float i0 = p0, i1 = p1, i2 = p2;
                         if (!(dot >= 0.f)) {
                             const float dsq = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), 1e-6f);
-                            const float a = FAST ? __fdividef(dot, dsq) : dot / dsq;
+                            const float a = FAST ? dot * rcp_fast(dsq) : dot / dsq;
                             i0 = __fsub_rn(p0, __fmul_rn(a, d0));
                             i1 = __fsub_rn(p1, __fmul_rn(a, d1));
                             i2 = __fsub_rn(p2, __fmul_rn(a, d2));
@@ -809,19 +823,6 @@ struct TailSmem {
 
 __device__ __forceinline__ uint32_t sw128_off(int r, int kappa) {      // element (row r, k index kappa < 32) of a K-major SWIZZLE_128B k-block
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kappa >> 2) ^ (r & 7))) << 4) + (kappa & 3) * 4);
-}
-
-// approximate reciprocal / reciprocal square root as ONE MUFU instruction each (the plain intrinsics add denormal range-scaling code;
-// every operand here is either >= 1e-6 or guarded by the caller)
-__device__ __forceinline__ float rcp_fast(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rsqrt_fast(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 // Backward of  y = w2 . leaky(BN(p), d)  for ONE (point, channel):  (p, d) -> (dL/dp, dL/dd) in place, given the point's output gradient

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const float* __restrict
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 const float pp = dot3l(p, p, l);
-                const float nn = (pp > 0.f ? pp * rsqrtf(pp) : 0.f) + VS_EPS;
+                const float nn = (pp > 0.f ? pp * mufu_rsqrt(pp) : 0.f) + VS_EPS;
                 f1[l] += nn;
                 f2[l] = fmaf(nn, nn, f2[l]);
             }

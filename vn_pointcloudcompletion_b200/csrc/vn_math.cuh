@@ -63,13 +63,28 @@ __device__ __forceinline__ ChanParams load_params(const float* stat, const float
 // Off in parity (fp32) mode, on in throughput (TF32) mode where GEMM operands are already rounded to 10 mantissa bits.
 bool fast_math_enabled();
 
+// ONE MUFU instruction each: the plain intrinsics (__fdividef, rsqrtf) wrap the same instruction in range-scaling code for denormal /
+// huge operands (4-5 extra instructions per call, which the instruction-bound streaming kernels pay per lane).  Every divisor on these
+// paths carries the layers' + 1e-6, and the square roots clamp their argument to the smallest normal number (a denormal squared norm
+// is treated like FLT_MIN: both are 13 orders of magnitude below the 1e-6 they are added to).
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(x, 1.17549435e-38f)));
+    return y;
+}
+
 template <bool FAST>
 __device__ __forceinline__ float vdiv(float a, float b) {
-    return FAST ? __fdividef(a, b) : a / b;
+    return FAST ? a * mufu_rcp(b) : a / b;
 }
 template <bool FAST>
 __device__ __forceinline__ float vsqrt(float a) {
-    return FAST ? (a > 0.f ? a * rsqrtf(a) : 0.f) : sqrtf(a);
+    return FAST ? (a > 0.f ? a * mufu_rsqrt(a) : 0.f) : sqrtf(a);
 }
 
 template <bool FAST>
@@ -80,7 +95,7 @@ __device__ __forceinline__ void bn_apply_lane_t(V4x3& v, int l, const ChanParams
     const float nhat = (n - cp.mean[l]) * cp.invstd[l];
     const float nb = nhat * cp.gamma[l] + cp.beta[l];
     if (FAST) {
-        const float t = __fdividef(nb, n);
+        const float t = nb * mufu_rcp(n);
         v.v[0][l] *= t;
         v.v[1][l] *= t;
         v.v[2][l] *= t;
@@ -137,8 +152,8 @@ __device__ __forceinline__ f2 operator*(f2 a, f2 b) { return {__fmul2_rn(a.v, b.
 __device__ __forceinline__ f2 fma2p(f2 a, f2 b, f2 c) { return {__ffma2_rn(a.v, b.v, c.v)}; }
 __device__ __forceinline__ f2 operator-(f2 a, f2 b) { return {__ffma2_rn(b.v, make_float2(-1.f, -1.f), a.v)}; }   // exact: a + (-1)*b
 __device__ __forceinline__ f2 neg2(f2 a) { return mk2(-a.v.x, -a.v.y); }
-__device__ __forceinline__ f2 rcp2(f2 a) { return mk2(__fdividef(1.f, a.v.x), __fdividef(1.f, a.v.y)); }
-__device__ __forceinline__ f2 rsqrt2(f2 a) { return mk2(rsqrtf(a.v.x), rsqrtf(a.v.y)); }
+__device__ __forceinline__ f2 rcp2(f2 a) { return mk2(mufu_rcp(a.v.x), mufu_rcp(a.v.y)); }
+__device__ __forceinline__ f2 rsqrt2(f2 a) { return mk2(mufu_rsqrt(a.v.x), mufu_rsqrt(a.v.y)); }
 // a where the mask half is true, 0 elsewhere
 __device__ __forceinline__ f2 sel0(bool mx, bool my, f2 a) { return mk2(mx ? a.v.x : 0.f, my ? a.v.y : 0.f); }
 __device__ __forceinline__ f2 dot3p(const f2 (&a)[3], const f2 (&b)[3]) { return fma2p(a[2], b[2], fma2p(a[1], b[1], a[0] * b[0])); }
@@ -177,7 +192,7 @@ __device__ __forceinline__ BNPair load_bn_pair(const float* stat, const float* g
 // approximate reciprocal / square root (MUFU, ~1 ulp): used by the BACKWARD kernels only -- gradients do not need the
 // op-by-op IEEE rounding the forward keeps for parity of masks and selections, and IEEE divisions (about ten per lane)
 // made those kernels instruction-bound
-__device__ __forceinline__ float frcp(float x) { return __fdividef(1.f, x); }
-__device__ __forceinline__ float fsqrt_fast(float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; }
+__device__ __forceinline__ float frcp(float x) { return mufu_rcp(x); }
+__device__ __forceinline__ float fsqrt_fast(float x) { return x > 0.f ? x * mufu_rsqrt(x) : 0.f; }
 
 }  // namespace vnpcc
