@@ -8,7 +8,8 @@ which is installed here, and holds no test or golden vector for them.  Their pub
   points_to_voxels   utils/voxel_util.py:89-105     pyntcloud VoxelGrid(n_x=n_y=n_z=n, regular_bounding_box=True): bounding box of the
                                                      cloud itself grown to a cube, segments = np.linspace(min, max, n + 1) per axis,
                                                      voxel index = clip(searchsorted(segments, x) - 1, 0, n - 1)  (float64 here)
-  iou                utils/voxel_util.py:5-14
+  iou                utils/voxel_util.py:5-14       (plain numpy in the reference: this one IS pinned -- tests/golden/eval_extras.npz holds
+                                                     the outputs of the reference's own function on seeded grids, tests/test_eval.py)
 """
 from __future__ import annotations
 

@@ -16,6 +16,8 @@ Fixtures:
                         rand(4,200,3) through chamfer_python.distChamfer (the reference's CPU-capable Chamfer),
                         plus a ragged/edge set and autograd gradients of sum(dist1)+sum(dist2) and of CD-L1.
   vn_layers.npz         every class of models/vn_layers.py on small seeded inputs: forward, backward, BN buffers.
+  eval_extras.npz       utils/voxel_util.py iou / voxel2mesh / write_obj (the pure-numpy part of SURVEY 8f row f4; the pyntcloud voxeliser and
+                        the open3d reader cannot run here) on seeded occupancy grids.
   loss_variants.npz     utils/loss.py calc_cd / calc_dcd (+ fscore) of the reference run unmodified on CPU.
   dgcnn_small.npz       VN_DGCNN_fps (models/dgcnn.py:164-324) at B=3, N=640 with the oracle's kNN / FPS restatement plugged into
                         its un-vendored knn_cuda / pointnet2_ops imports: searches, outputs, autograd gradients.
@@ -432,13 +434,41 @@ def gen_attn(out):
         out["dec.eval_pts"] = npy(dec(coarse, fg))
 
 
+def gen_eval_extras(out):
+    """reference utils/voxel_util.py:5-13 (iou), :22-47 (voxel2mesh), :50-62 (write_obj), run unmodified; pyntcloud (absent) is only needed
+    by the functions this fixture does not call"""
+    import tempfile
+    sys.modules.setdefault("pyntcloud", SimpleNamespace(PyntCloud=None))
+    spec = importlib.util.spec_from_file_location("ref_voxel_util", os.path.join(REF, "utils", "voxel_util.py"))
+    vu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vu)
+    rng = np.random.RandomState(11)
+    a = rng.rand(4, 16, 16, 16) > 0.6
+    b = rng.rand(4, 16, 16, 16) > 0.5
+    out["iou.a"], out["iou.b"] = a, b
+    out["iou.out"] = np.array([vu.iou(a[i], b[i]) for i in range(4)] + [vu.iou(a, b)], np.float64)
+    vox = (rng.rand(10, 12, 9) > 0.7).astype(np.float32)
+    vox[2:8, 3:9, 1:7] = 1.0                        # a solid block: its interior is hidden in surface view
+    vox[0, 0, 0] = vox[9, 11, 8] = 0.9               # corners (the reference's neighbourhood slice is empty / clipped there)
+    vox[5, 0, 4] = 0.31
+    vox[5, 1, 4] = 0.3                               # not > 0.3
+    out["mesh.vox"] = vox
+    for name, sv in (("surface", True), ("all", False)):
+        verts, faces = vu.voxel2mesh(vox.copy(), sv)
+        out[f"mesh.{name}.verts"], out[f"mesh.{name}.faces"] = np.asarray(verts, np.float64), np.asarray(faces, np.int64)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "m.obj")
+        vu.voxel2obj(path, vox.copy(), True)
+        out["mesh.obj_text"] = np.frombuffer(open(path, "rb").read(), np.uint8)
+
+
 def main():
     install_shim()
     torch.set_num_threads(os.cpu_count())
     # pcn_b6: same network at B=6 -- with more samples per batch the decoder's BatchNorm-on-norms is far better
     # conditioned than at B=2 (see DESIGN.md "conditioning"), so values can be compared at the north-star 1e-4.
     only = set(sys.argv[1:])
-    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants), ("dgcnn_small", gen_dgcnn), ("attn_small", gen_attn),
+    for name, fn in (("chamfer_unit", gen_chamfer), ("vn_layers", gen_layers), ("pcn_small", gen_pcn), ("loss_variants", gen_loss_variants), ("dgcnn_small", gen_dgcnn), ("attn_small", gen_attn), ("eval_extras", gen_eval_extras),
                      ("pcn_b6", lambda o: gen_pcn(o, B=6, n_partial=128, n_gt=1024, seed=17))):
         if only and name not in only:
             continue

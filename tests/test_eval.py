@@ -93,3 +93,46 @@ def test_input_helpers():
     # orthonormal, det +1
     R = rot.R.cpu().numpy()
     np.testing.assert_allclose(R @ R.transpose(0, 2, 1), np.tile(np.eye(3), (2, 1, 1)), atol=1e-6)
+
+
+# ---- the pure-numpy part of the reference's eval extras, pinned to the reference run (tests/golden/make_golden.py gen_eval_extras) ----
+def _extras():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_extras.npz"))
+
+
+def _compat_voxel_util():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat", "utils", "voxel_util.py")
+    spec = importlib.util.spec_from_file_location("compat_voxel_util", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_iou_vs_reference_golden():
+    """utils/voxel_util.py:5-13 run unmodified on seeded grids: the oracle, the compat mirror (numpy path) and torch path agree with it"""
+    import torch
+    from vn_pointcloudcompletion_b200 import eval_metrics as E
+    g = _extras()
+    vu = _compat_voxel_util()
+    a, b, want = g["iou.a"], g["iou.b"], g["iou.out"]
+    for i in range(4):
+        assert EO.iou(a[i], b[i]) == want[i]
+        assert vu.iou(a[i], b[i]) == want[i]
+        assert abs(E.iou(torch.from_numpy(a[i]), torch.from_numpy(b[i])).item() - want[i]) < 1e-7
+    assert vu.iou(a, b) == want[4]
+
+
+def test_voxel_mesh_export_vs_reference_golden(tmp_path):
+    """utils/voxel_util.py:22-62 (voxel2mesh / write_obj / voxel2obj): same vertices, faces and OBJ bytes as the reference's loops"""
+    g = _extras()
+    vu = _compat_voxel_util()
+    vox = g["mesh.vox"]
+    for name, sv in (("surface", True), ("all", False)):
+        verts, faces = vu.voxel2mesh(vox.copy(), sv)
+        np.testing.assert_allclose(verts, g[f"mesh.{name}.verts"], rtol=0, atol=1e-15)
+        np.testing.assert_array_equal(faces, g[f"mesh.{name}.faces"])
+    assert len(g["mesh.surface.verts"]) < len(g["mesh.all.verts"])          # the solid block's interior is hidden in surface view
+    path = tmp_path / "m.obj"
+    vu.voxel2obj(str(path), vox.copy(), True)
+    assert open(path, "rb").read() == g["mesh.obj_text"].tobytes()
