@@ -25,7 +25,9 @@ def tf32_mode():
     V.set_gemm_mode("fp32")
 
 
-SHAPES = [(512, 128, 512), (768, 512, 2048), (1000, 96, 200), (96, 2048, 1024), (4096, 256, 256), (300, 1024, 130), (70000, 64, 128)]
+SHAPES = [(512, 128, 512), (768, 512, 2048), (1000, 96, 200), (96, 2048, 1024), (4096, 256, 256), (300, 1024, 130), (70000, 64, 128),
+          # few rows: the contraction is split over CTAs and accumulated with red.add (K not a multiple of the split, one-tile outputs)
+          (96, 1024, 1024), (96, 1024, 3072), (64, 256, 512), (128, 1000, 384), (100, 4096, 64)]
 
 
 @pytest.mark.parametrize("R,K,Cout", SHAPES)

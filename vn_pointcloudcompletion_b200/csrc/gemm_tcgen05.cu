@@ -225,12 +225,16 @@ constexpr int ACC_STRIDE = 256;    // TMEM columns between the two accumulator s
 // In this variant the output leaves through shared memory and BULK TENSOR STORES (cp.async.bulk.tensor ... global.shared::cta, two
 // 48-row x 32-channel staging buffers per epilogue warp): when HBM back-pressures the stores the warp does not stall on them, so the
 // statistics arithmetic overlaps the draining stores instead of queueing behind them.
-template <int BN, int STAGES, bool HAS_BIAS, bool STATS, bool TMA_OUT = false>
+// SPLITK = true (few rows, R <= BN: the per-sample MLPs of the encoder / decoder heads, 96 rows against 1024 x 1024 weights): a tile is
+// (output-channel tile, K range) and its partial product is added to the zero-initialised Y with red.add -- 8 CTAs streaming 512 KB of
+// weights each become 64 CTAs streaming 64 KB.  kb_per = K blocks per split.
+template <int BN, int STAGES, bool HAS_BIAS, bool STATS, bool TMA_OUT = false, bool SPLITK = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_y, float* __restrict__ Y,
                       size_t ldy, long long R, int K, int Cout, const float* __restrict__ bias, size_t ldbias,
-                      long long rows_per_sample, int num_m, long long num_tiles, double* __restrict__ sums, int Cstat) {
+                      long long rows_per_sample, int num_m, long long num_tiles, double* __restrict__ sums, int Cstat, int kb_per) {
+    static_assert(!SPLITK || (!HAS_BIAS && !STATS), "split-K tiles only add partial products");
     using L = RowsSmem<BN, STAGES>;
     static_assert(!STATS || BN % 48 == 0, "the statistics epilogue walks whole points, 16 at a time");
     extern __shared__ uint8_t smem_raw[];
@@ -274,8 +278,10 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             PipeState ps;
             for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (int)(tile % num_m) * BM;
-                const long long n0 = (tile / num_m) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const long long n0 = SPLITK ? 0 : (tile / num_m) * BN;
+                const int kb0 = SPLITK ? (int)(tile / num_m) * kb_per : 0;
+                const int kb1 = SPLITK ? min(num_kb, kb0 + kb_per) : num_kb;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
                     uint8_t* sa = smem + ps.stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
@@ -296,7 +302,9 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = SPLITK ? (int)(tile / num_m) * kb_per : 0;
+                const int kb1 = SPLITK ? min(num_kb, kb0 + kb_per) : num_kb;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[ps.stage], ps.phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ps.stage * L::STAGE_BYTES);
@@ -305,7 +313,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = make_desc(sa + k * UMMA_K * 4, 16, 1024);
                         const uint64_t bd = make_desc(sb + k * UMMA_K * 4, 16, 1024);
-                        umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_tf32(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[ps.stage]);     // frees this smem stage once the MMAs above have read it
                     ps.advance<STAGES>();
@@ -324,7 +332,7 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         int out_buf = 0;
         for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (int)(tile % num_m) * BM;
-            const long long n0 = (tile / num_m) * BN;
+            const long long n0 = SPLITK ? 0 : (tile / num_m) * BN;
             const int o = m0 + quad * 32 + lane;
             const bool o_ok = o < Cout;
             // per-sample bias row (b, v) of output row r = (b*N + n)*3 + v.  A tile of BN rows touches at most two samples when
@@ -482,7 +490,11 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                         }
                     }
                 }
-                if (r0 + 32 <= R) {
+                if (SPLITK) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (r0 + j < R) atomicAdd(dst + (size_t)j * ldy, v[j]);
+                } else if (r0 + 32 <= R) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) dst[(size_t)j * ldy] = v[j];
                 } else {
@@ -1485,7 +1497,33 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     const long long num_tiles = num_m * num_n;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
     count_launch(), kern<<<grid, NUM_THREADS, SMEM, st>>>(mw, mx, my, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
-                                                         rps > 0 ? rps : 1, num_m, num_tiles, sums, Cstat);
+                                                         rps > 0 ? rps : 1, num_m, num_tiles, sums, Cstat, 0);
+    return last_error();
+}
+
+// few rows (R <= 128), no bias: split the contraction over CTAs (see the kernel's SPLITK note); Y is zeroed here
+static int launch_rows_splitk(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K, int Cout,
+                              int ksplit, cudaStream_t st) {
+    constexpr int BN = 128, STAGES = 4;
+    using L = RowsSmem<BN, STAGES>;
+    CUtensorMap mw, mx;
+    if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
+    if (!make_map(&mx, X, R, K, ldx, BK, BN)) return VNPCC_ERR_DRIVER;
+    auto kern = gemm_rows_tf32_kernel<BN, STAGES, false, false, false, true>;
+    static bool attr_done_dev[64] = {false};
+    bool& attr_done = attr_done_dev[current_device_slot()];
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
+        attr_done = true;
+    }
+    const int num_kb = (K + BK - 1) / BK;
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    ksplit = (num_kb + kb_per - 1) / kb_per;      // no empty split
+    const int num_m = (Cout + BM - 1) / BM;
+    const long long num_tiles = (long long)num_m * ksplit;
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    if (cudaMemset2DAsync(Y, (size_t)ldy * sizeof(float), 0, (size_t)Cout * sizeof(float), (size_t)R, st) != cudaSuccess) return last_error();
+    count_launch(), kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(mw, mx, mx, Y, (size_t)ldy, R, K, Cout, nullptr, 0, 1, num_m, num_tiles, nullptr, 0, kb_per);
     return last_error();
 }
 
@@ -1533,7 +1571,14 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
     if (Cout < 64 || R < 64) return VNPCC_ERR_UNSUPPORTED;
     if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;   // a sample is whole points (3 rows each)
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 128) return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+    if (R <= 128) {
+        // the grid would be Cout / 128 CTAs: split the contraction until about one CTA per SM streams >= 4 K blocks (128 columns of W)
+        const int num_m = (Cout + tc::BM - 1) / tc::BM, num_kb = (K + tc::BK - 1) / tc::BK;
+        int ksplit = sm_count() / num_m < num_kb / 4 ? sm_count() / num_m : num_kb / 4;
+        if (tuning(TUNE_GRID_LEGACY)) ksplit = 1;
+        if (!bias && ksplit >= 2) return tc::launch_rows_splitk(X, ldx, W, ldw, Y, ldy, R, K, Cout, ksplit, st);
+        return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+    }
     return tc::launch_rows<256, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
 }
 
