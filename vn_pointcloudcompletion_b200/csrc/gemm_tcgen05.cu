@@ -1754,6 +1754,8 @@ int vnpcc_gemm_wgrad_tf32(const float* dY, long long lddy, const float* X, long 
     (void)workspace;
     (void)workspace_bytes;
     if (Cout <= 0 || K <= 0) return 0;
+    // R < 256 (the per-sample heads, 96 rows): refused -- measured 23-26 us here (the tile leaves through per-element red.add) against
+    // 17 + 5 us for the SIMT kernel and its clear (tools/small_gemm_bench.py under ncu)
     if ((lddy & 3) || (ldx & 3) || !tc::aligned16(dY) || !tc::aligned16(X) || R >= (1ll << 31) || R < 256 || Cout < 32 || K < 32 ||
         (Cout & 3) || (K & 3))
         return VNPCC_ERR_UNSUPPORTED;
