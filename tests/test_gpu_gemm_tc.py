@@ -203,7 +203,10 @@ def test_fused_pool_gemm_selects_like_unfused(tf32_mode):
 
 
 @pytest.mark.parametrize("R,K,Cout,Cs,with_bias", [(3 * 1000, 64, 256, 128, False), (3 * 4321, 256, 512, 256, False), (3 * 2048 * 3, 512, 2048, 1024, True),
-                                                   (3 * 80, 32, 64, 32, False), (3 * 1110, 128, 256, 256, True)])
+                                                   (3 * 80, 32, 64, 32, False), (3 * 1110, 128, 256, 256, True),
+                                                   # K <= 256 and enough row blocks: the resident-weight variant (one channel tile per CTA)
+                                                   (3 * 8001, 128, 256, 256, True), (3 * 5000, 200, 384, 128, False), (3 * 40002, 256, 512, 256, True),
+                                                   (3 * 3000, 256, 1024, 256, False)])
 def test_gemm_rows_stats_epilogue(tf32_mode, R, K, Cout, Cs, with_bias):
     """vnpcc_gemm_rows_tf32_stats: the output equals the plain tcgen05 GEMM's bit for bit (same MMA sequence per element; only the row tile
     differs: 240 = 80 whole points instead of 256), and the BatchNorm-on-norm statistics accumulated in its epilogue equal a separate
