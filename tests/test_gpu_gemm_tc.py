@@ -319,3 +319,72 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
         print(key, names[i], rel)
         # (R < 64: the unfused dgrad falls back to the exact SIMT kernel, so the difference is TF32 operand rounding itself)
         assert rel < (2e-4 if R >= 64 else 3e-3), (names[i], rel)
+
+
+def _with_knob(knob, value, fn):
+    from vn_pointcloudcompletion_b200 import _lib
+    _lib.raw("vnpcc_set_tuning", knob, value)
+    try:
+        return fn()
+    finally:
+        _lib.raw("vnpcc_set_tuning", knob, 0)
+
+
+@pytest.mark.parametrize("R,K,Cout,Cs,nsamp", [(3 * 4000, 256, 512, 0, 0), (3 * 4000, 256, 512, 256, 0), (3 * 3003, 512, 1024, 512, 3), (3 * 9001, 320, 256, 0, 0),
+                                                (3 * 2750, 1024, 768, 0, 0)])
+def test_cta_pair_rows_gemm_equals_one_sm_kernel(tf32_mode, R, K, Cout, Cs, nsamp):
+    """tcgen05 cta_group::2 (two SMs per 256-channel tile, each staging half of the row block) against the one-SM kernel: the same MMA
+    sequence per output element -> identical bits, with and without the per-sample bias and the statistics epilogue; row counts that
+    leave partial tiles and an odd number of tiles per pair"""
+    from vn_pointcloudcompletion_b200 import ops
+    torch.manual_seed(R + K)
+    x = torch.randn(R, K, device="cuda")
+    w = torch.randn(Cout, K, device="cuda") / K ** 0.5
+    bias = torch.randn(nsamp * 3, Cout, device="cuda") if nsamp else None
+    rps = R // nsamp if nsamp else 0
+
+    def run():
+        sums = torch.zeros(2 * Cs, device="cuda", dtype=torch.float64) if Cs else None
+        y = ops.gemm_rows(x, w, False, bias, rps, stats=(sums, Cs)) if Cs else ops.gemm_rows(x, w, False, bias, rps)
+        return y, sums
+
+    y1, s1 = _with_knob(2, 1, run)      # knob 2 = 1: one SM per tile
+    y2, s2 = run()                      # default: CTA pairs where eligible (Cout % 256 == 0, K >= 256, R >= 8192)
+    assert torch.equal(y1, y2)
+    if Cs:
+        assert torch.allclose(s1, s2, rtol=1e-12, atol=0)      # fp64 atomics in a different order
+    ref = x.double() @ w.double().t()
+    if bias is not None:
+        ref = ref + bias.double().view(nsamp, 1, 3, Cout).expand(nsamp, R // (3 * nsamp), 3, Cout).reshape(R, Cout)
+    assert (y2.double() - ref).abs().max() <= 2.0 ** -9 * K ** 0.5 * 4
+
+
+def test_cta_pair_fused_vn_kernels_equal_one_sm_kernels(tf32_mode):
+    """the fused VN GEMM (BN + leaky epilogue, statistics-only, conv -> max-pool arg-max) on CTA pairs against one SM per tile"""
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200 import ops
+    torch.manual_seed(11)
+    B, N, K, C = 3, 1000, 256, 256
+    m = V.VNLinearLeakyReLU(K, C, dim=4).cuda().train()
+    rows = torch.randn(B * N * 3, K, device="cuda")
+    bias = torch.randn(B * 3, 2 * C, device="cuda")
+    w = torch.cat([m.map_to_feat.weight, m.map_to_dir.weight], 0).detach()
+    rm0 = m.batchnorm.bn.running_mean.clone()
+
+    def fused():
+        m.batchnorm.bn.running_mean.copy_(rm0)
+        with torch.no_grad():
+            return ops.linear_bn_leaky_fused_nograd(rows, w, bias, 3 * N, m.batchnorm.bn, True, 0.2)
+
+    a, b = fused(), _with_knob(2, 4, fused)      # knob 2 = 4: CTA pairs for the fused kernels (default: one SM per tile)
+    assert a is not None and b is not None
+    assert (a - b).abs().max() <= 1e-6 * a.abs().max()          # batch statistics: fp64 atomics in a different order
+    wl = torch.randn(2 * C, K, device="cuda") / K ** 0.5
+    wdir = torch.randn(2 * C, 2 * C, device="cuda") / (2 * C) ** 0.5
+
+    def pool():
+        with torch.no_grad():
+            return ops.linear_maxpool_rows(rows, wl, wdir, B, N)
+
+    (o1, i1), (o2, i2) = pool(), _with_knob(2, 4, pool)
+    assert torch.equal(i1, i2) and torch.equal(o1, o2)

@@ -133,6 +133,51 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA pair (cta_group::2): two SMs of a cluster work on one 256-channel tile; rank 0 issues the MMAs and owns the "full" barriers
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by both CTAs: the bytes land in the issuing CTA's shared memory, the transaction count on rank 0's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // 32 lanes x 32 consecutive columns: thread t of the warp gets lane (quadrant*32 + t), v[j] = column (col0 + j)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
@@ -201,12 +246,12 @@ struct PipeState {
 // ---------------------------------------------------------------------------------------------------------------
 // rows GEMM:  Y[r, o] = sum_k X[r, k] W[o, k] (+ bias[(r / rps)*3 + r%3, o])
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int GAP = 0>
 struct RowsSmem {
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + GAP;
     static constexpr int STATS_OFFSET = BAR_OFFSET + 256;   // STATS kernels: 2 * MAX_STAT_C doubles (per-CTA partial sums)
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
     // STATS kernels: + output staging for the TMA-store epilogue, per epilogue warp 2 buffers of 48 rows x 32 channels
@@ -228,14 +273,24 @@ constexpr int ACC_STRIDE = 256;    // TMEM columns between the two accumulator s
 // SPLITK = true (few rows, R <= BN: the per-sample MLPs of the encoder / decoder heads, 96 rows against 1024 x 1024 weights): a tile is
 // (output-channel tile, K range) and its partial product is added to the zero-initialised Y with red.add -- 8 CTAs streaming 512 KB of
 // weights each become 64 CTAs streaming 64 KB.  kb_per = K blocks per split.
-template <int BN, int STAGES, bool HAS_BIAS, bool STATS, bool TMA_OUT = false, bool SPLITK = false>
+// CTA2 = true: launched as clusters of two CTAs (one SM pair).  The pair computes a 256-channel x BN-row tile with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA stages ITS 128 channels of W and HALF of the row block of X (BN / 2 rows), the tensor
+// core reads both halves, each CTA's TMEM receives its 128 channels x BN rows and each CTA runs its own epilogue.  Per CTA the bytes
+// fetched per tile drop from 16 + 32 KB to 16 + 16 KB per K block: X crosses the L2 -> SM fabric once per 256 channels instead of once
+// per 128.  Rank 0 issues the MMAs; both producers signal rank 0's "full" barriers, the MMA commits free the stage in both CTAs.
+// num_m = number of 256-channel tile PAIRS, num_tiles = pairs x row blocks.
+template <int BN, int STAGES, bool HAS_BIAS, bool STATS, bool TMA_OUT = false, bool SPLITK = false, bool CTA2 = false, int GAP = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_y, float* __restrict__ Y,
                       size_t ldy, long long R, int K, int Cout, const float* __restrict__ bias, size_t ldbias,
                       long long rows_per_sample, int num_m, long long num_tiles, double* __restrict__ sums, int Cstat, int kb_per) {
     static_assert(!SPLITK || (!HAS_BIAS && !STATS), "split-K tiles only add partial products");
-    using L = RowsSmem<BN, STAGES>;
+    static_assert(!CTA2 || (!SPLITK && !TMA_OUT && BN % 16 == 0), "CTA pairs: plain tiles, N a multiple of 16");
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;
+    const long long tile_first = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const long long tile_step = CTA2 ? (gridDim.x >> 1) : gridDim.x;
+    using L = RowsSmem<CTA2 ? BN / 2 : BN, STAGES, GAP>;      // a CTA of a pair stages half of the row block
     static_assert(!STATS || BN % 48 == 0, "the statistics epilogue walks whole points, 16 at a time");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
@@ -261,23 +316,27 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], CTA2 ? 8 : 4);      // rank 0's barrier collects the epilogue warps of both CTAs
         }
         fence_barrier_init();
     }
     if (STATS)
         for (int i = threadIdx.x; i < 2 * Cstat; i += NUM_THREADS) s_stats[i] = 0.0;
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if (CTA2) tmem_alloc_2sm(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();      // the peer's barriers are initialised before anything is signalled across the pair
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             PipeState ps;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (int)(tile % num_m) * BM;
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int m0 = (int)((tile % num_m) * (CTA2 ? 2 : 1) + cta_rank) * BM;
                 const long long n0 = SPLITK ? 0 : (tile / num_m) * BN;
                 const int kb0 = SPLITK ? (int)(tile / num_m) * kb_per : 0;
                 const int kb1 = SPLITK ? min(num_kb, kb0 + kb_per) : num_kb;
@@ -285,20 +344,26 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
                     uint8_t* sa = smem + ps.stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
-                    mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
-                    tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
-                    tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
+                    if (CTA2) {
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[ps.stage], 2 * L::STAGE_BYTES);
+                        tma_load_2d_2sm(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
+                        tma_load_2d_2sm(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0 + (int)cta_rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
+                        tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
+                        tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
+                    }
                     ps.advance<STAGES>();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, 0, 0);
             PipeState ps;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
@@ -307,18 +372,23 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[ps.stage], ps.phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + ps.stage * L::STAGE_BYTES);
-                    const uint32_t sb = sa + L::A_BYTES;
+                    uint32_t sa = smem_u32(smem + ps.stage * L::STAGE_BYTES);
+                    uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = make_desc(sa + k * UMMA_K * 4, 16, 1024);
                         const uint64_t bd = make_desc(sb + k * UMMA_K * 4, 16, 1024);
-                        umma_tf32(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (CTA2) umma_tf32_2sm(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        else umma_tf32(d_tmem, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[ps.stage]);     // frees this smem stage once the MMAs above have read it
+                    // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+                    if (CTA2) umma_commit_2sm(&empty_bar[ps.stage]);
+                    else umma_commit(&empty_bar[ps.stage]);
                     ps.advance<STAGES>();
                 }
-                umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs of a pair)
+                if (CTA2) umma_commit_2sm(&tfull_bar[acc]);
+                else umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -330,8 +400,8 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         int acc = 0;
         uint32_t acc_phase = 0;
         int out_buf = 0;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (int)(tile % num_m) * BM;
+        for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const int m0 = (int)((tile % num_m) * (CTA2 ? 2 : 1) + cta_rank) * BM;
             const long long n0 = SPLITK ? 0 : (tile / num_m) * BN;
             const int o = m0 + quad * 32 + lane;
             const bool o_ok = o < Cout;
@@ -505,7 +575,10 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CTA2) mbar_arrive_rank0(&tempty_bar[acc]);
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -514,13 +587,17 @@ gemm_rows_tf32_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     }
     if (STATS && TMA_OUT && warp >= 4 && lane == 0) tma_store_wait_read<0>();      // staging buffers must outlive their bulk stores
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();      // neither CTA's shared memory / TMEM disappears while the pair still uses it
+    else __syncthreads();
     if (STATS)
         for (int i = threadIdx.x; i < 2 * Cstat; i += NUM_THREADS) {
             const double v = s_stats[i];
             if (v != 0.0) atomicAdd(sums + i, v);
         }
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) {
+        if (CTA2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 
@@ -554,13 +631,21 @@ struct FusedSmem {
 };
 
 
-template <int STAGES, int MODE, bool FAST, int FBN, int NACC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// CTA2 = true: CTA pairs (tcgen05 cta_group::2), as in gemm_rows_tf32_kernel: the pair owns 256 channels (each CTA the feat and dir weight
+// tiles of ITS 128 channels) and each CTA stages half of the row block; num_m then counts 256-channel pairs.
+// Eight epilogue warps (two per TMEM lane quadrant, alternating 48-column passes): with a single accumulator stage (STATS / POOL) the
+// epilogue is exposed between two tiles' MMAs, so it is spread over twice the warps.
+constexpr int FUSED_THREADS = 32 * 12;
+template <int STAGES, int MODE, bool FAST, int FBN, int NACC, bool CTA2 = false>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
 gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ out,
                      size_t ldo, long long R, int K, int C, const float* __restrict__ bias, size_t ldbias, long long rows_per_sample,
                      const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
                      double* __restrict__ sums, int num_m, long long num_tiles) {
-    using L = FusedSmem<STAGES, MODE, FBN>;
+    using L = FusedSmem<STAGES, MODE, CTA2 ? FBN / 2 : FBN>;      // a CTA of a pair stages half of the row block
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;
+    const long long tile_first = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const long long tile_step = CTA2 ? (gridDim.x >> 1) : gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -584,41 +669,52 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         }
         for (int a = 0; a < NACC; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], CTA2 ? 16 : 8);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if (CTA2) tmem_alloc_2sm(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             PipeState ps;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (int)(tile % num_m) * BM;
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int m0 = (int)((tile % num_m) * (CTA2 ? 2 : 1) + cta_rank) * BM;
                 const long long n0 = (tile / num_m) * FBN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
                     uint8_t* sa = smem + ps.stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::NA * L::A_BYTES;
-                    mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
-                    tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
-                    if (MODE != MODE_STATS) tma_load_2d(&map_w, &full_bar[ps.stage], sa + L::A_BYTES, kb * BK, C + m0);
-                    tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
+                    if (CTA2) {
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[ps.stage], 2 * L::STAGE_BYTES);
+                        tma_load_2d_2sm(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
+                        if (MODE != MODE_STATS) tma_load_2d_2sm(&map_w, &full_bar[ps.stage], sa + L::A_BYTES, kb * BK, C + m0);
+                        tma_load_2d_2sm(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0 + (int)cta_rank * (FBN / 2));
+                    } else {
+                        mbar_expect_tx(&full_bar[ps.stage], L::STAGE_BYTES);
+                        tma_load_2d(&map_w, &full_bar[ps.stage], sa, kb * BK, m0);
+                        if (MODE != MODE_STATS) tma_load_2d(&map_w, &full_bar[ps.stage], sa + L::A_BYTES, kb * BK, C + m0);
+                        tma_load_2d(&map_x, &full_bar[ps.stage], sb, kb * BK, (int)n0);
+                    }
                     ps.advance<STAGES>();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, FBN, 0, 0);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, FBN, 0, 0);
             PipeState ps;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t p_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
@@ -631,14 +727,22 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t bd = make_desc(sb + k * UMMA_K * 4, 16, 1024);
-                        umma_tf32(p_tmem, make_desc(sa + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (MODE != MODE_STATS)
-                            umma_tf32(d_tmem, make_desc(sa + L::A_BYTES + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CTA2) {
+                            umma_tf32_2sm(p_tmem, make_desc(sa + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (MODE != MODE_STATS)
+                                umma_tf32_2sm(d_tmem, make_desc(sa + L::A_BYTES + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        } else {
+                            umma_tf32(p_tmem, make_desc(sa + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (MODE != MODE_STATS)
+                                umma_tf32(d_tmem, make_desc(sa + L::A_BYTES + k * UMMA_K * 4, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty_bar[ps.stage]);
+                    if (CTA2) umma_commit_2sm(&empty_bar[ps.stage]);
+                    else umma_commit(&empty_bar[ps.stage]);
                     ps.advance<STAGES>();
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (CTA2) umma_commit_2sm(&tfull_bar[acc]);
+                else umma_commit(&tfull_bar[acc]);
                 if (++acc == NACC) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -656,8 +760,8 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         unsigned long long* pool_best = reinterpret_cast<unsigned long long*>(sums);
         const float k1 = 1.f - ns;
         const long long pts_per_sample = rows_per_sample > 0 ? rows_per_sample / 3 : 1;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (int)(tile % num_m) * BM;
+        for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const int m0 = (int)((tile % num_m) * (CTA2 ? 2 : 1) + cta_rank) * BM;
             const long long n0 = (tile / num_m) * FBN;
             const int c = m0 + quad * 32 + lane;             // C is a multiple of 128: always a valid channel
             if (MODE == MODE_STATS && c != stat_c) {
@@ -679,7 +783,7 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
-            for (int h = 0; h < FBN / 48; ++h) {             // 48 columns = 16 points per pass
+            for (int h = warp >= 8 ? 1 : 0; h < FBN / 48; h += 2) {      // 48 columns = 16 points per pass; the quadrant's two warps alternate
                 const long long r0 = n0 + h * 48;
                 if (r0 >= R) break;                          // warp-uniform
                 float pv[48], dv[48];
@@ -788,7 +892,10 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CTA2) mbar_arrive_rank0(&tempty_bar[acc]);
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == NACC) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -800,8 +907,12 @@ gemm_vn_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (CTA2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 2) {
+        if (CTA2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1501,6 +1612,49 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     return last_error();
 }
 
+// CTA pairs (see the kernel's CTA2 note): Cout a multiple of 256, many row blocks
+template <int BN, int STAGES, bool STATS, int GAP = 0>      // STAGES of 16 KB of W + BN / 2 rows of X
+static int launch_rows_pair(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K, int Cout,
+                            const float* bias, long long ldbias, long long rps, double* sums, int Cstat, cudaStream_t st) {
+    using L = RowsSmem<BN / 2, STAGES, GAP>;
+    constexpr int SMEM = STATS ? L::OUT_OFFSET + 1024 : L::TOTAL;
+    static_assert(SMEM <= 232448, "stage ring exceeds the 227 KB of one CTA");
+    CUtensorMap mw, mx;
+    if (!make_map(&mw, W, Cout, K, ldw, BK, BM)) return VNPCC_ERR_DRIVER;
+    if (!make_map(&mx, X, R, K, ldx, BK, BN / 2)) return VNPCC_ERR_DRIVER;      // each CTA of the pair stages half of the row block
+    auto kb = gemm_rows_tf32_kernel<BN, STAGES, true, STATS, false, false, true, GAP>;
+    auto kn = gemm_rows_tf32_kernel<BN, STAGES, false, STATS, false, false, true, GAP>;
+    static bool attr_done_dev[64] = {false};
+    bool& attr_done = attr_done_dev[current_device_slot()];
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+            return last_error();
+        attr_done = true;
+    }
+    const int num_mp = Cout / (2 * BM);
+    const long long num_n = (R + BN - 1) / BN;
+    const long long num_tiles = (long long)num_mp * num_n;
+    long long pairs = sm_count() / 2;
+    if (pairs > num_tiles) pairs = num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, bias ? kb : kn, mw, mx, mx, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
+                                             (long long)(rps > 0 ? rps : 1), num_mp, num_tiles, sums, Cstat, 0);
+    return e == cudaSuccess ? last_error() : (int)e;
+}
+
 // few rows (R <= 128), no bias: split the contraction over CTAs (see the kernel's SPLITK note); Y is zeroed here
 static int launch_rows_splitk(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K, int Cout,
                               int ksplit, cudaStream_t st) {
@@ -1528,6 +1682,7 @@ static int launch_rows_splitk(const float* X, long long ldx, const float* W, lon
 }
 
 
+constexpr int POOL_PAIR_FBN = 192;
 template <int MODE, bool FAST>
 static int launch_fused(const float* X, long long ldx, const float* Wcat, long long ldw, float* out, long long ldo, long long R, int K,
                         int C, const float* bias, long long ldbias, long long rps, const float* stat, const float* gamma,
@@ -1546,11 +1701,53 @@ static int launch_fused(const float* X, long long ldx, const float* Wcat, long l
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return last_error();
         attr_done = true;
     }
+    // CTA pairs are built and tested for this kernel too, but measured no faster (fused conv -> pool GEMM 2.50 vs 2.47 ms: it is bound by
+    // the tensor pipe and its exposed epilogue, not by operand traffic): one SM per tile unless vnpcc_set_tuning(2, 4)
+    if (tuning(TUNE_STATS_GEMM) == 4 && C % (2 * BM) == 0 && R >= 8192 && K >= 256) {
+        // CTA pairs: more stages fit because each CTA stages half of the row block.  POOL: with two SMs feeding one MMA the 96-row tile's
+        // operand traffic fits the shared-memory port (A 4 KB + half of B 1.5 KB per 48-cycle instruction), so the tile can be
+        // double-buffered in TMEM (2 x (P | D) x 96 columns) and the arg-max epilogue overlaps the next tile's MMAs
+        constexpr int PFBN = MODE == MODE_POOL ? (POOL_PAIR_FBN) : FBN;
+        constexpr int PNACC = MODE == MODE_POOL ? (PFBN == 96 ? 2 : 1) : NACC;
+        constexpr int PSTAGES = MODE == MODE_STATS ? 6 : (MODE == MODE_POOL ? (PFBN == 96 ? 5 : 5) : 5);
+        using LP = FusedSmem<PSTAGES, MODE, PFBN / 2>;
+        static_assert(LP::TOTAL <= 232448, "stage ring exceeds the 227 KB of one CTA");
+        CUtensorMap mxh;
+        if (!make_map(&mxh, X, R, K, ldx, BK, PFBN / 2)) return VNPCC_ERR_DRIVER;
+        auto kp = gemm_vn_fused_kernel<PSTAGES, MODE, FAST, PFBN, PNACC, true>;
+        static bool attr_done_p[64] = {false};
+        bool& done_p = attr_done_p[current_device_slot()];
+        if (!done_p) {
+            if (cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL) != cudaSuccess) return last_error();
+            done_p = true;
+        }
+        const long long num_n = (R + PFBN - 1) / PFBN;
+        const int num_mp = C / (2 * BM);
+        const long long tiles = (long long)num_mp * num_n;
+        long long pairs = sm_count() / 2;
+        if (pairs > tiles) pairs = tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(FUSED_THREADS);
+        cfg.dynamicSmemBytes = LP::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        count_launch();
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kp, mw, mxh, out, (size_t)ldo, R, K, C, bias, (size_t)ldbias, rps, stat, gamma, beta, ns,
+                                                 sums, num_mp, tiles);
+        return e == cudaSuccess ? last_error() : (int)e;
+    }
     const int num_m = C / BM;
     const long long num_n = (R + FBN - 1) / FBN;
     const long long num_tiles = num_m * num_n;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-    count_launch(), kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(mw, mx, out, (size_t)ldo, R, K, C, bias, (size_t)ldbias, rps, stat, gamma, beta,
+    count_launch(), kern<<<grid, FUSED_THREADS, L::TOTAL, st>>>(mw, mx, out, (size_t)ldo, R, K, C, bias, (size_t)ldbias, rps, stat, gamma, beta,
                                                              ns, sums, num_m, num_tiles);
     return last_error();
 }
@@ -1579,6 +1776,8 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
         if (!bias && ksplit >= 2) return tc::launch_rows_splitk(X, ldx, W, ldw, Y, ldy, R, K, Cout, ksplit, st);
         return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
     }
+    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256)
+        return tc::launch_rows_pair<256, 6, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
     return tc::launch_rows<256, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
 }
 
@@ -1599,6 +1798,10 @@ int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, lo
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cstat, st);
     const int kc = tuning(TUNE_STATS_NOMATH) ? 0 : Cstat;
+    // CTA pairs (tcgen05 cta_group::2) where a 256-channel tile exists and the contraction is long enough to amortise the pair's
+    // epilogues: measured 3-12 % faster than one SM per tile at the train step's shapes, 15 % slower at K = 128 (tools/pair_gemm_bench.py)
+    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256)
+        return tc::launch_rows_pair<240, 6, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
     switch (tuning(TUNE_STATS_GEMM)) {
         case 2: return tc::launch_rows<240, 3, true, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
         case 3: return tc::launch_rows<240, 3, true, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
