@@ -434,6 +434,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chamfer-leg", action="store_true", help="skip the Chamfer Gpairs/s leg of the default run (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (Python + autograd dispatch per kernel) instead of replaying "
+                    "the captured CUDA graph of the train step")
     ap.add_argument("--no-eval", action="store_true", help="skip the inference leg (profiling runs)")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
                     help="development A/B knob of the kernel library (vnpcc_set_tuning); recorded in config.tuning")
@@ -524,14 +526,28 @@ def main():
 
     timer = KernelTimer()
     ops.set_timer(timer)
-    for i in range(args.warmup):
-        step_resident(i)
+    # The W warm-up steps; then (default) the whole train step -- zero_grad, forward, both losses, backward, gradient exchange, Adam -- is
+    # captured once as a CUDA graph and every timed step is one replay (DataParallelTrainer.capture): the host no longer dispatches ~190
+    # kernels per step through Python and autograd (14 ms of host time per 18 ms step, which starves the GPUs when 8 ranks share the host).
+    use_graph = not args.no_graph
+    graph_note = None
+    if use_graph:
+        try:
+            trainer.capture(*resident[0], warmup=args.warmup)
+        except Exception as e:      # e.g. a model whose forward synchronises with the host: run eagerly and say so
+            use_graph = False
+            graph_note = f"capture failed, eager steps: {type(e).__name__}: {str(e)[:120]}"
+            trainer.release_graph()
+            torch.cuda.synchronize()
+    if not use_graph:
+        for i in range(args.warmup):
+            step_resident(i)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    timer.enabled = True
+    timer.enabled = not use_graph
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -540,13 +556,23 @@ def main():
     e1.record()
     barrier()
     timer.enabled = False
-    launches = _lib.launch_count() - l0
+    launches = (args.steps * trainer.graph_launches) if use_graph else (_lib.launch_count() - l0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     final_loss = float(loss.item())
+    # per-kernel-class CUDA-event timers live in the Python operators, which a graph replay does not execute: with the graph on, the classes
+    # are timed over a second region of eager steps right after the timed one (same inputs, same kernels, same stream)
+    class_steps = args.steps
+    if use_graph:
+        class_steps = min(args.steps, 10)
+        timer.enabled = True
+        for i in range(class_steps):
+            trainer._step_eager(*resident[i % pool])
+        torch.cuda.synchronize()
+        timer.enabled = False
     ksum = timer.summary()
 
     # end-to-end through the public API with host inputs
@@ -600,7 +626,29 @@ def main():
     # N > 1: how much of the step the one exchange (gradient all-reduce over NVLink) costs that is NOT hidden behind the backward pass:
     # the same K steps with the exchange switched off (ranks diverge afterwards -- this is the last leg), max over ranks
     comm_exposed_ms = None
+    ranks_in_sync = None
     if world > 1:
+        # the exchange really happened in every (replayed) step: identical initial weights + averaged gradients + deterministic Adam keep
+        # the parameters of all ranks bit-identical
+        hi, lo = trainer.opt.flat_p.clone(), trainer.opt.flat_p.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        ranks_in_sync = bool(torch.equal(hi, lo))
+        ms_on = ms_total
+        if use_graph:      # compare like with like: the eager step with the exchange against the eager step without it
+            trainer.release_graph()
+            for i in range(2):
+                step_resident(i)
+            barrier()
+            e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e8.record()
+            for i in range(args.steps):
+                step_resident(i)
+            e9.record()
+            barrier()
+            ms5 = torch.tensor([e8.elapsed_time(e9)], device=dev)
+            dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+            ms_on = float(ms5.item())
         trainer.exchange_off = True
         if trainer.exchange is not None:
             trainer.exchange.enabled = False
@@ -615,7 +663,7 @@ def main():
         barrier()
         ms4 = torch.tensor([e6.elapsed_time(e7)], device=dev)
         dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
-        comm_exposed_ms = (ms_total - float(ms4.item())) / args.steps
+        comm_exposed_ms = (ms_on - float(ms4.item())) / args.steps
 
     if rank == 0:
         pk = peaks()
@@ -639,8 +687,8 @@ def main():
                 ent = {"bound": "tensor" if peak else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                        "frac": (tf / peak) if peak else None,
                        "frac_vs_sustained_peak": (tf / (pk["bf16_sustained"] / 2.0)) if peak else None,
-                       "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
-                       "launches_per_step": d["launches"] / args.steps,
+                       "traffic": traffic.get(cls), "ms_per_step": d["ms"] / class_steps,
+                       "launches_per_step": d["launches"] / class_steps,
                        "flop_per_launch": d["work"] / max(d["launches"], 1),
                        "peak_note": f"bf16 burst ({pk['source']}) / 2 for TF32 operands; achieved = sum of 2*R*K*Cout "
                                     "over the class's launches / their CUDA-event time" if peak else
@@ -658,7 +706,7 @@ def main():
                 # the fused decoder-tail backward (sums pre-pass + tail_dgrad_tf32_kernel): HBM-bound by construction
                 gbs = d["bytes"] / sec / 1e9 if sec > 0 else 0.0
                 classes[cls] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                                "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] / args.steps,
+                                "traffic": traffic.get(cls), "ms_per_step": d["ms"] / class_steps, "launches_per_step": d["launches"] / class_steps,
                                 "tflops": d["work"] / sec / 1e12 if sec > 0 else 0.0,
                                 "peak_note": f"algorithmic bytes (pd read twice, gpd and gh written once) / CUDA-event time vs the measured copy "
                                              f"bandwidth ({pk['source']}); the write-heavy mix (3.2 GB in, 4.8 GB out) tops out near 4.7 TB/s"}
@@ -667,7 +715,7 @@ def main():
                 tc_cls = cls.endswith("tf32")
                 peak = pk["bf16_sustained"] / 2.0 if tc_cls else 2 * 148 * 128 * ((clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6) / 1e12
                 classes[cls] = {"bound": "tensor" if tc_cls else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                                "traffic": None, "ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] / args.steps,
+                                "traffic": None, "ms_per_step": d["ms"] / class_steps, "launches_per_step": d["launches"] / class_steps,
                                 "peak_note": "algorithmic attention FLOPs (4 N^2 d forward, 10 N^2 d backward per head) / CUDA-event time vs "
                                              + ("bf16 sustained / 2 (TF32 tcgen05)" if tc_cls else "148 SMs x 128 lanes x 2 x SM clock (fp32 FMA)")}
             elif cls == "chamfer_fwd":
@@ -676,8 +724,8 @@ def main():
                 peak_inst = 148 * 128 * fclk                 # FP32 lane-instructions / s
                 classes[cls] = {"bound": "fp32", "achieved": pairs / 1e9, "peak": peak_inst / 6 / 1e9, "unit": "Gpairs/s",
                                 "frac": 6 * pairs / peak_inst, "frac_of_issued_fma_peak": 3 * pairs / peak_inst,
-                                "traffic": traffic.get(cls), "ms_per_step": d["ms"] / args.steps,
-                                "launches_per_step": d["launches"] / args.steps,
+                                "traffic": traffic.get(cls), "ms_per_step": d["ms"] / class_steps,
+                                "launches_per_step": d["launches"] / class_steps,
                                 "peak_note": "148 SMs x 128 lanes x median SM clock under load / 6 FP32 instr per pair (the "
                                              "reference arithmetic, SURVEY 8d: frac can exceed 1); the pre-filtered search ISSUES 3 FMA lane-operations per pair "
                                              "(frac_of_issued_fma_peak) and re-evaluates only each query's winning chunk with the reference "
@@ -695,7 +743,13 @@ def main():
                 "eval": {"value": (B * world * args.steps / (eval_ms / 1e3)) if not args.no_eval else None, "unit": "samples/s",
                          "what": "eval-mode forward + l1_cd under no_grad (fused VN GEMM epilogue)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_classes": classes,
-                "final_loss": final_loss}
+                "final_loss": final_loss,
+                "cuda_graph": {"used": bool(use_graph), "kernels_per_replay": int(getattr(trainer, "graph_launches", 0)) if use_graph else None,
+                               "note": graph_note or ("timed steps are replays of one captured train step; kernel_classes / roofline were "
+                                                      f"timed over {class_steps} eager steps right after the timed region" if use_graph
+                                                      else "eager steps (--no-graph)")}}
+        if ranks_in_sync is not None:
+            line["ranks_in_sync"] = ranks_in_sync      # parameters bit-identical on all ranks after the timed steps
         if comm_exposed_ms is not None:
             line["comm_exposed_ms"] = comm_exposed_ms      # ms per step: timed region minus the same steps without the gradient exchange
         if world == 1 and headline and not args.no_chamfer_leg:

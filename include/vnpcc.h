@@ -296,6 +296,10 @@ int vnpcc_voxel_iou(const unsigned* bits_a, const unsigned* bits_b, int B, int w
 /* fused Adam over a flat fp32 buffer (torch.optim.Adam semantics, train.py:70): p,g,m,v length n */
 int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* the same update with lr and the step counter in device memory (state = {lr, 1 - beta1^t, sqrt(1 - beta2^t), t}: the call increments t and
+ * refreshes the two corrections on the device), so that a train step captured in a CUDA graph can be replayed (train.py:70, :165-173) */
+int vnpcc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1, float beta2, float eps,
+                        float weight_decay, float grad_scale, void* stream);
 #ifdef __cplusplus
 }
 #endif

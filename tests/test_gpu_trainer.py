@@ -65,3 +65,72 @@ def test_train_steps_reduce_loss_and_state_dict_roundtrip(tmp_path):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     finally:
         V.set_gemm_mode("fp32")
+
+
+def test_flat_adam_device_state_matches_host_state():
+    """vnpcc_adam_step_dev (lr / step / bias corrections in device memory, graph-replayable) against the host-scalar kernel, with a learning
+    rate change in between (what StepLR does, train.py:93)"""
+    from vn_pointcloudcompletion_b200.trainer import FlatAdam
+    torch.manual_seed(1)
+    a = [torch.nn.Parameter(torch.randn(1000, device="cuda"))]
+    b = [torch.nn.Parameter(a[0].detach().clone())]
+    oa, ob = FlatAdam(a, lr=1e-3), FlatAdam(b, lr=1e-3).make_capturable()
+    for step in range(6):
+        g = torch.randn(1000, device="cuda")
+        if step == 3:
+            oa.param_groups[0]["lr"] = ob.param_groups[0]["lr"] = 4e-4
+        for o in (oa, ob):
+            o.zero_grad()
+            o.params[0].grad.copy_(g)
+            o.step()
+        assert torch.equal(a[0], b[0]) or torch.allclose(a[0], b[0], rtol=1e-6, atol=1e-8), f"step {step}"
+    assert oa.step_count == ob.step_count == 6 and float(ob._dev_state[3]) == 6.0
+
+
+def test_captured_train_step_replays_the_eager_step():
+    """DataParallelTrainer.capture(): the whole step as ONE CUDA graph.  Loss trajectories from a random initialisation are chaotic (float
+    atomics flip VNMaxPool selections: two EAGER runs from the same seed differ by 10 % after two steps), so a replay is compared with an
+    eager step FROM THE SAME STATE: the graph trainer's parameters, Adam moments and BatchNorm buffers are overwritten with the eager
+    trainer's, then each takes one step on the same batch -- same loss (forward), same first moments (backward + exchange + Adam)."""
+    import vn_pointcloudcompletion_b200 as V
+    from vn_pointcloudcompletion_b200.synthetic import make_batch
+    from vn_pointcloudcompletion_b200.trainer import DataParallelTrainer
+    V.set_gemm_mode("tf32")
+    try:
+        cfg = SimpleNamespace(num_coarse=1024, latent_dim=2048, only_coarse=False, device="cuda", enc_pretrained="none")
+        data = [tuple(torch.from_numpy(x).cuda() for x in make_batch(4, 512, 4096, seed=50 + i)) for i in range(2)]
+        trs = []
+        for graph in (False, True):
+            torch.manual_seed(0)
+            net = V.PCNNet(cfg).train()
+            tr = DataParallelTrainer(net, lr=1e-4, world_size=1)
+            if graph:
+                tr.capture(*data[0], warmup=1)          # one eager (real) step on batch 0, then the capture
+            else:
+                tr.train_step(*data[0])
+            trs.append(tr)
+        tra, trg = trs
+        assert trg.graph_launches > 100                      # the replay really is the library's ~190 kernels
+        for rounds, lr in ((1, 1e-4), (2, 5e-5)):            # second round: after a learning-rate change (StepLR) between replays
+            trg.opt.flat_p.copy_(tra.opt.flat_p)
+            trg.opt.m.copy_(tra.opt.m)
+            trg.opt.v.copy_(tra.opt.v)
+            for ba, bg in zip(tra.model.buffers(), trg.model.buffers()):
+                bg.copy_(ba)
+            tra.opt.param_groups[0]["lr"] = trg.opt.param_groups[0]["lr"] = lr
+            p_before = tra.opt.flat_p.clone()
+            la, lg = float(tra.train_step(*data[1])), float(trg.train_step(*data[1]))
+            assert abs(la - lg) <= 1e-5 * abs(la), (la, lg)
+            assert tra.opt.step_count == trg.opt.step_count == float(trg.opt._dev_state[3])
+            ma, mg = tra.opt.m, trg.opt.m
+            assert (ma - mg).norm() <= 2e-2 * ma.norm(), float((ma - mg).norm() / ma.norm())
+            ua, ug = tra.opt.flat_p - p_before, trg.opt.flat_p - p_before
+            assert (ua - ug).norm() <= 1e-1 * ua.norm(), float((ua - ug).norm() / ua.norm())
+            assert abs(float(ua.abs().max()) / lr - 1.0) < 0.7     # an Adam step of the right size (|update| ~ lr early on)
+        # inputs of another shape are refused until the graph is released
+        with pytest.raises(ValueError):
+            trg.train_step(data[0][0][:2], data[0][1][:2], data[0][2][:2])
+        trg.release_graph()
+        trg.train_step(data[0][0][:2], data[0][1][:2], data[0][2][:2])
+    finally:
+        V.set_gemm_mode("fp32")

@@ -99,6 +99,7 @@ SIGNATURES = {
     "vnpcc_voxel_occupancy": (_i, [_p, _i, _i, _i, _p, _p]),
     "vnpcc_voxel_iou": (_i, [_p, _p, _i, _i, _p, _p]),
     "vnpcc_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "vnpcc_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _p]),
     "vnpcc_measure_fp32_peak": (_i, [_i, _i, _p, _p, _p, _p]),
 }
 

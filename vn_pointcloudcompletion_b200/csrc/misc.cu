@@ -126,6 +126,34 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// the same update with its step-dependent scalars in DEVICE memory, so that a captured CUDA graph of the whole train step can be replayed:
+// state = {lr, bias correction 1, sqrt(bias correction 2), step}.  adam_advance_kernel increments the step and refreshes the corrections
+// (double pow, as the host path), adam_dev_kernel reads them.
+__global__ void adam_advance_kernel(float* __restrict__ state, float b1, float b2) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double step = (double)state[3] + 1.0;
+        state[3] = (float)step;
+        state[1] = (float)(1.0 - pow((double)b1, step));
+        state[2] = (float)sqrt(1.0 - pow((double)b2, step));
+    }
+}
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, const float* __restrict__ state, float b1, float b2,
+                                                        float eps, float wd, float gscale) {
+    const float lr = state[0], bc1 = state[1], bc2_sqrt = state[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
 // ---- 3xTF32 operand split --------------------------------------------------------------------------------------
 // fp32-accurate GEMMs on the TF32 tensor cores: x = hi + lo with hi = tf32(x) (round to nearest, 11 significant bits) and lo = tf32(x - hi)
 // (x - hi is exact in fp32).  x . w = hi_x hi_w + lo_x hi_w + hi_x lo_w + O(2^-22 |x||w|): three TF32 products accumulated in fp32.  The
@@ -227,6 +255,16 @@ int vnpcc_adam_step(float* p, const float* g, float* m, float* v, long long n, f
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     count_launch(), adam_kernel<<<grid_for((size_t)n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                                              weight_decay, bc1, bc2_sqrt, grad_scale);
+    return last_error();
+}
+
+int vnpcc_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1, float beta2, float eps,
+                        float weight_decay, float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    if (!state) return VNPCC_ERR_BAD_ARG;
+    count_launch(), adam_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+    count_launch(), adam_dev_kernel<<<grid_for((size_t)n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, beta1, beta2, eps,
+                                                                                 weight_decay, grad_scale);
     return last_error();
 }
 

@@ -1042,6 +1042,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
          float(weight_decay), int(step), float(grad_scale), stream())
 
 
+def adam_step_dev(p, g, m, v, state, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    """adam_step with lr / step / bias corrections in the 4-float device tensor `state` (graph-replayable)"""
+    call("vnpcc_adam_step_dev", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(state), float(beta1), float(beta2), float(eps),
+         float(weight_decay), float(grad_scale), stream())
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # transformer-refined decoder (SURVEY 8f row f2): VNLayerNorm, residual add, VN multi-head attention core
 # ---------------------------------------------------------------------------------------------------------------

@@ -184,6 +184,23 @@ class FlatAdam(torch.optim.Optimizer):
                 o += k
         self._bound = [(p, p.data_ptr(), p.grad.data_ptr()) for p in self.params]
         self.step_count = 0
+        self._dev_state = None      # {lr, bias correction 1, sqrt(bias correction 2), step} on the device: set by make_capturable()
+        self._dev_lr = None
+
+    def make_capturable(self):
+        """keep lr and the step counter in device memory (vnpcc_adam_step_dev) so that step() can be captured in a CUDA graph and replayed;
+        the host-side step_count keeps mirroring it (state_dict, schedulers)"""
+        if self._dev_state is None:
+            self._dev_state = torch.tensor([self.lr, 0.0, 0.0, float(self.step_count)], device=self.flat_p.device, dtype=torch.float32)
+            self._dev_lr = self.lr
+        return self
+
+    def sync_device_state(self):
+        """push a changed learning rate (LR scheduler) or a restored step count to the device copy; called outside the captured region"""
+        if self._dev_state is not None:
+            if self._dev_lr != self.lr:
+                self._dev_state[0:1].fill_(self.lr)
+                self._dev_lr = self.lr
 
     # the hyper-parameters live in the param group (what LR schedulers edit)
     lr = property(lambda self: self.param_groups[0]["lr"])
@@ -210,8 +227,14 @@ class FlatAdam(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         self._check_bindings()
         self.step_count += 1
-        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                      self.step_count, grad_scale)
+        if self._dev_state is not None:
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_device_state()
+            ops.adam_step_dev(self.flat_p, self.flat_g, self.m, self.v, self._dev_state, self.betas[0], self.betas[1], self.eps, self.wd,
+                              grad_scale)
+        else:
+            ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                          self.step_count, grad_scale)
         return loss
 
     def state_dict(self):
@@ -252,6 +275,8 @@ class FlatAdam(torch.optim.Optimizer):
         self.step_count = steps[0] if steps else 0
         self.state.clear()
         self.params = self.param_groups[0]["params"]
+        if self._dev_state is not None:
+            self._dev_state[3:4].fill_(float(self.step_count))
 
 
 class DataParallelTrainer:
@@ -320,9 +345,61 @@ class DataParallelTrainer:
         coarse_m, dense_m = (acc[0] / acc[2]).item(), (acc[1] / acc[2]).item()
         return coarse_m, dense_m, coarse_m + dense_m
 
+    def capture(self, p, c, R=None, warmup=3):
+        """Capture the whole train step (zero_grad, forward, both losses, backward, gradient exchange, Adam) for inputs of these shapes in
+        ONE CUDA graph; train_step() then copies its inputs into the graph's static buffers and replays it: ~190 kernel launches, their
+        Python / autograd dispatch and their launch gaps become one graph launch.  The warm-up steps are real optimisation steps.
+        Anything that changes the launch sequence afterwards (gemm mode, tuning knobs, model.eval(), other input shapes) needs a new
+        capture (release_graph() first).  Returns the loss of the last warm-up step."""
+        from . import _lib
+        self.release_graph()
+        self.opt.make_capturable()
+        self._static_in = (p.clone(), c.clone(), R.clone() if R is not None else None)
+        side = torch.cuda.Stream(device=p.device)
+        side.wait_stream(torch.cuda.current_stream(p.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):      # lazy initialisation (function attributes, workspaces) must not happen under capture
+                loss = self._step_eager(*self._static_in)
+        torch.cuda.current_stream(p.device).wait_stream(side)
+        torch.cuda.synchronize(p.device)
+        steps_before = self.opt.step_count
+        l0 = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._static_loss = self._step_eager(*self._static_in)
+        self.graph_launches = _lib.launch_count() - l0      # this library's kernel launches inside one replay
+        # capturing enqueued nothing: undo the host-side bookkeeping of the captured step
+        self.opt.step_count = steps_before
+        self._graph = g
+        return loss
+
+    def release_graph(self):
+        self._graph = None
+        self._static_in = None
+        self._static_loss = None
+
     def train_step(self, p, c, R=None):
         """p [B,2048,3] partial, c [B,16384,3] complete, R [B,3,3] rotation already applied to both (train.py:133-138).
-        Returns the detached loss tensor (no host sync)."""
+        Returns the detached loss tensor (no host sync).  After capture() the step is a CUDA-graph replay."""
+        g = getattr(self, "_graph", None)
+        if g is not None and not self.exchange_off:
+            sp, sc, sR = self._static_in
+            if p.shape != sp.shape or c.shape != sc.shape or (R is None) != (sR is None):
+                raise ValueError("train_step inputs differ in shape from the captured step: call capture() again (or release_graph())")
+            if p.data_ptr() != sp.data_ptr():
+                sp.copy_(p, non_blocking=True)
+            if c.data_ptr() != sc.data_ptr():
+                sc.copy_(c, non_blocking=True)
+            if R is not None and R.data_ptr() != sR.data_ptr():
+                sR.copy_(R, non_blocking=True)
+            self.opt.sync_device_state()
+            g.replay()
+            self.opt.step_count += 1
+            return self._static_loss
+        return self._step_eager(p, c, R)
+
+    def _step_eager(self, p, c, R=None):
+        self.opt.sync_device_state()
         self.opt.zero_grad()
         coarse, dense = self.model(p, Rotate(R) if R is not None else None)
         loss = cd_loss_L1(coarse, c)
