@@ -350,7 +350,9 @@ class DataParallelTrainer:
         ONE CUDA graph; train_step() then copies its inputs into the graph's static buffers and replays it: ~190 kernel launches, their
         Python / autograd dispatch and their launch gaps become one graph launch.  The warm-up steps are real optimisation steps.
         Anything that changes the launch sequence afterwards (gemm mode, tuning knobs, model.eval(), other input shapes) needs a new
-        capture (release_graph() first).  Returns the loss of the last warm-up step."""
+        capture (release_graph() first).  Like every whole-step capture in PyTorch it needs the parameters' gradient accumulators to have
+        been created on a side stream: call it before the model has run a backward pass on the default stream whose autograd graph is
+        still alive (build the model, build the trainer, capture).  Returns the loss of the last warm-up step."""
         from . import _lib
         self.release_graph()
         self.opt.make_capturable()
