@@ -12,8 +12,16 @@
 extern "C" {
 #endif
 
-/* development knobs for A/B measurements (tools/stream_bench.py); every knob defaults to 0 = the shipped behaviour.
- * knob 0: 1 = legacy fixed grids instead of occupancy-sized single-wave grids;  knob 1: fused small-K backward register budget */
+/* development knobs for A/B measurements (tools/*_bench.py, tools/step_ab.py); every knob defaults to 0 = the shipped behaviour.
+ *   0  1 = legacy fixed grids instead of occupancy-sized single-wave grids; also disables split-K for the few-row GEMMs
+ *   1  fused small-K backward: 1 = four channels per thread at 1 CTA/SM, 2 = four channels at 2 CTAs/SM, 3 = two channels at 2 CTAs/SM,
+ *      0 / 4 = two channels, sums pass at 3 CTAs/SM (shipped), 5-7 = further occupancy variants (measured slower)
+ *   2  rows GEMM tiling: 0 = CTA pairs (tcgen05 cta_group::2) where eligible, 1 = one SM per tile (4 stages), 2 = one SM, 3 stages,
+ *      3 = one SM with the TMA-store statistics epilogue, 4 = CTA pairs also for the fused VN-epilogue kernels
+ *   3  1 = statistics epilogue without its arithmetic (timing experiments only: wrong statistics)
+ *   4  Chamfer planner: per-item overhead of the cost model in candidates (0 = 256)      5  search CTAs per SM the planner sizes for (0 = 8)
+ *   6  1 = scalar-FFMA ranking loop in the pre-filtered search                            7  1 = never use the fused tail weight-gradient kernel
+ *   8  fused small-K forward: 1 = fp64 statistics pass, 3 / 4 = forward at 3 / 4 CTAs per SM (measured slower) */
 void vnpcc_set_tuning(int knob, int value);
 
 /* host-logic introspection: the launch planners (work-item splits, chunk lengths, grids) as pure functions of the problem size, so that
