@@ -780,7 +780,10 @@ class _MaxPoolGatherTap(torch.autograd.Function):
     """_MaxPoolGather that also hands its input through (an alias): for an activation that feeds the pool AND a dense consumer
     (models/pcn.py:168-173: feature -> maxpool1 and -> cat -> second_conv).  The pooled gradient touches one point per (group, channel);
     the backward scatters it IN PLACE into the dense consumer's gradient instead of materialising a second dense tensor of zeros and
-    summing the two (a 400 MB fill + a 1.2 GB add per step at B = 32)."""
+    summing the two (a 400 MB fill + a 1.2 GB add per step at B = 32).
+    CONTRACT: the alias must be consumed by exactly one Function whose backward returns a freshly allocated gradient (here: the linear
+    layers' dgrad output, pcn.py).  A consumer that forwards its incoming gradient unchanged (an add, a view, a hook that keeps a
+    reference) would see the pooled gradient scattered into ITS tensor too -- route such a consumer through maxpool_rows(tap=False)."""
 
     @staticmethod
     def forward(ctx, x, idx, G, N):
