@@ -1612,6 +1612,7 @@ static int launch_rows(const float* X, long long ldx, const float* W, long long 
     return last_error();
 }
 
+constexpr int PAIR_LAUNCH_REFUSED = -77;
 // CTA pairs (see the kernel's CTA2 note): Cout a multiple of 256, many row blocks
 template <int BN, int STAGES, bool STATS, int GAP = 0>      // STAGES of 16 KB of W + BN / 2 rows of X
 static int launch_rows_pair(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R, int K, int Cout,
@@ -1652,7 +1653,11 @@ static int launch_rows_pair(const float* X, long long ldx, const float* W, long 
     count_launch();
     const cudaError_t e = cudaLaunchKernelEx(&cfg, bias ? kb : kn, mw, mx, mx, Y, (size_t)ldy, R, K, Cout, bias, (size_t)ldbias,
                                              (long long)(rps > 0 ? rps : 1), num_mp, num_tiles, sums, Cstat, 0);
-    return e == cudaSuccess ? last_error() : (int)e;
+    if (e != cudaSuccess) {      // the cluster launch itself was refused (e.g. a partition without SM pairs): the caller uses one SM per tile
+        (void)cudaGetLastError();
+        return PAIR_LAUNCH_REFUSED;
+    }
+    return last_error();
 }
 
 // few rows (R <= 128), no bias: split the contraction over CTAs (see the kernel's SPLITK note); Y is zeroed here
@@ -1776,8 +1781,10 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
         if (!bias && ksplit >= 2) return tc::launch_rows_splitk(X, ldx, W, ldw, Y, ldy, R, K, Cout, ksplit, st);
         return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
     }
-    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256)
-        return tc::launch_rows_pair<256, 6, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256) {
+        const int rc = tc::launch_rows_pair<256, 6, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+        if (rc != tc::PAIR_LAUNCH_REFUSED) return rc;
+    }
     return tc::launch_rows<256, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
 }
 
@@ -1800,8 +1807,10 @@ int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, lo
     const int kc = tuning(TUNE_STATS_NOMATH) ? 0 : Cstat;
     // CTA pairs (tcgen05 cta_group::2) where a 256-channel tile exists and the contraction is long enough to amortise the pair's
     // epilogues: measured 3-12 % faster than one SM per tile at the train step's shapes, 15 % slower at K = 128 (tools/pair_gemm_bench.py)
-    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256)
-        return tc::launch_rows_pair<240, 6, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
+    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256) {
+        const int rc = tc::launch_rows_pair<240, 6, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
+        if (rc != tc::PAIR_LAUNCH_REFUSED) return rc;
+    }
     switch (tuning(TUNE_STATS_GEMM)) {
         case 2: return tc::launch_rows<240, 3, true, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
         case 3: return tc::launch_rows<240, 3, true, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
