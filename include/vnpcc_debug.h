@@ -20,7 +20,7 @@ extern "C" {
  *      3 = one SM with the TMA-store statistics epilogue, 4 = CTA pairs also for the fused VN-epilogue kernels
  *   3  1 = statistics epilogue without its arithmetic (timing experiments only: wrong statistics)
  *   4  Chamfer planner: per-item overhead of the cost model in candidates (0 = 256)      5  search CTAs per SM the planner sizes for (0 = 8)
- *   6  1 = scalar-FFMA ranking loop in the pre-filtered search                            7  1 = never use the fused tail weight-gradient kernel
+ *   6  1 = scalar-FFMA ranking loop in the pre-filtered search                            7  1 = never use the fused tail weight-gradient kernel, 3 = tail dgrad with one SM per tile instead of CTA pairs
  *   8  fused small-K forward: 1 = fp64 statistics pass, 3 / 4 = forward at 3 / 4 CTAs per SM (measured slower) */
 void vnpcc_set_tuning(int knob, int value);
 

@@ -25,6 +25,15 @@ def tf32_mode():
     V.set_gemm_mode("fp32")
 
 
+def _with_knob(knob, value, fn):
+    from vn_pointcloudcompletion_b200 import _lib
+    _lib.raw("vnpcc_set_tuning", knob, value)
+    try:
+        return fn()
+    finally:
+        _lib.raw("vnpcc_set_tuning", knob, 0)
+
+
 SHAPES = [(512, 128, 512), (768, 512, 2048), (1000, 96, 200), (96, 2048, 1024), (4096, 256, 256), (300, 1024, 130), (70000, 64, 128),
           # few rows: the contraction is split over CTAs and accumulated with red.add (K not a multiple of the split, one-tile outputs)
           (96, 1024, 1024), (96, 1024, 3072), (64, 256, 512), (128, 1000, 384), (100, 4096, 64)]
@@ -273,7 +282,10 @@ def test_3xtf32_is_fp32_accurate(R, K, Cout):
     assert errs["tf32"][1] > 20 * e3y          # plain TF32 is far coarser
 
 
-@pytest.mark.parametrize("P,Cin,C,with_res", [(32 * 40 + 13, 256, 256, True), (5000, 128, 128, False), (7, 256, 128, True), (96 * 33, 256, 256, False)])
+@pytest.mark.parametrize("P,Cin,C,with_res", [(32 * 40 + 13, 256, 256, True), (5000, 128, 128, False), (7, 256, 128, True), (96 * 33, 256, 256, False),
+                                              # enough points for the CTA-pair form of tail_dgrad (Cin = 256): ragged last pair tile, one CTA
+                                              # of the last pair without rows
+                                              (64 * 74 + 21, 256, 256, True), (64 * 150 + 40, 256, 128, False)])
 def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
     """the decoder tail VNLinearLeakyReLU(Cin -> C) -> VNLinear(C, 1) (+ residual), models/pcn.py:340-345,387, as one autograd node: the fused
     TF32 backward (sums pre-pass + tail_dgrad_tf32_kernel, which forms the final gradient of (p | d) inside the dgrad GEMM) against the
@@ -306,6 +318,19 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
         finally:
             ops._TAIL_FUSED_BWD = True
             ops._TAIL_FUSED_WGRAD = False
+    # the CTA-pair and the one-SM form of tail_dgrad issue the same MMA sequence per element: identical input gradients
+    ops._TAIL_FUSED_BWD, ops._TAIL_FUSED_WGRAD = True, False
+
+    def one_sm():
+        bn = nn.BatchNorm1d(C).cuda().train()
+        with torch.no_grad():
+            bn.weight.copy_(bw)
+            bn.bias.copy_(bb)
+        hh = h.clone().requires_grad_(True)
+        ops.linear_bn_leaky_dot(hh, wcat.clone().requires_grad_(True), bn, True, 0.2, w2.clone().requires_grad_(True), None).backward(gy)
+        return hh.grad
+    gh_default, gh_one = one_sm(), _with_knob(7, 3, one_sm)
+    assert torch.equal(gh_default, gh_one)
     b = out[False]
     names = ["y", "gh", "gw", "gw2", "ggamma", "gbeta", "gres"]
     for key in (True, "no-wgrad"):
@@ -319,15 +344,6 @@ def test_tail_fused_backward_matches_unfused(tf32_mode, P, Cin, C, with_res):
         print(key, names[i], rel)
         # (R < 64: the unfused dgrad falls back to the exact SIMT kernel, so the difference is TF32 operand rounding itself)
         assert rel < (2e-4 if R >= 64 else 3e-3), (names[i], rel)
-
-
-def _with_knob(knob, value, fn):
-    from vn_pointcloudcompletion_b200 import _lib
-    _lib.raw("vnpcc_set_tuning", knob, value)
-    try:
-        return fn()
-    finally:
-        _lib.raw("vnpcc_set_tuning", knob, 0)
 
 
 @pytest.mark.parametrize("R,K,Cout,Cs,nsamp", [(3 * 4000, 256, 512, 0, 0), (3 * 4000, 256, 512, 256, 0), (3 * 3003, 512, 1024, 512, 3), (3 * 9001, 320, 256, 0, 0),

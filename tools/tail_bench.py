@@ -39,6 +39,12 @@ st = _lib.stream()
 h = torch.randn(R, Cin, device="cuda")
 gW = torch.empty(2 * C, Cin, device="cuda")
 t_fused = timeit(lambda: _lib.call("vnpcc_tail_bwd_tf32", gy, pd, 2 * C, P, C, stat, gamma, beta, 0.2, w2, wt, 2 * C, Cin, 1, sums, gw2, gpd, 2 * C, gh, Cin, None, 0, None, 0, st))
+gh1, gpd1 = gh.clone(), gpd.clone()
+_lib.raw("vnpcc_set_tuning", 7, 2)
+t_pair = timeit(lambda: _lib.call("vnpcc_tail_bwd_tf32", gy, pd, 2 * C, P, C, stat, gamma, beta, 0.2, w2, wt, 2 * C, Cin, 1, sums, gw2, gpd, 2 * C, gh, Cin, None, 0, None, 0, st))
+_lib.raw("vnpcc_set_tuning", 7, 0)
+print(f"CTA pairs: pre-pass + tail_dgrad {t_pair:.3f} ms (one SM per tile {t_fused:.3f}); gh equal {torch.equal(gh, gh1)}, gpd equal {torch.equal(gpd, gpd1)}, "
+      f"max diff gh {float((gh - gh1).abs().max()):.2e}", flush=True)
 t_fused_w = timeit(lambda: _lib.call("vnpcc_tail_bwd_tf32", gy, pd, 2 * C, P, C, stat, gamma, beta, 0.2, w2, wt, 2 * C, Cin, 1, sums, gw2, None, 0, gh, Cin, h, Cin, gW, Cin, st))
 t_wg = timeit(lambda: ops.gemm_wgrad(gpd, h, out=gW))
 t_b1 = timeit(lambda: _lib.call("vnpcc_bn_leaky_dot_bwd1", gy, pd, 2 * C, pd[:, C:], 2 * C, gpd, 2 * C, gpd[:, C:], 2 * C, P, C, stat, gamma, beta, 0.2, sums, w2, gw2, st))

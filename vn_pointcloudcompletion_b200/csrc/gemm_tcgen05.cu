@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "vnpcc_internal.h"
 
 namespace vnpcc {
@@ -935,14 +937,23 @@ constexpr int TB_SA = 2, TB_SB = 3;
 constexpr int TB_A_HALF = 256 * BK * 4;          // one half (p or d) of a weight stage: up to 256 output rows x 32 channels
 constexpr int TB_B_HALF = TB_BN * BK * 4;        // 96 rows x 32 channels
 constexpr int TB_MAX_C = 256;
-struct TailSmem {
-    static constexpr int A_STAGE = 2 * TB_A_HALF;
+template <int A_HALF_, int SA_, int SB_>
+struct TailSmemT {
+    static constexpr int A_HALF = A_HALF_, SA = SA_, SB = SB_;
+    static constexpr int A_STAGE = 2 * A_HALF;
     static constexpr int B_STAGE = 2 * TB_B_HALF;
-    static constexpr int B_OFFSET = TB_SA * A_STAGE;
-    static constexpr int PAR_OFFSET = B_OFFSET + TB_SB * B_STAGE;      // 7 per-channel parameter rows of TB_MAX_C floats
+    static constexpr int B_OFFSET = SA * A_STAGE;
+    static constexpr int PAR_OFFSET = B_OFFSET + SB * B_STAGE;      // 7 per-channel parameter rows of TB_MAX_C floats
     static constexpr int BAR_OFFSET = PAR_OFFSET + 7 * TB_MAX_C * 4;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int NUM_BARS = 2 * SA + 5 * SB + 4;      // a_full/a_empty, b_loaded/b_full/b_empty/b_stored/b_pair, t_full/t_empty x 2
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;     // barriers + TMEM slot, alignment slack
+    static_assert(NUM_BARS * 8 + 4 <= 512, "barrier block");
 };
+using TailSmem = TailSmemT<TB_A_HALF, TB_SA, TB_SB>;
+// CTA pairs: a CTA stages only its 128 output rows of Wcat^T (16 KB per half) -- the shared memory that frees deepens both rings
+using TailSmemPair = TailSmemT<BM * BK * 4, 3, 5>;
+static_assert(TailSmemPair::TOTAL <= 232448, "pair layout exceeds the 227 KB of one CTA");
+
 
 __device__ __forceinline__ uint32_t sw128_off(int r, int kappa) {      // element (row r, k index kappa < 32) of a K-major SWIZZLE_128B k-block
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kappa >> 2) ^ (r & 7))) << 4) + (kappa & 3) * 4);
@@ -994,30 +1005,39 @@ __device__ __forceinline__ void tail_grad_point(const TailChan& ch, float k1, bo
 // MMA operand layout) -- asynchronously, TB_SB stages deep, so HBM latency is covered by the ring and not by registers --, the producer warps
 // turn them IN PLACE into (gp | gd), the MMA contracts them and a store warp sends the same shared-memory blocks to gpd by bulk tensor stores.
 // Warp roles: 0 TMA loads (weights + pd), 1 MMA issuer, 2 TMEM allocator, 3 TMA stores (gpd), 4-7 epilogue (gh), 8-15 gradient producers.
-template <bool STORE_GPD>      // false: gpd is not written (the weight gradient comes from tail_wgrad_tf32_kernel, which forms it itself)
+// CTA2 = true (Cin = 256): CTA pairs.  The pair owns 192 rows (each CTA produces the gradients of ITS 96 rows) and the 256 output rows of
+// Wcat^T (each CTA stages the 128 rows it will store: half of the weight bytes per CTA); rank 0 issues tcgen05.mma.cta_group::2 (M = 256,
+// N = 192) once both CTAs' producers have arrived on its pair barrier.  num_tiles counts 192-row pair tiles.
+template <bool STORE_GPD, bool CTA2 = false>      // STORE_GPD false: gpd is not written (tail_wgrad_tf32_kernel forms the gradient itself)
 __global__ void __launch_bounds__(TB_THREADS, 1)
 tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_pd,
                        const __grid_constant__ CUtensorMap map_gpd, const float* __restrict__ gy, long long P, int C, int Cin,
                        const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, float ns,
                        const float* __restrict__ w2, const double* __restrict__ sums, double count, int training, float* __restrict__ gh,
                        size_t ldgh, long long num_tiles) {
-    using L = TailSmem;
+    using L = typename std::conditional<CTA2, TailSmemPair, TailSmem>::type;
+    constexpr int SA = L::SA, SB = L::SB, A_HALF = L::A_HALF;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1024-byte aligned; plain offset arithmetic keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
     float* s_par = reinterpret_cast<float*>(smem + L::PAR_OFFSET);      // [7][TB_MAX_C]: mean, invstd, gamma, beta, w2, m1, m2
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-    uint64_t* a_empty = a_full + TB_SA;
-    uint64_t* b_loaded = a_empty + TB_SA;      // TMA: the pd blocks of the stage have landed
-    uint64_t* b_full = b_loaded + TB_SB;       // producers: (gp | gd) written (count TB_PW); waited on by the MMA warp AND the store warp
-    uint64_t* b_empty = b_full + TB_SB;        // MMA: the stage has been read by the tensor core
-    uint64_t* b_stored = b_empty + TB_SB;      // store warp: the stage has been read by its bulk stores
-    uint64_t* t_full = b_stored + TB_SB;
+    uint64_t* a_empty = a_full + SA;
+    uint64_t* b_loaded = a_empty + SA;      // TMA: the pd blocks of the stage have landed
+    uint64_t* b_full = b_loaded + SB;       // producers: (gp | gd) written (count TB_PW); waited on by the MMA warp AND the store warp
+    uint64_t* b_empty = b_full + SB;        // MMA: the stage has been read by the tensor core
+    uint64_t* b_stored = b_empty + SB;      // store warp: the stage has been read by its bulk stores
+    uint64_t* t_full = b_stored + SB;
     uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* b_pair = t_empty + 2;            // CTA2: rank 0's copy collects the producers of both CTAs (count 2 * TB_PW) for the MMA thread
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_pair + SB);
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;
+    const long long tile_first = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const long long tile_step = CTA2 ? (gridDim.x >> 1) : gridDim.x;
+    constexpr int TILE_ROWS = CTA2 ? 2 * TB_BN : TB_BN;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncb = C / 32;            // channel blocks of the p (and of the d) half
-    const int MT = Cin / 128;          // output-row tiles of 128 TMEM lanes
+    const int MT = CTA2 ? 1 : Cin / 128;      // output-row tiles of 128 TMEM lanes per CTA (a pair splits Cin = 256 between its CTAs)
     const long long R = P * 3;
 
     if (warp == 0 && lane == 0) {
@@ -1026,19 +1046,20 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
         tma_prefetch_desc(&map_gpd);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TB_SA; ++s) {
+        for (int s = 0; s < SA; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
         }
-        for (int s = 0; s < TB_SB; ++s) {
+        for (int s = 0; s < SB; ++s) {
             mbar_init(&b_loaded[s], 1);
             mbar_init(&b_full[s], TB_PW);
             mbar_init(&b_empty[s], 1);
             mbar_init(&b_stored[s], 1);
+            mbar_init(&b_pair[s], 2 * TB_PW);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&t_full[a], 1);
-            mbar_init(&t_empty[a], 4);
+            mbar_init(&t_empty[a], CTA2 ? 8 : 4);
         }
         fence_barrier_init();
     }
@@ -1052,17 +1073,21 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
         s_par[5 * TB_MAX_C + c] = training ? (float)(sums[c] / count) * ga : 0.f;
         s_par[6 * TB_MAX_C + c] = training ? (float)(sums[C + c] / count) * ga : 0.f;
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if (CTA2) tmem_alloc_2sm(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             PipeState pa, pb;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int row0 = (int)(tile * TB_BN);
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int row0 = (int)(tile * TILE_ROWS + cta_rank * TB_BN);
                 for (int cb = 0; cb < ncb; ++cb) {
                     // pd blocks first (HBM latency), then this step's weights (L2)
                     mbar_wait(&b_empty[pb.stage], pb.phase ^ 1);
@@ -1071,30 +1096,36 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                     mbar_expect_tx(&b_loaded[pb.stage], (uint32_t)L::B_STAGE);
                     tma_load_2d(&map_pd, &b_loaded[pb.stage], sb, cb * 32, row0);
                     tma_load_2d(&map_pd, &b_loaded[pb.stage], sb + TB_B_HALF, C + cb * 32, row0);
-                    pb.advance<TB_SB>();
+                    pb.advance<SB>();
                     mbar_wait(&a_empty[pa.stage], pa.phase ^ 1);
                     uint8_t* sa = smem + pa.stage * L::A_STAGE;
-                    mbar_expect_tx(&a_full[pa.stage], (uint32_t)(2 * MT * BM * BK * 4));
-                    for (int m = 0; m < MT; ++m) {
-                        tma_load_2d(&map_wt, &a_full[pa.stage], sa + m * (BM * BK * 4), cb * 32, m * BM);                      // p-half columns
-                        tma_load_2d(&map_wt, &a_full[pa.stage], sa + TB_A_HALF + m * (BM * BK * 4), C + cb * 32, m * BM);      // d-half columns
+                    if (CTA2) {      // each CTA its 128 output rows, at the same offsets in both; bytes counted on rank 0's barrier
+                        if (cta_rank == 0) mbar_expect_tx(&a_full[pa.stage], (uint32_t)(2 * 2 * BM * BK * 4));
+                        tma_load_2d_2sm(&map_wt, &a_full[pa.stage], sa, cb * 32, (int)cta_rank * BM);
+                        tma_load_2d_2sm(&map_wt, &a_full[pa.stage], sa + A_HALF, C + cb * 32, (int)cta_rank * BM);
+                    } else {
+                        mbar_expect_tx(&a_full[pa.stage], (uint32_t)(2 * MT * BM * BK * 4));
+                        for (int m = 0; m < MT; ++m) {
+                            tma_load_2d(&map_wt, &a_full[pa.stage], sa + m * (BM * BK * 4), cb * 32, m * BM);                      // p-half columns
+                            tma_load_2d(&map_wt, &a_full[pa.stage], sa + A_HALF + m * (BM * BK * 4), C + cb * 32, m * BM);      // d-half columns
+                        }
                     }
-                    pa.advance<TB_SA>();
+                    pa.advance<SA>();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, TB_BN, 0, 0);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, TILE_ROWS, 0, 0);
             PipeState pa, pb;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&t_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 for (int cb = 0; cb < ncb; ++cb) {
                     mbar_wait(&a_full[pa.stage], pa.phase);
-                    mbar_wait(&b_full[pb.stage], pb.phase);
+                    mbar_wait(CTA2 ? &b_pair[pb.stage] : &b_full[pb.stage], pb.phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + pa.stage * L::A_STAGE);
                     const uint32_t sb = smem_u32(smem + L::B_OFFSET + pb.stage * L::B_STAGE);
@@ -1104,18 +1135,25 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                         for (int half = 0; half < 2; ++half) {
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k) {
-                                const uint64_t ad = make_desc(sa + half * TB_A_HALF + m * (BM * BK * 4) + k * UMMA_K * 4, 16, 1024);
+                                const uint64_t ad = make_desc(sa + half * A_HALF + m * (BM * BK * 4) + k * UMMA_K * 4, 16, 1024);
                                 const uint64_t bd = make_desc(sb + half * TB_B_HALF + k * UMMA_K * 4, 16, 1024);
-                                umma_tf32(d_tmem, ad, bd, idesc, (cb | half | k) != 0 ? 1u : 0u);
+                                if (CTA2) umma_tf32_2sm(d_tmem, ad, bd, idesc, (cb | half | k) != 0 ? 1u : 0u);
+                                else umma_tf32(d_tmem, ad, bd, idesc, (cb | half | k) != 0 ? 1u : 0u);
                             }
                         }
                     }
-                    umma_commit(&a_empty[pa.stage]);
-                    umma_commit(&b_empty[pb.stage]);
-                    pa.advance<TB_SA>();
-                    pb.advance<TB_SB>();
+                    if (CTA2) {
+                        umma_commit_2sm(&a_empty[pa.stage]);
+                        umma_commit_2sm(&b_empty[pb.stage]);
+                    } else {
+                        umma_commit(&a_empty[pa.stage]);
+                        umma_commit(&b_empty[pb.stage]);
+                    }
+                    pa.advance<SA>();
+                    pb.advance<SB>();
                 }
-                umma_commit(&t_full[acc]);
+                if (CTA2) umma_commit_2sm(&t_full[acc]);
+                else umma_commit(&t_full[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -1126,8 +1164,8 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
         // gpd leaves from the same shared-memory blocks the MMA reads: two bulk tensor stores per stage (clipped at the tensor bounds)
         if (lane == 0 && STORE_GPD) {
             PipeState pb;
-            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int row0 = (int)(tile * TB_BN);
+            for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int row0 = (int)(tile * TILE_ROWS + cta_rank * TB_BN);
                 for (int cb = 0; cb < ncb; ++cb) {
                     mbar_wait(&b_full[pb.stage], pb.phase);
                     const uint8_t* sb = smem + L::B_OFFSET + pb.stage * L::B_STAGE;
@@ -1136,7 +1174,7 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                     tma_store_commit();
                     tma_store_wait_read<0>();
                     mbar_arrive(&b_stored[pb.stage]);
-                    pb.advance<TB_SB>();
+                    pb.advance<SB>();
                 }
             }
         }
@@ -1145,15 +1183,15 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
         const int quad = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const long long n0 = tile * TB_BN;
+        for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const long long n0 = tile * TILE_ROWS;
             mbar_wait(&t_full[acc], acc_phase);
             tc_fence_after();
             for (int m = 0; m < MT; ++m) {
-                const int kch = m * BM + quad * 32 + lane;
+                const int kch = (CTA2 ? (int)cta_rank : m) * BM + quad * 32 + lane;
                 const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + m * 128);
 #pragma unroll 1
-                for (int c0 = 0; c0 < TB_BN; c0 += 32) {
+                for (int c0 = 0; c0 < TILE_ROWS; c0 += 32) {
                     const long long r0 = n0 + c0;
                     if (r0 >= R) break;
                     float v[32];
@@ -1171,7 +1209,10 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[acc]);
+            if (lane == 0) {
+                if (CTA2) mbar_arrive_rank0(&t_empty[acc]);
+                else mbar_arrive(&t_empty[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -1182,8 +1223,8 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
         const int pw = warp - 8;
         const float k1 = 1.f - ns;
         PipeState pb;
-        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const long long pt0 = tile * 32 + pw * 4;
+        for (long long tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const long long pt0 = tile * (TILE_ROWS / 3) + cta_rank * 32 + pw * 4;
             float gyv[4][3];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1213,14 +1254,21 @@ tail_dgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the async proxy (tensor core, bulk stores)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&b_full[pb.stage]);
-                pb.advance<TB_SB>();
+                if (lane == 0) {
+                    mbar_arrive(&b_full[pb.stage]);                      // this CTA's store warp (and, one SM per tile, its MMA thread)
+                    if (CTA2) mbar_arrive_rank0(&b_pair[pb.stage]);      // the pair's MMA thread
+                }
+                pb.advance<SB>();
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (CTA2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 2) {
+        if (CTA2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1893,9 +1941,44 @@ int vnpcc_tail_bwd_tf32(const float* gy, const float* pd, long long ldpd, long l
             return last_error();
         attr_done = true;
     }
+    bool launched = false;
+    if (Cin == 256 && tuning(TUNE_TAIL_WGRAD) != 3 && P >= 64 * (long long)(sm_count() / 2)) {
+        // CTA pairs (see the kernel's CTA2 note): 192-row pair tiles, one cluster of two CTAs per SM pair
+        static bool attr_p[64] = {false};
+        bool& done_p = attr_p[current_device_slot()];
+        auto k1 = tc::tail_dgrad_tf32_kernel<true, true>;
+        auto k0 = tc::tail_dgrad_tf32_kernel<false, true>;
+        if (!done_p) {
+            if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmemPair::TOTAL) != cudaSuccess ||
+                cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmemPair::TOTAL) != cudaSuccess)
+                return last_error();
+            done_p = true;
+        }
+        const long long tiles = (P + 63) / 64;
+        long long pairs = sm_count() / 2;
+        if (pairs > tiles) pairs = tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(tc::TB_THREADS);
+        cfg.dynamicSmemBytes = tc::TailSmemPair::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        count_launch();
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, fused_w ? k0 : k1, mwt, mpd, mgpd, gy, P, C, Cin, stat, gamma, beta, ns, w2,
+                                                 (const double*)sums, (double)P, training, gh, (size_t)ldgh, tiles);
+        if (e == cudaSuccess) launched = true;
+        else (void)cudaGetLastError();
+    }
     const long long num_tiles = (P + 31) / 32;
     const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-    if (fused_w)
+    if (launched) {
+    } else if (fused_w)
         count_launch(), tc::tail_dgrad_tf32_kernel<false><<<grid, tc::TB_THREADS, tc::TailSmem::TOTAL, st>>>(
             mwt, mpd, mgpd, gy, P, C, Cin, stat, gamma, beta, ns, w2, sums, (double)P, training, gh, (size_t)ldgh, num_tiles);
     else
