@@ -30,6 +30,8 @@ void vnpcc_debug_chamfer_plan(int B, int N, int M, int* out4);                  
 void vnpcc_debug_fold_geometry(int B, int N, int C, int resident, int lanes, int* out6); /* {grid.x, grid.y, block.x, block.y, chunk, row mode} */
 void vnpcc_debug_wgrad_plan(long long R, int Cout, int K, int sms, long long* out4);  /* {grid.x, grid.y, splits, rows per split} */
 int vnpcc_debug_plan_chunk_len(long long groups, int N, long long slots, int lanes, int min_chunk);
+/* rows GEMM form for a problem: {variant (0 one SM per tile, 1 CTA pairs, 2 split-K), K splits, rows per tile, grid, tiles} */
+void vnpcc_debug_rows_plan(long long R, int K, int Cout, int has_bias, int stats, int sms, long long* out5);
 
 /* Chamfer search variant: 0 = exact scalar search, 1 = exact packed-fp32 search, 2 (default, any other value) = pre-filtered search with
  * exact resolve.  All three give bit-identical results; tests/test_gpu_chamfer.py runs every case under each of them. */

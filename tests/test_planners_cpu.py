@@ -79,3 +79,44 @@ def test_plan_chunk_len(groups, N, slots, lanes, min_chunk):
         return math.ceil(groups * math.ceil(N / ln) / slots) * (math.ceil(ln / lanes) + 4)
     hi = max(1, min(max(1, N // min_chunk), math.ceil(8 * slots / groups)))
     assert cost(chunks) <= min(cost(c) for c in range(1, hi + 1))
+
+
+def _rows_plan(R, K, Cout, bias=0, stats=0, sms=SMS):
+    out = _ints(5, C.c_longlong)
+    _lib.raw("vnpcc_debug_rows_plan", R, K, Cout, bias, stats, sms, out)
+    return dict(zip(("variant", "ksplit", "bn", "grid", "tiles"), list(out)))
+
+
+def test_rows_gemm_plan_at_the_train_step_shapes():
+    """which form of the tcgen05 rows GEMM the BASELINE step's launches get: CTA pairs for the big K >= 256 layers,
+    one SM per tile for K = 128, split-K for the 96-row heads"""
+    dec_fwd = _rows_plan(1572864, 256, 512, stats=1)                    # decoder final_conv[1] forward with statistics
+    assert dec_fwd["variant"] == 1 and dec_fwd["bn"] == 240 and dec_fwd["grid"] == SMS
+    enc_fwd = _rows_plan(196608, 512, 2048, bias=1, stats=1)           # encoder second_conv[0] forward (per-sample bias)
+    assert enc_fwd["variant"] == 1 and enc_fwd["tiles"] == 8 * math.ceil(196608 / 240)
+    assert _rows_plan(1572864, 512, 256)["variant"] == 1                # decoder dgrad
+    assert _rows_plan(196608, 128, 512)["variant"] == 0                 # K = 128: measured slower on pairs
+    assert _rows_plan(196608, 512, 128)["variant"] == 0                 # no 256-channel tile
+    head = _rows_plan(96, 1024, 1024)                                   # per-sample heads: 8 CTAs -> 64
+    assert head["variant"] == 2 and head["ksplit"] == 8 and head["grid"] == 64 and head["bn"] == 128
+    assert _rows_plan(96, 1024, 1024, bias=1)["variant"] == 0           # partial products cannot carry the bias
+
+
+@pytest.mark.parametrize("R,K,Cout,bias,stats", [(96, 1024, 3072, 0, 0), (64, 256, 512, 0, 0), (128, 1000, 384, 0, 0), (100, 4096, 64, 0, 0),
+                                                  (96, 96, 1024, 0, 0), (8192, 256, 256, 0, 0), (8191, 256, 256, 0, 0), (30000, 320, 768, 1, 0),
+                                                  (3 * 5000, 200, 384, 0, 1), (10 ** 6, 2048, 4096, 0, 0), (300, 64, 128, 0, 0)])
+def test_rows_gemm_plan_invariants(R, K, Cout, bias, stats):
+    p = _rows_plan(R, K, Cout, bias, stats)
+    num_m, num_kb = math.ceil(Cout / 128), math.ceil(K / 32)
+    assert 1 <= p["grid"] <= SMS and p["grid"] <= max(p["tiles"], 1) * (2 if p["variant"] == 1 else 1)
+    if p["variant"] == 2:       # split-K: few rows, no bias, every split non-empty and at least ~4 K blocks long, about one CTA per SM at most
+        assert R <= 128 and not bias and not stats
+        kb_per = math.ceil(num_kb / p["ksplit"])
+        assert p["ksplit"] >= 2 and kb_per * (p["ksplit"] - 1) < num_kb and kb_per >= 4
+        assert p["tiles"] == num_m * p["ksplit"] and p["tiles"] <= SMS + num_m
+    elif p["variant"] == 1:     # CTA pairs: whole 256-channel tiles, long contraction, many row blocks; clusters of two CTAs
+        assert Cout % 256 == 0 and K >= 256 and R >= 8192
+        assert p["grid"] % 2 == 0 and p["tiles"] == (Cout // 256) * math.ceil(R / p["bn"])
+    else:
+        assert p["tiles"] == num_m * math.ceil(R / p["bn"]) and p["ksplit"] == 1
+    assert p["bn"] == (128 if (R <= 128 and not stats) else (240 if stats else 256))

@@ -23,6 +23,7 @@ SIGNATURES = {
     "vnpcc_debug_fold_geometry": (None, [_i, _i, _i, _i, _i, _p]),
     "vnpcc_debug_wgrad_plan": (None, [_ll, _i, _i, _i, _p]),
     "vnpcc_debug_plan_chunk_len": (_i, [_ll, _i, _ll, _i, _i]),
+    "vnpcc_debug_rows_plan": (None, [_ll, _i, _i, _i, _i, _i, _p]),
     "vnpcc_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "vnpcc_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "vnpcc_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

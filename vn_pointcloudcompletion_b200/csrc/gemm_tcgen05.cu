@@ -1812,6 +1812,54 @@ using namespace vnpcc;
 
 extern "C" {
 
+// Which form of the rows GEMM a problem gets -- a pure host function of the sizes (exported as vnpcc_debug_rows_plan for
+// tests/test_planners_cpu.py).  variant 0: one SM per 128-channel tile; 1: CTA pairs (256-channel tiles, cta_group::2); 2: split-K (few rows).
+struct RowsPlan {
+    int variant, ksplit, bn, grid;
+    long long tiles;
+};
+static RowsPlan plan_rows(long long R, int K, int Cout, bool has_bias, bool stats, int sms, int tiling_knob, int legacy_grid) {
+    RowsPlan p = {0, 1, stats ? 240 : 256, 0, 0};
+    const int num_m = (Cout + tc::BM - 1) / tc::BM, num_kb = (K + tc::BK - 1) / tc::BK;
+    if (!stats && R <= 128) {
+        // the grid would be Cout / 128 CTAs: split the contraction until about one CTA per SM streams >= 4 K blocks (128 columns of W)
+        p.bn = 128;
+        int ksplit = sms / num_m < num_kb / 4 ? sms / num_m : num_kb / 4;
+        if (legacy_grid) ksplit = 1;
+        if (!has_bias && ksplit >= 2) {
+            const int kb_per = (num_kb + ksplit - 1) / ksplit;
+            p.variant = 2;
+            p.ksplit = (num_kb + kb_per - 1) / kb_per;      // no empty split
+        }
+        p.tiles = (long long)num_m * p.ksplit;
+        p.grid = (int)(p.tiles < sms ? p.tiles : sms);
+        return p;
+    }
+    const long long num_n = (R + p.bn - 1) / p.bn;
+    // CTA pairs where a 256-channel tile exists and the contraction is long enough to amortise the pair's epilogues: measured 3-12 % faster
+    // than one SM per tile at the train step's shapes, 15 % slower at K = 128 (tools/pair_gemm_bench.py)
+    if ((tiling_knob == 0 || tiling_knob == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256 && sms >= 2) {
+        p.variant = 1;
+        p.tiles = (long long)(Cout / 256) * num_n;
+        const long long pairs = p.tiles < sms / 2 ? p.tiles : sms / 2;
+        p.grid = (int)(2 * pairs);
+        return p;
+    }
+    p.tiles = (long long)num_m * num_n;
+    p.grid = (int)(p.tiles < sms ? p.tiles : sms);
+    return p;
+}
+
+// include/vnpcc_debug.h: out = {variant, K splits, rows per tile, grid, tiles}
+void vnpcc_debug_rows_plan(long long R, int K, int Cout, int has_bias, int stats, int sms, long long* out) {
+    const RowsPlan p = plan_rows(R, K, Cout, has_bias != 0, stats != 0, sms > 0 ? sms : 148, 0, 0);
+    out[0] = p.variant;
+    out[1] = p.ksplit;
+    out[2] = p.bn;
+    out[3] = p.grid;
+    out[4] = p.tiles;
+}
+
 int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long long ldw, float* Y, long long ldy, long long R,
                          int K, int Cout, const float* bias, long long ldbias, long long rows_per_sample, void* stream) {
     if (R <= 0 || Cout <= 0) return 0;
@@ -1821,15 +1869,10 @@ int vnpcc_gemm_rows_tf32(const float* X, long long ldx, const float* W, long lon
     if (Cout < 64 || R < 64) return VNPCC_ERR_UNSUPPORTED;
     if (bias && (rows_per_sample <= 0 || rows_per_sample % 3 != 0)) return VNPCC_ERR_BAD_ARG;   // a sample is whole points (3 rows each)
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 128) {
-        // the grid would be Cout / 128 CTAs: split the contraction until about one CTA per SM streams >= 4 K blocks (128 columns of W)
-        const int num_m = (Cout + tc::BM - 1) / tc::BM, num_kb = (K + tc::BK - 1) / tc::BK;
-        int ksplit = sm_count() / num_m < num_kb / 4 ? sm_count() / num_m : num_kb / 4;
-        if (tuning(TUNE_GRID_LEGACY)) ksplit = 1;
-        if (!bias && ksplit >= 2) return tc::launch_rows_splitk(X, ldx, W, ldw, Y, ldy, R, K, Cout, ksplit, st);
-        return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
-    }
-    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256) {
+    const RowsPlan plan = plan_rows(R, K, Cout, bias != nullptr, false, sm_count(), tuning(TUNE_STATS_GEMM), tuning(TUNE_GRID_LEGACY));
+    if (plan.variant == 2) return tc::launch_rows_splitk(X, ldx, W, ldw, Y, ldy, R, K, Cout, plan.ksplit, st);
+    if (R <= 128) return tc::launch_rows<128, 4, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
+    if (plan.variant == 1) {
         const int rc = tc::launch_rows_pair<256, 6, false>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, nullptr, 0, st);
         if (rc != tc::PAIR_LAUNCH_REFUSED) return rc;
     }
@@ -1853,9 +1896,7 @@ int vnpcc_gemm_rows_tf32_stats(const float* X, long long ldx, const float* W, lo
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Cstat, st);
     const int kc = tuning(TUNE_STATS_NOMATH) ? 0 : Cstat;
-    // CTA pairs (tcgen05 cta_group::2) where a 256-channel tile exists and the contraction is long enough to amortise the pair's
-    // epilogues: measured 3-12 % faster than one SM per tile at the train step's shapes, 15 % slower at K = 128 (tools/pair_gemm_bench.py)
-    if ((tuning(TUNE_STATS_GEMM) == 0 || tuning(TUNE_STATS_GEMM) == 4) && Cout % 256 == 0 && R >= 8192 && K >= 256) {
+    if (plan_rows(R, K, Cout, bias != nullptr, true, sm_count(), tuning(TUNE_STATS_GEMM), 0).variant == 1) {
         const int rc = tc::launch_rows_pair<240, 6, true>(X, ldx, W, ldw, Y, ldy, R, K, Cout, bias, ldbias, rows_per_sample, sums, kc, st);
         if (rc != tc::PAIR_LAUNCH_REFUSED) return rc;
     }
