@@ -41,3 +41,26 @@ def test_bench_reference_arm_uses_the_staged_reference():
     src = inspect.getsource(bench.cpu_reference_step)
     assert "RM.available()" in src and '"kind": "reference"' in src and '"kind": "port"' in src
     assert callable(RM.build_pcnnet)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`python bench.py --impl reference --steps 1 --warmup 0` on the host cores: one JSON line with this arm's metric / config / unit and the
+    reference-arm keys the measurement contract names (impl, cpu_baseline.kind, e2e with zero copy bytes)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=repo)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "vn_pcn_train_samples_per_s" and line["unit"] == "samples/s"
+    assert line["steps"] == 1 and line["higher_is_better"] is True and line["value"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
